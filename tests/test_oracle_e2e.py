@@ -1,0 +1,144 @@
+"""The CPU oracle against the reference's end-to-end expectations and its shipped on-disk index."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from conftest import CARS_DESCRIPTION, COLLECTION, GOLDEN, REFERENCE_TESTDATA, TEST_DESCRIPTION
+from gobhdr import decode_header
+
+MODES = [(O.CANONICAL, O.CP_MERGE), (O.FAITHFUL, O.CP_MERGE), (O.FAITHFUL, O.SCAN_COUNT), (O.FAITHFUL, O.MERGE_SKIP),
+         (O.FAITHFUL, O.DIVIDE_SKIP)]
+
+
+@pytest.fixture(scope="module")
+def small_index():
+    return O.OracleIndex(**TEST_DESCRIPTION).add_docs(COLLECTION).commit()
+
+
+@pytest.fixture(scope="module")
+def cars_index(cars_lines):
+    return O.OracleIndex(**CARS_DESCRIPTION).add_docs(cars_lines).commit()
+
+
+# pkg/suggest/ngram_index_test.go:15-40 — ids in order
+@pytest.mark.parametrize("mode,merger", MODES)
+def test_suggest_auto(small_index, mode, merger):
+    ids, scores = small_index.suggest("Nissan ma", O.JACCARD, 0.5, 2, mode, merger)
+    assert ids.tolist() == [2, 0]
+    assert np.all(np.diff(scores) <= 0)
+
+
+# pkg/suggest/example_test.go:14-72 — alphabet english + "$" only
+@pytest.mark.parametrize("mode,merger", MODES)
+def test_example(mode, merger):
+    ix = O.OracleIndex(ngram_size=3, wrap=("$", "$"), pad="$", alphabet=("english", "$")).add_docs(COLLECTION).commit()
+    ids, _ = ix.suggest("niss ma", O.COSINE, 0.4, 5, mode, merger)
+    assert [COLLECTION[i] for i in ids] == ["Nissan Maxima", "Nissan March"]
+
+
+# pkg/suggest/service_test.go:35-59 — cars dictionary, Cosine 0.7, k=5
+@pytest.mark.parametrize("mode,merger", MODES)
+def test_service_cars(cars_index, cars_lines, mode, merger):
+    words = ["Nissan March", "Honda Fitt", "Wolfsvagen", "Tayota Corolla", "Micra Nissan"]
+    expected = [["NISSAN MARCH"], ["HONDA FIT"], [], ["TOYOTA COROLLA"], ["NISSAN MICRA"]]
+    for w, exp in zip(words, expected):
+        ids, _ = cars_index.suggest(w, O.COSINE, 0.7, 5, mode, merger)
+        assert [cars_lines[i].decode() for i in ids] == exp
+
+
+def test_cars_structure(cars_index):
+    # figures of SURVEY.md §6 / BASELINE.md §2
+    assert cars_index.n_docs == 5066
+    assert cars_index.segments == 52
+    assert cars_index.lists == 36285
+    assert cars_index.postings == 105818
+
+
+def _check_disk_index(ix, hd_path, dl_path, allow_roaring=False):
+    with open(hd_path, "rb") as f:
+        version, indices, terms = decode_header(f.read())
+    with open(dl_path, "rb") as f:
+        dl = f.read()
+    assert version == "v5.1"
+    assert indices == ix.segments
+    assert len(terms) == ix.lists
+    skipped = 0
+    for term, indice, size, pos, length in terms:
+        mine = ix.get_list(indice, term)
+        assert mine is not None and len(mine) == length, (term, indice)
+        blob = dl[pos:pos + size]
+        if length <= 65:
+            got = O.decode(O.CODEC_VB, blob, length)
+        elif length <= 256:
+            got = O.decode(O.CODEC_SKIPPING, blob, length, 64)
+        else:
+            assert allow_roaring
+            skipped += 1
+            continue
+        assert np.array_equal(got, mine), (term, indice)
+        # the encoder restatement must reproduce the Go writer's bytes exactly
+        codec = O.CODEC_VB if length <= 65 else O.CODEC_SKIPPING
+        assert O.encode(codec, mine, 64) == blob, (term, indice)
+    return skipped
+
+
+def test_cars_disk_index_bytes(cars_index):
+    """Every list of the shipped cars.dl decodes to, and re-encodes from, the oracle's rebuild of cars.dict."""
+    _check_disk_index(cars_index, os.path.join(GOLDEN, "cars.hd"), os.path.join(GOLDEN, "cars.dl"))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_TESTDATA), reason="reference checkout not present")
+def test_words_disk_index_bytes():
+    with open(os.path.join(REFERENCE_TESTDATA, "words.dict"), "rb") as f:
+        lines = f.read().split(b"\n")[:-1]
+    ix = O.OracleIndex(ngram_size=3, wrap=("^", "$"), pad="$", alphabet=("english", "numbers", "$^")).add_docs(lines)
+    skipped = _check_disk_index(ix, os.path.join(REFERENCE_TESTDATA, "db", "words.hd"),
+                                os.path.join(REFERENCE_TESTDATA, "db", "words.dl"), allow_roaring=True)
+    assert skipped == 1378  # roaring blobs (lists longer than 256), SURVEY.md §6
+
+
+@pytest.mark.parametrize("metric,alpha,k", [(O.COSINE, 0.7, 5), (O.JACCARD, 0.5, 10), (O.DICE, 0.5, 10)])
+def test_faithful_equals_canonical_on_cars(cars_index, cars_lines, metric, alpha, k):
+    """Line-faithful CPMerge path vs the canonical rule, every entry used as a query.
+
+    They may differ only where SURVEY.md §8c rule 5b applies: some returned document has duplicate
+    tokens after normalisation (the reference then emits a phantom twin id)."""
+    ids_c, sc_c, n_c = cars_index.suggest_batch(cars_lines, metric, alpha, k, O.CANONICAL, threads=8)
+    ids_f, sc_f, n_f = cars_index.suggest_batch(cars_lines, metric, alpha, k, O.FAITHFUL, O.CP_MERGE, threads=8)
+    dup = np.array([cars_index.has_duplicate_tokens(l) for l in cars_lines])
+    assert dup.sum() == 211
+    diverged = 0
+    for q in range(len(cars_lines)):
+        a = (ids_c[q, :n_c[q]].tolist(), sc_c[q, :n_c[q]].tolist())
+        b = (ids_f[q, :n_f[q]].tolist(), sc_f[q, :n_f[q]].tolist())
+        if a != b:
+            involved = set(a[0]) | set(b[0])
+            assert any(dup[i] for i in involved), (q, cars_lines[q], a, b)
+            diverged += 1
+    assert diverged <= 16
+
+
+def test_ram_ram_phantom_twin(cars_index, cars_lines):
+    # SURVEY.md §8c rule 5b worked example
+    ids, sc = cars_index.suggest("RAM RAM", O.COSINE, 0.7, 5, O.CANONICAL)
+    assert [cars_lines[i].decode() for i in ids] == ["RAM RAM", "RAM C/V", "RAM 1500", "RAM 2500", "RAM 3500"]
+    assert sc[0] == 1.0
+    ids_f, _ = cars_index.suggest("RAM RAM", O.COSINE, 0.7, 5, O.FAITHFUL, O.CP_MERGE)
+    assert len(set(ids_f.tolist())) < len(ids_f)  # the reference returns the same id twice here
+
+
+def test_degenerate_windows_return_empty(small_index):
+    # the reference panics (negative channel size) / deadlocks here; the contract is "empty"
+    long_q = "x" * 200
+    for mode, merger in MODES:
+        ids, _ = small_index.suggest(long_q, O.JACCARD, 0.9, 3, mode, merger)
+        assert len(ids) == 0
+    ids, _ = small_index.suggest("", O.JACCARD, 0.5, 3)
+    assert len(ids) == 0
+
+
+def test_query_stats_small(small_index):
+    st = small_index.query_stats("Nissan ma", O.JACCARD, 0.5)
+    assert st["size_a"] == 9 and st["segments"] > 0 and st["postings"] >= st["lists"] > 0
