@@ -1,0 +1,172 @@
+/*
+ * suggest_b200.h — C ABI of libsuggest_b200.so, the B200 (sm_100a) implementation of the
+ * suggest-go/suggest `Service.Suggest -> NGramIndex.Suggest` hot path.
+ *
+ * The reference has no FFI of its own (pure Go, CGO_ENABLED=0); its seam is the Go interface pair
+ *   suggest.Builder{ Build() (NGramIndex, error) }            pkg/suggest/ngram_index_builder.go:14-17
+ *   suggest.Suggester{ Suggest(query, similarity, metric, factory) ([]Candidate, error) }
+ *                                                              pkg/suggest/suggester.go:17-20
+ * A cgo shim implements those two interfaces on top of the entry points below,
+ * so `Service.AddIndex(name, dict, builder)` (pkg/suggest/service.go:78-91) accepts the GPU index
+ * unchanged.  Every entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every input and output buffer and the library
+ *     never keeps a pointer past the call (cgo pointer rules);
+ *   - return 0 on success, a negative sg_status otherwise; sg_last_error() gives the thread-local
+ *     message (Go side: errors.New(C.GoString(C.sg_last_error())));
+ *   - an sg_index is immutable after creation and may be searched from any number of host threads
+ *     at once (pkg/suggest/service_test.go:19-80 exercises exactly that); sg_index_free waits for
+ *     calls in flight;
+ *   - results are fixed stride: row q of out_ids/out_scores holds out_counts[q] <= k candidates
+ *     ordered (score desc, id asc) as pkg/suggest/collector.go:20-26 + topk.go:127-147 emit them.
+ */
+#ifndef SUGGEST_B200_H
+#define SUGGEST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SG_OK = 0,
+    SG_ERR_INVALID = -1,      /* bad argument (NewSearchConfig rules: k >= 1, 0 < similarity <= 1) */
+    SG_ERR_UNSUPPORTED = -2,  /* description outside what the device tokenizer encodes (see sg_index_build) */
+    SG_ERR_CUDA = -3,         /* CUDA runtime failure, message holds cudaGetErrorString */
+    SG_ERR_NOMEM = -4,
+    SG_ERR_QUERY_TOO_LONG = -5, /* some query has more than SG_MAX_QUERY_TOKENS n-grams; its count is SG_COUNT_UNSUPPORTED */
+    SG_ERR_IO = -6,
+    SG_ERR_FORMAT = -7        /* on-disk index is not "v5.1" or is corrupt */
+} sg_status;
+
+/* pkg/metric: JaccardMetric, CosineMetric, DiceMetric, OverlapMetric, ExactMetric */
+typedef enum { SG_JACCARD = 0, SG_COSINE = 1, SG_DICE = 2, SG_OVERLAP = 3, SG_EXACT = 4 } sg_metric;
+
+#define SG_MAX_NGRAM 8               /* pkg/analysis/ngram_tokenizer.go:3 (maxN) */
+#define SG_MAX_QUERY_TOKENS 128      /* per query; the reference saturates at 0xFFFF (pkg/merger/list_merger.go:9) */
+#define SG_MAX_TOPK 1024
+#define SG_COUNT_UNSUPPORTED 0xFFFFFFFFu
+
+/* suggest.IndexDescription, pkg/suggest/config.go:25-35 (tokenizer-relevant fields) */
+typedef struct {
+    int32_t ngram_size;            /* NGramSize, 1..8 */
+    const char *wrap_start;        /* Wrap[0], UTF-8 */
+    const char *wrap_end;          /* Wrap[1] */
+    const char *pad;               /* Pad: must decode to exactly one rune */
+    const char *const *alphabet;   /* Alphabet: "english" | "russian" | "numbers" | literal characters */
+    int32_t n_alphabet;
+    int32_t device;                /* CUDA device ordinal that will hold the index */
+} sg_config;
+
+typedef struct sg_index sg_index;
+
+typedef struct {
+    uint32_t n_docs;
+    uint32_t n_segments;     /* InvertedIndexIndices.Size() = largest cardinality + 1 */
+    uint32_t n_terms;        /* distinct n-grams */
+    uint64_t n_lists;        /* non-empty (segment, term) posting lists */
+    uint64_t n_postings;
+    uint64_t device_bytes;   /* HBM held by the handle */
+    uint32_t id_base;
+    int32_t device;
+} sg_index_info;
+
+/*
+ * Build the index on the GPU from the dictionary text.
+ * Replaces suggest.NewRAMBuilder(dict, description).Build()  (pkg/suggest/ngram_index_builder.go:27-83),
+ * i.e. suggest.Index (pkg/suggest/indexer.go:14-45) + index.Writer.AddDocument/Commit
+ * (pkg/index/indexer_writer.go:66-145) + index.Reader.Read (pkg/index/index_reader.go:29-120), with
+ * the posting lists kept decoded in HBM as CSR instead of VB/skipping/roaring bytes.
+ * Document i gets id id_base + i (pkg/dictionary/helpers.go:38-45: id = line number); id_base > 0
+ * is for record-id-range shards.
+ */
+int sg_index_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs,
+                   uint32_t id_base, sg_index **out);
+
+/*
+ * Build from posting lists the caller already decoded (for a Go shim that read `.hd/.dl` itself).
+ * list i belongs to cardinality segment list_segment[i] and term list_term_off[i]..list_term_off[i+1]
+ * of term_bytes, and holds ids[list_off[i]..list_off[i+1]) in ascending order.
+ * Replaces index.Reader.Read (pkg/index/index_reader.go:29-120).
+ */
+int sg_index_from_lists(const sg_config *cfg, uint32_t n_segments, uint64_t n_lists, const uint32_t *list_segment,
+                        const char *term_bytes, const uint64_t *list_term_off, const uint32_t *ids,
+                        const uint64_t *list_off, sg_index **out);
+
+/*
+ * Open an index written by the reference's `suggest indexer` (header `<name>.hd`, gob; lists
+ * `<name>.dl`, VB / skipping(64) / roaring by length class).  Replaces suggest.NewFSBuilder(...).Build()
+ * (pkg/suggest/ngram_index_builder.go:38-83, pkg/index/index_reader.go:29-120, pkg/compression).
+ */
+int sg_index_open_disk(const sg_config *cfg, const char *hd_path, const char *dl_path, sg_index **out);
+
+void sg_index_free(sg_index *ix);
+int sg_index_get_info(const sg_index *ix, sg_index_info *info);
+
+/*
+ * Batched NGramIndex.Suggest with a FuzzyCollectorManager(k): for every query
+ *   tokenise (pkg/suggest/tokenizer.go:9-20, pkg/analysis) -> segment window and thresholds
+ *   (pkg/suggest/suggester.go:46-131, pkg/metric) -> posting fetch + T-occurrence count
+ *   (pkg/index/searcher.go:28-78, pkg/merger) -> score (pkg/suggest/scorer.go:29-31) -> top-k
+ *   (pkg/suggest/collector.go:117-191, topk.go).
+ * HOST buffers; the call copies queries to the device, runs the kernels and copies results back.
+ * q_off has n_q + 1 entries.  out_ids / out_scores hold n_q * k entries, out_counts n_q.
+ * A single Suggest call is a batch of one.
+ */
+int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                    uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts);
+
+/*
+ * Same, every buffer already resident on the index's device; enqueued on `stream` (a cudaStream_t,
+ * NULL = default stream) without synchronising.  Queries must already be lower-cased if they hold
+ * non-ASCII bytes (sg_search_batch does that on the host, strings.ToLower semantics).
+ * d_stats may be NULL; otherwise it receives per query {admissible postings, admissible lists}
+ *  as two uint32.
+ */
+int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,
+                           double alpha, uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts,
+                           uint32_t *d_stats, void *stream);
+
+/*
+ * Cross-shard reduce for record-id-range shards: for every query pick the k best of n_parts
+ * per-shard results (layout [part][query][k] as an all-gather of sg_search_batch_device outputs
+ * delivers them) under the same (score desc, id asc) order.  Device buffers.
+ * The reference has no counterpart (single process); the order is FuzzyCollectorManager.Collect's
+ * queue merge, pkg/suggest/collector.go:165-178.
+ */
+int sg_merge_topk_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *d_part_ids,
+                         const double *d_part_scores, const uint32_t *d_part_counts, uint32_t *d_out_ids,
+                         double *d_out_scores, uint32_t *d_out_counts, void *stream);
+
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+uint64_t sg_kernel_launches(void);
+
+const char *sg_last_error(void);
+const char *sg_version(void);
+
+/*
+ * Host-only introspection (no GPU is touched): the tokenizer chain and the CSR build exactly as the
+ * library runs them before the upload, exposed so that the CPU test-suite can compare them with the
+ * reference's rules (pkg/suggest/tokenizer.go:9-20, pkg/index/indexer_writer.go:66-86).  Searching
+ * has no host implementation.
+ */
+typedef struct sg_host_index sg_host_index;
+int sg_host_tokenize(const sg_config *cfg, const char *text, uint32_t len, char *out_bytes, uint32_t cap,
+                     uint32_t *tok_off, uint32_t max_tok);   /* returns the token count; tok_off[count + 1] */
+int sg_host_to_lower(const char *text, uint32_t len, char *out, uint32_t cap); /* strings.ToLower; returns length */
+int sg_host_index_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs,
+                        sg_host_index **out);
+int sg_host_index_open_disk(const sg_config *cfg, const char *hd_path, const char *dl_path, sg_host_index **out);
+void sg_host_index_free(sg_host_index *hi);
+int sg_host_index_get_info(const sg_host_index *hi, sg_index_info *info);
+/* original ids of list (segment, term), ascending; returns the length, -1 if absent, -2 if cap is too small */
+int64_t sg_host_index_get_list(const sg_host_index *hi, uint32_t segment, const char *term, uint32_t term_len,
+                               uint32_t *out, uint64_t cap);
+const char *sg_host_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

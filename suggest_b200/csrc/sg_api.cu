@@ -1,0 +1,472 @@
+// sg_api.cu — the C ABI of libsuggest_b200 (include/suggest_b200.h): index handles in HBM, host <-> device
+// staging for sg_search_batch, per-call streams and scratch so one handle can be searched from many
+// host threads at once (pkg/suggest/service_test.go:19-80 is the reference's concurrency test).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/suggest_b200.h"
+#include "sg_host.h"
+#include "sg_kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+constexpr uint32_t kWorkRing = 1024;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define SG_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            std::string m__ = std::string(#expr) + ": " + cudaGetErrorString(e__);             \
+            cudaGetLastError();                                                                \
+            return fail(e__ == cudaErrorMemoryAllocation ? SG_ERR_NOMEM : SG_ERR_CUDA, m__);   \
+        }                                                                                      \
+    } while (0)
+
+struct DeviceGuard {  // the library never leaves the caller on another device
+    int prev = -1;
+    cudaError_t set(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        return dev == prev ? cudaSuccess : cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// one in-flight sg_search_batch: its stream and device staging
+struct CallCtx {
+    cudaStream_t stream = nullptr;
+    DevBuf<char> q_bytes;
+    DevBuf<uint32_t> q_off, ids, counts, work;
+    DevBuf<double> scores;
+};
+
+}  // namespace
+
+struct sg_index {
+    sg::HostIndex host;  // posting arrays are dropped after the upload; the description stays
+    sg::DevIndex dev{};
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    uint64_t device_bytes = 0;
+    std::vector<void *> allocations;
+    std::mutex mu;
+    std::condition_variable cv;
+    int inflight = 0;
+    bool closing = false;
+    std::vector<CallCtx *> pool;
+    uint32_t *work_ring = nullptr;       // kWorkRing query counters for sg_search_batch_device
+    std::atomic<uint32_t> work_rr{0};
+    uint32_t tbl_bytes = 16384;
+    int force_shift = -1;
+    int max_warps = 32;
+};
+
+namespace {
+
+template <typename T>
+int upload(sg_index *ix, const std::vector<T> &v, const T **out, size_t min_elems = 1) {
+    size_t n = v.size() > min_elems ? v.size() : min_elems;
+    void *d = nullptr;
+    SG_CUDA(cudaMalloc(&d, n * sizeof(T)));
+    ix->allocations.push_back(d);
+    ix->device_bytes += n * sizeof(T);
+    if (!v.empty()) SG_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (v.size() < n) SG_CUDA(cudaMemset((char *)d + v.size() * sizeof(T), 0, (n - v.size()) * sizeof(T)));
+    *out = (const T *)d;
+    return SG_OK;
+}
+
+void decode_runes(const std::string &s, uint32_t *out, int32_t *n) {
+    std::string low;
+    sg::to_lower((const uint8_t *)s.data(), s.size(), &low);
+    *n = 0;
+    for (size_t i = 0; i < low.size();) {
+        uint32_t r;
+        i += (size_t)sg::utf8_decode((const uint8_t *)low.data() + i, low.size() - i, &r);
+        out[(*n)++] = r;
+    }
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+// host arrays -> HBM, fill the DevIndex view
+int finalize(sg_index *ix) {
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    cudaDeviceProp prop;
+    SG_CUDA(cudaGetDeviceProperties(&prop, ix->device));
+    if (prop.major < 10) return fail(SG_ERR_UNSUPPORTED, "libsuggest_b200 needs an sm_100 device, found " + std::string(prop.name));
+    ix->sm_count = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    sg::HostIndex &h = ix->host;
+    sg::DevIndex &d = ix->dev;
+    d.n = h.text.n;
+    d.bits = h.text.bits;
+    d.pad_code = h.text.pad_code;
+    decode_runes(h.text.wrap_start, d.wrap_start, &d.n_wrap_start);
+    decode_runes(h.text.wrap_end, d.wrap_end, &d.n_wrap_end);
+    std::memcpy(d.ascii_code, h.text.ascii_code, sizeof(d.ascii_code));
+    d.n_ranges = (int32_t)h.text.ranges.size();
+    d.n_terms = (uint32_t)h.term_keys.size();
+    d.term_mask = (uint32_t)h.ht_keys.size() - 1;
+    d.n_segments = h.n_segments;
+    d.n_docs = h.n_docs;
+    d.id_base = h.id_base;
+    int rc;
+    if ((rc = upload(ix, h.text.ranges, &d.ranges)) != SG_OK) return rc;
+    if ((rc = upload(ix, h.ht_keys, &d.term_keys)) != SG_OK) return rc;
+    if ((rc = upload(ix, h.ht_vals, &d.term_vals)) != SG_OK) return rc;
+    if ((rc = upload(ix, h.seg_start, &d.seg_start)) != SG_OK) return rc;
+    if ((rc = upload(ix, h.list_off, &d.list_off)) != SG_OK) return rc;
+    if ((rc = upload(ix, h.postings, &d.postings, 8)) != SG_OK) return rc;
+    if ((rc = upload(ix, h.perm, &d.perm)) != SG_OK) return rc;
+    {
+        void *ring = nullptr;
+        SG_CUDA(cudaMalloc(&ring, kWorkRing * sizeof(uint32_t)));
+        ix->allocations.push_back(ring);
+        ix->work_ring = (uint32_t *)ring;
+    }
+    std::vector<uint32_t>().swap(h.postings);
+    std::vector<uint32_t>().swap(h.list_off);
+    std::vector<uint32_t>().swap(h.perm);
+    std::vector<uint64_t>().swap(h.ht_keys);
+    std::vector<uint32_t>().swap(h.ht_vals);
+    // tuning knobs (documented in DESIGN.md); defaults are what bench.py measures
+    int tb = env_int("SG_TBL_BYTES", 16384);
+    uint32_t t = 2048;
+    while (t < (uint32_t)tb && t < 131072u) t <<= 1;
+    ix->tbl_bytes = t;
+    ix->force_shift = env_int("SG_FORCE_SHIFT", -1);
+    ix->max_warps = env_int("SG_WARPS", 32);
+    if (ix->max_warps < 1) ix->max_warps = 1;
+    if (ix->max_warps > 32) ix->max_warps = 32;
+    return SG_OK;
+}
+
+void destroy(sg_index *ix) {
+    if (!ix) return;
+    DeviceGuard guard;
+    guard.set(ix->device);
+    for (CallCtx *c : ix->pool) {
+        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release();
+        if (c->stream) cudaStreamDestroy(c->stream);
+        delete c;
+    }
+    for (void *p : ix->allocations) cudaFree(p);
+    delete ix;
+}
+
+int check_config(const sg_config *cfg, sg_index **out) {
+    if (!cfg || !out) return fail(SG_ERR_INVALID, "null argument");
+    int n_dev = 0;
+    SG_CUDA(cudaGetDeviceCount(&n_dev));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(SG_ERR_INVALID, "no such CUDA device");
+    return SG_OK;
+}
+
+int make_index(const sg_config *cfg, sg_index **out, sg_index **ixp) {
+    int rc = check_config(cfg, out);
+    if (rc != SG_OK) return rc;
+    sg_index *ix = new (std::nothrow) sg_index();
+    if (!ix) return fail(SG_ERR_NOMEM, "out of host memory");
+    ix->device = cfg->device;
+    std::string err = ix->host.text.init(cfg->ngram_size, cfg->wrap_start, cfg->wrap_end, cfg->pad, cfg->alphabet, cfg->n_alphabet);
+    if (!err.empty()) { delete ix; return fail(SG_ERR_UNSUPPORTED, err); }
+    *ixp = ix;
+    return SG_OK;
+}
+
+struct Geometry { int blocks, warps; size_t smem; uint32_t warp_smem; };
+
+int geometry(const sg_index *ix, uint32_t n_q, uint32_t k, Geometry *g) {
+    uint32_t warp_smem = ix->tbl_bytes + 3u * sg::kMaxQueryTokens * 4u + k * 12u;
+    warp_smem = (warp_smem + 15u) & ~15u;
+    int warps = (int)(ix->smem_optin / warp_smem);
+    if (warps > ix->max_warps) warps = ix->max_warps;
+    if (warps < 1) return fail(SG_ERR_INVALID, "k too large for the shared-memory top-k at this table size");
+    int blocks = ix->sm_count;
+    if ((uint64_t)blocks * warps > n_q) {
+        blocks = (int)((n_q + warps - 1) / warps);
+        if (blocks < 1) blocks = 1;
+        if (blocks == 1) warps = (int)(n_q < (uint32_t)warps ? (n_q ? n_q : 1) : warps);
+    }
+    g->blocks = blocks;
+    g->warps = warps;
+    g->warp_smem = warp_smem;
+    g->smem = (size_t)warps * warp_smem;
+    return SG_OK;
+}
+
+int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, uint32_t k) {
+    if (!ix) return fail(SG_ERR_INVALID, "null index");
+    if (k < 1 || k > SG_MAX_TOPK) return fail(SG_ERR_INVALID, "topK is invalid");                    // search.go:18-21
+    if (!(alpha > 0.0) || alpha > 1.0) return fail(SG_ERR_INVALID, "similarity shoud be in (0.0, 1.0]");  // search.go:23-25
+    if (metric < SG_JACCARD || metric > SG_EXACT) return fail(SG_ERR_INVALID, "unknown metric");
+    (void)n_q;
+    return SG_OK;
+}
+
+int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
+                   uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
+                   cudaStream_t stream) {
+    Geometry g;
+    int rc = geometry(ix, n_q, k, &g);
+    if (rc != SG_OK) return rc;
+    sg::SearchParams p{};
+    p.q_bytes = d_q_bytes;
+    p.q_off = d_q_off;
+    p.n_q = n_q;
+    p.metric = metric;
+    p.alpha = alpha;
+    p.k = k;
+    p.out_ids = d_ids;
+    p.out_scores = d_scores;
+    p.out_counts = d_counts;
+    p.stats = d_stats;
+    p.work_counter = d_work;
+    p.tbl_bytes = ix->tbl_bytes;
+    p.warp_smem = g.warp_smem;
+    p.force_shift = ix->force_shift;
+    SG_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), stream));
+    SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SG_OK;
+}
+
+struct CtxLease {
+    sg_index *ix;
+    CallCtx *ctx = nullptr;
+    bool counted = false;
+    explicit CtxLease(sg_index *i) : ix(i) {}
+    int acquire() {
+        std::unique_lock<std::mutex> lk(ix->mu);
+        if (ix->closing) return fail(SG_ERR_INVALID, "index is being freed");
+        ix->inflight++;
+        counted = true;
+        if (!ix->pool.empty()) { ctx = ix->pool.back(); ix->pool.pop_back(); return SG_OK; }
+        lk.unlock();
+        ctx = new (std::nothrow) CallCtx();
+        if (!ctx) return fail(SG_ERR_NOMEM, "out of host memory");
+        cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { delete ctx; ctx = nullptr; return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
+        return SG_OK;
+    }
+    ~CtxLease() {
+        std::lock_guard<std::mutex> lk(ix->mu);
+        if (ctx) ix->pool.push_back(ctx);
+        if (counted) ix->inflight--;
+        ix->cv.notify_all();
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int sg_index_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs,
+                   uint32_t id_base, sg_index **out) {
+    sg_index *ix = nullptr;
+    int rc = make_index(cfg, out, &ix);
+    if (rc != SG_OK) return rc;
+    if (n_docs && (!doc_bytes || !doc_off)) { delete ix; return fail(SG_ERR_INVALID, "null documents"); }
+    ix->host.id_base = id_base;
+    static const uint64_t zero_off[1] = {0};
+    std::string err = sg::build_from_docs(&ix->host, doc_bytes, n_docs ? doc_off : zero_off, n_docs);
+    if (!err.empty()) { delete ix; return fail(SG_ERR_UNSUPPORTED, err); }
+    rc = finalize(ix);
+    if (rc != SG_OK) { destroy(ix); return rc; }
+    *out = ix;
+    return SG_OK;
+}
+
+int sg_index_from_lists(const sg_config *cfg, uint32_t n_segments, uint64_t n_lists, const uint32_t *list_segment,
+                        const char *term_bytes, const uint64_t *list_term_off, const uint32_t *ids,
+                        const uint64_t *list_off, sg_index **out) {
+    sg_index *ix = nullptr;
+    int rc = make_index(cfg, out, &ix);
+    if (rc != SG_OK) return rc;
+    if (n_segments == 0) n_segments = 1;
+    if (n_lists && (!list_segment || !term_bytes || !list_term_off || !ids || !list_off)) {
+        delete ix;
+        return fail(SG_ERR_INVALID, "null list arrays");
+    }
+    std::string err = sg::build_from_lists(&ix->host, n_segments, n_lists, list_segment, term_bytes, list_term_off, ids, list_off);
+    if (!err.empty()) { delete ix; return fail(SG_ERR_FORMAT, err); }
+    rc = finalize(ix);
+    if (rc != SG_OK) { destroy(ix); return rc; }
+    *out = ix;
+    return SG_OK;
+}
+
+int sg_index_open_disk(const sg_config *cfg, const char *hd_path, const char *dl_path, sg_index **out) {
+    sg_index *ix = nullptr;
+    int rc = make_index(cfg, out, &ix);
+    if (rc != SG_OK) return rc;
+    if (!hd_path || !dl_path) { delete ix; return fail(SG_ERR_INVALID, "null path"); }
+    std::string err = sg::build_from_disk(&ix->host, hd_path, dl_path);
+    if (!err.empty()) {
+        delete ix;
+        return fail(err.rfind("io:", 0) == 0 ? SG_ERR_IO : SG_ERR_FORMAT, err);
+    }
+    rc = finalize(ix);
+    if (rc != SG_OK) { destroy(ix); return rc; }
+    *out = ix;
+    return SG_OK;
+}
+
+void sg_index_free(sg_index *ix) {
+    if (!ix) return;
+    {
+        std::unique_lock<std::mutex> lk(ix->mu);
+        ix->closing = true;
+        ix->cv.wait(lk, [ix] { return ix->inflight == 0; });
+    }
+    destroy(ix);
+}
+
+int sg_index_get_info(const sg_index *ix, sg_index_info *info) {
+    if (!ix || !info) return fail(SG_ERR_INVALID, "null argument");
+    info->n_docs = ix->host.n_docs;
+    info->n_segments = ix->host.n_segments;
+    info->n_terms = (uint32_t)ix->host.term_keys.size();
+    info->n_lists = ix->host.n_lists;
+    info->n_postings = ix->host.n_postings;
+    info->device_bytes = ix->device_bytes;
+    info->id_base = ix->host.id_base;
+    info->device = ix->device;
+    return SG_OK;
+}
+
+int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                    uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+    int rc = validate_search(ix, n_q, metric, alpha, k);
+    if (rc != SG_OK) return rc;
+    if (n_q == 0) return SG_OK;
+    if (!q_off || !out_ids || !out_scores || !out_counts) return fail(SG_ERR_INVALID, "null buffer");
+    const uint32_t total = q_off[n_q];
+    if (total && !q_bytes) return fail(SG_ERR_INVALID, "null query bytes");
+
+    // strings.ToLower for queries holding non-ASCII bytes (the device lowers A-Z itself)
+    std::string low_bytes;
+    std::vector<uint32_t> low_off;
+    const char *src_bytes = q_bytes;
+    const uint32_t *src_off = q_off;
+    bool nonascii = false;
+    for (uint32_t i = 0; i < total; i++) if ((uint8_t)q_bytes[i] >= 0x80) { nonascii = true; break; }
+    if (nonascii) {
+        low_off.resize((size_t)n_q + 1);
+        low_bytes.reserve(total + 16);
+        for (uint32_t q = 0; q < n_q; q++) {
+            low_off[q] = (uint32_t)low_bytes.size();
+            sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &low_bytes);
+        }
+        low_off[n_q] = (uint32_t)low_bytes.size();
+        src_bytes = low_bytes.data();
+        src_off = low_off.data();
+    }
+    const uint32_t src_total = src_off[n_q];
+
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    CtxLease lease(ix);
+    rc = lease.acquire();
+    if (rc != SG_OK) return rc;
+    CallCtx *c = lease.ctx;
+    SG_CUDA(c->q_bytes.reserve((size_t)src_total + 16));
+    SG_CUDA(c->q_off.reserve((size_t)n_q + 1));
+    SG_CUDA(c->ids.reserve((size_t)n_q * k));
+    SG_CUDA(c->scores.reserve((size_t)n_q * k));
+    SG_CUDA(c->counts.reserve(n_q));
+    SG_CUDA(c->work.reserve(1));
+    if (src_total) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p, src_bytes, src_total, cudaMemcpyHostToDevice, c->stream));
+    SG_CUDA(cudaMemcpyAsync(c->q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p, n_q, metric, alpha, k, c->ids.p, c->scores.p, c->counts.p, nullptr,
+                        c->work.p, c->stream);
+    if (rc != SG_OK) return rc;
+    SG_CUDA(cudaMemcpyAsync(out_ids, c->ids.p, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SG_CUDA(cudaMemcpyAsync(out_scores, c->scores.p, (size_t)n_q * k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SG_CUDA(cudaMemcpyAsync(out_counts, c->counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SG_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t q = 0; q < n_q; q++)
+        if (out_counts[q] == SG_COUNT_UNSUPPORTED)
+            return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");
+    return SG_OK;
+}
+
+int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,
+                           double alpha, uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts,
+                           uint32_t *d_stats, void *stream) {
+    int rc = validate_search(ix, n_q, metric, alpha, k);
+    if (rc != SG_OK) return rc;
+    if (n_q == 0) return SG_OK;
+    if (!d_q_off || !d_out_ids || !d_out_scores || !d_out_counts) return fail(SG_ERR_INVALID, "null buffer");
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    // work counters for caller-owned streams come from a ring owned by the index: the memset and the
+    // kernel are ordered on the caller's stream, and a slot is only reused 1024 launches later
+    const uint32_t slot = ix->work_rr.fetch_add(1, std::memory_order_relaxed) & (kWorkRing - 1);
+    return enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, d_stats,
+                          ix->work_ring + slot, (cudaStream_t)stream);
+}
+
+int sg_merge_topk_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *d_part_ids,
+                         const double *d_part_scores, const uint32_t *d_part_counts, uint32_t *d_out_ids,
+                         double *d_out_scores, uint32_t *d_out_counts, void *stream) {
+    if (n_parts < 1 || n_parts > 32) return fail(SG_ERR_INVALID, "n_parts must be in 1..32");
+    if (k < 1 || k > SG_MAX_TOPK) return fail(SG_ERR_INVALID, "topK is invalid");
+    if (n_q == 0) return SG_OK;
+    if (!d_part_ids || !d_part_scores || !d_part_counts || !d_out_ids || !d_out_scores || !d_out_counts)
+        return fail(SG_ERR_INVALID, "null buffer");
+    DeviceGuard guard;
+    SG_CUDA(guard.set(device));
+    int blocks = (int)((n_q + 7) / 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    SG_CUDA(sg::launch_merge_topk(n_parts, n_q, k, d_part_ids, d_part_scores, d_part_counts, d_out_ids, d_out_scores,
+                                  d_out_counts, blocks, (cudaStream_t)stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SG_OK;
+}
+
+uint64_t sg_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char *sg_last_error(void) { return g_err.c_str(); }
+
+const char *sg_version(void) { return "suggest_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// sg_device.h — structures shared by the host side and the sm_100a kernels of libsuggest_b200.
+#pragma once
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define SG_HD __host__ __device__
+#else
+#define SG_HD
+#endif
+
+namespace sg {
+
+constexpr int kMaxNgram = 8;          // pkg/analysis/ngram_tokenizer.go:3
+constexpr int kMaxQueryTokens = 128;  // SG_MAX_QUERY_TOKENS
+constexpr int kMaxWrapRunes = 8;
+constexpr int kMaxRunes = kMaxQueryTokens + kMaxNgram;  // wrapped query runes staged per warp
+constexpr uint32_t kNoTerm = 0xFFFFFFFFu;
+constexpr uint32_t kCountUnsupported = 0xFFFFFFFFu;     // SG_COUNT_UNSUPPORTED
+
+// non-ASCII alphabet interval: rune r in [lo, hi] has symbol code base + (r - lo)
+struct RuneRange {
+    uint32_t lo, hi, base;
+};
+
+// Read-only view of an index in HBM; passed to kernels by value.
+struct DevIndex {
+    // ---- tokenizer (pkg/suggest/tokenizer.go:9-20) ----
+    int32_t n;               // nGramSize
+    int32_t bits;            // bits per symbol code inside a packed term key
+    uint32_t pad_code;       // code written for a rune outside the alphabet (pkg/analysis/normalizer.go:29-33)
+    int32_t n_wrap_start, n_wrap_end;
+    uint32_t wrap_start[kMaxWrapRunes], wrap_end[kMaxWrapRunes];  // Wrap[0], Wrap[1] as lower-cased runes
+    uint8_t ascii_code[128]; // 0 = not in the alphabet
+    const RuneRange *ranges; // sorted, disjoint
+    int32_t n_ranges;
+    // ---- term dictionary: packed key -> term id, open addressing, key 0 = empty ----
+    const uint64_t *term_keys;
+    const uint32_t *term_vals;
+    uint32_t term_mask;
+    uint32_t n_terms;
+    // ---- inverted index, CSR in HBM ----
+    // Documents are renumbered by (cardinality segment, original id); segment B owns new ids
+    // [seg_start[B], seg_start[B+1]).  All postings of one term are contiguous, ordered by
+    // (segment, new id): list (term t, segment B) = postings[list_off[t*(S+1)+B] .. list_off[t*(S+1)+B+1]).
+    uint32_t n_segments;     // S = InvertedIndexIndices.Size()
+    uint32_t n_docs;
+    uint32_t id_base;        // added to every returned id (record-id-range shards)
+    const uint32_t *seg_start;  // S + 1
+    const uint32_t *list_off;   // n_terms * (S + 1)
+    const uint32_t *postings;   // 16-byte aligned, padded with 4 trailing entries
+    const uint32_t *perm;       // new id -> original document id (without id_base)
+};
+
+struct SearchParams {
+    const char *q_bytes;
+    const uint32_t *q_off;
+    uint32_t n_q;
+    int32_t metric;
+    double alpha;
+    uint32_t k;
+    uint32_t *out_ids;
+    double *out_scores;
+    uint32_t *out_counts;
+    uint32_t *stats;          // optional: {admissible postings, admissible lists} per query
+    uint32_t *work_counter;   // zeroed before launch
+    uint32_t tbl_bytes;       // per-warp count table size (power of two)
+    uint32_t warp_smem;       // bytes of shared memory owned by one warp
+    int32_t force_shift;      // < 0: cost model picks the bucket width; otherwise log2(bucket width)
+};
+
+SG_HD static inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; host and device hash term keys with it
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+
+}  // namespace sg

@@ -1,0 +1,172 @@
+// sg_index.cpp — host construction of the HBM index layout (sg_device.h: DevIndex).
+//
+// The reference keeps one map[term][]docID per n-gram cardinality ("segment"), each list stored as
+// VB / skipping / roaring bytes and decoded lazily on every query (pkg/index/indexer_writer.go:66-145,
+// pkg/index/posting_list.go).  Here every list is decoded once and laid out so that a query reads
+// one contiguous run per query token: documents are renumbered by (segment, original id), and the
+// postings of a term are stored back to back over all segments, ascending in the new id.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+#include "sg_host.h"
+
+namespace sg {
+
+void HostIndex::build_hash() {
+    size_t cap = 16;
+    while (cap < term_keys.size() * 2 + 2) cap <<= 1;
+    ht_keys.assign(cap, 0);
+    ht_vals.assign(cap, kNoTerm);
+    for (size_t t = 0; t < term_keys.size(); t++) {
+        size_t h = (size_t)mix64(term_keys[t]) & (cap - 1);
+        while (ht_keys[h] != 0) h = (h + 1) & (cap - 1);
+        ht_keys[h] = term_keys[t];
+        ht_vals[h] = (uint32_t)t;
+    }
+}
+
+namespace {
+
+// Common tail: given per-document (segment, distinct term ids) produce the CSR arrays.
+// doc_terms[doc_term_off[d] .. doc_term_off[d+1]) are the distinct term ids of document d.
+std::string finish(HostIndex *ix, const std::vector<uint32_t> &doc_seg, const std::vector<uint64_t> &doc_term_off,
+                   const std::vector<uint32_t> &doc_terms, uint32_t n_segments) {
+    const uint32_t n_docs = (uint32_t)doc_seg.size();
+    const size_t n_terms = ix->term_keys.size();
+    const uint32_t S = n_segments;
+    ix->n_docs = n_docs;
+    ix->n_segments = S;
+    if ((uint64_t)n_terms * (S + 1) > 0xFFFFFFF0ull) return "term x segment offset table exceeds 32 bits";
+    if (doc_terms.size() > 0xFFFFFFF0ull) return "more than 2^32 postings";
+    // renumber: counting sort of documents by segment keeps the original id order inside a segment
+    ix->seg_start.assign((size_t)S + 1, 0);
+    for (uint32_t d = 0; d < n_docs; d++) ix->seg_start[doc_seg[d] + 1]++;
+    for (uint32_t b = 0; b < S; b++) ix->seg_start[b + 1] += ix->seg_start[b];
+    ix->perm.assign(n_docs, 0);
+    {
+        std::vector<uint32_t> cur(ix->seg_start.begin(), ix->seg_start.end() - 1);
+        for (uint32_t d = 0; d < n_docs; d++) ix->perm[cur[doc_seg[d]]++] = d;
+    }
+    // list sizes -> offsets, row-major [term][segment]
+    const size_t stride = (size_t)S + 1;
+    ix->list_off.assign(n_terms * stride, 0);
+    std::vector<uint32_t> &off = ix->list_off;
+    for (uint32_t d = 0; d < n_docs; d++)
+        for (uint64_t j = doc_term_off[d]; j < doc_term_off[d + 1]; j++) off[(size_t)doc_terms[j] * stride + doc_seg[d]]++;
+    uint64_t run = 0, lists = 0;
+    for (size_t t = 0; t < n_terms; t++) {
+        for (uint32_t b = 0; b < S; b++) {
+            uint32_t c = off[t * stride + b];
+            off[t * stride + b] = (uint32_t)run;
+            run += c;
+            lists += c != 0;
+        }
+        off[t * stride + S] = (uint32_t)run;
+    }
+    ix->n_postings = run;
+    ix->n_lists = lists;
+    ix->postings.assign(((size_t)run + 3) / 4 * 4 + 4, 0xFFFFFFFFu);
+    // fill in new-id order so that every list comes out ascending
+    std::vector<uint32_t> cur(n_terms * stride);
+    std::memcpy(cur.data(), off.data(), cur.size() * sizeof(uint32_t));
+    for (uint32_t nid = 0; nid < n_docs; nid++) {
+        uint32_t d = ix->perm[nid], b = doc_seg[d];
+        for (uint64_t j = doc_term_off[d]; j < doc_term_off[d + 1]; j++)
+            ix->postings[cur[(size_t)doc_terms[j] * stride + b]++] = nid;
+    }
+    ix->build_hash();
+    return "";
+}
+
+}  // namespace
+
+std::string build_from_docs(HostIndex *ix, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs) {
+    std::unordered_map<uint64_t, uint32_t> term_of;
+    term_of.reserve(1 << 16);
+    std::vector<uint32_t> doc_seg(n_docs);
+    std::vector<uint64_t> doc_term_off((size_t)n_docs + 1, 0);
+    std::vector<uint32_t> doc_terms;
+    doc_terms.reserve((size_t)n_docs * 16);
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> tids;
+    TokenScratch sc;
+    uint32_t max_card = 0;
+    ix->term_keys.clear();
+    for (uint32_t d = 0; d < n_docs; d++) {
+        tokenize_keys(ix->text, (const uint8_t *)doc_bytes + doc_off[d], (size_t)(doc_off[d + 1] - doc_off[d]), &keys, &sc);
+        // the segment counts duplicates (pkg/index/indexer_writer.go:67); a posting list holds the document once
+        if (keys.size() > 0xFFFFu) return "a document has more than 65535 n-grams";
+        uint32_t card = (uint32_t)keys.size();
+        doc_seg[d] = card;
+        max_card = std::max(max_card, card);
+        tids.clear();
+        for (uint64_t k : keys) {
+            auto it = term_of.find(k);
+            uint32_t t;
+            if (it == term_of.end()) {
+                t = (uint32_t)ix->term_keys.size();
+                term_of.emplace(k, t);
+                ix->term_keys.push_back(k);
+            } else t = it->second;
+            tids.push_back(t);
+        }
+        std::sort(tids.begin(), tids.end());
+        tids.erase(std::unique(tids.begin(), tids.end()), tids.end());
+        doc_terms.insert(doc_terms.end(), tids.begin(), tids.end());
+        doc_term_off[d + 1] = doc_terms.size();
+    }
+    return finish(ix, doc_seg, doc_term_off, doc_terms, max_card + 1);
+}
+
+std::string build_from_lists(HostIndex *ix, uint32_t n_segments, uint64_t n_lists, const uint32_t *list_segment,
+                             const char *term_bytes, const uint64_t *list_term_off, const uint32_t *ids,
+                             const uint64_t *list_off) {
+    // invert the lists back into per-document term sets; a document's segment is the segment of its lists
+    std::unordered_map<uint64_t, uint32_t> term_of;
+    ix->term_keys.clear();
+    uint32_t max_id = 0;
+    bool any = false;
+    for (uint64_t l = 0; l < n_lists; l++)
+        for (uint64_t j = list_off[l]; j < list_off[l + 1]; j++) { max_id = std::max(max_id, ids[j]); any = true; }
+    const uint32_t n_docs = any ? max_id + 1 : 0;
+    std::vector<uint32_t> doc_seg(n_docs, 0);
+    std::vector<uint64_t> doc_term_off((size_t)n_docs + 1, 0);
+    std::vector<uint32_t> list_tid(n_lists);
+    for (uint64_t l = 0; l < n_lists; l++) {
+        if (list_segment[l] >= n_segments) return "list segment out of range";
+        uint64_t key = ix->text.key_of_term((const uint8_t *)term_bytes + list_term_off[l],
+                                            (size_t)(list_term_off[l + 1] - list_term_off[l]));
+        if (key == 0) return "a term of the index cannot be produced by this index description";
+        auto it = term_of.find(key);
+        if (it == term_of.end()) {
+            list_tid[l] = (uint32_t)ix->term_keys.size();
+            term_of.emplace(key, list_tid[l]);
+            ix->term_keys.push_back(key);
+        } else list_tid[l] = it->second;
+        uint32_t prev = 0xFFFFFFFFu;
+        for (uint64_t j = list_off[l]; j < list_off[l + 1]; j++) {
+            if (ids[j] == prev) continue;  // an id repeated inside one list counts once (pkg/merger/scan_count.go:35-66)
+            if (prev != 0xFFFFFFFFu && ids[j] < prev) return "posting list is not ascending";
+            prev = ids[j];
+            doc_seg[ids[j]] = list_segment[l];
+            doc_term_off[(size_t)ids[j] + 1]++;
+        }
+    }
+    for (uint32_t d = 0; d < n_docs; d++) doc_term_off[d + 1] += doc_term_off[d];
+    std::vector<uint32_t> doc_terms(doc_term_off[n_docs]);
+    std::vector<uint64_t> cur(doc_term_off.begin(), doc_term_off.end() - 1);
+    for (uint64_t l = 0; l < n_lists; l++) {
+        uint32_t prev = 0xFFFFFFFFu;
+        for (uint64_t j = list_off[l]; j < list_off[l + 1]; j++) {
+            if (ids[j] == prev) continue;
+            prev = ids[j];
+            if (doc_seg[ids[j]] != list_segment[l]) return "a document appears in two segments";
+            doc_terms[cur[ids[j]]++] = list_tid[l];
+        }
+    }
+    return finish(ix, doc_seg, doc_term_off, doc_terms, n_segments);
+}
+
+}  // namespace sg

@@ -1,0 +1,603 @@
+// sg_kernels.cu — sm_100a kernels of libsuggest_b200.
+//
+// sg_search_kernel: one warp owns one query from tokenisation to its k results (persistent warps
+// pull query numbers from a global counter).  What the reference does per query with goroutines,
+// lazily decoded posting-list iterators, CPMerge and a heap
+//   (pkg/suggest/suggester.go:46-131, pkg/index/searcher.go:28-78, pkg/merger/cp_merge.go:19-120,
+//    pkg/suggest/collector.go:117-191, pkg/suggest/topk.go:66-175)
+// becomes:
+//   1. tokenise in shared memory (pkg/suggest/tokenizer.go:9-20 chain), look the n-grams up in the
+//      term hash table -> one contiguous posting run per query token (documents are renumbered by
+//      cardinality segment, so the segment window [MinY, MaxY] of a term is one slice of HBM);
+//   2. T-occurrence count (ScanCount semantics, pkg/merger/scan_count.go:14-88) in a warp-private
+//      byte-counter table in shared memory.  A posting run is ascending, so the postings one warp
+//      instruction handles land in distinct counters and the read-modify-write needs no atomics.
+//      The table covers the window's id range at a bucket width of 2^s documents chosen per query
+//      by a cost model: s = 0 counts documents exactly (dense dictionaries); s > 0 counts "lists
+//      that hit the bucket", an upper bound of any document's overlap, so buckets below the
+//      smallest admissible threshold are discarded wholesale and the few survivors are resolved
+//      exactly by a warp-wide merge of the run slices that fall into the bucket;
+//   3. threshold / score in float64 with the reference's operation order (pkg/metric/*.go,
+//      pkg/suggest/scorer.go:29-31) and a sorted top-k in shared memory ordered (score desc, id asc)
+//      (pkg/suggest/collector.go:20-26).
+//
+// sg_merge_topk_kernel: k best of the per-shard top-k lists for record-id-range shards.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <climits>
+
+#include "sg_device.h"
+#include "sg_kernels.h"
+
+namespace sg {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr uint32_t kInf = 0xFFFFFFFFu;
+
+enum { kJaccard = 0, kCosine = 1, kDice = 2, kOverlap = 3, kExact = 4 };
+
+// ---------------- pkg/metric, float64, one rounding per reference operation ----------------
+__device__ __forceinline__ int f2i(double v) {  // int(float64) with saturation; callers clamp anyway
+    if (!(v < 2147483647.0)) return 2147483647;
+    if (v < -2147483647.0) return -2147483647;
+    return (int)v;
+}
+
+__device__ int metric_min_y(int m, double a, int size) {
+    switch (m) {
+    case kJaccard: return f2i(ceil(__dmul_rn(a, (double)size)));                                   // jaccard.go:13
+    case kCosine: return f2i(ceil(__dmul_rn(__dmul_rn(a, a), (double)size)));                      // cosine.go:13
+    case kDice: return f2i(ceil(__dmul_rn(__ddiv_rn(a, __dsub_rn(2.0, a)), (double)size)));        // dice.go:13
+    case kOverlap: return 1;                                                                       // overlap.go:13
+    default: return size;                                                                          // exact.go:11
+    }
+}
+
+__device__ int metric_max_y(int m, double a, int size) {
+    switch (m) {
+    case kJaccard: return f2i(floor(__ddiv_rn((double)size, a)));
+    case kCosine: return f2i(floor(__ddiv_rn((double)size, __dmul_rn(a, a))));
+    case kDice: return f2i(floor(__dmul_rn(__ddiv_rn(__dsub_rn(2.0, a), a), (double)size)));
+    case kOverlap: return 32767;  // math.MaxInt16
+    default: return size;
+    }
+}
+
+__device__ int metric_threshold(int m, double a, int sa, int sb) {
+    switch (m) {
+    case kJaccard: return f2i(ceil(__ddiv_rn(__dmul_rn(a, (double)(sa + sb)), __dadd_rn(1.0, a))));
+    case kCosine: return f2i(ceil(__dmul_rn(a, __dsqrt_rn((double)(sa * sb)))));
+    case kDice: return f2i(ceil(__dmul_rn(__dmul_rn(0.5, a), (double)(sa + sb))));
+    case kOverlap: return f2i(ceil(__dmul_rn(a, (double)min(sa, sb))));
+    default: return sa;
+    }
+}
+
+// scorer.go:29-31: 1 - Distance(overlap, sizeA, sizeB)
+__device__ double metric_score(int m, int c, int sa, int sb) {
+    double d;
+    switch (m) {
+    case kJaccard: d = __dsub_rn(1.0, __ddiv_rn((double)c, (double)(sa + sb - c))); break;
+    case kCosine: d = __dsub_rn(1.0, __ddiv_rn((double)c, __dsqrt_rn((double)(sa * sb)))); break;
+    case kDice: d = __dsub_rn(1.0, __ddiv_rn((double)(2 * c), (double)(sa + sb))); break;
+    case kOverlap: d = __dsub_rn(1.0, __ddiv_rn((double)c, (double)min(sa, sb))); break;
+    default: d = 0.0; break;
+    }
+    return __dsub_rn(1.0, d);
+}
+
+__device__ __forceinline__ bool threshold_admits(int T, int sa, int sb) {  // suggester.go:76
+    return T != 0 && T <= sb && T <= sa;
+}
+
+// ---------------- small helpers ----------------
+__device__ __forceinline__ uint32_t symbol_code(const DevIndex &ix, uint32_t r) {  // normalizer.go:29-33
+    if (r < 128) {
+        uint32_t c = ix.ascii_code[r];
+        return c ? c : ix.pad_code;
+    }
+    int lo = 0, hi = ix.n_ranges;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (ix.ranges[mid].hi < r) lo = mid + 1; else hi = mid;
+    }
+    if (lo < ix.n_ranges && r >= ix.ranges[lo].lo) return ix.ranges[lo].base + (r - ix.ranges[lo].lo);
+    return ix.pad_code;
+}
+
+__device__ __forceinline__ uint32_t term_lookup(const DevIndex &ix, uint64_t key) {
+    uint32_t h = (uint32_t)mix64(key) & ix.term_mask;
+    for (;;) {
+        uint64_t k = __ldg(ix.term_keys + h);
+        if (k == key) return __ldg(ix.term_vals + h);
+        if (k == 0) return kNoTerm;
+        h = (h + 1) & ix.term_mask;
+    }
+}
+
+// first position in [a, b) whose posting is >= x
+__device__ __forceinline__ uint32_t lower_bound(const uint32_t *__restrict__ postings, uint32_t a, uint32_t b, uint32_t x) {
+    while (a < b) {
+        uint32_t mid = a + ((b - a) >> 1);
+        if (__ldg(postings + mid) < x) a = mid + 1; else b = mid;
+    }
+    return a;
+}
+
+// Go `for range` decoding step (utf8.DecodeRune acceptance), invalid byte -> U+FFFD, width 1
+__device__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *rune) {
+    uint32_t b0 = s[0];
+    if (b0 < 0x80) { *rune = b0; return 1; }
+    int need;
+    uint32_t r, lo = 0x80, hi = 0xBF;
+    if (b0 >= 0xC2 && b0 <= 0xDF) { need = 1; r = b0 & 0x1F; }
+    else if (b0 >= 0xE0 && b0 <= 0xEF) { need = 2; r = b0 & 0x0F; if (b0 == 0xE0) lo = 0xA0; if (b0 == 0xED) hi = 0x9F; }
+    else if (b0 >= 0xF0 && b0 <= 0xF4) { need = 3; r = b0 & 0x07; if (b0 == 0xF0) lo = 0x90; if (b0 == 0xF4) hi = 0x8F; }
+    else { *rune = 0xFFFD; return 1; }
+    if (len < (uint32_t)need + 1) { *rune = 0xFFFD; return 1; }
+    for (int i = 1; i <= need; i++) {
+        uint32_t b = s[i];
+        uint32_t l = i == 1 ? lo : 0x80, h = i == 1 ? hi : 0xBF;
+        if (b < l || b > h) { *rune = 0xFFFD; return 1; }
+        r = (r << 6) | (b & 0x3F);
+    }
+    *rune = r;
+    return need + 1;
+}
+
+__device__ __forceinline__ float ln_factorial(float n) {  // Stirling, good enough for the cost model
+    if (n < 2.0f) return 0.0f;
+    return n * __logf(n) - n + 0.5f * __logf(6.2831853f * n) + 1.0f / (12.0f * n);
+}
+
+// Per-query state that lives in registers, identical in every lane of the warp.
+struct QueryCtx {
+    int metric;
+    double alpha;
+    int size_a;
+    int b_lo, b_hi;   // admissible, non-empty segment range
+    uint32_t k;
+    int tk_len;
+    double *tk_score;
+    uint32_t *tk_id;
+};
+
+// sorted insert into the warp's top-k (best first); all lanes call with identical arguments
+__device__ void topk_insert(QueryCtx &c, double score, uint32_t id, int lane) {
+    const int k = (int)c.k;
+    if (c.tk_len == k) {
+        double ws = c.tk_score[k - 1];
+        uint32_t wi = c.tk_id[k - 1];
+        if (!(score > ws || (score == ws && id < wi))) return;  // Candidate.Less, collector.go:20-26
+    }
+    int better = 0;
+    for (int j = lane; j < c.tk_len; j += 32) {
+        double s = c.tk_score[j];
+        better += (s > score || (s == score && c.tk_id[j] < id)) ? 1 : 0;
+    }
+    const int pos = __reduce_add_sync(kFull, better);
+    const int new_len = min(c.tk_len + 1, k);
+    for (int hi = new_len - 1; hi > pos; hi -= 32) {
+        int j = hi - lane;
+        bool act = j > pos;
+        double sv = 0.0;
+        uint32_t iv = 0;
+        if (act) { sv = c.tk_score[j - 1]; iv = c.tk_id[j - 1]; }
+        __syncwarp();
+        if (act) { c.tk_score[j] = sv; c.tk_id[j] = iv; }
+        __syncwarp();
+    }
+    if (lane == 0) { c.tk_score[pos] = score; c.tk_id[pos] = id; }
+    __syncwarp();
+    c.tk_len = new_len;
+}
+
+// A document (new id) with an exact overlap count: apply the segment's threshold, score, offer to the top-k.
+// All lanes call with identical arguments.
+__device__ void emit_candidate(const DevIndex &ix, QueryCtx &c, uint32_t new_id, int count, int lane) {
+    int lo = c.b_lo, hi = c.b_hi;  // segment of the document: last B with seg_start[B] <= new_id
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(ix.seg_start + mid) <= new_id) lo = mid; else hi = mid - 1;
+    }
+    const int size_b = lo;
+    const int T = metric_threshold(c.metric, c.alpha, c.size_a, size_b);
+    if (!threshold_admits(T, c.size_a, size_b) || count < T) return;
+    const double score = metric_score(c.metric, count, c.size_a, size_b);
+    topk_insert(c, score, __ldg(ix.perm + new_id), lane);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(1024, 1) sg_search_kernel(const DevIndex ix, const SearchParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t *wsm = smem + (size_t)warp * p.warp_smem;
+    uint8_t *tbl = wsm;                                         // [tbl_bytes] byte counters
+    uint32_t *s_cur = (uint32_t *)(wsm + p.tbl_bytes);          // [128] start of the not yet counted part of a run
+    uint32_t *s_end = s_cur + kMaxQueryTokens;                  // [128] end of the run slice inside the current chunk
+    uint32_t *s_rend = s_end + kMaxQueryTokens;                 // [128] end of the run (segment window)
+    double *tk_score = (double *)(s_rend + kMaxQueryTokens);    // [k]
+    uint32_t *tk_id = (uint32_t *)(tk_score + p.k);             // [k]
+    // tokeniser scratch overlays the counter table (the table is cleared after the runs are known)
+    uint32_t *s_runes = (uint32_t *)tbl;                        // [kMaxRunes]
+    uint32_t *s_lterm = s_runes + kMaxRunes;                    // [128] term id of every list to open
+
+    const uint32_t S = ix.n_segments;
+    const uint32_t stride = S + 1;
+    const uint32_t *__restrict__ postings = ix.postings;
+
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(p.work_counter, 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= p.n_q) break;
+
+        QueryCtx c;
+        c.metric = p.metric;
+        c.alpha = p.alpha;
+        c.k = p.k;
+        c.tk_len = 0;
+        c.tk_score = tk_score;
+        c.tk_id = tk_id;
+        c.size_a = 0;
+        c.b_lo = 0;
+        c.b_hi = -1;
+        bool unsupported = false;
+        uint32_t st_postings = 0, st_lists = 0;
+
+        // ---------------- 1. tokenise: wrap -> lower -> trim -> n-gram windows (dedupe) -> normalise ----------------
+        const uint32_t qb = __ldg(p.q_off + q), qe = __ldg(p.q_off + q + 1);
+        const uint32_t qlen = qe - qb;
+        const uint8_t *qp = (const uint8_t *)p.q_bytes + qb;
+        const int nws = ix.n_wrap_start, nwe = ix.n_wrap_end;
+        bool nonascii = false;
+        for (uint32_t i = lane; i < qlen; i += 32) nonascii |= qp[i] >= 0x80;
+        nonascii = __any_sync(kFull, nonascii);
+        int nq_runes = 0;
+        if (!nonascii) {
+            if (nws + qlen + nwe > (uint32_t)kMaxRunes) unsupported = true;
+            else {
+                for (uint32_t i = lane; i < qlen; i += 32) {
+                    uint32_t ch = qp[i];
+                    s_runes[nws + i] = (ch >= 'A' && ch <= 'Z') ? ch + 32 : ch;
+                }
+                nq_runes = (int)qlen;
+            }
+        } else {
+            // queries holding non-ASCII bytes arrive lower-cased (sg_search_batch does it on the host)
+            int cnt = 0;
+            if (lane == 0) {
+                uint32_t i = 0;
+                while (i < qlen) {
+                    uint32_t r;
+                    i += (uint32_t)utf8_step(qp + i, qlen - i, &r);
+                    if (nws + cnt + nwe >= kMaxRunes) { cnt = -1; break; }
+                    s_runes[nws + cnt++] = (r >= 'A' && r <= 'Z') ? r + 32 : r;
+                }
+            }
+            cnt = __shfl_sync(kFull, cnt, 0);
+            if (cnt < 0) unsupported = true; else nq_runes = cnt;
+        }
+        int n_win = 0, wlen = 0, first = 0;
+        if (!unsupported) {
+            if (lane < nws) s_runes[lane] = ix.wrap_start[lane];
+            if (lane < nwe) s_runes[nws + nq_runes + lane] = ix.wrap_end[lane];
+            __syncwarp();
+            const int nr = nws + nq_runes + nwe;
+            int f = INT_MAX, l = -1, bytes = 0;
+            for (int i = lane; i < nr; i += 32) {  // strings.Trim(text, " ")
+                if (s_runes[i] != ' ') { f = min(f, i); l = max(l, i); }
+            }
+            f = __reduce_min_sync(kFull, f);
+            l = __reduce_max_sync(kFull, l);
+            if (l >= 0) {
+                for (int i = f + lane; i <= l; i += 32) {
+                    uint32_t r = s_runes[i];
+                    bytes += r < 0x80 ? 1 : r < 0x800 ? 2 : r < 0x10000 ? 3 : 4;
+                }
+            }
+            bytes = __reduce_add_sync(kFull, bytes);
+            const int R = l >= 0 ? l - f + 1 : 0;
+            first = f;
+            if (R > 0 && bytes >= ix.n) {  // ngram_tokenizer.go:18: the early-out compares bytes
+                if (R < ix.n) { n_win = 1; wlen = R; } else { n_win = R - ix.n + 1; wlen = ix.n; }
+            }
+            if (n_win > kMaxQueryTokens) { unsupported = true; n_win = 0; }
+        }
+        int n_lists = 0;
+        for (int base = 0; base < n_win; base += 32) {
+            const int i = base + lane;
+            bool keep = i < n_win;
+            if (keep) {  // appendUnique, ngram_tokenizer.go:46-54: raw windows, first occurrence wins
+                for (int j = 0; j < i && keep; j++) {
+                    bool eq = true;
+                    for (int cpos = 0; cpos < wlen; cpos++) eq &= s_runes[first + i + cpos] == s_runes[first + j + cpos];
+                    keep = !eq;
+                }
+            }
+            uint32_t term = kNoTerm;
+            if (keep) {
+                uint64_t key = 0;
+                for (int cpos = 0; cpos < wlen; cpos++)
+                    key |= (uint64_t)symbol_code(ix, s_runes[first + i + cpos]) << (ix.bits * cpos);
+                term = term_lookup(ix, key);
+            }
+            c.size_a += __popc(__ballot_sync(kFull, keep));
+            const unsigned tm = __ballot_sync(kFull, term != kNoTerm);
+            if (term != kNoTerm) s_lterm[n_lists + __popc(tm & ((1u << lane) - 1u))] = term;
+            n_lists += __popc(tm);
+        }
+        __syncwarp();
+
+        // ---------------- 2. segment window and thresholds (suggester.go:53-59, :73-78) ----------------
+        int theta = INT_MAX;
+        if (c.size_a > 0) {
+            const int b_min = max(metric_min_y(c.metric, c.alpha, c.size_a), 0);
+            int b_max = metric_max_y(c.metric, c.alpha, c.size_a);
+            if (b_max >= (int)S) b_max = (int)S - 1;
+            int lo = INT_MAX, hi = -1;
+            for (int B = b_min + lane; B <= b_max; B += 32) {
+                const int T = metric_threshold(c.metric, c.alpha, c.size_a, B);
+                if (threshold_admits(T, c.size_a, B) && __ldg(ix.seg_start + B + 1) > __ldg(ix.seg_start + B)) {
+                    theta = min(theta, T);
+                    lo = min(lo, B);
+                    hi = max(hi, B);
+                }
+            }
+            theta = __reduce_min_sync(kFull, theta);
+            c.b_lo = __reduce_min_sync(kFull, lo);
+            c.b_hi = __reduce_max_sync(kFull, hi);
+            if (p.stats != nullptr) {  // admissible postings and lists
+                for (int B = b_min; B <= b_max; B++) {
+                    const int T = metric_threshold(c.metric, c.alpha, c.size_a, B);
+                    if (!threshold_admits(T, c.size_a, B)) continue;
+                    for (int j = lane; j < n_lists; j += 32) {
+                        const uint32_t *o = ix.list_off + (size_t)s_lterm[j] * stride + B;
+                        const uint32_t len = __ldg(o + 1) - __ldg(o);
+                        st_postings += len;
+                        st_lists += len != 0;
+                    }
+                }
+                st_postings = __reduce_add_sync(kFull, st_postings);
+                st_lists = __reduce_add_sync(kFull, st_lists);
+            }
+        }
+
+        if (c.b_hi >= 0 && n_lists > 0) {
+            // ---------------- 3. one posting run per list ----------------
+            float total = 0.0f;
+            for (int j = lane; j < n_lists; j += 32) {
+                const uint32_t *o = ix.list_off + (size_t)s_lterm[j] * stride;
+                const uint32_t r0 = __ldg(o + c.b_lo), r1 = __ldg(o + c.b_hi + 1);
+                s_cur[j] = r0;
+                s_rend[j] = r1;
+                total += (float)(r1 - r0);
+            }
+            for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
+            __syncwarp();
+
+            // ---------------- 4. bucket width: minimise chunks * per-chunk cost + expected false candidates ----------------
+            const uint32_t c_base = __ldg(ix.seg_start + c.b_lo);
+            const uint32_t D = __ldg(ix.seg_start + c.b_hi + 1) - c_base;
+            const uint32_t NB = p.tbl_bytes;
+            int shift = 0;
+            if (p.force_shift >= 0) shift = p.force_shift;
+            else {
+                float best = FLT_MAX;
+                const float lnf = ln_factorial((float)theta);
+                for (int s = 0; s < 24; s++) {
+                    const uint32_t nb_total = ((D - 1) >> s) + 1;
+                    const uint32_t nch = (nb_total + NB - 1) / NB;
+                    float est = 0.0f;
+                    if (s > 0) {
+                        const float lam = total * (float)(1u << s) / (float)D;
+                        float tail = 1.0f;
+                        if (lam < 0.5f * (float)theta && lam > 0.0f)
+                            tail = fminf(1.0f, 2.0f * __expf(-lam + (float)theta * __logf(lam) - lnf));
+                        else if (lam <= 0.0f) tail = 0.0f;
+                        est = tail * (float)nb_total;
+                    }
+                    const float cost = (float)nch * ((float)min(nb_total, NB) * (1.0f / 32.0f) + 400.0f + 24.0f * (float)n_lists) +
+                                       est * 1200.0f;
+                    if (cost < best) { best = cost; shift = s; }
+                    if (nch == 1) break;
+                }
+            }
+            while (shift < 31 && (((uint64_t)(D - 1) >> shift) + 1 + NB - 1) / NB > 0xFFFFu) shift++;  // keep the chunk loop bounded
+            const uint64_t chunk_docs = (uint64_t)NB << shift;
+            const uint32_t th4 = (uint32_t)min(theta, 255) * 0x01010101u;
+
+            for (uint64_t cs = 0; cs < D; cs += chunk_docs) {
+                const uint32_t ce = (uint32_t)min((unsigned long long)D, (unsigned long long)(cs + chunk_docs));
+                const uint32_t lo_id = c_base + (uint32_t)cs;  // first id of the chunk
+                const uint32_t hi_id = c_base + ce;            // one past the last (may wrap to 0 only if it equals 2^32; n_docs < 2^32-1)
+                const uint32_t n_buckets = ((ce - (uint32_t)cs - 1) >> shift) + 1;
+                // slice of every run inside the chunk
+                for (int j = lane; j < n_lists; j += 32)
+                    s_end[j] = ce == D ? s_rend[j] : lower_bound(postings, s_cur[j], s_rend[j], hi_id);
+                const uint32_t n_vec = (n_buckets + 15) >> 4;
+                for (uint32_t w = lane; w < n_vec; w += 32) ((uint4 *)tbl)[w] = make_uint4(0, 0, 0, 0);
+                __syncwarp();
+
+                // ---- count: tbl[bucket(id)]++ for the first posting of every bucket inside a 128-posting group ----
+                for (int j = 0; j < n_lists; j++) {
+                    const uint32_t a = s_cur[j], b = s_end[j];
+                    if (a >= b) continue;
+                    uint32_t base = a & ~3u;
+                    uint32_t pos = base + lane * 4;
+                    uint4 v = pos < b ? __ldg((const uint4 *)(postings + pos)) : make_uint4(0, 0, 0, 0);
+                    for (; base < b; base += 128) {
+                        pos = base + lane * 4;
+                        const uint32_t npos = pos + 128;
+                        uint4 vn = make_uint4(0, 0, 0, 0);
+                        if (npos < b) vn = __ldg((const uint4 *)(postings + npos));
+                        const bool v0 = pos >= a && pos < b, v1 = pos + 1 >= a && pos + 1 < b;
+                        const bool v2 = pos + 2 >= a && pos + 2 < b, v3 = pos + 3 >= a && pos + 3 < b;
+                        const uint32_t b0 = v0 ? (v.x - lo_id) >> shift : kInf, b1 = v1 ? (v.y - lo_id) >> shift : kInf;
+                        const uint32_t b2 = v2 ? (v.z - lo_id) >> shift : kInf, b3 = v3 ? (v.w - lo_id) >> shift : kInf;
+                        uint32_t prev = __shfl_up_sync(kFull, b3, 1);
+                        if (lane == 0) prev = kInf;
+                        const bool h0 = v0 && b0 != prev, h1 = v1 && b1 != b0, h2 = v2 && b2 != b1, h3 = v3 && b3 != b2;
+                        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                        if (h0) c0 = tbl[b0];
+                        if (h1) c1 = tbl[b1];
+                        if (h2) c2 = tbl[b2];
+                        if (h3) c3 = tbl[b3];
+                        if (h0) tbl[b0] = (uint8_t)(c0 + (c0 != 255u));
+                        if (h1) tbl[b1] = (uint8_t)(c1 + (c1 != 255u));
+                        if (h2) tbl[b2] = (uint8_t)(c2 + (c2 != 255u));
+                        if (h3) tbl[b3] = (uint8_t)(c3 + (c3 != 255u));
+                        __syncwarp();
+                        v = vn;
+                    }
+                }
+
+                // ---- scan: buckets whose counter reaches the smallest admissible threshold ----
+                for (uint32_t w0 = 0; w0 < n_vec; w0 += 32) {
+                    const uint32_t w = w0 + lane;
+                    uint4 x = make_uint4(0, 0, 0, 0);
+                    if (w < n_vec) x = ((const uint4 *)tbl)[w];
+                    unsigned m16 = 0;
+                    m16 |= (((__vcmpgeu4(x.x, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+                    m16 |= ((((__vcmpgeu4(x.y, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 4;
+                    m16 |= ((((__vcmpgeu4(x.z, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 8;
+                    m16 |= ((((__vcmpgeu4(x.w, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 12;
+                    unsigned bal;
+                    while ((bal = __ballot_sync(kFull, m16 != 0)) != 0) {
+                        const int src = __ffs(bal) - 1;
+                        unsigned mm = __shfl_sync(kFull, m16, src);
+                        if (lane == src) m16 = 0;
+                        while (mm) {
+                            const int bit = __ffs(mm) - 1;
+                            mm &= mm - 1;
+                            const uint32_t bucket = (w0 + (uint32_t)src) * 16u + (uint32_t)bit;
+                            if (bucket >= n_buckets) continue;
+                            if (shift == 0) {
+                                emit_candidate(ix, c, lo_id + bucket, (int)tbl[bucket], lane);
+                                continue;
+                            }
+                            // resolve the bucket exactly: warp-wide merge of the run slices inside its id range
+                            const uint32_t blo = lo_id + (bucket << shift);
+                            const unsigned long long bhi64 = min((unsigned long long)blo + (1ull << shift), (unsigned long long)c_base + ce);
+                            uint32_t pp[4], pe[4], vv[4];
+#pragma unroll
+                            for (int g = 0; g < 4; g++) {
+                                const int j = lane + 32 * g;
+                                vv[g] = kInf;
+                                pp[g] = pe[g] = 0;
+                                if (j < n_lists) {
+                                    pe[g] = s_end[j];
+                                    pp[g] = lower_bound(postings, s_cur[j], pe[g], blo);
+                                    if (pp[g] < pe[g]) {
+                                        const uint32_t x2 = __ldg(postings + pp[g]);
+                                        if ((unsigned long long)x2 < bhi64) vv[g] = x2;
+                                    }
+                                }
+                            }
+                            for (;;) {
+                                const uint32_t mine = min(min(vv[0], vv[1]), min(vv[2], vv[3]));
+                                const uint32_t m = __reduce_min_sync(kFull, mine);
+                                if (m == kInf) break;
+                                int cnt = 0;
+#pragma unroll
+                                for (int g = 0; g < 4; g++) cnt += vv[g] == m;
+                                cnt = __reduce_add_sync(kFull, cnt);
+#pragma unroll
+                                for (int g = 0; g < 4; g++) {
+                                    if (vv[g] == m) {
+                                        vv[g] = kInf;
+                                        if (++pp[g] < pe[g]) {
+                                            const uint32_t x2 = __ldg(postings + pp[g]);
+                                            if ((unsigned long long)x2 < bhi64) vv[g] = x2;
+                                        }
+                                    }
+                                }
+                                emit_candidate(ix, c, m, cnt, lane);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                for (int j = lane; j < n_lists; j += 32) s_cur[j] = s_end[j];
+                __syncwarp();
+            }
+        }
+
+        // ---------------- 5. results: GetCandidates order, fixed stride k ----------------
+        const size_t row = (size_t)q * p.k;
+        for (uint32_t j = lane; j < p.k; j += 32) {
+            const bool has = (int)j < c.tk_len;
+            p.out_ids[row + j] = has ? ix.id_base + tk_id[j] : 0u;
+            p.out_scores[row + j] = has ? tk_score[j] : 0.0;
+        }
+        if (lane == 0) {
+            p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)c.tk_len;
+            if (p.stats != nullptr) { p.stats[2 * q] = st_postings; p.stats[2 * q + 1] = st_lists; }
+        }
+        __syncwarp();
+    }
+}
+
+// k best of n_parts sorted lists per query, (score desc, id asc).  One warp per query, lane = part.
+__global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *__restrict__ part_ids,
+                                     const double *__restrict__ part_scores, const uint32_t *__restrict__ part_counts,
+                                     uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_q; q += warps) {
+        uint32_t cur = 0, cnt = 0;
+        size_t row = 0;
+        bool unsupported = false;
+        if ((uint32_t)lane < n_parts) {
+            cnt = part_counts[(size_t)lane * n_q + q];
+            row = ((size_t)lane * n_q + q) * k;
+            if (cnt == kCountUnsupported) { unsupported = true; cnt = 0; }
+            if (cnt > k) cnt = k;
+        }
+        unsupported = __any_sync(kFull, unsupported);
+        uint32_t n_out = 0;
+        for (; n_out < k; n_out++) {
+            bool has = cur < cnt;
+            double s = has ? part_scores[row + cur] : 0.0;
+            uint32_t id = has ? part_ids[row + cur] : kInf;
+            int who = lane;
+            for (int o = 16; o; o >>= 1) {
+                const bool oh = __shfl_xor_sync(kFull, has, o);
+                const double os = __shfl_xor_sync(kFull, s, o);
+                const uint32_t oi = __shfl_xor_sync(kFull, id, o);
+                const int ow = __shfl_xor_sync(kFull, who, o);
+                const bool take = oh && (!has || os > s || (os == s && (oi < id || (oi == id && ow < who))));
+                if (take) { has = oh; s = os; id = oi; who = ow; }
+            }
+            if (!has) break;
+            if (lane == 0) { out_ids[(size_t)q * k + n_out] = id; out_scores[(size_t)q * k + n_out] = s; }
+            if (lane == who) cur++;
+        }
+        for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[(size_t)q * k + j] = 0; out_scores[(size_t)q * k + j] = 0.0; }
+        if (lane == 0) out_counts[q] = unsupported ? kCountUnsupported : n_out;
+    }
+}
+
+// ---------------- launchers (host) ----------------
+cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks, int warps_per_block, size_t smem_bytes,
+                          cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(sg_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    sg_search_kernel<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(ix, p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
+                              const uint32_t *part_counts, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
+                              int blocks, cudaStream_t stream) {
+    sg_merge_topk_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, part_ids, part_scores, part_counts, out_ids,
+                                                     out_scores, out_counts);
+    return cudaGetLastError();
+}
+
+}  // namespace sg

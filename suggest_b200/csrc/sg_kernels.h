@@ -1,0 +1,15 @@
+// sg_kernels.h — host-callable launchers of the sm_100a kernels in sg_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sg_device.h"
+
+namespace sg {
+
+cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks, int warps_per_block, size_t smem_bytes,
+                          cudaStream_t stream);
+cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
+                              const uint32_t *part_counts, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
+                              int blocks, cudaStream_t stream);
+
+}  // namespace sg

@@ -1,0 +1,317 @@
+"""pkg/suggest mirror over the C ABI: IndexDescription, Builder, NGramIndex (Suggester), Service, SearchConfig.
+
+Same names, argument meaning and error behaviour as the reference for the Suggest path
+(pkg/suggest/{config,ngram_index_builder,ngram_index,suggester,service,search}.go); the work itself
+happens in libsuggest_b200.so on the GPU.  `SuggestBatch` is the one addition: the reference has no
+batched call, a single Suggest is a batch of one.
+"""
+import ctypes as C
+import json
+import os
+import threading
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import SuggestError
+from .metric import Metric
+
+RAMDriver = "RAM"
+DiscDriver = "DISC"
+
+
+def _b(s):
+    return s.encode("utf-8") if isinstance(s, str) else bytes(s)
+
+
+def pack_strings(strings, offset_dtype=np.uint32):
+    """list of str/bytes -> (uint8 array, offsets[n+1])"""
+    bs = [_b(s) for s in strings]
+    off = np.zeros(len(bs) + 1, dtype=offset_dtype)
+    if bs:
+        off[1:] = np.cumsum([len(x) for x in bs])
+    data = np.frombuffer(b"".join(bs), dtype=np.uint8).copy() if bs else np.zeros(0, dtype=np.uint8)
+    return data, off
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+@dataclass
+class IndexDescription:
+    """suggest.IndexDescription, pkg/suggest/config.go:25-35"""
+    Name: str = ""
+    NGramSize: int = 3
+    Alphabet: Sequence[str] = ("english", "russian", "numbers", "$")
+    Pad: str = "$"
+    Wrap: Sequence[str] = ("$", "$")
+    Driver: str = RAMDriver
+    SourcePath: str = ""
+    OutputPath: str = ""
+    basePath: str = ""
+    Device: int = 0  # CUDA ordinal holding the index (not in the reference)
+
+    def GetSourcePath(self):
+        return self.SourcePath if os.path.isabs(self.SourcePath) else f"{self.basePath}/{self.SourcePath}"
+
+    def GetIndexPath(self):
+        return self.OutputPath if os.path.isabs(self.OutputPath) else f"{self.basePath}/{self.OutputPath}"
+
+    def GetDictionaryFile(self):
+        return f"{self.GetIndexPath()}/{self.Name}.cdb"
+
+    def getHeaderFile(self):
+        return f"{self.Name}.hd"
+
+    def getDocumentListFile(self):
+        return f"{self.Name}.dl"
+
+    def c_config(self):
+        return _capi.make_config(self.NGramSize, tuple(self.Wrap), self.Pad, tuple(self.Alphabet), self.Device)
+
+
+def ReadConfigs(config_path):
+    """suggest.ReadConfigs, pkg/suggest/config.go:84-112"""
+    with open(config_path, "rb") as f:
+        raw = json.load(f)
+    base = os.path.dirname(config_path)
+    return [IndexDescription(Name=c.get("name", ""), NGramSize=c.get("nGramSize", 0), Alphabet=tuple(c.get("alphabet", ())),
+                             Pad=c.get("pad", ""), Wrap=tuple(c.get("wrap", ("", ""))), Driver=c.get("driver", ""),
+                             SourcePath=c.get("source", ""), OutputPath=c.get("output", ""), basePath=base) for c in raw]
+
+
+@dataclass
+class Candidate:
+    """suggest.Candidate, pkg/suggest/collector.go:12-17"""
+    Key: int
+    Score: float
+
+
+@dataclass
+class ResultItem:
+    """suggest.ResultItem, pkg/suggest/service.go:11-16"""
+    Score: float
+    Value: str
+
+
+@dataclass
+class SearchConfig:
+    query: str
+    topK: int
+    metric: Metric
+    similarity: float
+
+
+def NewSearchConfig(query, topK, metric, similarity):
+    """suggest.NewSearchConfig, pkg/suggest/search.go:18-33"""
+    if topK <= 0:
+        raise ValueError("topK should be greater or equal to 1")
+    if similarity <= 0 or similarity > 1:
+        raise ValueError("similarity shouble be in (0.0, 1.0]")
+    return SearchConfig(query, topK, metric, similarity)
+
+
+def open_ram_dictionary(path):
+    """dictionary.OpenRAMDictionary, pkg/dictionary/helpers.go:25-48: one entry per line, id = line number"""
+    with open(path, "rb") as f:
+        data = f.read()
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return [ln[:-1] if ln.endswith(b"\r") else ln for ln in lines]  # bufio.ScanLines drops a trailing \r
+
+
+class NGramIndex:
+    """suggest.NGramIndex (pkg/suggest/ngram_index.go:7-10) backed by an sg_index handle in HBM."""
+
+    def __init__(self, handle, description):
+        self._h = C.c_void_p(handle)
+        self.description = description
+        self._lock = threading.Lock()
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        with self._lock:
+            if self._h is not None and self._h.value:
+                _capi.lib().sg_index_free(self._h)
+                self._h = None
+
+    def __del__(self):  # the reference relies on GC finalizers as well (pkg/index/index_reader.go:49-51)
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self):
+        if self._h is None:
+            raise SuggestError(_capi.SG_ERR_INVALID, "index is closed")
+        return self._h
+
+    def info(self):
+        info = _capi.SgIndexInfo()
+        _capi.check(_capi.lib().sg_index_get_info(self.handle, C.byref(info)))
+        return {name: getattr(info, name) for name, _ in info._fields_}
+
+    # -- Suggester ------------------------------------------------------------------------------
+    def Suggest(self, query, similarity, metric, topK) -> List[Candidate]:
+        """nGramSuggester.Suggest (pkg/suggest/suggester.go:46-131) with a FuzzyCollectorManager(topK)."""
+        ids, scores, counts = self.SuggestBatch([query], similarity, metric, topK)
+        n = int(counts[0])
+        return [Candidate(int(ids[0, i]), float(scores[0, i])) for i in range(n)]
+
+    def SuggestBatch(self, queries, similarity, metric, topK, packed=None, out=None):
+        """Batched Suggest through sg_search_batch (host buffers).
+
+        Returns (ids[n_q, k] uint32, scores[n_q, k] float64, counts[n_q] uint32); row q holds counts[q]
+        candidates ordered (score desc, id asc)."""
+        data, off = packed if packed is not None else pack_strings(queries)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        n_q = len(off) - 1
+        k = int(topK)
+        if out is None:
+            ids = np.zeros((n_q, max(k, 0)), dtype=np.uint32)
+            scores = np.zeros((n_q, max(k, 0)), dtype=np.float64)
+            counts = np.zeros(n_q, dtype=np.uint32)
+        else:
+            ids, scores, counts = out
+        rc = _capi.lib().sg_search_batch(self.handle, _ptr(data), _ptr(off), n_q, metric.code, float(similarity),
+                                         max(k, 0), _ptr(ids), _ptr(scores), _ptr(counts))
+        _capi.check(rc)
+        return ids, scores, counts
+
+    def SuggestBatchDevice(self, d_q_bytes, d_q_off, n_q, similarity, metric, topK, d_ids, d_scores, d_counts,
+                           d_stats=0, stream=0):
+        """sg_search_batch_device: every argument is a device pointer (int); asynchronous on `stream`."""
+        rc = _capi.lib().sg_search_batch_device(self.handle, d_q_bytes, d_q_off, n_q, metric.code, float(similarity),
+                                                int(topK), d_ids, d_scores, d_counts, d_stats or None, stream or None)
+        _capi.check(rc)
+
+
+class Builder:
+    """suggest.Builder, pkg/suggest/ngram_index_builder.go:14-17"""
+
+    def Build(self) -> NGramIndex:
+        raise NotImplementedError
+
+
+class _RAMBuilder(Builder):
+    def __init__(self, dictionary, description, id_base=0):
+        self.dictionary = dictionary
+        self.description = description
+        self.id_base = id_base
+
+    def Build(self):
+        d = self.dictionary
+        if isinstance(d, tuple) and len(d) == 2 and isinstance(d[0], np.ndarray):
+            data, off = d
+        else:
+            data, off = pack_strings(d, np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        cfg, keep = self.description.c_config()
+        h = C.c_void_p()
+        rc = _capi.lib().sg_index_build(C.byref(cfg), _ptr(data), _ptr(off), len(off) - 1, self.id_base, C.byref(h))
+        del keep
+        if rc < 0:
+            raise SuggestError(rc, "failed to build NGramIndex: " + (_capi.lib().sg_last_error() or b"").decode())
+        return NGramIndex(h.value, self.description)
+
+
+class _FSBuilder(Builder):
+    def __init__(self, description):
+        self.description = description
+
+    def Build(self):
+        d = self.description
+        cfg, keep = d.c_config()
+        h = C.c_void_p()
+        base = d.GetIndexPath()
+        rc = _capi.lib().sg_index_open_disk(C.byref(cfg), _b(os.path.join(base, d.getHeaderFile())),
+                                            _b(os.path.join(base, d.getDocumentListFile())), C.byref(h))
+        del keep
+        if rc < 0:
+            raise SuggestError(rc, "failed to open FS inverted index: " + (_capi.lib().sg_last_error() or b"").decode())
+        return NGramIndex(h.value, d)
+
+
+def NewRAMBuilder(dictionary, description, id_base=0) -> Builder:
+    """suggest.NewRAMBuilder (pkg/suggest/ngram_index_builder.go:27-35).  `dictionary` is the list of values in id
+    order (dictionary.Dictionary.Iterate) or an already packed (uint8 bytes, uint64 offsets) pair."""
+    return _RAMBuilder(dictionary, description, id_base)
+
+
+def NewFSBuilder(description) -> Builder:
+    """suggest.NewFSBuilder (pkg/suggest/ngram_index_builder.go:38-57): `<output>/<name>.hd` + `.dl`"""
+    return _FSBuilder(description)
+
+
+class Service:
+    """suggest.Service, pkg/suggest/service.go:18-139"""
+
+    def __init__(self):
+        self._lock = threading.RLock()
+        self.indexes = {}
+        self.dictionaries = {}
+
+    def AddIndexByDescription(self, description):
+        if description.Driver == RAMDriver:
+            return self.AddRunTimeIndex(description)
+        return self.AddOnDiscIndex(description)
+
+    def AddRunTimeIndex(self, description):
+        try:
+            dictionary = open_ram_dictionary(description.GetSourcePath())
+        except OSError as e:
+            raise SuggestError(_capi.SG_ERR_IO, f"failed to create RAMDriver builder: {e}")
+        return self.AddIndex(description.Name, dictionary, NewRAMBuilder(dictionary, description))
+
+    def AddOnDiscIndex(self, description, dictionary=None):
+        """The reference opens `<name>.cdb` for the values; the CDB reader stays on the Go side of the shim
+        (SURVEY.md section 2 row 9), so here the values come from `dictionary` or the description's source file."""
+        if dictionary is None:
+            try:
+                dictionary = open_ram_dictionary(description.GetSourcePath())
+            except OSError as e:
+                raise SuggestError(_capi.SG_ERR_IO, f"failed to create CDB dictionary: {e}")
+        return self.AddIndex(description.Name, dictionary, NewFSBuilder(description))
+
+    def AddIndex(self, name, dictionary, builder):
+        try:
+            index = builder.Build()
+        except SuggestError as e:
+            raise SuggestError(e.code, f"failed to build NGramIndex: {e}")
+        with self._lock:
+            self.indexes[name] = index  # an index being replaced stays alive until its searches drain (refcount)
+            self.dictionaries[name] = dictionary
+
+    def GetDictionaries(self):
+        with self._lock:
+            return list(self.dictionaries)
+
+    def Suggest(self, dictName, config) -> List[ResultItem]:
+        with self._lock:
+            index = self.indexes.get(dictName)
+            dictionary = self.dictionaries.get(dictName)
+        if index is None or dictionary is None:
+            raise KeyError(f"given dictionary {dictName} is not exists")
+        candidates = index.Suggest(config.query, config.similarity, config.metric, config.topK)
+        out = []
+        for c in candidates:
+            v = dictionary[c.Key]
+            out.append(ResultItem(c.Score, v.decode("utf-8", "replace") if isinstance(v, bytes) else v))
+        return out
+
+
+def NewService():
+    return Service()

@@ -1,0 +1,403 @@
+"""Parity of the CUDA Suggest path (through the C ABI) with the CPU oracle.  Needs a B200: `pytest -m gpu`.
+
+ids must be identical, order included; scores are compared with == (both sides evaluate the same
+float64 expression) and, per the contract, within 1e-6.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import CARS_DESCRIPTION, COLLECTION, TEST_DESCRIPTION
+from oracle import oracle as O
+import suggest_b200 as S
+from suggest_b200 import _capi
+from suggest_b200.suggest import IndexDescription, pack_strings
+from suggest_b200.workload import synthetic_workload, unpack
+
+pytestmark = pytest.mark.gpu
+
+METRICS = {O.JACCARD: S.JaccardMetric(), O.COSINE: S.CosineMetric(), O.DICE: S.DiceMetric(), O.OVERLAP: S.OverlapMetric(),
+           O.EXACT: S.ExactMetric()}
+SCORE_TOL = 1e-6
+
+
+def description(d, name="t"):
+    return IndexDescription(Name=name, NGramSize=d["ngram_size"], Alphabet=tuple(d["alphabet"]), Pad=d["pad"],
+                            Wrap=tuple(d["wrap"]))
+
+
+def build_gpu(desc, docs, env=None):
+    """GPU index; env = tuning knobs read at index creation"""
+    old = {}
+    for k_, v in (env or {}).items():
+        old[k_] = os.environ.get(k_)
+        os.environ[k_] = str(v)
+    try:
+        gx = S.NewRAMBuilder(docs, description(desc)).Build()
+    finally:
+        for k_, v in old.items():
+            if v is None:
+                os.environ.pop(k_, None)
+            else:
+                os.environ[k_] = v
+    return gx
+
+
+def build_pair(desc, docs, env=None):
+    """(GPU index, oracle index) over the same documents"""
+    ox = O.OracleIndex(desc["ngram_size"], desc["wrap"], desc["pad"], desc["alphabet"]).add_docs(docs)
+    return build_gpu(desc, docs, env), ox
+
+
+def assert_same(gx, ox, queries, metric, alpha, k, what=""):
+    ids_g, sc_g, n_g = gx.SuggestBatch(queries, alpha, METRICS[metric], k)
+    ids_o, sc_o, n_o = ox.suggest_batch(queries, metric, alpha, k, O.CANONICAL, threads=8)
+    bad = np.nonzero(n_g != n_o)[0]
+    assert len(bad) == 0, (what, "count differs", bad[:5], [queries[i] for i in bad[:5]], n_g[bad[:5]], n_o[bad[:5]])
+    mask = np.arange(k)[None, :] < n_o[:, None]
+    diff = (ids_g != ids_o) & mask
+    if diff.any():
+        q = int(np.nonzero(diff.any(axis=1))[0][0])
+        raise AssertionError((what, "ids differ", q, queries[q], ids_g[q, :n_g[q]], ids_o[q, :n_o[q]], sc_g[q, :n_g[q]], sc_o[q, :n_o[q]]))
+    assert np.all(np.abs(sc_g - sc_o)[mask] <= SCORE_TOL), what
+    assert np.array_equal(sc_g[mask], sc_o[mask]), (what, "scores not bit-equal")
+    return n_o
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own end-to-end expectations
+# ---------------------------------------------------------------------------------------------------
+def test_ngram_index_test_go():
+    # pkg/suggest/ngram_index_test.go:15-40
+    gx = S.NewRAMBuilder(COLLECTION, description(TEST_DESCRIPTION)).Build()
+    got = gx.Suggest("Nissan ma", 0.5, S.JaccardMetric(), 2)
+    assert [c.Key for c in got] == [2, 0]
+    gx.close()
+
+
+def test_example_test_go():
+    # pkg/suggest/example_test.go:14-72
+    d = IndexDescription(Name="cars", NGramSize=3, Wrap=("$", "$"), Pad="$", Alphabet=("english", "$"))
+    gx = S.NewRAMBuilder(COLLECTION, d).Build()
+    got = gx.Suggest("niss ma", 0.4, S.CosineMetric(), 5)
+    assert [COLLECTION[c.Key] for c in got] == ["Nissan Maxima", "Nissan March"]
+
+
+def test_service_test_go(cars_lines, tmp_path):
+    # pkg/suggest/service_test.go:11-80 (RAM driver): Cosine 0.7, k=5, concurrent re-adds of the index
+    src = tmp_path / "cars.dict"
+    src.write_bytes(b"\n".join(cars_lines) + b"\n")
+    d = description(CARS_DESCRIPTION, "cars")
+    d.SourcePath = str(src)
+    service = S.NewService()
+    service.AddRunTimeIndex(d)
+    words = ["Nissan March", "Honda Fitt", "Wolfsvagen", "Tayota Corolla", "Micra Nissan"]
+    expected = [["NISSAN MARCH"], ["HONDA FIT"], [], ["TOYOTA COROLLA"], ["NISSAN MICRA"]]
+    errors = []
+
+    def search():
+        try:
+            for _ in range(3):
+                for w, exp in zip(words, expected):
+                    res = service.Suggest("cars", S.NewSearchConfig(w, 5, S.CosineMetric(), 0.7))
+                    if [r.Value for r in res] != exp:
+                        errors.append((w, res))
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def reindex():
+        try:
+            service.AddRunTimeIndex(d)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=search) for _ in range(5)] + [threading.Thread(target=reindex) for _ in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    with pytest.raises(KeyError):
+        service.Suggest("nope", S.NewSearchConfig("x", 5, S.CosineMetric(), 0.7))
+    with pytest.raises(ValueError):
+        S.NewSearchConfig("x", 0, S.CosineMetric(), 0.7)
+    with pytest.raises(ValueError):
+        S.NewSearchConfig("x", 5, S.CosineMetric(), 1.5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# cars: every entry as a query, all metrics
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def cars_pair(cars_lines):
+    return build_pair(CARS_DESCRIPTION, cars_lines)
+
+
+@pytest.mark.parametrize("metric,alpha,k", [(O.COSINE, 0.7, 5), (O.JACCARD, 0.5, 10), (O.DICE, 0.5, 10), (O.COSINE, 0.5, 5),
+                                            (O.OVERLAP, 0.9, 7), (O.EXACT, 1.0, 3), (O.JACCARD, 1.0, 4), (O.JACCARD, 0.2, 40),
+                                            (O.DICE, 0.35, 100)])
+def test_cars_every_entry(cars_pair, cars_lines, metric, alpha, k):
+    gx, ox = cars_pair
+    n = assert_same(gx, ox, cars_lines, metric, alpha, k, f"cars m={metric} a={alpha} k={k}")
+    assert n.sum() > 0
+
+
+def test_cars_misspelled_queries(cars_pair):
+    # pkg/suggest/ngram_index_test.go:196-206 (benchmark query set, no expected output in the reference)
+    gx, ox = cars_pair
+    queries = ["Nissan Mar", "Hnda Fi", "Mersdes Benz", "Tayota Corolla", "Nssan Skylike", "Nissan Juke", "Dodje iper",
+               "Hummer", "tayota"]
+    for metric, alpha in ((O.COSINE, 0.5), (O.JACCARD, 0.3), (O.DICE, 0.4)):
+        assert_same(gx, ox, queries, metric, alpha, 5)
+
+
+@pytest.mark.parametrize("env", [dict(SG_FORCE_SHIFT=0, SG_TBL_BYTES=2048), dict(SG_FORCE_SHIFT=2, SG_TBL_BYTES=2048),
+                                 dict(SG_FORCE_SHIFT=5), dict(SG_FORCE_SHIFT=13), dict(SG_TBL_BYTES=4096, SG_WARPS=3),
+                                 dict(SG_TBL_BYTES=65536)])
+def test_cars_bucket_widths_and_table_sizes(cars_lines, cars_pair, env):
+    """Every bucket width / chunking gives the same answer (exact counters, bucket filter + merge, multi-chunk)."""
+    gx = build_gpu(CARS_DESCRIPTION, cars_lines, env)
+    _, ox = cars_pair
+    q = cars_lines[::3]
+    assert_same(gx, ox, q, O.JACCARD, 0.5, 10, str(env))
+    assert_same(gx, ox, q, O.COSINE, 0.6, 3, str(env))
+    gx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic a-z dictionaries (BASELINE.json configs #2/#3 at a size the oracle finishes in seconds)
+# ---------------------------------------------------------------------------------------------------
+def synthetic(n_docs, n_queries, seed=12345):
+    (d, off), (q, q_off), _ = synthetic_workload(n_docs, n_queries, seed)
+    return unpack(d, off), unpack(q, q_off)
+
+
+@pytest.fixture(scope="module")
+def synth_pairs():
+    docs, queries = synthetic(60000, 3000)
+    out = {}
+    for n in (2, 3, 4):
+        desc = dict(TEST_DESCRIPTION, ngram_size=n)
+        out[n] = build_pair(desc, docs) + (queries,)
+    return out
+
+
+@pytest.mark.parametrize("n", [2, 3, 4])
+@pytest.mark.parametrize("metric,alpha", [(O.JACCARD, 0.5), (O.COSINE, 0.5), (O.DICE, 0.5), (O.JACCARD, 0.25), (O.OVERLAP, 0.7)])
+def test_synthetic_sweep(synth_pairs, n, metric, alpha):
+    gx, ox, queries = synth_pairs[n]
+    cnt = assert_same(gx, ox, queries, metric, alpha, 10, f"synthetic n={n} m={metric} a={alpha}")
+    assert (cnt > 0).mean() > 0.5
+
+
+def test_synthetic_stats_match_oracle(synth_pairs):
+    """{admissible postings, lists} of sg_search_batch_device = SURVEY.md 8(d) ingredients from the oracle"""
+    import torch
+    gx, ox, queries = synth_pairs[3]
+    q = queries[:200]
+    data, off = pack_strings(q)
+    dev = torch.device("cuda:0")
+    d_q = torch.from_numpy(data).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int32)).to(dev)
+    k = 10
+    d_ids = torch.zeros(len(q) * k, dtype=torch.int32, device=dev)
+    d_sc = torch.zeros(len(q) * k, dtype=torch.float64, device=dev)
+    d_cnt = torch.zeros(len(q), dtype=torch.int32, device=dev)
+    d_st = torch.zeros(len(q) * 2, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    gx.SuggestBatchDevice(d_q.data_ptr(), d_off.data_ptr(), len(q), 0.5, S.JaccardMetric(), k, d_ids.data_ptr(),
+                          d_sc.data_ptr(), d_cnt.data_ptr(), d_st.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st = d_st.cpu().numpy().reshape(-1, 2)
+    ids_o, sc_o, n_o = ox.suggest_batch(q, O.JACCARD, 0.5, k, O.CANONICAL, threads=4)
+    assert np.array_equal(d_cnt.cpu().numpy().astype(np.uint32), n_o)
+    assert np.array_equal(d_ids.cpu().numpy().astype(np.uint32).reshape(-1, k), ids_o)
+    for i, query in enumerate(q):
+        want = ox.query_stats(query, O.JACCARD, 0.5)
+        assert (int(st[i, 0]), int(st[i, 1])) == (want["postings"], want["lists"]), (i, query)
+
+
+# ---------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------
+def test_empty_short_and_degenerate_queries(cars_pair):
+    gx, ox = cars_pair
+    queries = ["", " ", "a", "zz", "$", "    ", "x" * 120, "qqqqqqqqqqqqqqqqqqqqqqqq", "RAM RAM", "ram  ram", "A4", "Z"]
+    for metric, alpha in ((O.JACCARD, 0.5), (O.JACCARD, 0.9), (O.COSINE, 0.3), (O.OVERLAP, 0.5), (O.EXACT, 0.5)):
+        assert_same(gx, ox, queries, metric, alpha, 5, f"edge m={metric} a={alpha}")
+
+
+def test_empty_batch_and_empty_dictionary():
+    gx = S.NewRAMBuilder([], description(TEST_DESCRIPTION)).Build()
+    assert gx.Suggest("anything", 0.5, S.JaccardMetric(), 3) == []
+    ids, sc, n = gx.SuggestBatch([], 0.5, S.JaccardMetric(), 3)
+    assert ids.shape == (0, 3) and n.shape == (0,)
+    gx2 = S.NewRAMBuilder(["", "", "a"], description(TEST_DESCRIPTION)).Build()
+    assert [c.Key for c in gx2.Suggest("a", 0.5, S.JaccardMetric(), 3)] == [2]
+
+
+def test_unicode_dictionary_and_queries():
+    docs = ["Жигули", "жигулёвское", "Ёлка", "ёлочка", "Москвич 412", "МОСКВА", "Nissan ёж", "日本語", "İstanbul", "straße", "STRASSE"]
+    queries = ["жигули", "ЖИГУЛИ", "елка", "Ёлка", "москвич", "Москва 41", "nissan еж", "日本", "istanbul", "ıstanbul", "Straße",
+               b"\xd0\xb6\xd0\xb8\xd0\xb3\xff\xd1\x83", "ж", "ЖИГУЛЁВСКОЕ"]
+    gx, ox = build_pair(TEST_DESCRIPTION, docs)
+    for metric, alpha in ((O.JACCARD, 0.3), (O.COSINE, 0.4), (O.DICE, 0.2)):
+        assert_same(gx, ox, queries, metric, alpha, 4, f"unicode m={metric}")
+
+
+def test_alternative_descriptions():
+    docs = [f"item {i:04d} " + "abc"[i % 3] * (i % 5) for i in range(500)] + ["^caret$", "tail ", " lead"]
+    queries = ["item 0042", "item 42", "ITEM 0499 c", "caret", "tail", "lead", "0007"]
+    for desc in (dict(ngram_size=2, wrap=("", ""), pad="_", alphabet=("english", "numbers")),
+                 dict(ngram_size=4, wrap=("^", "$"), pad="$", alphabet=("english", "numbers", "$^")),
+                 dict(ngram_size=3, wrap=("  ", " "), pad="#", alphabet=("english", "numbers", " ")),
+                 dict(ngram_size=1, wrap=("", ""), pad="?", alphabet=("numbers",))):
+        gx, ox = build_pair(desc, docs)
+        for metric, alpha in ((O.JACCARD, 0.4), (O.COSINE, 0.5)):
+            assert_same(gx, ox, queries, metric, alpha, 6, str(desc))
+
+
+def test_large_k(cars_pair, cars_lines):
+    gx, ox = cars_pair
+    q = cars_lines[:200]
+    for k in (1, 32, 33, 250, 1024):
+        assert_same(gx, ox, q, O.JACCARD, 0.15, k, f"k={k}")
+
+
+def test_invalid_arguments_and_too_long_query(cars_pair):
+    gx, _ = cars_pair
+    with pytest.raises(S.SuggestError) as e:
+        gx.SuggestBatch(["a"], 0.5, S.JaccardMetric(), 0)
+    assert e.value.code == _capi.SG_ERR_INVALID
+    with pytest.raises(S.SuggestError):
+        gx.SuggestBatch(["a"], 0.0, S.JaccardMetric(), 5)
+    with pytest.raises(S.SuggestError):
+        gx.SuggestBatch(["a"], 1.01, S.JaccardMetric(), 5)
+    with pytest.raises(S.SuggestError):
+        gx.SuggestBatch(["a"], 0.5, S.JaccardMetric(), 2000)
+    with pytest.raises(S.SuggestError) as e:
+        gx.SuggestBatch(["ok", "y" * 300], 0.5, S.JaccardMetric(), 5)
+    assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG
+    with pytest.raises(S.SuggestError):
+        S.NewRAMBuilder(["a"], IndexDescription(NGramSize=3, Pad="")).Build()
+
+
+def test_from_lists_matches_build(cars_lines, cars_pair):
+    """sg_index_from_lists (what a Go shim that decoded .hd/.dl itself would call) == sg_index_build"""
+    _, ox = cars_pair
+    segs, terms, ids, loff, toff = [], [], [], [0], [0]
+    for seg, term, lst in ox.iter_lists():
+        segs.append(seg)
+        terms.append(term)
+        ids.append(lst)
+        loff.append(loff[-1] + len(lst))
+        toff.append(toff[-1] + len(term))
+    segs = np.array(segs, dtype=np.uint32)
+    ids = np.concatenate(ids).astype(np.uint32)
+    loff = np.array(loff, dtype=np.uint64)
+    toff = np.array(toff, dtype=np.uint64)
+    tb = np.frombuffer(b"".join(terms), dtype=np.uint8)
+    cfg, keep = description(CARS_DESCRIPTION).c_config()
+    h = C.c_void_p()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    _capi.check(_capi.lib().sg_index_from_lists(C.byref(cfg), ox.segments, len(segs), p(segs), p(tb), p(toff), p(ids), p(loff), C.byref(h)))
+    gx = S.NGramIndex(h.value, description(CARS_DESCRIPTION))
+    assert_same(gx, ox, cars_lines[::5], O.COSINE, 0.7, 5, "from_lists")
+    assert gx.info()["n_postings"] == cars_pair[0].info()["n_postings"]
+
+
+def test_shards_and_merge(cars_lines, cars_pair):
+    """record-id-range shards + sg_merge_topk_device == one index"""
+    import torch
+    _, ox = cars_pair
+    n_parts, k = 3, 10
+    bounds = [0, 1500, 3700, len(cars_lines)]
+    shards = [S.NewRAMBuilder(cars_lines[bounds[i]:bounds[i + 1]], description(CARS_DESCRIPTION), id_base=bounds[i]).Build()
+              for i in range(n_parts)]
+    q = cars_lines[::4]
+    nq = len(q)
+    ids = np.zeros((n_parts, nq, k), dtype=np.uint32)
+    sc = np.zeros((n_parts, nq, k), dtype=np.float64)
+    cnt = np.zeros((n_parts, nq), dtype=np.uint32)
+    for i, sh in enumerate(shards):
+        ids[i], sc[i], cnt[i] = sh.SuggestBatch(q, 0.5, S.JaccardMetric(), k)
+    # the reference's segment count is a per-index property: a shard sees fewer segments than the whole
+    # dictionary, which only removes empty segments from the window, never candidates
+    dev = torch.device("cuda:0")
+    d_ids = torch.from_numpy(ids.view(np.int32)).to(dev)
+    d_sc = torch.from_numpy(sc).to(dev)
+    d_cnt = torch.from_numpy(cnt.view(np.int32)).to(dev)
+    o_ids = torch.zeros(nq * k, dtype=torch.int32, device=dev)
+    o_sc = torch.zeros(nq * k, dtype=torch.float64, device=dev)
+    o_cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    _capi.check(_capi.lib().sg_merge_topk_device(0, n_parts, nq, k, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
+                                                 o_ids.data_ptr(), o_sc.data_ptr(), o_cnt.data_ptr(),
+                                                 torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ids_o, sc_o, n_o = ox.suggest_batch(q, O.JACCARD, 0.5, k, O.CANONICAL, threads=8)
+    got_n = o_cnt.cpu().numpy().astype(np.uint32)
+    assert np.array_equal(got_n, n_o)
+    mask = np.arange(k)[None, :] < n_o[:, None]
+    got_ids = o_ids.cpu().numpy().astype(np.uint32).reshape(nq, k)
+    assert np.array_equal(got_ids[mask], ids_o[mask])
+    assert np.array_equal(o_sc.cpu().numpy().reshape(nq, k)[mask], sc_o[mask])
+
+
+def test_concurrent_searches_on_one_handle(cars_pair, cars_lines):
+    gx, ox = cars_pair
+    q = cars_lines[100:400]
+    want = ox.suggest_batch(q, O.COSINE, 0.6, 5, O.CANONICAL, threads=8)
+    errors = []
+
+    def worker():
+        try:
+            for _ in range(4):
+                got = gx.SuggestBatch(q, 0.6, S.CosineMetric(), 5)
+                if not (np.array_equal(got[2], want[2]) and np.array_equal(got[0], want[0])):
+                    errors.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker) for _ in range(8)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors[:2]
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json config #2 at full size: properties + a sample against the oracle
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_1m_jaccard():
+    (d, off), (qb, q_off), pick = synthetic_workload(1_000_000, 65536)
+    gx = S.NewRAMBuilder((d, off), description(TEST_DESCRIPTION)).Build()
+    ox = O.OracleIndex(**TEST_DESCRIPTION).add_packed(d, off)
+    info = gx.info()
+    assert info["n_docs"] == 1_000_000 and info["n_postings"] == ox.postings and info["n_lists"] == ox.lists
+    k = 10
+    ids, sc, n = gx.SuggestBatch(None, 0.5, S.JaccardMetric(), k, packed=(qb, q_off))
+    # properties that hold for every row: scores descending, ties by ascending id, scores in [alpha, 1], ids valid
+    mask = np.arange(k)[None, :] < n[:, None]
+    assert n.max() <= k and ids[mask].max() < 1_000_000
+    assert np.all(sc[mask] >= 0.5) and np.all(sc[mask] <= 1.0)
+    pair_ok = (sc[:, :-1] > sc[:, 1:]) | ((sc[:, :-1] == sc[:, 1:]) & (ids[:, :-1] < ids[:, 1:]))
+    assert np.all(pair_ok | ~mask[:, 1:])
+    found = n > 0
+    assert found.mean() > 0.6  # two substitutions keep most queries above Jaccard 0.5 of their source entry
+    assert (ids[found, 0] == pick[found]).mean() > 0.99  # and the source entry is the best match
+    # idempotence: a second call returns the same bytes
+    ids2, sc2, n2 = gx.SuggestBatch(None, 0.5, S.JaccardMetric(), k, packed=(qb, q_off))
+    assert np.array_equal(ids, ids2) and np.array_equal(sc, sc2) and np.array_equal(n, n2)
+    # a sample against the oracle
+    sample = np.arange(0, 65536, 16)
+    queries = unpack(qb, q_off)
+    ids_o, sc_o, n_o = ox.suggest_batch([queries[i] for i in sample], O.JACCARD, 0.5, k, O.CANONICAL, threads=8)
+    assert np.array_equal(n[sample], n_o)
+    m2 = np.arange(k)[None, :] < n_o[:, None]
+    assert np.array_equal(ids[sample][m2], ids_o[m2])
+    assert np.array_equal(sc[sample][m2], sc_o[m2])
