@@ -190,7 +190,7 @@ def synth_pairs():
 def test_synthetic_sweep(synth_pairs, n, metric, alpha):
     gx, ox, queries = synth_pairs[n]
     cnt = assert_same(gx, ox, queries, metric, alpha, 10, f"synthetic n={n} m={metric} a={alpha}")
-    assert (cnt > 0).mean() > 0.5
+    assert (cnt > 0).mean() > 0.3
 
 
 def test_synthetic_stats_match_oracle(synth_pairs):
