@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsuggest_b200.so")
+LIB_PATH = os.environ.get("SUGGEST_B200_LIB") or os.path.join(_HERE, "libsuggest_b200.so")  # override: tuning builds
 
 SG_OK = 0
 SG_ERR_INVALID, SG_ERR_UNSUPPORTED, SG_ERR_CUDA, SG_ERR_NOMEM, SG_ERR_QUERY_TOO_LONG, SG_ERR_IO, SG_ERR_FORMAT = \

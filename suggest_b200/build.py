@@ -28,5 +28,14 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_variant(name, defines):
+    """Tuning builds (e.g. other TMA ring geometries) next to the product library; select one with SUGGEST_B200_LIB."""
+    out = os.path.join(HERE, "variants", f"libsuggest_b200_{name}.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [NVCC] + FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -21,6 +21,8 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 constexpr uint32_t kWorkRing = 1024;
+constexpr int kMaxWarps = sg::kMaxSearchThreads / 32;
+constexpr int kDefaultTblBytes = 8192;     // 16 warps per SM at k = 10; one pass covers 1M documents at 128 per bucket
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -89,9 +91,9 @@ struct sg_index {
     std::vector<CallCtx *> pool;
     uint32_t *work_ring = nullptr;       // kWorkRing query counters for sg_search_batch_device
     std::atomic<uint32_t> work_rr{0};
-    uint32_t tbl_bytes = 16384;
+    uint32_t tbl_bytes = kDefaultTblBytes;
     int force_shift = -1;
-    int max_warps = 32;
+    int max_warps = kMaxWarps;
 };
 
 namespace {
@@ -168,14 +170,14 @@ int finalize(sg_index *ix) {
     std::vector<uint64_t>().swap(h.ht_keys);
     std::vector<uint32_t>().swap(h.ht_vals);
     // tuning knobs (documented in DESIGN.md); defaults are what bench.py measures
-    int tb = env_int("SG_TBL_BYTES", 16384);
-    uint32_t t = 2048;
-    while (t < (uint32_t)tb && t < 131072u) t <<= 1;
-    ix->tbl_bytes = t;
+    int tb = env_int("SG_TBL_BYTES", kDefaultTblBytes);
+    if (tb < 2048) tb = 2048;
+    if (tb > 200000) tb = 200000;
+    ix->tbl_bytes = ((uint32_t)tb + 15u) & ~15u;
     ix->force_shift = env_int("SG_FORCE_SHIFT", -1);
-    ix->max_warps = env_int("SG_WARPS", 32);
+    ix->max_warps = env_int("SG_WARPS", kMaxWarps);
     if (ix->max_warps < 1) ix->max_warps = 1;
-    if (ix->max_warps > 32) ix->max_warps = 32;
+    if (ix->max_warps > kMaxWarps) ix->max_warps = kMaxWarps;
     return SG_OK;
 }
 
@@ -215,7 +217,7 @@ int make_index(const sg_config *cfg, sg_index **out, sg_index **ixp) {
 struct Geometry { int blocks, warps; size_t smem; uint32_t warp_smem; };
 
 int geometry(const sg_index *ix, uint32_t n_q, uint32_t k, Geometry *g) {
-    uint32_t warp_smem = ix->tbl_bytes + 3u * sg::kMaxQueryTokens * 4u + k * 12u;
+    uint32_t warp_smem = ix->tbl_bytes + sg::kWarpFixedSmem + k * 12u;  // layout: sg_search_kernel
     warp_smem = (warp_smem + 15u) & ~15u;
     int warps = (int)(ix->smem_optin / warp_smem);
     if (warps > ix->max_warps) warps = ix->max_warps;

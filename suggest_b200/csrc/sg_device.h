@@ -15,6 +15,17 @@ constexpr int kMaxQueryTokens = 128;  // SG_MAX_QUERY_TOKENS
 constexpr int kMaxWrapRunes = 8;
 constexpr int kMaxRunes = kMaxQueryTokens + kMaxNgram;  // wrapped query runes staged per warp
 constexpr uint32_t kNoTerm = 0xFFFFFFFFu;
+// per-warp shared memory of sg_search_kernel: [counter table | TMA ring | mbarriers | run slices | thresholds | top-k]
+#ifndef SG_SLICE_BYTES
+#define SG_SLICE_BYTES 2048
+#endif
+#ifndef SG_RING_SLOTS
+#define SG_RING_SLOTS 2
+#endif
+constexpr uint32_t kSliceBytes = SG_SLICE_BYTES;  // one TMA bulk copy: 512 postings
+constexpr uint32_t kRingSlots = SG_RING_SLOTS;    // slices in flight per warp (at most 8)
+constexpr uint32_t kWarpFixedSmem = kRingSlots * kSliceBytes + 64 + 128 + 64 + 3 * kMaxQueryTokens * 4 + 256;
+constexpr int kMaxSearchThreads = 768;       // launch bound of sg_search_kernel (24 warps)
 constexpr uint32_t kCountUnsupported = 0xFFFFFFFFu;     // SG_COUNT_UNSUPPORTED
 
 // non-ASCII alphabet interval: rune r in [lo, hi] has symbol code base + (r - lo)

@@ -10,13 +10,15 @@
 //      term hash table -> one contiguous posting run per query token (documents are renumbered by
 //      cardinality segment, so the segment window [MinY, MaxY] of a term is one slice of HBM);
 //   2. T-occurrence count (ScanCount semantics, pkg/merger/scan_count.go:14-88) in a warp-private
-//      byte-counter table in shared memory.  A posting run is ascending, so the postings one warp
-//      instruction handles land in distinct counters and the read-modify-write needs no atomics.
-//      The table covers the window's id range at a bucket width of 2^s documents chosen per query
-//      by a cost model: s = 0 counts documents exactly (dense dictionaries); s > 0 counts "lists
-//      that hit the bucket", an upper bound of any document's overlap, so buckets below the
-//      smallest admissible threshold are discarded wholesale and the few survivors are resolved
-//      exactly by a warp-wide merge of the run slices that fall into the bucket;
+//      table of byte counters in shared memory, updated with 32-bit shared atomics (ATOMS.ADD on the
+//      byte's field; measured on B200 at the cost of a plain scattered store, 2.7x cheaper than a
+//      byte load + store).  The table covers the window's id range at a bucket width of 2^s
+//      documents chosen per query by a cost model: s = 0 counts documents exactly (dense
+//      dictionaries); s > 0 counts "lists that hit the bucket" - every (list, bucket) pair adds one,
+//      so a counter is bounded by the number of lists (<= 128) and bounds every overlap inside the
+//      bucket - then the table is scanned segment by segment against that segment's threshold and
+//      the few surviving buckets are resolved exactly by a warp-wide merge of the run slices that
+//      fall into them;
 //   3. threshold / score in float64 with the reference's operation order (pkg/metric/*.go,
 //      pkg/suggest/scorer.go:29-31) and a sorted top-k in shared memory ordered (score desc, id asc)
 //      (pkg/suggest/collector.go:20-26).
@@ -36,6 +38,8 @@ namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kInf = 0xFFFFFFFFu;
+constexpr int kThrCache = 256;  // window segments whose threshold is cached in shared memory
+constexpr uint32_t kSlicePostings = kSliceBytes / 4;
 
 enum { kJaccard = 0, kCosine = 1, kDice = 2, kOverlap = 3, kExact = 4 };
 
@@ -195,41 +199,156 @@ __device__ void topk_insert(QueryCtx &c, double score, uint32_t id, int lane) {
     c.tk_len = new_len;
 }
 
-// A document (new id) with an exact overlap count: apply the segment's threshold, score, offer to the top-k.
-// All lanes call with identical arguments.
-__device__ void emit_candidate(const DevIndex &ix, QueryCtx &c, uint32_t new_id, int count, int lane) {
-    int lo = c.b_lo, hi = c.b_hi;  // segment of the document: last B with seg_start[B] <= new_id
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (__ldg(ix.seg_start + mid) <= new_id) lo = mid; else hi = mid - 1;
-    }
-    const int size_b = lo;
-    const int T = metric_threshold(c.metric, c.alpha, c.size_a, size_b);
-    if (!threshold_admits(T, c.size_a, size_b) || count < T) return;
+// A document (new id) of segment size_b with an exact overlap count: apply the segment's threshold T,
+// score, offer to the top-k.  All lanes call with identical arguments.
+__device__ __forceinline__ void emit_candidate(const DevIndex &ix, QueryCtx &c, uint32_t new_id, int count, int size_b, int T,
+                                               int lane) {
+    if (count < T) return;
     const double score = metric_score(c.metric, count, c.size_a, size_b);
     topk_insert(c, score, __ldg(ix.perm + new_id), lane);
 }
 
+// P(Poisson(lam) >= t), upper-ish estimate for the bucket-width cost model
+__device__ __forceinline__ float poisson_tail(float lam, int t) {
+    if (lam <= 0.0f) return 0.0f;
+    const float ft = (float)t;
+    if (lam >= 0.7f * ft) return 1.0f;
+    return fminf(1.0f, __expf(-lam + ft * __logf(lam) - ln_factorial(ft)) / (1.0f - lam / (ft + 1.0f)));
+}
+
+// ---------------- shared-memory staging: TMA bulk copies + mbarriers, red.shared counters ----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+
+// Converged warp: one elected lane arms the mbarrier with the byte count and issues the global -> shared bulk copy
+// (UBLKCP); the copy's completion is counted in bytes on the same mbarrier.
+__device__ __forceinline__ void tma_issue(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+        "@p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t"
+        "}" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(mbar)
+        : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(mbar), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+// counter += inc: the byte counters are fields of 32-bit words; ATOMS.ADD without a return value, never branched
+// around (ptxas turns a predicated red into a branch, and a divergent branch costs more than an add of zero)
+// No "memory" clobber on purpose: the table is only read back after a __syncwarp(), and without the clobber the
+// compiler may issue the next group's shared loads ahead of these.
+__device__ __forceinline__ void red_add(uint32_t saddr, uint32_t inc) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(inc));
+}
+
+// Count one group of 128 postings (4 per lane, ascending over the warp): every (list, bucket) pair adds exactly one to
+// the bucket's byte counter, so a counter never exceeds the number of lists (<= 128).  `carry` is the bucket of the
+// posting just before this group in the same list.  Returns the bucket of the group's last posting.
+// pos = index of this lane's first posting, [a, b) = the list's slice; kAllValid: the whole group lies inside it.
+// A posting that is not the first of its bucket adds zero to its own (valid) word; a slot outside [a, b) adds zero to
+// this lane's word of a scratch line.
+template <bool kAllValid>
+__device__ __forceinline__ uint32_t count_group(uint32_t tbl_saddr, uint32_t scratch_saddr, const uint4 x, uint32_t pos, uint32_t a,
+                                                uint32_t b, uint32_t lo_id, int shift, uint32_t carry, int lane) {
+    uint32_t b0 = (x.x - lo_id) >> shift, b1 = (x.y - lo_id) >> shift, b2 = (x.z - lo_id) >> shift, b3 = (x.w - lo_id) >> shift;
+    if (!kAllValid) {
+        const uint32_t d = pos - a, len = b - a;  // unsigned: positions before a wrap around and fail the test too
+        if (d >= len) b0 = kInf;
+        if (d + 1 >= len) b1 = kInf;
+        if (d + 2 >= len) b2 = kInf;
+        if (d + 3 >= len) b3 = kInf;
+    }
+    uint32_t prev = __shfl_up_sync(kFull, b3, 1);
+    if (lane == 0) prev = carry;
+    // head << ((bucket & 3) * 8): the funnel shift takes its amount modulo 32
+    uint32_t i0 = __funnelshift_l(0u, (uint32_t)(b0 != prev), b0 << 3), i1 = __funnelshift_l(0u, (uint32_t)(b1 != b0), b1 << 3);
+    uint32_t i2 = __funnelshift_l(0u, (uint32_t)(b2 != b1), b2 << 3), i3 = __funnelshift_l(0u, (uint32_t)(b3 != b2), b3 << 3);
+    uint32_t a0 = tbl_saddr + (b0 & ~3u), a1 = tbl_saddr + (b1 & ~3u), a2 = tbl_saddr + (b2 & ~3u), a3 = tbl_saddr + (b3 & ~3u);
+    if (!kAllValid) {
+        if (b0 == kInf) { a0 = scratch_saddr; i0 = 0u; }
+        if (b1 == kInf) { a1 = scratch_saddr; i1 = 0u; }
+        if (b2 == kInf) { a2 = scratch_saddr; i2 = 0u; }
+        if (b3 == kInf) { a3 = scratch_saddr; i3 = 0u; }
+    }
+    red_add(a0, i0);
+    red_add(a1, i1);
+    red_add(a2, i2);
+    red_add(a3, i3);
+    return __shfl_sync(kFull, b3, 31);
+}
+
+// Walks the posting-run slices of one chunk in order, kSlicePostings at a time (the TMA producer's cursor).
+struct SliceWalker {
+    int j;               // list
+    uint32_t a, b, base; // slice of the list inside the chunk, first posting (multiple of 4) of the current piece
+    bool valid;
+    __device__ __forceinline__ void start(const uint32_t *s_cur, const uint32_t *s_end, int n_lists) {
+        j = -1;
+        a = b = base = 0;
+        valid = true;
+        next(s_cur, s_end, n_lists);
+    }
+    __device__ __forceinline__ void next(const uint32_t *s_cur, const uint32_t *s_end, int n_lists) {
+        if (j >= 0 && base + kSlicePostings < b) { base += kSlicePostings; return; }
+        for (++j; j < n_lists; ++j) {
+            a = s_cur[j];
+            b = s_end[j];
+            if (a < b) { base = a & ~3u; return; }
+        }
+        valid = false;
+    }
+    __device__ __forceinline__ uint32_t bytes() const {  // whole 16-byte units; the postings array is padded
+        const uint32_t end = min(base + kSlicePostings, (b + 3u) & ~3u);
+        return (end - base) * 4u;
+    }
+};
+
 }  // namespace
 
-__global__ void __launch_bounds__(1024, 1) sg_search_kernel(const DevIndex ix, const SearchParams p) {
+__global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const DevIndex ix, const SearchParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint8_t *wsm = smem + (size_t)warp * p.warp_smem;
-    uint8_t *tbl = wsm;                                         // [tbl_bytes] byte counters
-    uint32_t *s_cur = (uint32_t *)(wsm + p.tbl_bytes);          // [128] start of the not yet counted part of a run
+    uint8_t *tbl = wsm;                                         // [tbl_bytes] byte counters, updated as fields of 32-bit words
+    uint8_t *ring = wsm + p.tbl_bytes;                          // [kRingSlots][kSliceBytes] posting slices landed by TMA
+    uint64_t *mbar = (uint64_t *)(ring + kRingSlots * kSliceBytes);  // [kRingSlots] one mbarrier per slot (64 bytes) + scratch line (128)
+    uint4 *s_meta = (uint4 *)(ring + kRingSlots * kSliceBytes + 192);  // [kRingSlots] {a, b, base} of the slice in each slot (64 bytes)
+    uint32_t *s_cur = (uint32_t *)(ring + kRingSlots * kSliceBytes + 256);  // [128] start of the not yet counted part of a run
     uint32_t *s_end = s_cur + kMaxQueryTokens;                  // [128] end of the run slice inside the current chunk
     uint32_t *s_rend = s_end + kMaxQueryTokens;                 // [128] end of the run (segment window)
-    double *tk_score = (double *)(s_rend + kMaxQueryTokens);    // [k]
+    uint8_t *s_thr = (uint8_t *)(s_rend + kMaxQueryTokens);     // [256] threshold of window segment b_min + i, 0 = skip
+    double *tk_score = (double *)(s_thr + kThrCache);           // [k]
     uint32_t *tk_id = (uint32_t *)(tk_score + p.k);             // [k]
     // tokeniser scratch overlays the counter table (the table is cleared after the runs are known)
     uint32_t *s_runes = (uint32_t *)tbl;                        // [kMaxRunes]
     uint32_t *s_lterm = s_runes + kMaxRunes;                    // [128] term id of every list to open
+    uint32_t *s_hash = s_lterm + kMaxQueryTokens;               // [128] hash of every raw n-gram window
 
     const uint32_t S = ix.n_segments;
     const uint32_t stride = S + 1;
     const uint32_t *__restrict__ postings = ix.postings;
+    const uint32_t tbl_saddr = smem_u32(tbl), ring_saddr = smem_u32(ring), mbar_saddr = smem_u32(mbar);
+    const uint32_t scratch_saddr = mbar_saddr + 64 + lane * 4;  // this lane's word of the scratch line behind the mbarriers
+    if (lane == 0) {
+        for (uint32_t sl = 0; sl < kRingSlots; sl++) mbar_init(mbar_saddr + 8 * sl, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t n_filled = 0, n_used = 0;  // slices issued to / consumed from the ring since the kernel started
 
     for (;;) {
         uint32_t q = 0;
@@ -310,11 +429,20 @@ __global__ void __launch_bounds__(1024, 1) sg_search_kernel(const DevIndex ix, c
             if (n_win > kMaxQueryTokens) { unsupported = true; n_win = 0; }
         }
         int n_lists = 0;
+        for (int i = lane; i < n_win; i += 32) {
+            uint32_t h = 2166136261u;
+            for (int cpos = 0; cpos < wlen; cpos++) h = (h ^ s_runes[first + i + cpos]) * 16777619u;
+            s_hash[i] = h;
+        }
+        __syncwarp();
         for (int base = 0; base < n_win; base += 32) {
             const int i = base + lane;
             bool keep = i < n_win;
-            if (keep) {  // appendUnique, ngram_tokenizer.go:46-54: raw windows, first occurrence wins
-                for (int j = 0; j < i && keep; j++) {
+            // appendUnique, ngram_tokenizer.go:46-54: raw windows, first occurrence wins (hash first, runes on a hit)
+            const uint32_t my_hash = keep ? s_hash[i] : 0u;
+            const int j_end = min(base + 31, n_win - 1);
+            for (int j = 0; j < j_end; j++) {
+                if (keep && j < i && s_hash[j] == my_hash) {
                     bool eq = true;
                     for (int cpos = 0; cpos < wlen; cpos++) eq &= s_runes[first + i + cpos] == s_runes[first + j + cpos];
                     keep = !eq;
@@ -335,21 +463,18 @@ __global__ void __launch_bounds__(1024, 1) sg_search_kernel(const DevIndex ix, c
         __syncwarp();
 
         // ---------------- 2. segment window and thresholds (suggester.go:53-59, :73-78) ----------------
-        int theta = INT_MAX;
+        int b_min = 0;
         if (c.size_a > 0) {
-            const int b_min = max(metric_min_y(c.metric, c.alpha, c.size_a), 0);
+            b_min = max(metric_min_y(c.metric, c.alpha, c.size_a), 0);
             int b_max = metric_max_y(c.metric, c.alpha, c.size_a);
             if (b_max >= (int)S) b_max = (int)S - 1;
             int lo = INT_MAX, hi = -1;
             for (int B = b_min + lane; B <= b_max; B += 32) {
                 const int T = metric_threshold(c.metric, c.alpha, c.size_a, B);
-                if (threshold_admits(T, c.size_a, B) && __ldg(ix.seg_start + B + 1) > __ldg(ix.seg_start + B)) {
-                    theta = min(theta, T);
-                    lo = min(lo, B);
-                    hi = max(hi, B);
-                }
+                const bool use = threshold_admits(T, c.size_a, B) && __ldg(ix.seg_start + B + 1) > __ldg(ix.seg_start + B);
+                if (use) { lo = min(lo, B); hi = max(hi, B); }
+                if (B - b_min < kThrCache) s_thr[B - b_min] = use ? (uint8_t)T : (uint8_t)0;
             }
-            theta = __reduce_min_sync(kFull, theta);
             c.b_lo = __reduce_min_sync(kFull, lo);
             c.b_hi = __reduce_max_sync(kFull, hi);
             if (p.stats != nullptr) {  // admissible postings and lists
@@ -366,7 +491,14 @@ __global__ void __launch_bounds__(1024, 1) sg_search_kernel(const DevIndex ix, c
                 st_postings = __reduce_add_sync(kFull, st_postings);
                 st_lists = __reduce_add_sync(kFull, st_lists);
             }
+            __syncwarp();
         }
+        // threshold of an admissible, non-empty window segment; 0 = nothing to find there
+        auto thr_of = [&](int B) -> int {
+            if (B - b_min < kThrCache) return (int)s_thr[B - b_min];
+            const int T = metric_threshold(c.metric, c.alpha, c.size_a, B);
+            return (threshold_admits(T, c.size_a, B) && __ldg(ix.seg_start + B + 1) > __ldg(ix.seg_start + B)) ? T : 0;
+        };
 
         if (c.b_hi >= 0 && n_lists > 0) {
             // ---------------- 3. one posting run per list ----------------
@@ -381,41 +513,44 @@ __global__ void __launch_bounds__(1024, 1) sg_search_kernel(const DevIndex ix, c
             for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
             __syncwarp();
 
-            // ---------------- 4. bucket width: minimise chunks * per-chunk cost + expected false candidates ----------------
+            // ---------------- 4. bucket width ----------------
+            // shift = 0 counts documents exactly but may need many passes over the table; a wider bucket counts
+            // "lists that hit the bucket" (an upper bound of every overlap inside it) in one pass and pays an exact
+            // merge for the buckets that reach their segment's threshold.  Minimise the estimated cost.
             const uint32_t c_base = __ldg(ix.seg_start + c.b_lo);
             const uint32_t D = __ldg(ix.seg_start + c.b_hi + 1) - c_base;
             const uint32_t NB = p.tbl_bytes;
             int shift = 0;
-            if (p.force_shift >= 0) shift = p.force_shift;
-            else {
-                float best = FLT_MAX;
-                const float lnf = ln_factorial((float)theta);
-                for (int s = 0; s < 24; s++) {
-                    const uint32_t nb_total = ((D - 1) >> s) + 1;
-                    const uint32_t nch = (nb_total + NB - 1) / NB;
+            if (p.force_shift >= 0) shift = min(p.force_shift, 30);
+            else if (D > NB) {
+                int s1 = 1;
+                while ((((uint64_t)(D - 1) >> s1) + 1) > NB) s1++;
+                const float fl = (float)n_lists, fd = (float)D;
+                const float chunk_cost = (float)NB * (1.0f / 32.0f) + 400.0f + 30.0f * fl;
+                float best = (float)((D + NB - 1) / NB) * chunk_cost;  // shift 0
+                for (int s = max(1, s1 - 3); s <= s1; s++) {
+                    const float w = (float)(1u << s);
+                    const float lam = fl * (1.0f - __expf(-(total / fl) * w / fd));
                     float est = 0.0f;
-                    if (s > 0) {
-                        const float lam = total * (float)(1u << s) / (float)D;
-                        float tail = 1.0f;
-                        if (lam < 0.5f * (float)theta && lam > 0.0f)
-                            tail = fminf(1.0f, 2.0f * __expf(-lam + (float)theta * __logf(lam) - lnf));
-                        else if (lam <= 0.0f) tail = 0.0f;
-                        est = tail * (float)nb_total;
+                    for (int B = c.b_lo + lane; B <= c.b_hi; B += 32) {
+                        const int T = thr_of(B);
+                        if (T == 0) continue;
+                        const float docs = (float)(__ldg(ix.seg_start + B + 1) - __ldg(ix.seg_start + B));
+                        est += (docs / w + 1.0f) * poisson_tail(lam, T);
                     }
-                    const float cost = (float)nch * ((float)min(nb_total, NB) * (1.0f / 32.0f) + 400.0f + 24.0f * (float)n_lists) +
-                                       est * 1200.0f;
+                    for (int o = 16; o; o >>= 1) est += __shfl_xor_sync(kFull, est, o);
+                    const uint32_t nb_total = ((D - 1) >> s) + 1;
+                    const float cost = (float)((nb_total + NB - 1) / NB) * chunk_cost + est * 2000.0f;
                     if (cost < best) { best = cost; shift = s; }
-                    if (nch == 1) break;
                 }
             }
-            while (shift < 31 && (((uint64_t)(D - 1) >> shift) + 1 + NB - 1) / NB > 0xFFFFu) shift++;  // keep the chunk loop bounded
+            while (shift < 30 && (((uint64_t)(D - 1) >> shift) + NB) / NB > 0xFFFFu) shift++;  // keep the chunk loop bounded
             const uint64_t chunk_docs = (uint64_t)NB << shift;
-            const uint32_t th4 = (uint32_t)min(theta, 255) * 0x01010101u;
 
             for (uint64_t cs = 0; cs < D; cs += chunk_docs) {
                 const uint32_t ce = (uint32_t)min((unsigned long long)D, (unsigned long long)(cs + chunk_docs));
                 const uint32_t lo_id = c_base + (uint32_t)cs;  // first id of the chunk
-                const uint32_t hi_id = c_base + ce;            // one past the last (may wrap to 0 only if it equals 2^32; n_docs < 2^32-1)
+                const uint32_t hi_id = c_base + ce;            // one past its last id
                 const uint32_t n_buckets = ((ce - (uint32_t)cs - 1) >> shift) + 1;
                 // slice of every run inside the chunk
                 for (int j = lane; j < n_lists; j += 32)
@@ -424,100 +559,122 @@ __global__ void __launch_bounds__(1024, 1) sg_search_kernel(const DevIndex ix, c
                 for (uint32_t w = lane; w < n_vec; w += 32) ((uint4 *)tbl)[w] = make_uint4(0, 0, 0, 0);
                 __syncwarp();
 
-                // ---- count: tbl[bucket(id)]++ for the first posting of every bucket inside a 128-posting group ----
-                for (int j = 0; j < n_lists; j++) {
-                    const uint32_t a = s_cur[j], b = s_end[j];
-                    if (a >= b) continue;
-                    uint32_t base = a & ~3u;
-                    uint32_t pos = base + lane * 4;
-                    uint4 v = pos < b ? __ldg((const uint4 *)(postings + pos)) : make_uint4(0, 0, 0, 0);
-                    for (; base < b; base += 128) {
-                        pos = base + lane * 4;
-                        const uint32_t npos = pos + 128;
-                        uint4 vn = make_uint4(0, 0, 0, 0);
-                        if (npos < b) vn = __ldg((const uint4 *)(postings + npos));
-                        const bool v0 = pos >= a && pos < b, v1 = pos + 1 >= a && pos + 1 < b;
-                        const bool v2 = pos + 2 >= a && pos + 2 < b, v3 = pos + 3 >= a && pos + 3 < b;
-                        const uint32_t b0 = v0 ? (v.x - lo_id) >> shift : kInf, b1 = v1 ? (v.y - lo_id) >> shift : kInf;
-                        const uint32_t b2 = v2 ? (v.z - lo_id) >> shift : kInf, b3 = v3 ? (v.w - lo_id) >> shift : kInf;
-                        uint32_t prev = __shfl_up_sync(kFull, b3, 1);
-                        if (lane == 0) prev = kInf;
-                        const bool h0 = v0 && b0 != prev, h1 = v1 && b1 != b0, h2 = v2 && b2 != b1, h3 = v3 && b3 != b2;
-                        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-                        if (h0) c0 = tbl[b0];
-                        if (h1) c1 = tbl[b1];
-                        if (h2) c2 = tbl[b2];
-                        if (h3) c3 = tbl[b3];
-                        if (h0) tbl[b0] = (uint8_t)(c0 + (c0 != 255u));
-                        if (h1) tbl[b1] = (uint8_t)(c1 + (c1 != 255u));
-                        if (h2) tbl[b2] = (uint8_t)(c2 + (c2 != 255u));
-                        if (h3) tbl[b3] = (uint8_t)(c3 + (c3 != 255u));
-                        __syncwarp();
-                        v = vn;
+                // ---- count: the runs stream through a ring of shared-memory slots filled by TMA bulk copies ----
+                {
+                    SliceWalker prod;
+                    prod.start(s_cur, s_end, n_lists);
+                    auto fill = [&]() {  // next slice -> slot n_filled % kRingSlots
+                        if (!prod.valid) return;
+                        const uint32_t slot = n_filled % kRingSlots;
+                        s_meta[slot] = make_uint4(prod.a, prod.b, prod.base, 0u);  // every lane stores the same words
+                        tma_issue(ring_saddr + slot * kSliceBytes, postings + prod.base, prod.bytes(), mbar_saddr + 8 * slot);
+                        n_filled++;
+                        prod.next(s_cur, s_end, n_lists);
+                    };
+                    for (uint32_t sl = 0; sl < kRingSlots; sl++) fill();
+                    uint32_t carry = kInf;
+                    while (n_used != n_filled) {
+                        const uint32_t slot = n_used % kRingSlots;
+                        mbar_wait(mbar_saddr + 8 * slot, (n_used / kRingSlots) & 1u);
+                        const uint4 meta = s_meta[slot];
+                        const uint32_t a = meta.x, b = meta.y;
+                        if (meta.z == (a & ~3u)) carry = kInf;  // first slice of a list
+                        const uint32_t end = min(meta.z + kSlicePostings, b);
+                        const uint4 *src = (const uint4 *)(ring + slot * kSliceBytes) + lane;
+                        uint4 x = src[0];
+                        for (uint32_t g = meta.z; g < end; g += 128) {
+                            src += 32;
+                            uint4 xn = x;
+                            if (g + 128 < end) xn = src[0];  // next group's postings while this one is counted
+                            if (g >= a && g + 128 <= b)
+                                carry = count_group<true>(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
+                            else
+                                carry = count_group<false>(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
+                            x = xn;
+                        }
+                        __syncwarp();  // every lane has read the slot before it is refilled
+                        n_used++;
+                        fill();
                     }
                 }
+                __syncwarp();
 
-                // ---- scan: buckets whose counter reaches the smallest admissible threshold ----
-                for (uint32_t w0 = 0; w0 < n_vec; w0 += 32) {
-                    const uint32_t w = w0 + lane;
-                    uint4 x = make_uint4(0, 0, 0, 0);
-                    if (w < n_vec) x = ((const uint4 *)tbl)[w];
-                    unsigned m16 = 0;
-                    m16 |= (((__vcmpgeu4(x.x, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
-                    m16 |= ((((__vcmpgeu4(x.y, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 4;
-                    m16 |= ((((__vcmpgeu4(x.z, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 8;
-                    m16 |= ((((__vcmpgeu4(x.w, th4) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 12;
-                    unsigned bal;
-                    while ((bal = __ballot_sync(kFull, m16 != 0)) != 0) {
-                        const int src = __ffs(bal) - 1;
-                        unsigned mm = __shfl_sync(kFull, m16, src);
-                        if (lane == src) m16 = 0;
-                        while (mm) {
-                            const int bit = __ffs(mm) - 1;
-                            mm &= mm - 1;
-                            const uint32_t bucket = (w0 + (uint32_t)src) * 16u + (uint32_t)bit;
-                            if (bucket >= n_buckets) continue;
-                            if (shift == 0) {
-                                emit_candidate(ix, c, lo_id + bucket, (int)tbl[bucket], lane);
-                                continue;
-                            }
-                            // resolve the bucket exactly: warp-wide merge of the run slices inside its id range
-                            const uint32_t blo = lo_id + (bucket << shift);
-                            const unsigned long long bhi64 = min((unsigned long long)blo + (1ull << shift), (unsigned long long)c_base + ce);
-                            uint32_t pp[4], pe[4], vv[4];
-#pragma unroll
-                            for (int g = 0; g < 4; g++) {
-                                const int j = lane + 32 * g;
-                                vv[g] = kInf;
-                                pp[g] = pe[g] = 0;
-                                if (j < n_lists) {
-                                    pe[g] = s_end[j];
-                                    pp[g] = lower_bound(postings, s_cur[j], pe[g], blo);
-                                    if (pp[g] < pe[g]) {
-                                        const uint32_t x2 = __ldg(postings + pp[g]);
-                                        if ((unsigned long long)x2 < bhi64) vv[g] = x2;
-                                    }
+                // ---- scan, segment by segment: buckets whose counter reaches the segment's threshold ----
+                for (int B = c.b_lo; B <= c.b_hi; B++) {
+                    const int T = thr_of(B);
+                    if (T == 0) continue;
+                    const uint32_t r0 = max(__ldg(ix.seg_start + B), lo_id), r1 = min(__ldg(ix.seg_start + B + 1), hi_id);
+                    if (r0 >= r1) continue;
+                    const uint32_t bk0 = (r0 - lo_id) >> shift, bk1 = (r1 - 1 - lo_id) >> shift;  // inclusive
+                    const uint32_t th4 = (uint32_t)T * 0x01010101u;
+                    for (uint32_t w0 = bk0 >> 4; w0 <= (bk1 >> 4); w0 += 32) {
+                        const uint32_t w = w0 + lane;
+                        uint4 x = make_uint4(0, 0, 0, 0);
+                        if (w <= (bk1 >> 4)) x = ((const uint4 *)tbl)[w];
+                        const unsigned g0 = __vcmpgeu4(x.x, th4), g1 = __vcmpgeu4(x.y, th4), g2 = __vcmpgeu4(x.z, th4),
+                                       g3 = __vcmpgeu4(x.w, th4);
+                        unsigned m16 = 0;
+                        if ((g0 | g1 | g2 | g3) != 0) {
+                            m16 = (((g0 & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+                            m16 |= ((((g1 & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 4;
+                            m16 |= ((((g2 & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 8;
+                            m16 |= ((((g3 & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << 12;
+                            const uint32_t vb = w * 16u;  // first bucket of this vector; keep buckets inside [bk0, bk1]
+                            if (vb < bk0) m16 &= ~((1u << (bk0 - vb)) - 1u);
+                            if (vb + 15u > bk1) m16 &= (2u << (bk1 - vb)) - 1u;
+                        }
+                        unsigned bal;
+                        while ((bal = __ballot_sync(kFull, m16 != 0)) != 0) {
+                            const int src = __ffs(bal) - 1;
+                            unsigned mm = __shfl_sync(kFull, m16, src);
+                            if (lane == src) m16 = 0;
+                            while (mm) {
+                                const int bit = __ffs(mm) - 1;
+                                mm &= mm - 1;
+                                const uint32_t bucket = (w0 + (uint32_t)src) * 16u + (uint32_t)bit;
+                                if (shift == 0) {
+                                    emit_candidate(ix, c, lo_id + bucket, (int)tbl[bucket], B, T, lane);
+                                    continue;
                                 }
-                            }
-                            for (;;) {
-                                const uint32_t mine = min(min(vv[0], vv[1]), min(vv[2], vv[3]));
-                                const uint32_t m = __reduce_min_sync(kFull, mine);
-                                if (m == kInf) break;
-                                int cnt = 0;
-#pragma unroll
-                                for (int g = 0; g < 4; g++) cnt += vv[g] == m;
-                                cnt = __reduce_add_sync(kFull, cnt);
+                                // resolve the bucket exactly: warp-wide merge of the run slices inside its id range
+                                const uint32_t blo = max(lo_id + (bucket << shift), r0);
+                                const unsigned long long bhi64 =
+                                    min((unsigned long long)lo_id + ((unsigned long long)(bucket + 1) << shift), (unsigned long long)r1);
+                                uint32_t pp[4], pe[4], vv[4];
 #pragma unroll
                                 for (int g = 0; g < 4; g++) {
-                                    if (vv[g] == m) {
-                                        vv[g] = kInf;
-                                        if (++pp[g] < pe[g]) {
+                                    const int j = lane + 32 * g;
+                                    vv[g] = kInf;
+                                    pp[g] = pe[g] = 0;
+                                    if (j < n_lists) {
+                                        pe[g] = s_end[j];
+                                        pp[g] = lower_bound(postings, s_cur[j], pe[g], blo);
+                                        if (pp[g] < pe[g]) {
                                             const uint32_t x2 = __ldg(postings + pp[g]);
                                             if ((unsigned long long)x2 < bhi64) vv[g] = x2;
                                         }
                                     }
                                 }
-                                emit_candidate(ix, c, m, cnt, lane);
+                                for (;;) {
+                                    const uint32_t mine = min(min(vv[0], vv[1]), min(vv[2], vv[3]));
+                                    const uint32_t m = __reduce_min_sync(kFull, mine);
+                                    if (m == kInf) break;
+                                    int cnt = 0;
+#pragma unroll
+                                    for (int g = 0; g < 4; g++) cnt += vv[g] == m;
+                                    cnt = __reduce_add_sync(kFull, cnt);
+#pragma unroll
+                                    for (int g = 0; g < 4; g++) {
+                                        if (vv[g] == m) {
+                                            vv[g] = kInf;
+                                            if (++pp[g] < pe[g]) {
+                                                const uint32_t x2 = __ldg(postings + pp[g]);
+                                                if ((unsigned long long)x2 < bhi64) vv[g] = x2;
+                                            }
+                                        }
+                                    }
+                                    emit_candidate(ix, c, m, cnt, B, T, lane);
+                                }
                             }
                         }
                     }
