@@ -21,6 +21,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 constexpr uint32_t kWorkRing = 1024;
+constexpr uint32_t kMaxSlices = 16;        // sg_search_batch pipelines a batch in at most this many slices
 constexpr int kMaxWarps = sg::kMaxSearchThreads / 32;
 constexpr int kDefaultTblBytes = 8192;     // 16 warps per SM at k = 10; one pass covers 1M documents at 128 per bucket
 
@@ -68,7 +69,8 @@ struct DevBuf {
 
 // one in-flight sg_search_batch: its stream and device staging
 struct CallCtx {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;   // slices of one call alternate between the two streams so that the copies of
+    cudaStream_t stream2 = nullptr;  // one slice overlap the kernel of the other
     DevBuf<char> q_bytes;
     DevBuf<uint32_t> q_off, ids, counts, work;
     DevBuf<double> scores;
@@ -92,6 +94,7 @@ struct sg_index {
     uint32_t *work_ring = nullptr;       // kWorkRing query counters for sg_search_batch_device
     std::atomic<uint32_t> work_rr{0};
     uint32_t tbl_bytes = kDefaultTblBytes;
+    uint32_t slice_queries = 16384;      // queries per pipelined slice of sg_search_batch
     int force_shift = -1;
     int max_warps = kMaxWarps;
 };
@@ -175,6 +178,8 @@ int finalize(sg_index *ix) {
     if (tb > 200000) tb = 200000;
     ix->tbl_bytes = ((uint32_t)tb + 15u) & ~15u;
     ix->force_shift = env_int("SG_FORCE_SHIFT", -1);
+    int sq = env_int("SG_SLICE_QUERIES", 16384);
+    ix->slice_queries = sq < 256 ? 256u : (uint32_t)sq;
     ix->max_warps = env_int("SG_WARPS", kMaxWarps);
     if (ix->max_warps < 1) ix->max_warps = 1;
     if (ix->max_warps > kMaxWarps) ix->max_warps = kMaxWarps;
@@ -188,6 +193,7 @@ void destroy(sg_index *ix) {
     for (CallCtx *c : ix->pool) {
         c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release();
         if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->stream2) cudaStreamDestroy(c->stream2);
         delete c;
     }
     for (void *p : ix->allocations) cudaFree(p);
@@ -286,7 +292,13 @@ struct CtxLease {
         ctx = new (std::nothrow) CallCtx();
         if (!ctx) return fail(SG_ERR_NOMEM, "out of host memory");
         cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-        if (e != cudaSuccess) { delete ctx; ctx = nullptr; return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            if (ctx->stream) cudaStreamDestroy(ctx->stream);
+            delete ctx;
+            ctx = nullptr;
+            return fail(SG_ERR_CUDA, cudaGetErrorString(e));
+        }
         return SG_OK;
     }
     ~CtxLease() {
@@ -389,8 +401,9 @@ int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, ui
     std::vector<uint32_t> low_off;
     const char *src_bytes = q_bytes;
     const uint32_t *src_off = q_off;
-    bool nonascii = false;
-    for (uint32_t i = 0; i < total; i++) if ((uint8_t)q_bytes[i] >= 0x80) { nonascii = true; break; }
+    unsigned char high = 0;  // no early exit: the loop vectorises
+    for (uint32_t i = 0; i < total; i++) high |= (unsigned char)q_bytes[i];
+    const bool nonascii = (high & 0x80) != 0;
     if (nonascii) {
         low_off.resize((size_t)n_q + 1);
         low_bytes.reserve(total + 16);
@@ -415,16 +428,30 @@ int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, ui
     SG_CUDA(c->ids.reserve((size_t)n_q * k));
     SG_CUDA(c->scores.reserve((size_t)n_q * k));
     SG_CUDA(c->counts.reserve(n_q));
-    SG_CUDA(c->work.reserve(1));
-    if (src_total) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p, src_bytes, src_total, cudaMemcpyHostToDevice, c->stream));
-    SG_CUDA(cudaMemcpyAsync(c->q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p, n_q, metric, alpha, k, c->ids.p, c->scores.p, c->counts.p, nullptr,
-                        c->work.p, c->stream);
-    if (rc != SG_OK) return rc;
-    SG_CUDA(cudaMemcpyAsync(out_ids, c->ids.p, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    SG_CUDA(cudaMemcpyAsync(out_scores, c->scores.p, (size_t)n_q * k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    SG_CUDA(cudaMemcpyAsync(out_counts, c->counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SG_CUDA(c->work.reserve(kMaxSlices));
+    // Slices of the batch go down two streams: the H2D / D2H copies of one slice overlap the kernel of the other.
+    // Offsets stay absolute, so a slice only copies its own byte range of the query text.
+    uint32_t n_slices = (n_q + ix->slice_queries - 1) / ix->slice_queries;
+    if (n_slices > kMaxSlices) n_slices = kMaxSlices;
+    if (n_slices < 1) n_slices = 1;
+    for (uint32_t sl = 0; sl < n_slices; sl++) {
+        const uint32_t lo = (uint32_t)((uint64_t)n_q * sl / n_slices), hi = (uint32_t)((uint64_t)n_q * (sl + 1) / n_slices);
+        if (lo == hi) continue;
+        cudaStream_t st = (sl & 1) ? c->stream2 : c->stream;
+        const uint32_t b0 = src_off[lo], b1 = src_off[hi];
+        if (b1 > b0) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p + b0, src_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(c->q_off.p + lo, src_off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p + lo, hi - lo, metric, alpha, k, c->ids.p + (size_t)lo * k,
+                            c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl, st);
+        if (rc != SG_OK) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }
+        SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, c->ids.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(out_scores + (size_t)lo * k, c->scores.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(out_counts + lo, c->counts.p + lo, (size_t)(hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
     SG_CUDA(cudaStreamSynchronize(c->stream));
+    SG_CUDA(cudaStreamSynchronize(c->stream2));
     for (uint32_t q = 0; q < n_q; q++)
         if (out_counts[q] == SG_COUNT_UNSUPPORTED)
             return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");

@@ -25,7 +25,7 @@ constexpr uint32_t kNoTerm = 0xFFFFFFFFu;
 constexpr uint32_t kSliceBytes = SG_SLICE_BYTES;  // one TMA bulk copy: 512 postings
 constexpr uint32_t kRingSlots = SG_RING_SLOTS;    // slices in flight per warp (at most 8)
 constexpr uint32_t kWarpFixedSmem = kRingSlots * kSliceBytes + 64 + 128 + 64 + 3 * kMaxQueryTokens * 4 + 256;
-constexpr int kMaxSearchThreads = 768;       // launch bound of sg_search_kernel (24 warps)
+constexpr int kMaxSearchThreads = 512;       // launch bound of sg_search_kernel (16 warps)
 constexpr uint32_t kCountUnsupported = 0xFFFFFFFFu;     // SG_COUNT_UNSUPPORTED
 
 // non-ASCII alphabet interval: rune r in [lo, hi] has symbol code base + (r - lo)

@@ -40,6 +40,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr int kThrCache = 256;  // window segments whose threshold is cached in shared memory
 constexpr uint32_t kSlicePostings = kSliceBytes / 4;
+constexpr uint32_t kSliceGroups = kSlicePostings / 128;  // warp-wide groups of 4 postings per lane in one slice
 
 enum { kJaccard = 0, kCosine = 1, kDice = 2, kOverlap = 3, kExact = 4 };
 
@@ -580,17 +581,20 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
                         const uint32_t a = meta.x, b = meta.y;
                         if (meta.z == (a & ~3u)) carry = kInf;  // first slice of a list
                         const uint32_t end = min(meta.z + kSlicePostings, b);
+                        // the slot's groups of 128 postings, all loaded up front (bytes past `end` are stale but never counted)
                         const uint4 *src = (const uint4 *)(ring + slot * kSliceBytes) + lane;
-                        uint4 x = src[0];
-                        for (uint32_t g = meta.z; g < end; g += 128) {
-                            src += 32;
-                            uint4 xn = x;
-                            if (g + 128 < end) xn = src[0];  // next group's postings while this one is counted
-                            if (g >= a && g + 128 <= b)
-                                carry = count_group<true>(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
-                            else
-                                carry = count_group<false>(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
-                            x = xn;
+                        uint4 x[kSliceGroups];
+#pragma unroll
+                        for (uint32_t u = 0; u < kSliceGroups; u++) x[u] = src[32 * u];
+#pragma unroll
+                        for (uint32_t u = 0; u < kSliceGroups; u++) {
+                            const uint32_t g = meta.z + 128 * u;
+                            if (g < end) {
+                                if (g >= a && g + 128 <= b)
+                                    carry = count_group<true>(tbl_saddr, scratch_saddr, x[u], g + lane * 4, a, b, lo_id, shift, carry, lane);
+                                else
+                                    carry = count_group<false>(tbl_saddr, scratch_saddr, x[u], g + lane * 4, a, b, lo_id, shift, carry, lane);
+                            }
                         }
                         __syncwarp();  // every lane has read the slot before it is refilled
                         n_used++;

@@ -41,3 +41,43 @@ def main(path, top=40):
 
 if __name__ == "__main__":
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40)
+
+
+def regions(path, src_path, n_queries=65536):
+    """instruction / sample share of the kernel's phases (markers looked up in the source, kernel body only)"""
+    rows = list(csv.reader(open(path)))
+    hdr, data, cur = None, [], None
+    for r in rows:
+        if len(r) >= 2 and r[0] == 'File Path':
+            cur = r[1].split('/')[-1]
+            continue
+        if len(r) > 2 and r[0] == 'Line No':
+            hdr = r
+            continue
+        if hdr and len(r) == len(hdr) and r[2] == '-' and r[0].isdigit():
+            data.append((cur, int(r[0]), r))
+    isamp, iinst = hdr.index('# Samples'), hdr.index('Instructions Executed')
+    src = open(src_path).read().split('\n')
+    kstart = next(i + 1 for i, l in enumerate(src) if l.startswith('__global__') and 'sg_search_kernel' in l)
+
+    def find(s, start=0):
+        return next(i + 1 for i, l in enumerate(src) if i + 1 >= start and s in l)
+    marks = [('helpers', 1), ('topk/emit', find('struct QueryCtx')), ('tma+count_group', find('shared-memory staging')),
+             ('walker', find('struct SliceWalker')), ('prologue', kstart), ('tokenize', find('1. tokenise', kstart)),
+             ('window', find('2. segment window', kstart)), ('runs', find('3. one posting run', kstart)),
+             ('costmodel', find('4. bucket width', kstart)), ('chunk setup', find('for (uint64_t cs = 0', kstart)),
+             ('count loop', find('---- count:', kstart)), ('scan', find('---- scan, segment', kstart)),
+             ('verify', find('resolve the bucket exactly', kstart)), ('epilogue', find('5. results', kstart)),
+             ('end', find('k best of n_parts', kstart))]
+    ks = [d for d in data if d[0] == 'sg_kernels.cu']
+    tot = sum(num(r[iinst]) for f, l, r in ks)
+    tots = sum(num(r[isamp]) for f, l, r in ks)
+    for i, (name, a) in enumerate(marks[:-1]):
+        b = marks[i + 1][1] - 1
+        ii = sum(num(r[iinst]) for f, l, r in ks if a <= l <= b)
+        ss = sum(num(r[isamp]) for f, l, r in ks if a <= l <= b)
+        print(f"{name:16s} lines {a:4d}-{b:4d}  inst {100 * ii / tot:5.1f}% ({ii / n_queries:7.0f}/query)  samples {100 * ss / tots:5.1f}%")
+
+
+if __name__ == "__main__" and len(sys.argv) > 3:
+    regions(sys.argv[1], sys.argv[3])
