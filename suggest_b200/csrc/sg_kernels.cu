@@ -40,7 +40,6 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr int kThrCache = 256;  // window segments whose threshold is cached in shared memory
 constexpr uint32_t kSlicePostings = kSliceBytes / 4;
-constexpr uint32_t kSliceGroups = kSlicePostings / 128;  // warp-wide groups of 4 postings per lane in one slice
 
 enum { kJaccard = 0, kCosine = 1, kDice = 2, kOverlap = 3, kExact = 4 };
 
@@ -71,7 +70,7 @@ __device__ int metric_max_y(int m, double a, int size) {
     }
 }
 
-__device__ int metric_threshold(int m, double a, int sa, int sb) {
+__device__ __noinline__ int metric_threshold(int m, double a, int sa, int sb) {
     switch (m) {
     case kJaccard: return f2i(ceil(__ddiv_rn(__dmul_rn(a, (double)(sa + sb)), __dadd_rn(1.0, a))));
     case kCosine: return f2i(ceil(__dmul_rn(a, __dsqrt_rn((double)(sa * sb)))));
@@ -82,7 +81,7 @@ __device__ int metric_threshold(int m, double a, int sa, int sb) {
 }
 
 // scorer.go:29-31: 1 - Distance(overlap, sizeA, sizeB)
-__device__ double metric_score(int m, int c, int sa, int sb) {
+__device__ __noinline__ double metric_score(int m, int c, int sa, int sb) {
     double d;
     switch (m) {
     case kJaccard: d = __dsub_rn(1.0, __ddiv_rn((double)c, (double)(sa + sb - c))); break;
@@ -133,7 +132,7 @@ __device__ __forceinline__ uint32_t lower_bound(const uint32_t *__restrict__ pos
 }
 
 // Go `for range` decoding step (utf8.DecodeRune acceptance), invalid byte -> U+FFFD, width 1
-__device__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *rune) {
+__device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *rune) {
     uint32_t b0 = s[0];
     if (b0 < 0x80) { *rune = b0; return 1; }
     int need;
@@ -171,7 +170,7 @@ struct QueryCtx {
 };
 
 // sorted insert into the warp's top-k (best first); all lanes call with identical arguments
-__device__ void topk_insert(QueryCtx &c, double score, uint32_t id, int lane) {
+__device__ __noinline__ void topk_insert(QueryCtx &c, double score, uint32_t id, int lane) {
     const int k = (int)c.k;
     if (c.tk_len == k) {
         double ws = c.tk_score[k - 1];
@@ -207,6 +206,49 @@ __device__ __forceinline__ void emit_candidate(const DevIndex &ix, QueryCtx &c, 
     if (count < T) return;
     const double score = metric_score(c.metric, count, c.size_a, size_b);
     topk_insert(c, score, __ldg(ix.perm + new_id), lane);
+}
+
+// A bucket whose counter reached its segment's threshold: find the documents of [blo, bhi) exactly.  Every lane
+// binary-searches the runs it owns (lists lane, lane + 32, ...) for the range, then the warp repeatedly takes the smallest
+// id and counts the lists holding it.  Rare (about 1.1 buckets per query on config #2, the true match included), so out of line.
+__device__ __noinline__ void resolve_bucket(const DevIndex &ix, QueryCtx &c, const uint32_t *__restrict__ postings,
+                                            const uint32_t *s_cur, const uint32_t *s_end, int n_lists, uint32_t blo,
+                                            unsigned long long bhi64, int size_b, int T, int lane) {
+    uint32_t pp[4], pe[4], vv[4];
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const int j = lane + 32 * g;
+        vv[g] = kInf;
+        pp[g] = pe[g] = 0;
+        if (j < n_lists) {
+            pe[g] = s_end[j];
+            pp[g] = lower_bound(postings, s_cur[j], pe[g], blo);
+            if (pp[g] < pe[g]) {
+                const uint32_t x2 = __ldg(postings + pp[g]);
+                if ((unsigned long long)x2 < bhi64) vv[g] = x2;
+            }
+        }
+    }
+    for (;;) {
+        const uint32_t mine = min(min(vv[0], vv[1]), min(vv[2], vv[3]));
+        const uint32_t m = __reduce_min_sync(kFull, mine);
+        if (m == kInf) break;
+        int cnt = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) cnt += vv[g] == m;
+        cnt = __reduce_add_sync(kFull, cnt);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            if (vv[g] == m) {
+                vv[g] = kInf;
+                if (++pp[g] < pe[g]) {
+                    const uint32_t x2 = __ldg(postings + pp[g]);
+                    if ((unsigned long long)x2 < bhi64) vv[g] = x2;
+                }
+            }
+        }
+        emit_candidate(ix, c, m, cnt, size_b, T, lane);
+    }
 }
 
 // P(Poisson(lam) >= t), upper-ish estimate for the bucket-width cost model
@@ -262,8 +304,8 @@ __device__ __forceinline__ void red_add(uint32_t saddr, uint32_t inc) {
 // A posting that is not the first of its bucket adds zero to its own (valid) word; a slot outside [a, b) adds zero to
 // this lane's word of a scratch line.
 template <bool kAllValid>
-__device__ __forceinline__ uint32_t count_group(uint32_t tbl_saddr, uint32_t scratch_saddr, const uint4 x, uint32_t pos, uint32_t a,
-                                                uint32_t b, uint32_t lo_id, int shift, uint32_t carry, int lane) {
+__device__ __forceinline__ uint32_t count_group_impl(uint32_t tbl_saddr, uint32_t scratch_saddr, const uint4 x, uint32_t pos, uint32_t a,
+                                                     uint32_t b, uint32_t lo_id, int shift, uint32_t carry, int lane) {
     uint32_t b0 = (x.x - lo_id) >> shift, b1 = (x.y - lo_id) >> shift, b2 = (x.z - lo_id) >> shift, b3 = (x.w - lo_id) >> shift;
     if (!kAllValid) {
         const uint32_t d = pos - a, len = b - a;  // unsigned: positions before a wrap around and fail the test too
@@ -289,6 +331,19 @@ __device__ __forceinline__ uint32_t count_group(uint32_t tbl_saddr, uint32_t scr
     red_add(a2, i2);
     red_add(a3, i3);
     return __shfl_sync(kFull, b3, 31);
+}
+
+// the group lies wholly inside its list's slice: the hot loop
+__device__ __forceinline__ uint32_t count_group_full(uint32_t tbl_saddr, const uint4 x, uint32_t lo_id, int shift, uint32_t carry,
+                                                     int lane) {
+    return count_group_impl<true>(tbl_saddr, 0u, x, 0u, 0u, 0u, lo_id, shift, carry, lane);
+}
+
+// first / last group of a list (about two in seven): kept out of line so that the hot loop stays small in the
+// instruction cache
+__device__ __noinline__ uint32_t count_group_partial(uint32_t tbl_saddr, uint32_t scratch_saddr, const uint4 x, uint32_t pos, uint32_t a,
+                                                     uint32_t b, uint32_t lo_id, int shift, uint32_t carry, int lane) {
+    return count_group_impl<false>(tbl_saddr, scratch_saddr, x, pos, a, b, lo_id, shift, carry, lane);
 }
 
 // Walks the posting-run slices of one chunk in order, kSlicePostings at a time (the TMA producer's cursor).
@@ -581,20 +636,16 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
                         const uint32_t a = meta.x, b = meta.y;
                         if (meta.z == (a & ~3u)) carry = kInf;  // first slice of a list
                         const uint32_t end = min(meta.z + kSlicePostings, b);
-                        // the slot's groups of 128 postings, all loaded up front (bytes past `end` are stale but never counted)
+                        // groups of 128 postings; the next group's LDS.128 is issued before this group's atomics (the read may
+                        // run past `end` into stale bytes of the warp's own shared memory, which are then not used)
                         const uint4 *src = (const uint4 *)(ring + slot * kSliceBytes) + lane;
-                        uint4 x[kSliceGroups];
-#pragma unroll
-                        for (uint32_t u = 0; u < kSliceGroups; u++) x[u] = src[32 * u];
-#pragma unroll
-                        for (uint32_t u = 0; u < kSliceGroups; u++) {
-                            const uint32_t g = meta.z + 128 * u;
-                            if (g < end) {
-                                if (g >= a && g + 128 <= b)
-                                    carry = count_group<true>(tbl_saddr, scratch_saddr, x[u], g + lane * 4, a, b, lo_id, shift, carry, lane);
-                                else
-                                    carry = count_group<false>(tbl_saddr, scratch_saddr, x[u], g + lane * 4, a, b, lo_id, shift, carry, lane);
-                            }
+                        uint4 x = src[0];
+                        for (uint32_t g = meta.z; g < end; g += 128) {
+                            src += 32;
+                            const uint4 xn = src[0];
+                            if (g >= a && g + 128 <= b) carry = count_group_full(tbl_saddr, x, lo_id, shift, carry, lane);
+                            else carry = count_group_partial(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
+                            x = xn;
                         }
                         __syncwarp();  // every lane has read the slot before it is refilled
                         n_used++;
@@ -644,41 +695,7 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
                                 const uint32_t blo = max(lo_id + (bucket << shift), r0);
                                 const unsigned long long bhi64 =
                                     min((unsigned long long)lo_id + ((unsigned long long)(bucket + 1) << shift), (unsigned long long)r1);
-                                uint32_t pp[4], pe[4], vv[4];
-#pragma unroll
-                                for (int g = 0; g < 4; g++) {
-                                    const int j = lane + 32 * g;
-                                    vv[g] = kInf;
-                                    pp[g] = pe[g] = 0;
-                                    if (j < n_lists) {
-                                        pe[g] = s_end[j];
-                                        pp[g] = lower_bound(postings, s_cur[j], pe[g], blo);
-                                        if (pp[g] < pe[g]) {
-                                            const uint32_t x2 = __ldg(postings + pp[g]);
-                                            if ((unsigned long long)x2 < bhi64) vv[g] = x2;
-                                        }
-                                    }
-                                }
-                                for (;;) {
-                                    const uint32_t mine = min(min(vv[0], vv[1]), min(vv[2], vv[3]));
-                                    const uint32_t m = __reduce_min_sync(kFull, mine);
-                                    if (m == kInf) break;
-                                    int cnt = 0;
-#pragma unroll
-                                    for (int g = 0; g < 4; g++) cnt += vv[g] == m;
-                                    cnt = __reduce_add_sync(kFull, cnt);
-#pragma unroll
-                                    for (int g = 0; g < 4; g++) {
-                                        if (vv[g] == m) {
-                                            vv[g] = kInf;
-                                            if (++pp[g] < pe[g]) {
-                                                const uint32_t x2 = __ldg(postings + pp[g]);
-                                                if ((unsigned long long)x2 < bhi64) vv[g] = x2;
-                                            }
-                                        }
-                                    }
-                                    emit_candidate(ix, c, m, cnt, B, T, lane);
-                                }
+                                resolve_bucket(ix, c, postings, s_cur, s_end, n_lists, blo, bhi64, B, T, lane);
                             }
                         }
                     }

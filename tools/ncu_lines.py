@@ -39,7 +39,7 @@ def main(path, top=40):
         print(f"{f}:{l:>4} {100 * s / tot:5.1f}% inst {100 * num(r[iinst]) / toti:5.1f}%  {stalls}  | {r[1].strip()[:70]}")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and sys.argv[0].endswith("ncu_lines.py"):
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40)
 
 
@@ -79,5 +79,5 @@ def regions(path, src_path, n_queries=65536):
         print(f"{name:16s} lines {a:4d}-{b:4d}  inst {100 * ii / tot:5.1f}% ({ii / n_queries:7.0f}/query)  samples {100 * ss / tots:5.1f}%")
 
 
-if __name__ == "__main__" and len(sys.argv) > 3:
+if __name__ == "__main__" and len(sys.argv) > 3 and sys.argv[0].endswith("ncu_lines.py"):
     regions(sys.argv[1], sys.argv[3])
