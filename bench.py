@@ -65,7 +65,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                          stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
@@ -169,7 +169,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="replicated", choices=["replicated", "sharded"])
@@ -263,10 +263,10 @@ def main():
     first_counts = d_cnt.cpu().numpy().copy()
     first_ids = d_ids.cpu().numpy().copy()
 
+    sampler = ClockSampler(local) if rank == 0 else None  # runs through both timed regions (device-resident and e2e)
     for _ in range(args.warmup):
         step_device()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = L.sg_kernel_launches()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

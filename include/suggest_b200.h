@@ -119,6 +119,15 @@ int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, ui
                     uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts);
 
 /*
+ * Batched NGramIndex.Autocomplete with a FirstKCollectorManager(limit)  (pkg/suggest/autocomplete.go:40-77,
+ * collector.go:48-115): the query is tokenised without the tail wrap (pkg/suggest/tokenizer.go:23-34), a candidate must
+ * hold every query n-gram (threshold = len(tokens), segments len(tokens)..Size()-1) and the `limit` lowest ids win,
+ * returned ascending with score = -id as the reference's queue scores them.  Same buffers as sg_search_batch.
+ */
+int sg_autocomplete_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, uint32_t limit,
+                          uint32_t *out_ids, double *out_scores, uint32_t *out_counts);
+
+/*
  * Same, every buffer already resident on the index's device; enqueued on `stream` (a cudaStream_t,
  * NULL = default stream) without synchronising.  Queries must already be lower-cased if they hold
  * non-ASCII bytes (sg_search_batch does that on the host, strings.ToLower semantics).

@@ -138,6 +138,20 @@ class NGramIndex {
         return out;
     }
 
+    // nGramAutocomplete.Autocomplete with a FirstKCollectorManager(limit), autocomplete.go:40-77
+    std::vector<Candidate> Autocomplete(const std::string &query, int limit) const {
+        const uint32_t off[2] = {0, (uint32_t)query.size()};
+        const size_t k = limit > 0 ? (size_t)limit : 0;
+        std::vector<uint32_t> ids(k + 1);
+        std::vector<double> scores(k + 1);
+        uint32_t count = 0;
+        int rc = sg_autocomplete_batch(h_, query.data(), off, 1, (uint32_t)k, ids.data(), scores.data(), &count);
+        if (rc != SG_OK) throw Error(rc, sg_last_error());
+        std::vector<Candidate> out;
+        for (uint32_t i = 0; i < count; i++) out.push_back(Candidate{ids[i], scores[i]});
+        return out;
+    }
+
     sg_index_info Info() const {
         sg_index_info info{};
         sg_index_get_info(h_, &info);
@@ -267,6 +281,24 @@ class Service {  // service.go:18-139
         std::vector<ResultItem> result;
         for (const Candidate &c : index->Suggest(config.query, config.similarity, config.metric, config.topK))
             result.push_back(ResultItem{c.Score, dict->at(c.Key)});
+        return result;
+    }
+
+    // Service.Autocomplete, service.go:141-172 (score 0 for every item, as the reference reports it)
+    std::vector<ResultItem> Autocomplete(const std::string &dictName, const std::string &query, int limit) const {
+        std::shared_ptr<NGramIndex> index;
+        std::shared_ptr<Dictionary> dict;
+        {
+            std::shared_lock<std::shared_mutex> lk(mu_);
+            auto i = indexes_.find(dictName);
+            auto d = dictionaries_.find(dictName);
+            if (i == indexes_.end() || d == dictionaries_.end())
+                throw Error(SG_ERR_INVALID, "given dictionary " + dictName + " is not exists");
+            index = i->second;
+            dict = d->second;
+        }
+        std::vector<ResultItem> result;
+        for (const Candidate &c : index->Autocomplete(query, limit)) result.push_back(ResultItem{0.0, dict->at(c.Key)});
         return result;
     }
 

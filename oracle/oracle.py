@@ -83,6 +83,7 @@ def lib():
         L.so_query_stats.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_double, _u64p, _u64p, _u32p,
                                      _u32p]
         L.so_has_duplicate_tokens.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32]
+        L.so_autocomplete.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -197,6 +198,15 @@ class OracleIndex:
         n = lib().so_suggest(self._h, q, len(q), metric, alpha, k, mode, merger, _ptr(ids), _ptr(scores))
         if n < 0:
             raise RuntimeError("oracle suggest failed")
+        return ids[:n].copy(), scores[:n].copy()
+
+    def autocomplete(self, query, limit):
+        q = _b(query)
+        ids = np.zeros(limit, dtype=np.uint32)
+        scores = np.zeros(limit, dtype=np.float64)
+        n = lib().so_autocomplete(self._h, q, len(q), limit, _ptr(ids), _ptr(scores))
+        if n < 0:
+            raise RuntimeError("oracle autocomplete failed")
         return ids[:n].copy(), scores[:n].copy()
 
     def suggest_batch(self, queries, metric, alpha, k, mode=CANONICAL, merger=CP_MERGE, threads=1, packed=None):

@@ -150,5 +150,6 @@ struct so_index {
 
 so_list *so_index_find(const so_index *ix, uint32_t segment, const uint8_t *term, uint32_t term_len);
 void so_tokenize_into(const so_index *ix, const uint8_t *text, size_t len, so_tokens *out, so_bytes *scratch);
+void so_tokenize_mode(const so_index *ix, const uint8_t *text, size_t len, so_tokens *out, so_bytes *scratch, int tail_wrap);
 
 #endif

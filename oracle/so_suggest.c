@@ -361,6 +361,55 @@ int so_suggest_batch(const so_index *ix, const char *q_bytes, const uint64_t *q_
     return failed ? -1 : 0;
 }
 
+/* ---------------- autocomplete (pkg/suggest/autocomplete.go:40-77) ---------------- */
+int so_autocomplete(const so_index *ix, const char *query, uint32_t qlen, uint32_t limit, uint32_t *out_ids,
+                    double *out_scores) {
+    if (limit == 0) return -1;
+    so_work w;
+    work_init(&w, ix);
+    so_tokenize_mode(ix, (const uint8_t *)query, qlen, &w.toks, &w.scratch, 0);
+    int terms_len = (int)so_tokens_count(&w.toks);
+    so_queue q;
+    q_init(&q, (int)limit);
+    /* termsLen == 0: mergerOptimizer.Merge returns at once for an empty rid (list_merger.go:76-78) */
+    for (int size = terms_len; terms_len > 0 && size < (int)ix->n_segs; size++) {
+        if (ix->segs[size].used == 0) continue;
+        /* searcher.Search with threshold = termsLen: every token must be present, then k-way intersection */
+        int present = 1;
+        for (int t = 0; t < terms_len && present; t++)
+            present = so_index_find(ix, (uint32_t)size, w.toks.bytes.p + w.toks.off.p[t], w.toks.off.p[t + 1] - w.toks.off.p[t]) != NULL;
+        if (!present) continue;
+        w.n_touched = 0;
+        for (int t = 0; t < terms_len; t++) {
+            so_list *l = so_index_find(ix, (uint32_t)size, w.toks.bytes.p + w.toks.off.p[t], w.toks.off.p[t + 1] - w.toks.off.p[t]);
+            uint32_t prev = 0xFFFFFFFFu;
+            for (size_t i = 0; i < l->ids.n; i++) {
+                uint32_t id = l->ids.p[i];
+                if (id == prev) continue;
+                prev = id;
+                if (w.counts[id] == 0) {
+                    if (w.n_touched == w.cap_touched) {
+                        w.cap_touched = w.cap_touched ? w.cap_touched * 2 : 1024;
+                        w.touched = (uint32_t *)realloc(w.touched, w.cap_touched * sizeof(uint32_t));
+                    }
+                    w.touched[w.n_touched++] = id;
+                }
+                w.counts[id]++;
+            }
+        }
+        for (size_t i = 0; i < w.n_touched; i++) {
+            uint32_t id = w.touched[i];
+            int c = w.counts[id];
+            w.counts[id] = 0;
+            if (c >= terms_len) q_add(&q, id, -(double)id); /* FirstKCollectorManager.Collect, collector.go:104-106 */
+        }
+    }
+    int cnt = q_drain(&q, out_ids, out_scores);
+    q_free(&q);
+    work_free(&w);
+    return cnt;
+}
+
 /* ---------------- admissible postings / lists of one query ---------------- */
 int so_query_stats(const so_index *ix, const char *query, uint32_t qlen, int metric, double alpha,
                    uint64_t *postings, uint64_t *lists, uint32_t *segments, uint32_t *size_a_out) {

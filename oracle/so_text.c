@@ -201,10 +201,15 @@ int so_ngram_tokenize(const char *text, uint32_t len, int n, char *out, uint32_t
 
 /* wrap -> lower -> trim -> ngram -> normalise */
 void so_tokenize_into(const so_index *ix, const uint8_t *text, size_t len, so_tokens *out, so_bytes *scratch) {
+    so_tokenize_mode(ix, text, len, out, scratch, 1);
+}
+
+/* tail_wrap = 0: NewAutocompleteTokenizer, pkg/suggest/tokenizer.go:23-34 (no wrap symbol at the tail of the query) */
+void so_tokenize_mode(const so_index *ix, const uint8_t *text, size_t len, so_tokens *out, so_bytes *scratch, int tail_wrap) {
     so_bytes wrapped = {0};
     so_bytes_push(&wrapped, ix->wrap_start.p, ix->wrap_start.n);
     so_bytes_push(&wrapped, text, len);
-    so_bytes_push(&wrapped, ix->wrap_end.p, ix->wrap_end.n);
+    if (tail_wrap) so_bytes_push(&wrapped, ix->wrap_end.p, ix->wrap_end.n);
     scratch->n = 0;
     so_lower_into(wrapped.p, wrapped.n, scratch);
     free(wrapped.p);

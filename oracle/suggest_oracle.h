@@ -107,6 +107,11 @@ int so_suggest(const so_index *ix, const char *query, uint32_t qlen, int metric,
 int so_suggest_batch(const so_index *ix, const char *q_bytes, const uint64_t *q_off, uint32_t n_q, int metric,
                      double alpha, uint32_t k, int mode, int merger_algo, int n_threads, uint32_t *out_ids,
                      double *out_scores, uint32_t *out_counts);
+/* nGramAutocomplete.Autocomplete with a FirstKCollectorManager(limit) (pkg/suggest/autocomplete.go:40-77,
+ * collector.go:48-115): documents of every segment >= len(tokens) that hold all query tokens (tokenizer without the
+ * tail wrap), the `limit` lowest ids, score = -id.  Returns the count, -1 on error. */
+int so_autocomplete(const so_index *ix, const char *query, uint32_t qlen, uint32_t limit, uint32_t *out_ids,
+                    double *out_scores);
 /* SURVEY.md §8(d) algorithmic-bytes ingredients for one query */
 int so_query_stats(const so_index *ix, const char *query, uint32_t qlen, int metric, double alpha,
                    uint64_t *postings, uint64_t *lists, uint32_t *segments, uint32_t *size_a);

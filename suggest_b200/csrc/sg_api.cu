@@ -252,7 +252,7 @@ int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, 
 
 int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int mode = 0) {
     Geometry g;
     int rc = geometry(ix, n_q, k, &g);
     if (rc != SG_OK) return rc;
@@ -271,6 +271,7 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.tbl_bytes = ix->tbl_bytes;
     p.warp_smem = g.warp_smem;
     p.force_shift = ix->force_shift;
+    p.mode = mode;
     SG_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), stream));
     SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -387,8 +388,8 @@ int sg_index_get_info(const sg_index *ix, sg_index_info *info) {
     return SG_OK;
 }
 
-int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
-                    uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                             uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int mode) {
     int rc = validate_search(ix, n_q, metric, alpha, k);
     if (rc != SG_OK) return rc;
     if (n_q == 0) return SG_OK;
@@ -442,7 +443,7 @@ int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, ui
         if (b1 > b0) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p + b0, src_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, st));
         SG_CUDA(cudaMemcpyAsync(c->q_off.p + lo, src_off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p + lo, hi - lo, metric, alpha, k, c->ids.p + (size_t)lo * k,
-                            c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl, st);
+                            c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl, st, mode);
         if (rc != SG_OK) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }
         SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, c->ids.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, st));
@@ -456,6 +457,16 @@ int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, ui
         if (out_counts[q] == SG_COUNT_UNSUPPORTED)
             return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");
     return SG_OK;
+}
+
+int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                    uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+    return search_batch_impl(ix, q_bytes, q_off, n_q, metric, alpha, k, out_ids, out_scores, out_counts, 0);
+}
+
+int sg_autocomplete_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, uint32_t limit,
+                          uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+    return search_batch_impl(ix, q_bytes, q_off, n_q, SG_EXACT, 1.0, limit, out_ids, out_scores, out_counts, 1);
 }
 
 int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,

@@ -77,6 +77,7 @@ struct SearchParams {
     uint32_t tbl_bytes;       // per-warp count table size (power of two)
     uint32_t warp_smem;       // bytes of shared memory owned by one warp
     int32_t force_shift;      // < 0: cost model picks the bucket width; otherwise log2(bucket width)
+    int32_t mode;             // 0: Suggest; 1: Autocomplete (no tail wrap, every token required, lowest ids win)
 };
 
 SG_HD static inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; host and device hash term keys with it

@@ -41,7 +41,7 @@ constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr int kThrCache = 256;  // window segments whose threshold is cached in shared memory
 constexpr uint32_t kSlicePostings = kSliceBytes / 4;
 
-enum { kJaccard = 0, kCosine = 1, kDice = 2, kOverlap = 3, kExact = 4 };
+enum { kJaccard = 0, kCosine = 1, kDice = 2, kOverlap = 3, kExact = 4, kAutocomplete = 5 };
 
 // ---------------- pkg/metric, float64, one rounding per reference operation ----------------
 __device__ __forceinline__ int f2i(double v) {  // int(float64) with saturation; callers clamp anyway
@@ -66,6 +66,7 @@ __device__ int metric_max_y(int m, double a, int size) {
     case kCosine: return f2i(floor(__ddiv_rn((double)size, __dmul_rn(a, a))));
     case kDice: return f2i(floor(__dmul_rn(__ddiv_rn(__dsub_rn(2.0, a), a), (double)size)));
     case kOverlap: return 32767;  // math.MaxInt16
+    case kAutocomplete: return 2147483647;  // every segment from len(terms) up, pkg/suggest/autocomplete.go:47
     default: return size;
     }
 }
@@ -204,8 +205,10 @@ __device__ __noinline__ void topk_insert(QueryCtx &c, double score, uint32_t id,
 __device__ __forceinline__ void emit_candidate(const DevIndex &ix, QueryCtx &c, uint32_t new_id, int count, int size_b, int T,
                                                int lane) {
     if (count < T) return;
-    const double score = metric_score(c.metric, count, c.size_a, size_b);
-    topk_insert(c, score, __ldg(ix.perm + new_id), lane);
+    const uint32_t id = __ldg(ix.perm + new_id);
+    // FirstKCollectorManager.Collect scores a position with -position (pkg/suggest/collector.go:104-106)
+    const double score = c.metric == kAutocomplete ? -(double)(ix.id_base + id) : metric_score(c.metric, count, c.size_a, size_b);
+    topk_insert(c, score, id, lane);
 }
 
 // A bucket whose counter reached its segment's threshold: find the documents of [blo, bhi) exactly.  Every lane
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
         if (q >= p.n_q) break;
 
         QueryCtx c;
-        c.metric = p.metric;
+        c.metric = p.mode == 1 ? (int)kAutocomplete : p.metric;
         c.alpha = p.alpha;
         c.k = p.k;
         c.tk_len = 0;
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
         const uint32_t qb = __ldg(p.q_off + q), qe = __ldg(p.q_off + q + 1);
         const uint32_t qlen = qe - qb;
         const uint8_t *qp = (const uint8_t *)p.q_bytes + qb;
-        const int nws = ix.n_wrap_start, nwe = ix.n_wrap_end;
+        const int nws = ix.n_wrap_start, nwe = p.mode == 1 ? 0 : ix.n_wrap_end;  // NewAutocompleteTokenizer: no tail wrap
         bool nonascii = false;
         for (uint32_t i = lane; i < qlen; i += 32) nonascii |= qp[i] >= 0x80;
         nonascii = __any_sync(kFull, nonascii);
@@ -556,6 +559,7 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
             return (threshold_admits(T, c.size_a, B) && __ldg(ix.seg_start + B + 1) > __ldg(ix.seg_start + B)) ? T : 0;
         };
 
+        if (p.mode == 1 && n_lists < c.size_a) n_lists = 0;  // a query token that is in no list: nothing can hold them all
         if (c.b_hi >= 0 && n_lists > 0) {
             // ---------------- 3. one posting run per list ----------------
             float total = 0.0f;

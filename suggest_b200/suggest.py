@@ -190,6 +190,25 @@ class NGramIndex:
         _capi.check(rc)
         return ids, scores, counts
 
+    # -- Autocomplete ---------------------------------------------------------------------------
+    def Autocomplete(self, query, limit) -> List[Candidate]:
+        """nGramAutocomplete.Autocomplete (pkg/suggest/autocomplete.go:40-77) with a FirstKCollectorManager(limit)."""
+        ids, scores, counts = self.AutocompleteBatch([query], limit)
+        return [Candidate(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
+
+    def AutocompleteBatch(self, queries, limit, packed=None):
+        data, off = packed if packed is not None else pack_strings(queries)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        n_q = len(off) - 1
+        k = max(int(limit), 0)
+        ids = np.zeros((n_q, k), dtype=np.uint32)
+        scores = np.zeros((n_q, k), dtype=np.float64)
+        counts = np.zeros(n_q, dtype=np.uint32)
+        _capi.check(_capi.lib().sg_autocomplete_batch(self.handle, _ptr(data), _ptr(off), n_q, k, _ptr(ids), _ptr(scores),
+                                                      _ptr(counts)))
+        return ids, scores, counts
+
     def SuggestBatchDevice(self, d_q_bytes, d_q_off, n_q, similarity, metric, topK, d_ids, d_scores, d_counts,
                            d_stats=0, stream=0):
         """sg_search_batch_device: every argument is a device pointer (int); asynchronous on `stream`."""
@@ -310,6 +329,24 @@ class Service:
         for c in candidates:
             v = dictionary[c.Key]
             out.append(ResultItem(c.Score, v.decode("utf-8", "replace") if isinstance(v, bytes) else v))
+        return out
+
+
+    def _lookup(self, dictName):
+        with self._lock:
+            index = self.indexes.get(dictName)
+            dictionary = self.dictionaries.get(dictName)
+        if index is None or dictionary is None:
+            raise KeyError(f"given dictionary {dictName} is not exists")
+        return index, dictionary
+
+    def Autocomplete(self, dictName, query, limit) -> List[ResultItem]:
+        """Service.Autocomplete, pkg/suggest/service.go:141-172 (the reference reports score 0 for every item)"""
+        index, dictionary = self._lookup(dictName)
+        out = []
+        for c in index.Autocomplete(query, limit):
+            v = dictionary[c.Key]
+            out.append(ResultItem(0.0, v.decode("utf-8", "replace") if isinstance(v, bytes) else v))
         return out
 
 

@@ -26,6 +26,10 @@ int main(int argc, char **argv) {
         auto got = index->Suggest("Nissan ma", 0.5, metric::JaccardMetric(), 2);
         CHECK(got.size() == 2 && got[0].Key == 2 && got[1].Key == 0);
         CHECK(got[0].Score >= got[1].Score);
+        // TestAutoComplete, ngram_index_test.go:42-67
+        auto ac = index->Autocomplete("Niss", 5);
+        CHECK(ac.size() == 5);
+        for (uint32_t i = 0; i < 5; i++) CHECK(ac[i].Key == i);
     }
     {  // Example
         suggest::IndexDescription d;

@@ -401,3 +401,56 @@ def test_full_size_1m_jaccard():
     m2 = np.arange(k)[None, :] < n_o[:, None]
     assert np.array_equal(ids[sample][m2], ids_o[m2])
     assert np.array_equal(sc[sample][m2], sc_o[m2])
+
+
+# ---------------------------------------------------------------------------------------------------
+# Autocomplete: pkg/suggest/autocomplete.go:40-77 with a FirstKCollectorManager
+# ---------------------------------------------------------------------------------------------------
+def assert_same_autocomplete(gx, ox, queries, limit, what=""):
+    ids_g, sc_g, n_g = gx.AutocompleteBatch(queries, limit)
+    for q, query in enumerate(queries):
+        ids_o, sc_o = ox.autocomplete(query, limit)
+        assert n_g[q] == len(ids_o), (what, query, ids_g[q, :n_g[q]], ids_o)
+        assert np.array_equal(ids_g[q, :n_g[q]], ids_o), (what, query, ids_g[q, :n_g[q]], ids_o)
+        assert np.array_equal(sc_g[q, :n_g[q]], sc_o), (what, query)
+
+
+def test_autocomplete_ngram_index_test_go():
+    # pkg/suggest/ngram_index_test.go:42-67
+    gx = S.NewRAMBuilder(COLLECTION, description(TEST_DESCRIPTION)).Build()
+    assert [c.Key for c in gx.Autocomplete("Niss", 5)] == [0, 1, 2, 3, 4]
+    assert [c.Score for c in gx.Autocomplete("Niss", 3)] == [0.0, -1.0, -2.0]
+
+
+def test_autocomplete_cars(cars_pair, cars_lines):
+    gx, ox = cars_pair
+    rng = np.random.default_rng(11)
+    queries = ["", "N", "Ni", "Nis", "niss", "NISSAN ", "toyota c", "zzzz", "RAM RAM", "ram", "a", "4", "BMW 3", "x" * 40]
+    for line in cars_lines[::97]:
+        cut = int(rng.integers(1, len(line) + 1))
+        queries.append(line[:cut])
+    for limit in (1, 5, 50):
+        assert_same_autocomplete(gx, ox, queries, limit, f"cars limit={limit}")
+
+
+def test_autocomplete_synthetic_and_service(synth_pairs, cars_lines, tmp_path):
+    gx, ox, queries = synth_pairs[3]
+    prefixes = [q[:n] for q, n in zip(queries[:300], [3, 4, 5, 6, 8, 12] * 50)]
+    assert_same_autocomplete(gx, ox, prefixes, 10, "synthetic prefixes")
+    src = tmp_path / "cars.dict"
+    src.write_bytes(b"\n".join(cars_lines) + b"\n")
+    d = description(CARS_DESCRIPTION, "cars")
+    d.SourcePath = str(src)
+    service = S.NewService()
+    service.AddRunTimeIndex(d)
+    items = service.Autocomplete("cars", "Nissan Mi", 3)
+    assert len(items) == 3 and all(i.Value.startswith("NISSAN MI") and i.Score == 0.0 for i in items)
+
+
+def test_autocomplete_forced_bucket_widths(cars_lines, cars_pair):
+    _, ox = cars_pair
+    q = [l[:max(2, len(l) // 2)] for l in cars_lines[::41]]
+    for env in (dict(SG_FORCE_SHIFT=0, SG_TBL_BYTES=2048), dict(SG_FORCE_SHIFT=4), dict(SG_FORCE_SHIFT=9)):
+        gx = build_gpu(CARS_DESCRIPTION, cars_lines, env)
+        assert_same_autocomplete(gx, ox, q, 7, str(env))
+        gx.close()

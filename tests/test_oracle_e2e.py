@@ -142,3 +142,14 @@ def test_degenerate_windows_return_empty(small_index):
 def test_query_stats_small(small_index):
     st = small_index.query_stats("Nissan ma", O.JACCARD, 0.5)
     assert st["size_a"] == 9 and st["segments"] > 0 and st["postings"] >= st["lists"] > 0
+
+
+# pkg/suggest/ngram_index_test.go:42-67 — first five ids that complete "Niss"
+def test_autocomplete_kat(small_index):
+    ids, scores = small_index.autocomplete("Niss", 5)
+    assert ids.tolist() == [0, 1, 2, 3, 4]
+    assert scores.tolist() == [-0.0, -1.0, -2.0, -3.0, -4.0]  # FirstKCollectorManager scores a position with -position
+    assert small_index.autocomplete("Toyota Cor", 5)[0].tolist() == [6, 7]
+    assert small_index.autocomplete("Niss", 2)[0].tolist() == [0, 1]
+    assert len(small_index.autocomplete("", 5)[0]) == 0
+    assert len(small_index.autocomplete("Nizz", 5)[0]) == 0
