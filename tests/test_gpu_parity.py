@@ -443,8 +443,10 @@ def test_autocomplete_synthetic_and_service(synth_pairs, cars_lines, tmp_path):
     d.SourcePath = str(src)
     service = S.NewService()
     service.AddRunTimeIndex(d)
-    items = service.Autocomplete("cars", "Nissan Mi", 3)
-    assert len(items) == 3 and all(i.Value.startswith("NISSAN MI") and i.Score == 0.0 for i in items)
+    items = service.Autocomplete("cars", "Nissan M", 3)
+    want = O.OracleIndex(**CARS_DESCRIPTION).add_docs(cars_lines).autocomplete("Nissan M", 3)[0]
+    assert [i.Value for i in items] == [cars_lines[k].decode() for k in want] and len(items) == 3
+    assert all(i.Value.startswith("NISSAN M") and i.Score == 0.0 for i in items)
 
 
 def test_autocomplete_forced_bucket_widths(cars_lines, cars_pair):
