@@ -211,11 +211,11 @@ def main():
     description = IndexDescription(Name="bench", NGramSize=desc["ngram_size"], Alphabet=desc["alphabet"], Pad=desc["pad"],
                                    Wrap=desc["wrap"], Device=local)
     t0 = time.perf_counter()
+    sharded_index = None
     if sharded:
-        lo_doc, hi_doc = rank * n_docs // world, (rank + 1) * n_docs // world
-        sub_off = d_off[lo_doc:hi_doc + 1] - d_off[lo_doc]
-        sub = d_bytes[int(d_off[lo_doc]):int(d_off[hi_doc])]
-        index = S.NewRAMBuilder((sub, sub_off), description, id_base=lo_doc).Build()
+        from suggest_b200.sharding import ShardedIndex
+        sharded_index = ShardedIndex((d_bytes, d_off), description, rank, world, S.NewRAMBuilder)
+        index = sharded_index.index
     else:
         index = S.NewRAMBuilder((d_bytes, d_off), description).Build()
     build_s = time.perf_counter() - t0
@@ -230,24 +230,20 @@ def main():
     d_sc = torch.zeros(nq * K, dtype=torch.float64, device=dev)
     d_cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
     d_stats = torch.zeros(nq * 2, dtype=torch.int32, device=dev)
-    g_ids = g_sc = g_cnt = m_ids = m_sc = m_cnt = None
+    g_ids = None
+    m_ids = m_sc = m_cnt = None
     if sharded and world > 1:
-        g_ids = torch.zeros(world * nq * K, dtype=torch.int32, device=dev)
-        g_sc = torch.zeros(world * nq * K, dtype=torch.float64, device=dev)
-        g_cnt = torch.zeros(world * nq, dtype=torch.int32, device=dev)
+        g_ids = True  # per-shard rows are all-gathered and merged (suggest_b200/sharding.py)
         m_ids, m_sc, m_cnt = torch.zeros_like(d_ids), torch.zeros_like(d_sc), torch.zeros_like(d_cnt)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
 
     def step_device(stats_ptr=0):
+        if g_ids is not None and not stats_ptr:  # config #4: local search, all-gather of per-shard top-k, merge on the device
+            sharded_index.SuggestBatchDevice(dq, doff, nq, ALPHA, metric, K, m_ids, m_sc, m_cnt)
+            return
         index.SuggestBatchDevice(dq.data_ptr(), doff.data_ptr(), nq, ALPHA, metric, K, d_ids.data_ptr(), d_sc.data_ptr(),
                                  d_cnt.data_ptr(), stats_ptr, stream.cuda_stream)
-        if g_ids is not None:  # config #4: all-gather per-shard top-k, merge on the device
-            dist.all_gather_into_tensor(g_ids, d_ids)
-            dist.all_gather_into_tensor(g_sc, d_sc)
-            dist.all_gather_into_tensor(g_cnt, d_cnt)
-            _capi.check(L.sg_merge_topk_device(local, world, nq, K, g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(),
-                                               m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr(), stream.cuda_stream))
 
     def barrier():
         torch.cuda.synchronize()
@@ -312,17 +308,16 @@ def main():
     packed = (hq.numpy(), hoff.numpy().view(np.uint32))
 
     def step_e2e():
-        index.SuggestBatch(None, ALPHA, metric, K, packed=packed, out=out)
-        if g_ids is not None:
-            d_ids.copy_(h_ids, non_blocking=True)
-            d_sc.copy_(h_sc, non_blocking=True)
-            d_cnt.copy_(h_cnt, non_blocking=True)
-            dist.all_gather_into_tensor(g_ids, d_ids)
-            dist.all_gather_into_tensor(g_sc, d_sc)
-            dist.all_gather_into_tensor(g_cnt, d_cnt)
-            _capi.check(L.sg_merge_topk_device(local, world, nq, K, g_ids.data_ptr(), g_sc.data_ptr(), g_cnt.data_ptr(),
-                                               m_ids.data_ptr(), m_sc.data_ptr(), m_cnt.data_ptr(), stream.cuda_stream))
+        if g_ids is not None:  # queries from pinned host memory, merged rows back to the host
+            dq.copy_(hq, non_blocking=True)
+            doff.copy_(hoff, non_blocking=True)
+            sharded_index.SuggestBatchDevice(dq, doff, nq, ALPHA, metric, K, m_ids, m_sc, m_cnt)
+            h_ids.copy_(m_ids, non_blocking=True)
+            h_sc.copy_(m_sc, non_blocking=True)
+            h_cnt.copy_(m_cnt, non_blocking=True)
             torch.cuda.synchronize()
+            return
+        index.SuggestBatch(None, ALPHA, metric, K, packed=packed, out=out)
 
     for _ in range(args.warmup):
         step_e2e()
@@ -338,8 +333,9 @@ def main():
         e2e_s = float(t.item())
     e2e_value = queries_per_step * args.steps / e2e_s
     clocks = sampler.stop() if sampler else None
-    assert np.array_equal(out[2].astype(np.int32), first_counts) and np.array_equal(h_ids.numpy(), first_ids), \
-        "host-buffer and device-buffer paths disagree"
+    if g_ids is None:
+        assert np.array_equal(out[2].astype(np.int32), first_counts) and np.array_equal(h_ids.numpy(), first_ids), \
+            "host-buffer and device-buffer paths disagree"
     h2d = int(q_bytes.nbytes + 4 * (nq + 1))
     d2h = int(nq * K * 4 + nq * K * 8 + nq * 4)
 
@@ -356,8 +352,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u32 postings / u8 counters / f64 scores",
         "data": "synthetic",
-        "config": {"workload": ("10M-entry dictionary sharded by record-id range, per-shard top-k + NCCL all-gather + merge"
-                                if sharded else "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10, 64K-query batch"),
+        "config": {"workload": (f"{n_docs}-entry dictionary sharded by record-id range over {world} GPU(s), per-shard top-k + NCCL "
+                                "all-gather + merge" if sharded else "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10, 64K-query batch"),
                    "n_docs": n_docs, "queries_per_step_per_gpu": nq, "k": K, "similarity": ALPHA, "metric": args.metric,
                    "ngram": args.ngram, "parallelism": ("record-id-range shards" if sharded else "replicated index, queries split"),
                    "postings": int(info["n_postings"]), "index_bytes": int(info["device_bytes"]), "index_build_s": round(build_s, 2),

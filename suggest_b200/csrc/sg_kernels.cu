@@ -644,6 +644,26 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
                         // run past `end` into stale bytes of the warp's own shared memory, which are then not used)
                         const uint4 *src = (const uint4 *)(ring + slot * kSliceBytes) + lane;
                         uint4 x = src[0];
+#ifdef SG_PAIR_GROUPS
+                        for (uint32_t g = meta.z; g < end;) {
+                            if (g >= a && g + 256 <= b && g + 256 <= meta.z + kSlicePostings) {  // two full groups at once
+                                const uint4 x1 = src[32];
+                                src += 64;
+                                const uint4 xn = src[0];
+                                carry = count_group_full(tbl_saddr, x, lo_id, shift, carry, lane);
+                                carry = count_group_full(tbl_saddr, x1, lo_id, shift, carry, lane);
+                                x = xn;
+                                g += 256;
+                            } else {
+                                src += 32;
+                                const uint4 xn = src[0];
+                                if (g >= a && g + 128 <= b) carry = count_group_full(tbl_saddr, x, lo_id, shift, carry, lane);
+                                else carry = count_group_partial(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
+                                x = xn;
+                                g += 128;
+                            }
+                        }
+#else
                         for (uint32_t g = meta.z; g < end; g += 128) {
                             src += 32;
                             const uint4 xn = src[0];
@@ -651,6 +671,7 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
                             else carry = count_group_partial(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
                             x = xn;
                         }
+#endif
                         __syncwarp();  // every lane has read the slot before it is refilled
                         n_used++;
                         fill();

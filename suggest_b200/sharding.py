@@ -1,0 +1,80 @@
+"""Record-id-range shards of one dictionary over the GPUs of a box (BASELINE.json config #4).
+
+The reference is a single process and has nothing like this.  A query's answer is the top-k of the union of
+the per-shard top-k lists, so: rank r indexes documents [lo_r, hi_r) with id_base = lo_r (returned ids stay
+global, which keeps the (score desc, id asc) order meaningful across shards), every rank searches the same
+query batch, the per-shard rows are all-gathered ([part][query][k], NCCL over NVLink) and sg_merge_topk_device
+re-selects k per query on every rank.
+"""
+import numpy as np
+
+from . import _capi
+
+
+def shard_bounds(n_docs, world):
+    """contiguous, balanced [lo, hi) per rank"""
+    return [(r * n_docs // world, (r + 1) * n_docs // world) for r in range(world)]
+
+
+def slice_packed(data, off, lo, hi):
+    """documents [lo, hi) of a packed (bytes, offsets) dictionary, offsets rebased to 0"""
+    sub_off = (off[lo:hi + 1] - off[lo]).astype(off.dtype)
+    return data[int(off[lo]):int(off[hi])], sub_off
+
+
+class ShardedIndex:
+    """One rank's shard plus the cross-shard reduce.  Needs torch.distributed initialised with the nccl backend."""
+
+    def __init__(self, dictionary, description, rank, world, builder_factory):
+        data, off = dictionary
+        self.rank, self.world = rank, world
+        self.lo, self.hi = shard_bounds(len(off) - 1, world)[rank]
+        self.index = builder_factory(slice_packed(data, off, self.lo, self.hi), description, self.lo).Build()
+        self._buffers = None
+
+    def _alloc(self, n_q, k, device):
+        import torch
+        key = (n_q, k, str(device))
+        if self._buffers is None or self._buffers[0] != key:
+            w = self.world
+            self._buffers = (key, dict(
+                ids=torch.zeros(n_q * k, dtype=torch.int32, device=device), sc=torch.zeros(n_q * k, dtype=torch.float64, device=device),
+                cnt=torch.zeros(n_q, dtype=torch.int32, device=device),
+                g_ids=torch.zeros(w * n_q * k, dtype=torch.int32, device=device), g_sc=torch.zeros(w * n_q * k, dtype=torch.float64, device=device),
+                g_cnt=torch.zeros(w * n_q, dtype=torch.int32, device=device)))
+        return self._buffers[1]
+
+    def SuggestBatchDevice(self, d_q, d_off, n_q, similarity, metric, k, out_ids, out_scores, out_counts):
+        """d_q / d_off / out_*: torch tensors on this rank's device.  Enqueued on torch's current stream."""
+        import torch
+        import torch.distributed as dist
+        b = self._alloc(n_q, k, d_q.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        self.index.SuggestBatchDevice(d_q.data_ptr(), d_off.data_ptr(), n_q, similarity, metric, k, b["ids"].data_ptr(),
+                                      b["sc"].data_ptr(), b["cnt"].data_ptr(), 0, stream)
+        if self.world == 1:
+            out_ids.copy_(b["ids"]); out_scores.copy_(b["sc"]); out_counts.copy_(b["cnt"])
+            return
+        dist.all_gather_into_tensor(b["g_ids"], b["ids"])
+        dist.all_gather_into_tensor(b["g_sc"], b["sc"])
+        dist.all_gather_into_tensor(b["g_cnt"], b["cnt"])
+        _capi.check(_capi.lib().sg_merge_topk_device(d_q.device.index, self.world, n_q, k, b["g_ids"].data_ptr(), b["g_sc"].data_ptr(),
+                                                     b["g_cnt"].data_ptr(), out_ids.data_ptr(), out_scores.data_ptr(),
+                                                     out_counts.data_ptr(), stream))
+
+
+def merge_rows_reference(part_ids, part_scores, part_counts, k):
+    """numpy statement of the merge order ([part][query][k] -> [query][k]); what sg_merge_topk_kernel computes.
+    Used by the CPU tests of the sharding plan; never on the product path."""
+    n_parts, n_q = part_counts.shape
+    ids = np.zeros((n_q, k), dtype=np.uint32)
+    scores = np.zeros((n_q, k), dtype=np.float64)
+    counts = np.zeros(n_q, dtype=np.uint32)
+    for q in range(n_q):
+        rows = [(-float(part_scores[p, q, i]), int(part_ids[p, q, i])) for p in range(n_parts) for i in range(int(part_counts[p, q]))]
+        rows.sort()
+        rows = rows[:k]
+        counts[q] = len(rows)
+        for i, (neg, idx) in enumerate(rows):
+            ids[q, i], scores[q, i] = idx, -neg
+    return ids, scores, counts
