@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--docs", type=int, default=None, help="dictionary size (default 1M; sharded: 10M)")
     ap.add_argument("--metric", default="Jaccard", choices=["Jaccard", "Cosine", "Dice"])
     ap.add_argument("--ngram", type=int, default=3)
+    ap.add_argument("--data", default="uniform", choices=["uniform", "zipf"], help="letter distribution of the dictionary")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -204,7 +205,7 @@ def main():
     desc = dict(DESCRIPTION, ngram_size=args.ngram)
 
     # ---- data: identical dictionary on every rank; replicated mode gives every rank its own query batch ----
-    d_bytes, d_off, rng = synthetic_dictionary(n_docs)
+    d_bytes, d_off, rng = synthetic_dictionary(n_docs, skew=None if args.data == "uniform" else args.data)
     if not sharded and rank > 0:
         rng = np.random.default_rng(12345 + 7919 * rank)
     q_bytes, q_off, pick = synthetic_queries(d_bytes, d_off, N_QUERIES, rng)
@@ -355,7 +356,7 @@ def main():
         "config": {"workload": (f"{n_docs}-entry dictionary sharded by record-id range over {world} GPU(s), per-shard top-k + NCCL "
                                 "all-gather + merge" if sharded else "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10, 64K-query batch"),
                    "n_docs": n_docs, "queries_per_step_per_gpu": nq, "k": K, "similarity": ALPHA, "metric": args.metric,
-                   "ngram": args.ngram, "parallelism": ("record-id-range shards" if sharded else "replicated index, queries split"),
+                   "ngram": args.ngram, "letters": args.data, "parallelism": ("record-id-range shards" if sharded else "replicated index, queries split"),
                    "postings": int(info["n_postings"]), "index_bytes": int(info["device_bytes"]), "index_build_s": round(build_s, 2),
                    "l2": "flushed between timed steps (256 MiB write, untimed); inside a step the index is re-read ~58x "
                          "and stays L2-resident, which is the steady state of this workload"},
@@ -368,7 +369,7 @@ def main():
         "results": {"queries_with_a_match": float((first_counts > 0).mean())},
     }
 
-    if world == 1 and not args.no_cpu_baseline and not sharded and args.metric == "Jaccard" and args.ngram == 3:
+    if world == 1 and not args.no_cpu_baseline and not sharded and args.metric == "Jaccard" and args.ngram == 3 and args.data == "uniform":
         ox = oracle_index((d_bytes, d_off))
         threads = host_threads()
         sample = 16384

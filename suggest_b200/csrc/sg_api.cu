@@ -73,6 +73,7 @@ struct CallCtx {
     cudaStream_t stream2 = nullptr;  // one slice overlap the kernel of the other
     DevBuf<char> q_bytes;
     DevBuf<uint32_t> q_off, ids, counts, work;
+    DevBuf<uint8_t> plans;   // sg::kPlanStride bytes per query, sg_plan_kernel -> sg_search_kernel
     DevBuf<double> scores;
 };
 
@@ -191,7 +192,7 @@ void destroy(sg_index *ix) {
     DeviceGuard guard;
     guard.set(ix->device);
     for (CallCtx *c : ix->pool) {
-        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release();
+        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release();
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         delete c;
@@ -252,7 +253,7 @@ int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, 
 
 int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
-                   cudaStream_t stream, int mode = 0) {
+                   uint8_t *d_plans, cudaStream_t stream, int mode = 0) {
     Geometry g;
     int rc = geometry(ix, n_q, k, &g);
     if (rc != SG_OK) return rc;
@@ -268,13 +269,14 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.out_counts = d_counts;
     p.stats = d_stats;
     p.work_counter = d_work;
+    p.plans = d_plans;
     p.tbl_bytes = ix->tbl_bytes;
     p.warp_smem = g.warp_smem;
     p.force_shift = ix->force_shift;
     p.mode = mode;
     SG_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), stream));
     SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_launches.fetch_add(2, std::memory_order_relaxed);  // sg_plan_kernel + sg_search_kernel
     return SG_OK;
 }
 
@@ -430,6 +432,7 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     SG_CUDA(c->scores.reserve((size_t)n_q * k));
     SG_CUDA(c->counts.reserve(n_q));
     SG_CUDA(c->work.reserve(kMaxSlices));
+    SG_CUDA(c->plans.reserve((size_t)n_q * sg::kPlanStride));
     // Slices of the batch go down two streams: the H2D / D2H copies of one slice overlap the kernel of the other.
     // Offsets stay absolute, so a slice only copies its own byte range of the query text.
     uint32_t n_slices = (n_q + ix->slice_queries - 1) / ix->slice_queries;
@@ -443,7 +446,8 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         if (b1 > b0) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p + b0, src_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, st));
         SG_CUDA(cudaMemcpyAsync(c->q_off.p + lo, src_off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p + lo, hi - lo, metric, alpha, k, c->ids.p + (size_t)lo * k,
-                            c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl, st, mode);
+                            c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl,
+                            c->plans.p + (size_t)lo * sg::kPlanStride, st, mode);
         if (rc != SG_OK) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }
         SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, c->ids.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, st));
@@ -481,8 +485,14 @@ int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *
     // work counters for caller-owned streams come from a ring owned by the index: the memset and the
     // kernel are ordered on the caller's stream, and a slot is only reused 1024 launches later
     const uint32_t slot = ix->work_rr.fetch_add(1, std::memory_order_relaxed) & (kWorkRing - 1);
-    return enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, d_stats,
-                          ix->work_ring + slot, (cudaStream_t)stream);
+    // the query plans live in stream-ordered scratch: allocated, used by the two kernels and freed on the caller's stream
+    void *plans = nullptr;
+    SG_CUDA(cudaMallocAsync(&plans, (size_t)n_q * sg::kPlanStride, (cudaStream_t)stream));
+    rc = enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, d_stats,
+                        ix->work_ring + slot, (uint8_t *)plans, (cudaStream_t)stream);
+    cudaError_t fe = cudaFreeAsync(plans, (cudaStream_t)stream);
+    if (rc == SG_OK && fe != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(fe));
+    return rc;
 }
 
 int sg_merge_topk_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *d_part_ids,

@@ -62,6 +62,20 @@ struct DevIndex {
     const uint32_t *perm;       // new id -> original document id (without id_base)
 };
 
+// One per query, written by sg_plan_kernel and read by sg_search_kernel: kPlanStride bytes =
+// [QueryPlan (32) | thresholds of the window segments b_min + i (256) | posting runs {first, end} per list (128 x 8)]
+struct QueryPlan {
+    uint32_t flags;      // 1: more than 128 n-grams (SG_ERR_QUERY_TOO_LONG)
+    int32_t size_a;      // len(tokens), suggester.go:53
+    int32_t b_min;       // MinY
+    int32_t b_lo, b_hi;  // first / last admissible non-empty segment; b_hi < b_lo: nothing to search
+    int32_t n_lists;     // posting runs to read; 0: nothing to search
+    int32_t shift;       // log2(documents per counter bucket)
+    int32_t reserved;
+};
+constexpr uint32_t kPlanThrOffset = 32, kPlanRunsOffset = 32 + 256;
+constexpr uint32_t kPlanStride = kPlanRunsOffset + kMaxQueryTokens * 8;
+
 struct SearchParams {
     const char *q_bytes;
     const uint32_t *q_off;
@@ -74,6 +88,7 @@ struct SearchParams {
     uint32_t *out_counts;
     uint32_t *stats;          // optional: {admissible postings, admissible lists} per query
     uint32_t *work_counter;   // zeroed before launch
+    uint8_t *plans;           // n_q * kPlanStride bytes of scratch
     uint32_t tbl_bytes;       // per-warp count table size (power of two)
     uint32_t warp_smem;       // bytes of shared memory owned by one warp
     int32_t force_shift;      // < 0: cost model picks the bucket width; otherwise log2(bucket width)

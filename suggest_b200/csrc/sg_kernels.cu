@@ -40,6 +40,7 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr uint32_t kInf = 0xFFFFFFFFu;
 constexpr int kThrCache = 256;  // window segments whose threshold is cached in shared memory
 constexpr uint32_t kSlicePostings = kSliceBytes / 4;
+constexpr int kPlanThreads = 256;  // sg_plan_kernel: 8 queries per CTA
 
 enum { kJaccard = 0, kCosine = 1, kDice = 2, kOverlap = 3, kExact = 4, kAutocomplete = 5 };
 
@@ -377,56 +378,35 @@ struct SliceWalker {
 
 }  // namespace
 
-__global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const DevIndex ix, const SearchParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
+// ---------------------------------------------------------------------------------------------------------------
+// sg_plan_kernel: steps 1-4 for every query (tokenise, segment window + thresholds, posting runs, bucket width),
+// written as one QueryPlan per query.  Light on shared memory, so it runs at full occupancy and its dependent global
+// loads (query bytes -> term hash -> list offsets) hide behind other warps; keeping this code out of sg_search_kernel
+// also keeps that kernel's hot loop resident in the instruction cache.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPlanThreads) sg_plan_kernel(const DevIndex ix, const SearchParams p) {
+    __shared__ __align__(16) uint32_t s_scratch[kPlanThreads / 32][kMaxRunes + 2 * kMaxQueryTokens + kThrCache / 4];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint8_t *wsm = smem + (size_t)warp * p.warp_smem;
-    uint8_t *tbl = wsm;                                         // [tbl_bytes] byte counters, updated as fields of 32-bit words
-    uint8_t *ring = wsm + p.tbl_bytes;                          // [kRingSlots][kSliceBytes] posting slices landed by TMA
-    uint64_t *mbar = (uint64_t *)(ring + kRingSlots * kSliceBytes);  // [kRingSlots] one mbarrier per slot (64 bytes) + scratch line (128)
-    uint4 *s_meta = (uint4 *)(ring + kRingSlots * kSliceBytes + 192);  // [kRingSlots] {a, b, base} of the slice in each slot (64 bytes)
-    uint32_t *s_cur = (uint32_t *)(ring + kRingSlots * kSliceBytes + 256);  // [128] start of the not yet counted part of a run
-    uint32_t *s_end = s_cur + kMaxQueryTokens;                  // [128] end of the run slice inside the current chunk
-    uint32_t *s_rend = s_end + kMaxQueryTokens;                 // [128] end of the run (segment window)
-    uint8_t *s_thr = (uint8_t *)(s_rend + kMaxQueryTokens);     // [256] threshold of window segment b_min + i, 0 = skip
-    double *tk_score = (double *)(s_thr + kThrCache);           // [k]
-    uint32_t *tk_id = (uint32_t *)(tk_score + p.k);             // [k]
-    // tokeniser scratch overlays the counter table (the table is cleared after the runs are known)
-    uint32_t *s_runes = (uint32_t *)tbl;                        // [kMaxRunes]
+    uint32_t *s_runes = s_scratch[warp];                        // [kMaxRunes]
     uint32_t *s_lterm = s_runes + kMaxRunes;                    // [128] term id of every list to open
     uint32_t *s_hash = s_lterm + kMaxQueryTokens;               // [128] hash of every raw n-gram window
-
+    uint8_t *s_thr = (uint8_t *)(s_hash + kMaxQueryTokens);     // [256] threshold of window segment b_min + i, 0 = skip
     const uint32_t S = ix.n_segments;
     const uint32_t stride = S + 1;
-    const uint32_t *__restrict__ postings = ix.postings;
-    const uint32_t tbl_saddr = smem_u32(tbl), ring_saddr = smem_u32(ring), mbar_saddr = smem_u32(mbar);
-    const uint32_t scratch_saddr = mbar_saddr + 64 + lane * 4;  // this lane's word of the scratch line behind the mbarriers
-    if (lane == 0) {
-        for (uint32_t sl = 0; sl < kRingSlots; sl++) mbar_init(mbar_saddr + 8 * sl, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    uint32_t n_filled = 0, n_used = 0;  // slices issued to / consumed from the ring since the kernel started
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
 
-    for (;;) {
-        uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(p.work_counter, 1u);
-        q = __shfl_sync(kFull, q, 0);
-        if (q >= p.n_q) break;
-
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < p.n_q; q += n_warps) {
         QueryCtx c;
         c.metric = p.mode == 1 ? (int)kAutocomplete : p.metric;
         c.alpha = p.alpha;
-        c.k = p.k;
-        c.tk_len = 0;
-        c.tk_score = tk_score;
-        c.tk_id = tk_id;
         c.size_a = 0;
         c.b_lo = 0;
         c.b_hi = -1;
         bool unsupported = false;
         uint32_t st_postings = 0, st_lists = 0;
+        for (int i = lane; i < kThrCache / 4; i += 32) ((uint32_t *)s_thr)[i] = 0u;
+        __syncwarp();
 
         // ---------------- 1. tokenise: wrap -> lower -> trim -> n-gram windows (dedupe) -> normalise ----------------
         const uint32_t qb = __ldg(p.q_off + q), qe = __ldg(p.q_off + q + 1);
@@ -560,14 +540,17 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
         };
 
         if (p.mode == 1 && n_lists < c.size_a) n_lists = 0;  // a query token that is in no list: nothing can hold them all
+        uint8_t *plan_base = p.plans + (size_t)q * kPlanStride;
+        QueryPlan *plan = (QueryPlan *)plan_base;
+        uint2 *plan_runs = (uint2 *)(plan_base + kPlanRunsOffset);
+        int shift = 0;
         if (c.b_hi >= 0 && n_lists > 0) {
             // ---------------- 3. one posting run per list ----------------
             float total = 0.0f;
             for (int j = lane; j < n_lists; j += 32) {
                 const uint32_t *o = ix.list_off + (size_t)s_lterm[j] * stride;
                 const uint32_t r0 = __ldg(o + c.b_lo), r1 = __ldg(o + c.b_hi + 1);
-                s_cur[j] = r0;
-                s_rend[j] = r1;
+                plan_runs[j] = make_uint2(r0, r1);
                 total += (float)(r1 - r0);
             }
             for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
@@ -580,7 +563,6 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
             const uint32_t c_base = __ldg(ix.seg_start + c.b_lo);
             const uint32_t D = __ldg(ix.seg_start + c.b_hi + 1) - c_base;
             const uint32_t NB = p.tbl_bytes;
-            int shift = 0;
             if (p.force_shift >= 0) shift = min(p.force_shift, 30);
             else if (D > NB) {
                 int s1 = 1;
@@ -605,6 +587,94 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
                 }
             }
             while (shift < 30 && (((uint64_t)(D - 1) >> shift) + NB) / NB > 0xFFFFu) shift++;  // keep the chunk loop bounded
+        } else {
+            n_lists = 0;
+        }
+        for (int i = lane; i < kThrCache / 16; i += 32) ((uint4 *)(plan_base + kPlanThrOffset))[i] = ((const uint4 *)s_thr)[i];
+        if (lane == 0) {
+            plan->flags = unsupported ? 1u : 0u;
+            plan->size_a = c.size_a;
+            plan->b_min = b_min;
+            plan->b_lo = c.b_lo;
+            plan->b_hi = c.b_hi;
+            plan->n_lists = n_lists;
+            plan->shift = shift;
+            if (p.stats != nullptr) { p.stats[2 * q] = st_postings; p.stats[2 * q + 1] = st_lists; }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sg_search_kernel: steps 5-8 (count, scan, resolve, score / top-k) from the QueryPlans.  Persistent: one CTA per SM,
+// one warp per query, query numbers from a global counter.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const DevIndex ix, const SearchParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint8_t *wsm = smem + (size_t)warp * p.warp_smem;
+    uint8_t *tbl = wsm;                                         // [tbl_bytes] byte counters, updated as fields of 32-bit words
+    uint8_t *ring = wsm + p.tbl_bytes;                          // [kRingSlots][kSliceBytes] posting slices landed by TMA
+    uint64_t *mbar = (uint64_t *)(ring + kRingSlots * kSliceBytes);  // [kRingSlots] one mbarrier per slot (64 bytes) + scratch line (128)
+    uint4 *s_meta = (uint4 *)(ring + kRingSlots * kSliceBytes + 192);  // [kRingSlots] {a, b, base} of the slice in each slot (64 bytes)
+    uint32_t *s_cur = (uint32_t *)(ring + kRingSlots * kSliceBytes + 256);  // [128] start of the not yet counted part of a run
+    uint32_t *s_end = s_cur + kMaxQueryTokens;                  // [128] end of the run slice inside the current chunk
+    uint32_t *s_rend = s_end + kMaxQueryTokens;                 // [128] end of the run (segment window)
+    uint8_t *s_thr = (uint8_t *)(s_rend + kMaxQueryTokens);     // [256] threshold of window segment b_min + i, 0 = skip
+    double *tk_score = (double *)(s_thr + kThrCache);           // [k]
+    uint32_t *tk_id = (uint32_t *)(tk_score + p.k);             // [k]
+
+    const uint32_t *__restrict__ postings = ix.postings;
+    const uint32_t tbl_saddr = smem_u32(tbl), ring_saddr = smem_u32(ring), mbar_saddr = smem_u32(mbar);
+    const uint32_t scratch_saddr = mbar_saddr + 64 + lane * 4;  // this lane's word of the scratch line behind the mbarriers
+    if (lane == 0) {
+        for (uint32_t sl = 0; sl < kRingSlots; sl++) mbar_init(mbar_saddr + 8 * sl, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t n_filled = 0, n_used = 0;  // slices issued to / consumed from the ring since the kernel started
+
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(p.work_counter, 1u);
+        q = __shfl_sync(kFull, q, 0);
+        if (q >= p.n_q) break;
+
+        const uint8_t *plan_base = p.plans + (size_t)q * kPlanStride;
+        const uint4 h0 = __ldg((const uint4 *)plan_base), h1 = __ldg((const uint4 *)plan_base + 1);  // QueryPlan
+        QueryCtx c;
+        c.metric = p.mode == 1 ? (int)kAutocomplete : p.metric;
+        c.alpha = p.alpha;
+        c.k = p.k;
+        c.tk_len = 0;
+        c.tk_score = tk_score;
+        c.tk_id = tk_id;
+        c.size_a = (int)h0.y;
+        c.b_lo = (int)h0.w;
+        c.b_hi = (int)h1.x;
+        const bool unsupported = h0.x != 0u;
+        const int b_min = (int)h0.z;
+        const int n_lists = (int)h1.y;
+        const int shift = (int)h1.z;
+        // threshold of an admissible, non-empty window segment; 0 = nothing to find there
+        auto thr_of = [&](int B) -> int {
+            if (B - b_min < kThrCache) return (int)s_thr[B - b_min];
+            const int T = metric_threshold(c.metric, c.alpha, c.size_a, B);
+            return (threshold_admits(T, c.size_a, B) && __ldg(ix.seg_start + B + 1) > __ldg(ix.seg_start + B)) ? T : 0;
+        };
+
+        if (n_lists > 0) {
+            for (int i = lane; i < kThrCache / 16; i += 32) ((uint4 *)s_thr)[i] = __ldg((const uint4 *)(plan_base + kPlanThrOffset) + i);
+            for (int j = lane; j < n_lists; j += 32) {
+                const uint2 r = __ldg((const uint2 *)(plan_base + kPlanRunsOffset) + j);
+                s_cur[j] = r.x;
+                s_rend[j] = r.y;
+            }
+            const uint32_t c_base = __ldg(ix.seg_start + c.b_lo);
+            const uint32_t D = __ldg(ix.seg_start + c.b_hi + 1) - c_base;
+            const uint32_t NB = p.tbl_bytes;
+            __syncwarp();
             const uint64_t chunk_docs = (uint64_t)NB << shift;
 
             for (uint64_t cs = 0; cs < D; cs += chunk_docs) {
@@ -740,7 +810,6 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
         }
         if (lane == 0) {
             p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)c.tk_len;
-            if (p.stats != nullptr) { p.stats[2 * q] = st_postings; p.stats[2 * q + 1] = st_lists; }
         }
         __syncwarp();
     }
@@ -790,6 +859,10 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
 cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks, int warps_per_block, size_t smem_bytes,
                           cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(sg_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    const int plan_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
+    sg_plan_kernel<<<plan_blocks < 148 * 8 ? plan_blocks : 148 * 8, kPlanThreads, 0, stream>>>(ix, p);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     sg_search_kernel<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(ix, p);
     return cudaGetLastError();

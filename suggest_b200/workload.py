@@ -8,12 +8,18 @@ Everything is returned packed: (uint8 bytes, offsets[n+1]).
 import numpy as np
 
 
-def synthetic_dictionary(n_docs, seed=12345, lo=8, hi=32, rng=None):
+def synthetic_dictionary(n_docs, seed=12345, lo=8, hi=32, rng=None, skew=None):
+    """skew=None: uniform letters (BASELINE.json config #2).  skew="zipf": letter i drawn with probability ~ 1/(i+1), the
+    labelled real-language-like variant of SURVEY.md 8(d) (posting lists about 10x longer for the frequent n-grams)."""
     rng = rng if rng is not None else np.random.default_rng(seed)
     lens = rng.integers(lo, hi + 1, size=n_docs)
     off = np.zeros(n_docs + 1, dtype=np.uint64)
     off[1:] = np.cumsum(lens)
-    data = (rng.integers(0, 26, size=int(off[-1]), dtype=np.uint8) + np.uint8(97))
+    if skew == "zipf":
+        p = 1.0 / np.arange(1, 27)
+        data = rng.choice(26, size=int(off[-1]), p=p / p.sum()).astype(np.uint8) + np.uint8(97)
+    else:
+        data = (rng.integers(0, 26, size=int(off[-1]), dtype=np.uint8) + np.uint8(97))
     return data, off, rng
 
 
