@@ -302,52 +302,43 @@ __device__ __forceinline__ void red_add(uint32_t saddr, uint32_t inc) {
 }
 
 // Count one group of 128 postings (4 per lane, ascending over the warp): every (list, bucket) pair adds exactly one to
-// the bucket's byte counter, so a counter never exceeds the number of lists (<= 128).  `carry` is the bucket of the
-// posting just before this group in the same list.  Returns the bucket of the group's last posting.
-// pos = index of this lane's first posting, [a, b) = the list's slice; kAllValid: the whole group lies inside it.
-// A posting that is not the first of its bucket adds zero to its own (valid) word; a slot outside [a, b) adds zero to
-// this lane's word of a scratch line.
-template <bool kAllValid>
-__device__ __forceinline__ uint32_t count_group_impl(uint32_t tbl_saddr, uint32_t scratch_saddr, const uint4 x, uint32_t pos, uint32_t a,
-                                                     uint32_t b, uint32_t lo_id, int shift, uint32_t carry, int lane) {
-    uint32_t b0 = (x.x - lo_id) >> shift, b1 = (x.y - lo_id) >> shift, b2 = (x.z - lo_id) >> shift, b3 = (x.w - lo_id) >> shift;
-    if (!kAllValid) {
-        const uint32_t d = pos - a, len = b - a;  // unsigned: positions before a wrap around and fail the test too
-        if (d >= len) b0 = kInf;
-        if (d + 1 >= len) b1 = kInf;
-        if (d + 2 >= len) b2 = kInf;
-        if (d + 3 >= len) b3 = kInf;
-    }
-    uint32_t prev = __shfl_up_sync(kFull, b3, 1);
-    if (lane == 0) prev = carry;
+// the bucket's byte counter, so a counter never exceeds the number of lists (<= 128).  `prev` is the bucket of the
+// posting just before this lane's four (read from the slice in shared memory, or carried over from the previous slice).
+// A posting that is not the first of its bucket adds zero to its own word.
+__device__ __forceinline__ void count_group_full(uint32_t tbl_saddr, const uint4 x, uint32_t prev, uint32_t lo_id, int shift) {
+    const uint32_t b0 = (x.x - lo_id) >> shift, b1 = (x.y - lo_id) >> shift, b2 = (x.z - lo_id) >> shift, b3 = (x.w - lo_id) >> shift;
     // head << ((bucket & 3) * 8): the funnel shift takes its amount modulo 32
+    const uint32_t i0 = __funnelshift_l(0u, (uint32_t)(b0 != prev), b0 << 3), i1 = __funnelshift_l(0u, (uint32_t)(b1 != b0), b1 << 3);
+    const uint32_t i2 = __funnelshift_l(0u, (uint32_t)(b2 != b1), b2 << 3), i3 = __funnelshift_l(0u, (uint32_t)(b3 != b2), b3 << 3);
+    red_add(tbl_saddr + (b0 & ~3u), i0);
+    red_add(tbl_saddr + (b1 & ~3u), i1);
+    red_add(tbl_saddr + (b2 & ~3u), i2);
+    red_add(tbl_saddr + (b3 & ~3u), i3);
+}
+
+// First / last group of a list (about two in seven), some slots lie outside the list's slice [a, b): those add zero to
+// this lane's word of a scratch line.  pos = index of this lane's first posting.  Out of line so that the hot loop stays
+// small in the instruction cache.
+__device__ __noinline__ void count_group_partial(uint32_t tbl_saddr, uint32_t scratch_saddr, const uint4 x, uint32_t prev, uint32_t pos,
+                                                 uint32_t a, uint32_t b, uint32_t lo_id, int shift) {
+    uint32_t b0 = (x.x - lo_id) >> shift, b1 = (x.y - lo_id) >> shift, b2 = (x.z - lo_id) >> shift, b3 = (x.w - lo_id) >> shift;
+    const uint32_t d = pos - a, len = b - a;  // unsigned: positions before a wrap around and fail the test too
+    if (d - 1 >= len) prev = kInf;
+    if (d >= len) b0 = kInf;
+    if (d + 1 >= len) b1 = kInf;
+    if (d + 2 >= len) b2 = kInf;
+    if (d + 3 >= len) b3 = kInf;
     uint32_t i0 = __funnelshift_l(0u, (uint32_t)(b0 != prev), b0 << 3), i1 = __funnelshift_l(0u, (uint32_t)(b1 != b0), b1 << 3);
     uint32_t i2 = __funnelshift_l(0u, (uint32_t)(b2 != b1), b2 << 3), i3 = __funnelshift_l(0u, (uint32_t)(b3 != b2), b3 << 3);
     uint32_t a0 = tbl_saddr + (b0 & ~3u), a1 = tbl_saddr + (b1 & ~3u), a2 = tbl_saddr + (b2 & ~3u), a3 = tbl_saddr + (b3 & ~3u);
-    if (!kAllValid) {
-        if (b0 == kInf) { a0 = scratch_saddr; i0 = 0u; }
-        if (b1 == kInf) { a1 = scratch_saddr; i1 = 0u; }
-        if (b2 == kInf) { a2 = scratch_saddr; i2 = 0u; }
-        if (b3 == kInf) { a3 = scratch_saddr; i3 = 0u; }
-    }
+    if (b0 == kInf) { a0 = scratch_saddr; i0 = 0u; }
+    if (b1 == kInf) { a1 = scratch_saddr; i1 = 0u; }
+    if (b2 == kInf) { a2 = scratch_saddr; i2 = 0u; }
+    if (b3 == kInf) { a3 = scratch_saddr; i3 = 0u; }
     red_add(a0, i0);
     red_add(a1, i1);
     red_add(a2, i2);
     red_add(a3, i3);
-    return __shfl_sync(kFull, b3, 31);
-}
-
-// the group lies wholly inside its list's slice: the hot loop
-__device__ __forceinline__ uint32_t count_group_full(uint32_t tbl_saddr, const uint4 x, uint32_t lo_id, int shift, uint32_t carry,
-                                                     int lane) {
-    return count_group_impl<true>(tbl_saddr, 0u, x, 0u, 0u, 0u, lo_id, shift, carry, lane);
-}
-
-// first / last group of a list (about two in seven): kept out of line so that the hot loop stays small in the
-// instruction cache
-__device__ __noinline__ uint32_t count_group_partial(uint32_t tbl_saddr, uint32_t scratch_saddr, const uint4 x, uint32_t pos, uint32_t a,
-                                                     uint32_t b, uint32_t lo_id, int shift, uint32_t carry, int lane) {
-    return count_group_impl<false>(tbl_saddr, scratch_saddr, x, pos, a, b, lo_id, shift, carry, lane);
 }
 
 // Walks the posting-run slices of one chunk in order, kSlicePostings at a time (the TMA producer's cursor).
@@ -710,38 +701,27 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
                         const uint32_t a = meta.x, b = meta.y;
                         if (meta.z == (a & ~3u)) carry = kInf;  // first slice of a list
                         const uint32_t end = min(meta.z + kSlicePostings, b);
-                        // groups of 128 postings; the next group's LDS.128 is issued before this group's atomics (the read may
-                        // run past `end` into stale bytes of the warp's own shared memory, which are then not used)
-                        const uint4 *src = (const uint4 *)(ring + slot * kSliceBytes) + lane;
-                        uint4 x = src[0];
-#ifdef SG_PAIR_GROUPS
-                        for (uint32_t g = meta.z; g < end;) {
-                            if (g >= a && g + 256 <= b && g + 256 <= meta.z + kSlicePostings) {  // two full groups at once
-                                const uint4 x1 = src[32];
-                                src += 64;
-                                const uint4 xn = src[0];
-                                carry = count_group_full(tbl_saddr, x, lo_id, shift, carry, lane);
-                                carry = count_group_full(tbl_saddr, x1, lo_id, shift, carry, lane);
-                                x = xn;
-                                g += 256;
-                            } else {
-                                src += 32;
-                                const uint4 xn = src[0];
-                                if (g >= a && g + 128 <= b) carry = count_group_full(tbl_saddr, x, lo_id, shift, carry, lane);
-                                else carry = count_group_partial(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
-                                x = xn;
-                                g += 128;
-                            }
+                        // Groups of 128 postings, lane l takes words 4l..4l+3 of a group.  The posting before a lane's four
+                        // comes from the word just below them (bank-conflict 4, but no shuffle and no convergence branch);
+                        // lane 0 of the slice's first group takes the carry from the previous slice instead.
+                        const uint32_t *w = (const uint32_t *)(ring + slot * kSliceBytes) + 4 * lane;
+                        const bool use_carry = lane == 0;
+                        uint32_t g = meta.z;
+                        {   // first group: the only one that can start before a, and the one that needs the carry
+                            const uint4 x = *(const uint4 *)w;
+                            uint32_t prev = (w[-1] - lo_id) >> shift;  // lane 0 reads the word below the slot: unused
+                            if (use_carry) prev = carry;
+                            if (g >= a && g + 128 <= b) count_group_full(tbl_saddr, x, prev, lo_id, shift);
+                            else count_group_partial(tbl_saddr, scratch_saddr, x, prev, g + lane * 4, a, b, lo_id, shift);
+                            g += 128;
+                            w += 128;
                         }
-#else
-                        for (uint32_t g = meta.z; g < end; g += 128) {
-                            src += 32;
-                            const uint4 xn = src[0];
-                            if (g >= a && g + 128 <= b) carry = count_group_full(tbl_saddr, x, lo_id, shift, carry, lane);
-                            else carry = count_group_partial(tbl_saddr, scratch_saddr, x, g + lane * 4, a, b, lo_id, shift, carry, lane);
-                            x = xn;
-                        }
-#endif
+                        for (; g + 128 <= end; g += 128, w += 128)  // groups wholly inside [a, b)
+                            count_group_full(tbl_saddr, *(const uint4 *)w, (w[-1] - lo_id) >> shift, lo_id, shift);
+                        if (g < end)  // the list ends inside this group
+                            count_group_partial(tbl_saddr, scratch_saddr, *(const uint4 *)w, (w[-1] - lo_id) >> shift, g + lane * 4, a, b, lo_id,
+                                                shift);
+                        carry = (((const uint32_t *)(ring + slot * kSliceBytes))[end - 1 - meta.z] - lo_id) >> shift;
                         __syncwarp();  // every lane has read the slot before it is refilled
                         n_used++;
                         fill();
