@@ -96,6 +96,9 @@ struct sg_index {
     std::atomic<uint32_t> work_rr{0};
     uint32_t tbl_bytes = kDefaultTblBytes;
     uint32_t slice_queries = 16384;      // queries per pipelined slice of sg_search_batch
+    size_t l2_persist_bytes = 0;         // persisting-L2 carve-out used for the posting array (0: none)
+    size_t l2_window_bytes = 0;
+    float l2_hit_ratio = 1.0f;
     int force_shift = -1;
     int max_warps = kMaxWarps;
 };
@@ -179,6 +182,22 @@ int finalize(sg_index *ix) {
     if (tb > 200000) tb = 200000;
     ix->tbl_bytes = ((uint32_t)tb + 15u) & ~15u;
     ix->force_shift = env_int("SG_FORCE_SHIFT", -1);
+    {   // sg_search_batch_device takes its query-plan scratch from the stream-ordered pool: keep freed blocks cached
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, ix->device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
+    if (env_int("SG_L2_PERSIST", 0)) {
+        size_t want = (size_t)prop.persistingL2CacheMaxSize;
+        const size_t bytes = ((size_t)h.n_postings + 8) * sizeof(uint32_t);
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            ix->l2_persist_bytes = want;
+            ix->l2_window_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+            ix->l2_hit_ratio = bytes <= want ? 1.0f : (float)want / (float)bytes;
+        }
+    }
     int sq = env_int("SG_SLICE_QUERIES", 16384);
     ix->slice_queries = sq < 256 ? 256u : (uint32_t)sq;
     ix->max_warps = env_int("SG_WARPS", kMaxWarps);
@@ -274,6 +293,16 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.warp_smem = g.warp_smem;
     p.force_shift = ix->force_shift;
     p.mode = mode;
+    if (ix->l2_persist_bytes) {
+        // keep the posting array resident in L2: query plans and result rows stream through the same cache
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = (void *)ix->dev.postings;
+        attr.accessPolicyWindow.num_bytes = ix->l2_window_bytes;
+        attr.accessPolicyWindow.hitRatio = ix->l2_hit_ratio;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
     SG_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), stream));
     SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);  // sg_plan_kernel + sg_search_kernel
