@@ -43,7 +43,8 @@ if __name__ == "__main__" and sys.argv[0].endswith("ncu_lines.py"):
     main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40)
 
 
-def regions(path, src_path, n_queries=65536):
+def regions(path, src_path, n_queries=65536, launches=1):
+    n_queries *= launches
     """instruction / sample share of the kernel's phases (markers looked up in the source, kernel body only)"""
     rows = list(csv.reader(open(path)))
     hdr, data, cur = None, [], None
@@ -62,13 +63,11 @@ def regions(path, src_path, n_queries=65536):
 
     def find(s, start=0):
         return next(i + 1 for i, l in enumerate(src) if i + 1 >= start and s in l)
-    marks = [('helpers', 1), ('topk/emit', find('struct QueryCtx')), ('tma+count_group', find('shared-memory staging')),
-             ('walker', find('struct SliceWalker')), ('prologue', kstart), ('tokenize', find('1. tokenise', kstart)),
-             ('window', find('2. segment window', kstart)), ('runs', find('3. one posting run', kstart)),
-             ('costmodel', find('4. bucket width', kstart)), ('chunk setup', find('for (uint64_t cs = 0', kstart)),
+    marks = [('metric/text helpers', 1), ('topk/emit/resolve', find('struct QueryCtx')), ('tma + count_group', find('shared-memory staging')),
+             ('slice walker', find('struct SliceWalker')), ('(plan kernel)', find('sg_plan_kernel: steps')),
+             ('load plan', kstart), ('chunk setup', find('for (uint64_t cs = 0', kstart)),
              ('count loop', find('---- count:', kstart)), ('scan', find('---- scan, segment', kstart)),
-             ('verify', find('resolve the bucket exactly', kstart)), ('epilogue', find('5. results', kstart)),
-             ('end', find('k best of n_parts', kstart))]
+             ('results', find('5. results', kstart)), ('end', find('k best of n_parts', kstart))]
     ks = [d for d in data if d[0] == 'sg_kernels.cu']
     tot = sum(num(r[iinst]) for f, l, r in ks)
     tots = sum(num(r[isamp]) for f, l, r in ks)

@@ -56,7 +56,7 @@ def main():
     old = sys.stdout
     sys.stdout = buf
     try:
-        ncu_lines.regions(src_csv, os.path.join(ROOT, "suggest_b200", "csrc", "sg_kernels.cu"))
+        ncu_lines.regions(src_csv, os.path.join(ROOT, "suggest_b200", "csrc", "sg_kernels.cu"), launches=max(1, len(rows) - 2))
         print()
         ncu_lines.main(src_csv, 25)
     finally:
