@@ -196,6 +196,7 @@ __device__ __noinline__ void topk_insert(QueryCtx &c, double score, uint32_t id,
         if (act) { c.tk_score[j] = sv; c.tk_id[j] = iv; }
         __syncwarp();
     }
+    __syncwarp();  // the reads of the ranking loop above are ordered before this write (racecheck cannot see it through the reduce)
     if (lane == 0) { c.tk_score[pos] = score; c.tk_id[pos] = id; }
     __syncwarp();
     c.tk_len = new_len;
