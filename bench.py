@@ -169,7 +169,7 @@ def oracle_run(ox, q_bytes, q_off, lo, hi, threads):
     return time.perf_counter() - t0, res
 
 
-def run_reference(args):
+def run_reference(args, out_stream):
     """--impl reference: the reference's own CPU implementation of the path.  No Go toolchain exists in this image,
     so this is the oracle's line-faithful port (oracle/so_suggest.c FAITHFUL mode), all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +193,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32 postings / f64 scores", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10", "n_docs": N_DOCS,
                    "queries_per_step": sample, "note": "each step is a bounded 8192-query sample of the 65536-query batch"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
@@ -201,11 +201,21 @@ def run_reference(args):
                                    "bounded heap), one query per thread"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out_stream, flush=True)
     return 0
 
 
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not add to
+    it: keep the real stdout for the result and point fd 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out_stream = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -220,7 +230,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, out_stream)
 
     import torch
     import torch.distributed as dist
@@ -390,7 +400,7 @@ def main():
     line = {
         "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u32 postings / u8 counters / f64 scores",
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": (f"{n_docs}-entry dictionary sharded by record-id range over {world} GPU(s), per-shard top-k + NCCL "
                                 "all-gather + merge" if sharded else "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10, 64K-query batch"),
@@ -423,7 +433,7 @@ def main():
                                           "decode, bounded heap), one query per thread", "gpu_results_identical": ok}
         if not ok:
             line["parity_error"] = "GPU results differ from the oracle on the cpu_baseline sample"
-    print(json.dumps(line))
+    print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -456,3 +456,27 @@ def test_autocomplete_forced_bucket_widths(cars_lines, cars_pair):
         gx = build_gpu(CARS_DESCRIPTION, cars_lines, env)
         assert_same_autocomplete(gx, ox, q, 7, str(env))
         gx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# randomised sweep: small alphabets give dense overlaps, ties and duplicate n-grams
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(8))
+def test_random_dictionaries(seed):
+    rng = np.random.default_rng(1000 + seed)
+    letters = ["ab", "abc", "abcde", "abcdefgh", "abcdefghijkl", "ab ", "aB1", "абвг"][seed % 8]
+    n_docs = int(rng.integers(50, 3000))
+    docs = ["".join(rng.choice(list(letters), size=int(rng.integers(0, 24)))) for _ in range(n_docs)]
+    queries = ["".join(rng.choice(list(letters), size=int(rng.integers(0, 20)))) for _ in range(150)] + docs[::max(1, n_docs // 60)]
+    desc = dict(ngram_size=int(rng.integers(1, 5)), wrap=[("$", "$"), ("", ""), ("^", ""), ("<<", ">")][int(rng.integers(0, 4))],
+                pad=["$", "_", "a"][int(rng.integers(0, 3))],
+                alphabet=[("english", "russian", "numbers", "$"), ("english",), ("abв",), ("numbers", " ")][int(rng.integers(0, 4))])
+    env = [None, dict(SG_FORCE_SHIFT=1, SG_TBL_BYTES=2048), dict(SG_FORCE_SHIFT=3), dict(SG_TBL_BYTES=2048)][seed % 4]
+    gx = build_gpu(desc, docs, env)
+    ox = O.OracleIndex(desc["ngram_size"], desc["wrap"], desc["pad"], desc["alphabet"]).add_docs(docs)
+    for metric in (O.JACCARD, O.COSINE, O.DICE, O.OVERLAP, O.EXACT):
+        alpha = float(rng.choice([0.2, 0.34, 0.5, 0.75, 1.0]))
+        k = int(rng.choice([1, 3, 10, 37]))
+        assert_same(gx, ox, queries, metric, alpha, k, f"seed={seed} desc={desc} m={metric} a={alpha} k={k} env={env}")
+    assert_same_autocomplete(gx, ox, queries[:60], int(rng.choice([1, 4, 20])), f"seed={seed} autocomplete")
+    gx.close()
