@@ -106,6 +106,22 @@ void sg_index_free(sg_index *ix);
 int sg_index_get_info(const sg_index *ix, sg_index_info *info);
 
 /*
+ * How the handle lays the index out in HBM.  Documents are renumbered ("slots") by cardinality segment
+ * (pkg/index/indexer_writer.go:66-86 files a document under len(tokens)); next to the decoded posting lists every
+ * term owns one row of bits, one bit per bucket of 2^bucket_shift consecutive slots, which is what the bitmap engine
+ * reads.  engine 0 = scan-count kernel over the posting lists (used when the bitmaps exceed their memory budget or
+ * SG_ENGINE=scancount), engine 1 = bitmap kernel.
+ */
+typedef struct {
+    uint32_t n_slots;        /* document slots, alignment holes between segments included */
+    uint32_t bucket_shift;
+    uint32_t row_words;      /* 32-bit words per bitmap row; 0: built without bitmaps */
+    uint32_t engine;
+    uint64_t bitmap_bytes;
+} sg_index_layout;
+int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout);
+
+/*
  * Batched NGramIndex.Suggest with a FuzzyCollectorManager(k): for every query
  *   tokenise (pkg/suggest/tokenizer.go:9-20, pkg/analysis) -> segment window and thresholds
  *   (pkg/suggest/suggester.go:46-131, pkg/metric) -> posting fetch + T-occurrence count
@@ -173,6 +189,14 @@ int sg_host_index_get_info(const sg_host_index *hi, sg_index_info *info);
 /* original ids of list (segment, term), ascending; returns the length, -1 if absent, -2 if cap is too small */
 int64_t sg_host_index_get_list(const sg_host_index *hi, uint32_t segment, const char *term, uint32_t term_len,
                                uint32_t *out, uint64_t cap);
+int sg_host_index_get_layout(const sg_host_index *hi, sg_index_layout *layout);
+/* first slot of every segment, n_segments + 1 entries; returns the count or -2 if cap is too small */
+int64_t sg_host_index_get_segments(const sg_host_index *hi, uint32_t *out, uint64_t cap);
+/* slots (not original ids) of list (segment, term); same return convention as sg_host_index_get_list */
+int64_t sg_host_index_get_list_slots(const sg_host_index *hi, uint32_t segment, const char *term, uint32_t term_len,
+                                     uint32_t *out, uint64_t cap);
+/* the term's bitmap row, row_words entries; -1 if the term is absent or the index has no bitmaps, -2 if cap is too small */
+int64_t sg_host_index_get_bitmap(const sg_host_index *hi, const char *term, uint32_t term_len, uint32_t *out, uint64_t cap);
 const char *sg_host_last_error(void);
 
 #ifdef __cplusplus

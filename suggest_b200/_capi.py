@@ -27,6 +27,11 @@ class SgIndexInfo(C.Structure):
                 ("n_postings", C.c_uint64), ("device_bytes", C.c_uint64), ("id_base", C.c_uint32), ("device", C.c_int32)]
 
 
+class SgIndexLayout(C.Structure):
+    _fields_ = [("n_slots", C.c_uint32), ("bucket_shift", C.c_uint32), ("row_words", C.c_uint32), ("engine", C.c_uint32),
+                ("bitmap_bytes", C.c_uint64)]
+
+
 # every symbol include/suggest_b200.h declares, with its signature
 SIGNATURES = {
     "sg_index_build": (C.c_int, [C.POINTER(SgConfig), C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
@@ -35,6 +40,7 @@ SIGNATURES = {
     "sg_index_open_disk": (C.c_int, [C.POINTER(SgConfig), C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     "sg_index_free": (None, [C.c_void_p]),
     "sg_index_get_info": (C.c_int, [C.c_void_p, C.POINTER(SgIndexInfo)]),
+    "sg_index_get_layout": (C.c_int, [C.c_void_p, C.POINTER(SgIndexLayout)]),
     "sg_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "sg_autocomplete_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
@@ -53,6 +59,10 @@ SIGNATURES = {
     "sg_host_index_free": (None, [C.c_void_p]),
     "sg_host_index_get_info": (C.c_int, [C.c_void_p, C.POINTER(SgIndexInfo)]),
     "sg_host_index_get_list": (C.c_int64, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "sg_host_index_get_layout": (C.c_int, [C.c_void_p, C.POINTER(SgIndexLayout)]),
+    "sg_host_index_get_segments": (C.c_int64, [C.c_void_p, C.c_void_p, C.c_uint64]),
+    "sg_host_index_get_list_slots": (C.c_int64, [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint64]),
+    "sg_host_index_get_bitmap": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint64]),
     "sg_host_last_error": (C.c_char_p, []),
 }
 

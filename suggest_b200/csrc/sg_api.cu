@@ -73,7 +73,8 @@ struct CallCtx {
     cudaStream_t stream2 = nullptr;  // one slice overlap the kernel of the other
     DevBuf<char> q_bytes;
     DevBuf<uint32_t> q_off, ids, counts, work;
-    DevBuf<uint8_t> plans;   // sg::kPlanStride bytes per query, sg_plan_kernel -> sg_search_kernel
+    DevBuf<uint8_t> plans;   // per-query plans, sg_plan_kernel -> sg_search_kernel or sg_tokens_kernel -> sg_bitmap_search_kernel
+    DevBuf<uint8_t> wtab;    // window tables of the bitmap engine, one set per slice
     DevBuf<double> scores;
 };
 
@@ -101,6 +102,9 @@ struct sg_index {
     float l2_hit_ratio = 1.0f;
     int force_shift = -1;
     int max_warps = kMaxWarps;
+    bool bitmap_engine = false;          // searches run sg_bitmap_search_kernel (default when the bitmaps fit their budget)
+    size_t plan_stride = sg::kPlanStride;
+    size_t wtab_bytes = 0;               // window tables per launch
 };
 
 namespace {
@@ -165,6 +169,24 @@ int finalize(sg_index *ix) {
     if ((rc = upload(ix, h.list_off, &d.list_off)) != SG_OK) return rc;
     if ((rc = upload(ix, h.postings, &d.postings, 8)) != SG_OK) return rc;
     if ((rc = upload(ix, h.perm, &d.perm)) != SG_OK) return rc;
+    d.n_ids = h.n_ids;
+    d.bshift = h.bshift;
+    d.row_words = h.row_words;
+    d.bitmaps = nullptr;
+    if (h.row_words) {
+        if ((rc = upload(ix, h.bitmaps, &d.bitmaps)) != SG_OK) return rc;
+        std::vector<uint32_t>().swap(h.bitmaps);
+    }
+    {
+        const char *eng = std::getenv("SG_ENGINE");
+        const bool want_scan = eng && std::strcmp(eng, "scancount") == 0;
+        if (eng && *eng && !want_scan && std::strcmp(eng, "bitmap") != 0) return fail(SG_ERR_INVALID, "SG_ENGINE must be bitmap or scancount");
+        ix->bitmap_engine = h.row_words != 0 && !want_scan;
+        if (eng && std::strcmp(eng, "bitmap") == 0 && !ix->bitmap_engine) return fail(SG_ERR_NOMEM, "the bucket bitmaps do not fit their memory budget");
+        ix->plan_stride = ix->bitmap_engine ? sg::kTokStride : sg::kPlanStride;
+        const size_t rows = sg::kWindowRows;
+        ix->wtab_bytes = ((rows * h.n_segments + 15) & ~(size_t)15) + ((rows * h.row_words + 15) & ~(size_t)15) + rows * sizeof(sg::WordRange);
+    }
     {
         void *ring = nullptr;
         SG_CUDA(cudaMalloc(&ring, kWorkRing * sizeof(uint32_t)));
@@ -211,7 +233,7 @@ void destroy(sg_index *ix) {
     DeviceGuard guard;
     guard.set(ix->device);
     for (CallCtx *c : ix->pool) {
-        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release();
+        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release(); c->wtab.release();
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         delete c;
@@ -236,6 +258,14 @@ int make_index(const sg_config *cfg, sg_index **out, sg_index **ixp) {
     ix->device = cfg->device;
     std::string err = ix->host.text.init(cfg->ngram_size, cfg->wrap_start, cfg->wrap_end, cfg->pad, cfg->alphabet, cfg->n_alphabet);
     if (!err.empty()) { delete ix; return fail(SG_ERR_UNSUPPORTED, err); }
+    {   // bucket bitmaps: at most half of the free HBM, or SG_BITMAP_MAX_MB
+        DeviceGuard guard;
+        size_t free_b = 0, total_b = 0;
+        if (guard.set(cfg->device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) ix->host.bitmap_budget = free_b / 2;
+        const int mb = env_int("SG_BITMAP_MAX_MB", -1);
+        if (mb >= 0) ix->host.bitmap_budget = (uint64_t)mb << 20;
+        ix->host.want_bshift = env_int("SG_BUCKET_SHIFT", -1);
+    }
     *ixp = ix;
     return SG_OK;
 }
@@ -272,10 +302,10 @@ int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, 
 
 int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
-                   uint8_t *d_plans, cudaStream_t stream, int mode = 0) {
-    Geometry g;
-    int rc = geometry(ix, n_q, k, &g);
-    if (rc != SG_OK) return rc;
+                   uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0) {
+    Geometry g{};
+    int rc = SG_OK;
+    if (!ix->bitmap_engine && (rc = geometry(ix, n_q, k, &g)) != SG_OK) return rc;
     sg::SearchParams p{};
     p.q_bytes = d_q_bytes;
     p.q_off = d_q_off;
@@ -304,6 +334,17 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
         cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
     }
     SG_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), stream));
+    if (ix->bitmap_engine) {
+        const size_t rows = sg::kWindowRows;
+        p.wt.seg_thr = d_wtab;
+        p.wt.word_thr = d_wtab + ((rows * ix->dev.n_segments + 15) & ~(size_t)15);
+        p.wt.win = (sg::WordRange *)(p.wt.word_thr + ((rows * ix->dev.row_words + 15) & ~(size_t)15));
+        p.warp_smem = (uint32_t)sg::bitmap_warp_smem(k);
+        if ((size_t)p.warp_smem * 8 > ix->smem_optin) return fail(SG_ERR_INVALID, "k too large for the shared-memory top-k");
+        SG_CUDA(sg::launch_bitmap_search(ix->dev, p, ix->sm_count, stream));
+        g_launches.fetch_add(3, std::memory_order_relaxed);  // sg_window_kernel + sg_tokens_kernel + sg_bitmap_search_kernel
+        return SG_OK;
+    }
     SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream));
     g_launches.fetch_add(2, std::memory_order_relaxed);  // sg_plan_kernel + sg_search_kernel
     return SG_OK;
@@ -419,6 +460,16 @@ int sg_index_get_info(const sg_index *ix, sg_index_info *info) {
     return SG_OK;
 }
 
+int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout) {
+    if (!ix || !layout) return fail(SG_ERR_INVALID, "null argument");
+    layout->n_slots = ix->host.n_ids;
+    layout->bucket_shift = ix->host.bshift;
+    layout->row_words = ix->host.row_words;
+    layout->engine = ix->bitmap_engine ? 1u : 0u;
+    layout->bitmap_bytes = (uint64_t)(ix->host.term_keys.size() + 1) * ix->host.row_words * sizeof(uint32_t);
+    return SG_OK;
+}
+
 static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
                              uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int mode) {
     int rc = validate_search(ix, n_q, metric, alpha, k);
@@ -461,7 +512,8 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     SG_CUDA(c->scores.reserve((size_t)n_q * k));
     SG_CUDA(c->counts.reserve(n_q));
     SG_CUDA(c->work.reserve(kMaxSlices));
-    SG_CUDA(c->plans.reserve((size_t)n_q * sg::kPlanStride));
+    SG_CUDA(c->plans.reserve((size_t)n_q * ix->plan_stride));
+    SG_CUDA(c->wtab.reserve(ix->wtab_bytes * kMaxSlices));
     // Slices of the batch go down two streams: the H2D / D2H copies of one slice overlap the kernel of the other.
     // Offsets stay absolute, so a slice only copies its own byte range of the query text.
     uint32_t n_slices = (n_q + ix->slice_queries - 1) / ix->slice_queries;
@@ -476,7 +528,7 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         SG_CUDA(cudaMemcpyAsync(c->q_off.p + lo, src_off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p + lo, hi - lo, metric, alpha, k, c->ids.p + (size_t)lo * k,
                             c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl,
-                            c->plans.p + (size_t)lo * sg::kPlanStride, st, mode);
+                            c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st, mode);
         if (rc != SG_OK) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }
         SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, c->ids.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, st));
@@ -516,9 +568,10 @@ int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *
     const uint32_t slot = ix->work_rr.fetch_add(1, std::memory_order_relaxed) & (kWorkRing - 1);
     // the query plans live in stream-ordered scratch: allocated, used by the two kernels and freed on the caller's stream
     void *plans = nullptr;
-    SG_CUDA(cudaMallocAsync(&plans, (size_t)n_q * sg::kPlanStride, (cudaStream_t)stream));
+    const size_t plan_bytes = ((size_t)n_q * ix->plan_stride + 255) & ~(size_t)255;
+    SG_CUDA(cudaMallocAsync(&plans, plan_bytes + ix->wtab_bytes, (cudaStream_t)stream));
     rc = enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, d_stats,
-                        ix->work_ring + slot, (uint8_t *)plans, (cudaStream_t)stream);
+                        ix->work_ring + slot, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, (cudaStream_t)stream);
     cudaError_t fe = cudaFreeAsync(plans, (cudaStream_t)stream);
     if (rc == SG_OK && fe != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(fe));
     return rc;

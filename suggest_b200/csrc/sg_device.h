@@ -27,6 +27,7 @@ constexpr uint32_t kRingSlots = SG_RING_SLOTS;    // slices in flight per warp (
 constexpr uint32_t kWarpFixedSmem = kRingSlots * kSliceBytes + 64 + 128 + 64 + 3 * kMaxQueryTokens * 4 + 256;
 constexpr int kMaxSearchThreads = 512;       // launch bound of sg_search_kernel (16 warps)
 constexpr uint32_t kCountUnsupported = 0xFFFFFFFFu;     // SG_COUNT_UNSUPPORTED
+constexpr uint32_t kMaxBucketShift = 8;      // at most 256 documents per bitmap bucket
 
 // non-ASCII alphabet interval: rune r in [lo, hi] has symbol code base + (r - lo)
 struct RuneRange {
@@ -59,7 +60,15 @@ struct DevIndex {
     const uint32_t *seg_start;  // S + 1
     const uint32_t *list_off;   // n_terms * (S + 1)
     const uint32_t *postings;   // 16-byte aligned, padded with 4 trailing entries
-    const uint32_t *perm;       // new id -> original document id (without id_base)
+    const uint32_t *perm;       // new id -> original document id (without id_base); n_ids entries, holes are never read
+    // ---- bucket bitmaps (sg_bitmap.cu) ----
+    // Segment starts are aligned to 2^bshift new ids, so a bucket (2^bshift consecutive new ids) lies inside one
+    // segment.  Row t holds one bit per bucket: set iff term t has a posting in that bucket.  Rows are row_words
+    // 32-bit words (a multiple of 32) apart; row n_terms is all zero (padding lists of a query).
+    uint32_t n_ids;          // seg_start[S]: new ids including the alignment holes
+    uint32_t bshift;         // log2(new ids per bucket), 0..kMaxBucketShift
+    uint32_t row_words;      // 0: the index has no bitmaps (over the memory budget) and is searched by sg_search_kernel
+    const uint32_t *bitmaps; // (n_terms + 1) * row_words
 };
 
 // One per query, written by sg_plan_kernel and read by sg_search_kernel: kPlanStride bytes =
@@ -75,6 +84,29 @@ struct QueryPlan {
 };
 constexpr uint32_t kPlanThrOffset = 32, kPlanRunsOffset = 32 + 256;
 constexpr uint32_t kPlanStride = kPlanRunsOffset + kMaxQueryTokens * 8;
+
+// Bitmap engine: one per query, written by sg_tokens_kernel and read by sg_bitmap_search_kernel:
+// kTokStride bytes = [TokenPlan (16) | term id of every list to open (128 x 4)]
+struct TokenPlan {
+    uint32_t flags;      // 1: more than 128 n-grams (SG_ERR_QUERY_TOO_LONG)
+    int32_t size_a;      // len(tokens), suggester.go:53
+    int32_t n_lists;     // tokens that are terms of the index, with multiplicity
+    int32_t reserved;
+};
+constexpr uint32_t kTokTermsOffset = 16;
+constexpr uint32_t kTokStride = kTokTermsOffset + kMaxQueryTokens * 4;
+
+// Per call (metric, similarity, mode are per call): everything that depends on the query only through len(tokens).
+// Row a = len(tokens) in 0..kMaxQueryTokens.
+struct alignas(8) WordRange {
+    uint32_t x, y;       // {first, one past last} bitmap word
+};
+struct WindowTables {
+    uint8_t *seg_thr;    // [129][S]          Threshold(alpha, a, B) of an admissible, non-empty segment of the window, else 0
+    uint8_t *word_thr;   // [129][row_words]  smallest such threshold over the segments owning buckets of the bitmap word; 255: none
+    WordRange *win;      // [129]             bitmap words with a threshold
+};
+constexpr uint32_t kWindowRows = kMaxQueryTokens + 1;
 
 struct SearchParams {
     const char *q_bytes;
@@ -93,6 +125,7 @@ struct SearchParams {
     uint32_t warp_smem;       // bytes of shared memory owned by one warp
     int32_t force_shift;      // < 0: cost model picks the bucket width; otherwise log2(bucket width)
     int32_t mode;             // 0: Suggest; 1: Autocomplete (no tail wrap, every token required, lowest ids win)
+    WindowTables wt;          // bitmap engine only
 };
 
 SG_HD static inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; host and device hash term keys with it

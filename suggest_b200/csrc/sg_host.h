@@ -60,8 +60,13 @@ struct HostIndex {
     std::vector<uint32_t> seg_start;   // S + 1
     std::vector<uint32_t> list_off;    // n_terms * (S + 1)
     std::vector<uint32_t> postings;    // padded to a multiple of 4 plus 4
-    std::vector<uint32_t> perm;        // new id -> original id
+    std::vector<uint32_t> perm;        // new id -> original id (n_ids entries, 0xFFFFFFFF in the alignment holes)
     uint64_t n_postings = 0;
+    // bucket bitmaps (sg_device.h: DevIndex::bitmaps)
+    int want_bshift = -1;              // in: < 0 lets the build choose
+    uint64_t bitmap_budget = 1ull << 62;  // in: bytes the bitmaps may take; over it the index is built without them
+    uint32_t n_ids = 0, bshift = 0, row_words = 0;
+    std::vector<uint32_t> bitmaps;     // (n_terms + 1) * row_words, empty if over the budget
 
     void build_hash();
 };

@@ -1,6 +1,7 @@
 // sg_hostapi.cpp — host-only introspection entry points (no GPU needed): the tokenizer chain and the
 // CSR build exactly as the library performs them before the upload.  The CPU test-suite checks them
 // against the oracle; the search path itself has no host implementation.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -63,6 +64,8 @@ int sg_host_index_build(const sg_config *cfg, const char *doc_bytes, const uint6
     if (!hi) return SG_ERR_NOMEM;
     std::string err = hi->h.text.init(cfg->ngram_size, cfg->wrap_start, cfg->wrap_end, cfg->pad, cfg->alphabet, cfg->n_alphabet);
     static const uint64_t zero_off[1] = {0};
+    if (const char *v = std::getenv("SG_BUCKET_SHIFT")) if (*v) hi->h.want_bshift = std::atoi(v);
+    if (const char *v = std::getenv("SG_BITMAP_MAX_MB")) if (*v) hi->h.bitmap_budget = (uint64_t)std::atoll(v) << 20;
     if (err.empty()) err = sg::build_from_docs(&hi->h, doc_bytes, n_docs ? doc_off : zero_off, n_docs);
     if (!err.empty()) { g_host_err = err; delete hi; return SG_ERR_UNSUPPORTED; }
     *out = hi;
@@ -95,23 +98,65 @@ int sg_host_index_get_info(const sg_host_index *hi, sg_index_info *info) {
     return SG_OK;
 }
 
-int64_t sg_host_index_get_list(const sg_host_index *hi, uint32_t segment, const char *term, uint32_t term_len,
-                               uint32_t *out, uint64_t cap) {
-    if (!hi || segment >= hi->h.n_segments) return -1;
-    const sg::HostIndex &h = hi->h;
+static int64_t term_id_of(const sg::HostIndex &h, const char *term, uint32_t term_len) {
     uint64_t key = h.text.key_of_term((const uint8_t *)term, term_len);
     if (key == 0) return -1;
     size_t m = h.ht_keys.size() - 1, s = (size_t)sg::mix64(key) & m;
     while (h.ht_keys[s] != 0 && h.ht_keys[s] != key) s = (s + 1) & m;
     if (h.ht_keys[s] == 0) return -1;
+    return (int64_t)h.ht_vals[s];
+}
+
+static int64_t get_list(const sg_host_index *hi, uint32_t segment, const char *term, uint32_t term_len, uint32_t *out,
+                        uint64_t cap, bool slots) {
+    if (!hi || segment >= hi->h.n_segments) return -1;
+    const sg::HostIndex &h = hi->h;
+    const int64_t t = term_id_of(h, term, term_len);
+    if (t < 0) return -1;
     const size_t stride = (size_t)h.n_segments + 1;
-    const uint32_t a = h.list_off[h.ht_vals[s] * stride + segment], b = h.list_off[h.ht_vals[s] * stride + segment + 1];
+    const uint32_t a = h.list_off[(size_t)t * stride + segment], b = h.list_off[(size_t)t * stride + segment + 1];
     if (a == b) return -1;
     if (out) {
         if (cap < b - a) return -2;
-        for (uint32_t i = a; i < b; i++) out[i - a] = h.perm[h.postings[i]];
+        for (uint32_t i = a; i < b; i++) out[i - a] = slots ? h.postings[i] : h.perm[h.postings[i]];
     }
     return (int64_t)(b - a);
+}
+
+int64_t sg_host_index_get_list(const sg_host_index *hi, uint32_t segment, const char *term, uint32_t term_len,
+                               uint32_t *out, uint64_t cap) {
+    return get_list(hi, segment, term, term_len, out, cap, false);
+}
+
+int64_t sg_host_index_get_list_slots(const sg_host_index *hi, uint32_t segment, const char *term, uint32_t term_len,
+                                     uint32_t *out, uint64_t cap) {
+    return get_list(hi, segment, term, term_len, out, cap, true);
+}
+
+int sg_host_index_get_layout(const sg_host_index *hi, sg_index_layout *layout) {
+    if (!hi || !layout) return SG_ERR_INVALID;
+    layout->n_slots = hi->h.n_ids;
+    layout->bucket_shift = hi->h.bshift;
+    layout->row_words = hi->h.row_words;
+    layout->engine = hi->h.row_words != 0;
+    layout->bitmap_bytes = (uint64_t)hi->h.bitmaps.size() * sizeof(uint32_t);
+    return SG_OK;
+}
+
+int64_t sg_host_index_get_segments(const sg_host_index *hi, uint32_t *out, uint64_t cap) {
+    if (!hi || !out) return -1;
+    if (cap < hi->h.seg_start.size()) return -2;
+    std::memcpy(out, hi->h.seg_start.data(), hi->h.seg_start.size() * sizeof(uint32_t));
+    return (int64_t)hi->h.seg_start.size();
+}
+
+int64_t sg_host_index_get_bitmap(const sg_host_index *hi, const char *term, uint32_t term_len, uint32_t *out, uint64_t cap) {
+    if (!hi || hi->h.row_words == 0) return -1;
+    const int64_t t = term_id_of(hi->h, term, term_len);
+    if (t < 0) return -1;
+    if (cap < hi->h.row_words) return -2;
+    if (out) std::memcpy(out, hi->h.bitmaps.data() + (size_t)t * hi->h.row_words, (size_t)hi->h.row_words * sizeof(uint32_t));
+    return (int64_t)hi->h.row_words;
 }
 
 }  // extern "C"

@@ -6,6 +6,7 @@
 // one contiguous run per query token: documents are renumbered by (segment, original id), and the
 // postings of a term are stored back to back over all segments, ascending in the new id.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <unordered_map>
@@ -40,11 +41,39 @@ std::string finish(HostIndex *ix, const std::vector<uint32_t> &doc_seg, const st
     ix->n_segments = S;
     if ((uint64_t)n_terms * (S + 1) > 0xFFFFFFF0ull) return "term x segment offset table exceeds 32 bits";
     if (doc_terms.size() > 0xFFFFFFF0ull) return "more than 2^32 postings";
-    // renumber: counting sort of documents by segment keeps the original id order inside a segment
+    // Bucket width of the bitmaps: 2^bshift new ids per bit.  Small dictionaries get one bit per document (the bit
+    // count is then the overlap itself); otherwise aim at rows about 1/8 full, where some 2-3 of a query's 20 lists hit
+    // a bucket by chance and its thresholds (>= ~10) leave almost no bucket to resolve.
+    std::vector<uint32_t> seg_count((size_t)S, 0);
+    for (uint32_t d = 0; d < n_docs; d++) seg_count[doc_seg[d]]++;
+    auto ids_at = [&](uint32_t s) {  // new ids once every segment start is aligned to 2^s
+        uint64_t n = 0;
+        for (uint32_t b = 0; b < S; b++) n = ((n + ((1ull << s) - 1)) >> s << s) + seg_count[b];
+        return n;
+    };
+    auto row_words_at = [&](uint32_t s) { return (((ids_at(s) + ((1ull << s) - 1)) >> s) + 1023) / 1024 * 32 + (ids_at(s) ? 0 : 32); };
+    uint32_t bs = 0;
+    if (ix->want_bshift >= 0) bs = std::min<uint32_t>((uint32_t)ix->want_bshift, kMaxBucketShift);
+    else if (n_docs > 16384 && n_terms > 0 && !doc_terms.empty()) {
+        const double d0 = (double)doc_terms.size() / ((double)n_terms * (double)n_docs);
+        const double want = std::log2(0.125 / d0);
+        bs = want <= 0.0 ? 0u : std::min<uint32_t>((uint32_t)std::lround(want), kMaxBucketShift);
+    }
+    while (bs < kMaxBucketShift && (n_terms + 1) * row_words_at(bs) * 4 > ix->bitmap_budget) bs++;
+    const bool with_bitmaps = (n_terms + 1) * row_words_at(bs) * 4 <= ix->bitmap_budget && (n_terms + 1) * row_words_at(bs) < 0xFFFFFFF0ull;
+    if (ids_at(bs) > 0xFFFFFFF0ull) return "more than 2^32 document ids";
+    ix->bshift = bs;
+    ix->row_words = with_bitmaps ? (uint32_t)row_words_at(bs) : 0u;
+    // renumber: counting sort of documents by segment keeps the original id order inside a segment; every segment
+    // starts at a multiple of the bucket width, so a bucket never holds documents of two segments
     ix->seg_start.assign((size_t)S + 1, 0);
-    for (uint32_t d = 0; d < n_docs; d++) ix->seg_start[doc_seg[d] + 1]++;
-    for (uint32_t b = 0; b < S; b++) ix->seg_start[b + 1] += ix->seg_start[b];
-    ix->perm.assign(n_docs, 0);
+    for (uint32_t b = 0; b < S; b++) {
+        const uint64_t a = ((uint64_t)ix->seg_start[b] + ((1ull << bs) - 1)) >> bs << bs;
+        ix->seg_start[b] = (uint32_t)a;  // an empty segment moves with its successor's alignment
+        ix->seg_start[b + 1] = (uint32_t)(a + seg_count[b]);
+    }
+    ix->n_ids = ix->seg_start[S];
+    ix->perm.assign(ix->n_ids, 0xFFFFFFFFu);
     {
         std::vector<uint32_t> cur(ix->seg_start.begin(), ix->seg_start.end() - 1);
         for (uint32_t d = 0; d < n_docs; d++) ix->perm[cur[doc_seg[d]]++] = d;
@@ -71,10 +100,17 @@ std::string finish(HostIndex *ix, const std::vector<uint32_t> &doc_seg, const st
     // fill in new-id order so that every list comes out ascending
     std::vector<uint32_t> cur(n_terms * stride);
     std::memcpy(cur.data(), off.data(), cur.size() * sizeof(uint32_t));
-    for (uint32_t nid = 0; nid < n_docs; nid++) {
-        uint32_t d = ix->perm[nid], b = doc_seg[d];
-        for (uint64_t j = doc_term_off[d]; j < doc_term_off[d + 1]; j++)
-            ix->postings[cur[(size_t)doc_terms[j] * stride + b]++] = nid;
+    const size_t rw = ix->row_words;
+    ix->bitmaps.assign(rw ? (n_terms + 1) * rw : 0, 0u);
+    for (uint32_t nid = 0; nid < ix->n_ids; nid++) {
+        const uint32_t d = ix->perm[nid];
+        if (d == 0xFFFFFFFFu) continue;  // alignment hole
+        const uint32_t b = doc_seg[d], bucket = nid >> bs;
+        for (uint64_t j = doc_term_off[d]; j < doc_term_off[d + 1]; j++) {
+            const size_t t = doc_terms[j];
+            ix->postings[cur[t * stride + b]++] = nid;
+            if (rw) ix->bitmaps[t * rw + (bucket >> 5)] |= 1u << (bucket & 31);
+        }
     }
     ix->build_hash();
     return "";

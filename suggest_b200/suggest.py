@@ -162,6 +162,12 @@ class NGramIndex:
         _capi.check(_capi.lib().sg_index_get_info(self.handle, C.byref(info)))
         return {name: getattr(info, name) for name, _ in info._fields_}
 
+    def layout(self):
+        """Slots, bucket width and engine of the handle (sg_index_get_layout)."""
+        lay = _capi.SgIndexLayout()
+        _capi.check(_capi.lib().sg_index_get_layout(self.handle, C.byref(lay)))
+        return {name: getattr(lay, name) for name, _ in lay._fields_}
+
     # -- Suggester ------------------------------------------------------------------------------
     def Suggest(self, query, similarity, metric, topK) -> List[Candidate]:
         """nGramSuggester.Suggest (pkg/suggest/suggester.go:46-131) with a FuzzyCollectorManager(topK)."""

@@ -154,12 +154,19 @@ def test_cars_misspelled_queries(cars_pair):
         assert_same(gx, ox, queries, metric, alpha, 5)
 
 
-@pytest.mark.parametrize("env", [dict(SG_FORCE_SHIFT=0, SG_TBL_BYTES=2048), dict(SG_FORCE_SHIFT=2, SG_TBL_BYTES=2048),
-                                 dict(SG_FORCE_SHIFT=5), dict(SG_FORCE_SHIFT=13), dict(SG_TBL_BYTES=4096, SG_WARPS=3),
-                                 dict(SG_TBL_BYTES=65536)])
+SCAN = dict(SG_ENGINE="scancount")
+
+
+@pytest.mark.parametrize("env", [dict(SCAN, SG_FORCE_SHIFT=0, SG_TBL_BYTES=2048), dict(SCAN, SG_FORCE_SHIFT=2, SG_TBL_BYTES=2048),
+                                 dict(SCAN, SG_FORCE_SHIFT=5), dict(SCAN, SG_FORCE_SHIFT=13), dict(SCAN, SG_TBL_BYTES=4096, SG_WARPS=3),
+                                 dict(SCAN, SG_TBL_BYTES=65536), dict(SCAN), dict(SG_BITMAP_MAX_MB=0),
+                                 dict(SG_BUCKET_SHIFT=0), dict(SG_BUCKET_SHIFT=1), dict(SG_BUCKET_SHIFT=3), dict(SG_BUCKET_SHIFT=5),
+                                 dict(SG_BUCKET_SHIFT=8), dict(SG_ENGINE="bitmap", SG_BUCKET_SHIFT=2)])
 def test_cars_bucket_widths_and_table_sizes(cars_lines, cars_pair, env):
-    """Every bucket width / chunking gives the same answer (exact counters, bucket filter + merge, multi-chunk)."""
+    """Both engines, every bucket width / chunking give the same answer (scan-count: exact counters, bucket filter + merge,
+    multi-chunk; bitmap: one bit per document up to 256 documents per bit)."""
     gx = build_gpu(CARS_DESCRIPTION, cars_lines, env)
+    assert gx.layout()["engine"] == (0 if env.get("SG_ENGINE") == "scancount" or "SG_BITMAP_MAX_MB" in env else 1)
     _, ox = cars_pair
     q = cars_lines[::3]
     assert_same(gx, ox, q, O.JACCARD, 0.5, 10, str(env))
@@ -191,6 +198,26 @@ def test_synthetic_sweep(synth_pairs, n, metric, alpha):
     gx, ox, queries = synth_pairs[n]
     cnt = assert_same(gx, ox, queries, metric, alpha, 10, f"synthetic n={n} m={metric} a={alpha}")
     assert (cnt > 0).mean() > 0.3
+
+
+@pytest.mark.parametrize("env", [SCAN, dict(SG_BUCKET_SHIFT=5), dict(SG_BUCKET_SHIFT=8), dict(SG_BUCKET_SHIFT=0)])
+def test_synthetic_other_engines_and_widths(synth_pairs, env):
+    """The default index of the sweep above uses the bitmap engine at the width the build picks; here the same data
+    through the scan-count engine and through other bucket widths."""
+    _, ox, queries = synth_pairs[3]
+    docs, _ = synthetic(60000, 3000)
+    gx = build_gpu(TEST_DESCRIPTION, docs, env)
+    assert gx.layout()["engine"] == (0 if env is SCAN else 1)
+    for metric, alpha in ((O.JACCARD, 0.5), (O.COSINE, 0.4), (O.OVERLAP, 0.8)):
+        assert_same(gx, ox, queries[:1500], metric, alpha, 10, f"{env} m={metric} a={alpha}")
+    gx.close()
+
+
+def test_default_engine_is_bitmap(synth_pairs, cars_pair):
+    assert cars_pair[0].layout()["engine"] == 1 and cars_pair[0].layout()["bucket_shift"] == 0
+    for n in (2, 3, 4):
+        lay = synth_pairs[n][0].layout()
+        assert lay["engine"] == 1 and lay["row_words"] > 0, lay
 
 
 def test_synthetic_stats_match_oracle(synth_pairs):
@@ -452,7 +479,8 @@ def test_autocomplete_synthetic_and_service(synth_pairs, cars_lines, tmp_path):
 def test_autocomplete_forced_bucket_widths(cars_lines, cars_pair):
     _, ox = cars_pair
     q = [l[:max(2, len(l) // 2)] for l in cars_lines[::41]]
-    for env in (dict(SG_FORCE_SHIFT=0, SG_TBL_BYTES=2048), dict(SG_FORCE_SHIFT=4), dict(SG_FORCE_SHIFT=9)):
+    for env in (dict(SCAN, SG_FORCE_SHIFT=0, SG_TBL_BYTES=2048), dict(SCAN, SG_FORCE_SHIFT=4), dict(SCAN, SG_FORCE_SHIFT=9),
+                dict(SG_BUCKET_SHIFT=0), dict(SG_BUCKET_SHIFT=4), dict(SG_BUCKET_SHIFT=8)):
         gx = build_gpu(CARS_DESCRIPTION, cars_lines, env)
         assert_same_autocomplete(gx, ox, q, 7, str(env))
         gx.close()
@@ -471,7 +499,8 @@ def test_random_dictionaries(seed):
     desc = dict(ngram_size=int(rng.integers(1, 5)), wrap=[("$", "$"), ("", ""), ("^", ""), ("<<", ">")][int(rng.integers(0, 4))],
                 pad=["$", "_", "a"][int(rng.integers(0, 3))],
                 alphabet=[("english", "russian", "numbers", "$"), ("english",), ("abв",), ("numbers", " ")][int(rng.integers(0, 4))])
-    env = [None, dict(SG_FORCE_SHIFT=1, SG_TBL_BYTES=2048), dict(SG_FORCE_SHIFT=3), dict(SG_TBL_BYTES=2048)][seed % 4]
+    env = [None, dict(SCAN, SG_FORCE_SHIFT=1, SG_TBL_BYTES=2048), dict(SG_BUCKET_SHIFT=3), dict(SCAN, SG_TBL_BYTES=2048),
+           dict(SG_BUCKET_SHIFT=6), dict(SCAN, SG_FORCE_SHIFT=3), dict(SG_BUCKET_SHIFT=1), dict(SG_BUCKET_SHIFT=8)][seed % 8]
     gx = build_gpu(desc, docs, env)
     ox = O.OracleIndex(desc["ngram_size"], desc["wrap"], desc["pad"], desc["alphabet"]).add_docs(docs)
     for metric in (O.JACCARD, O.COSINE, O.DICE, O.OVERLAP, O.EXACT):

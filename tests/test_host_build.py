@@ -117,3 +117,65 @@ def test_index_synthetic_matches_oracle():
     lens = rng.integers(8, 33, size=3000)
     docs = ["".join(chr(97 + c) for c in rng.integers(0, 26, size=l)) for l in lens]
     check_index_equals_oracle(TEST_DESCRIPTION, docs)
+
+
+def check_bitmaps(desc, docs, monkeypatch, shift):
+    """Segments start on bucket boundaries; bit b of a term's row is set iff one of its lists holds a slot of bucket b."""
+    if shift is None:
+        monkeypatch.delenv("SG_BUCKET_SHIFT", raising=False)
+    else:
+        monkeypatch.setenv("SG_BUCKET_SHIFT", str(shift))
+    ox = oracle.OracleIndex(desc["ngram_size"], desc["wrap"], desc["pad"], desc["alphabet"]).add_docs(docs)
+    h = host_index(desc, docs)
+    L = _capi.lib()
+    try:
+        lay = _capi.SgIndexLayout()
+        assert L.sg_host_index_get_layout(h, C.byref(lay)) == 0
+        s = lay.bucket_shift
+        if shift is not None:
+            assert s == min(shift, 8)
+        assert lay.row_words % 32 == 0 and lay.row_words * 32 >= -(-lay.n_slots // (1 << s))
+        seg = np.zeros(ox.segments + 1, dtype=np.uint32)
+        assert L.sg_host_index_get_segments(h, seg.ctypes.data_as(C.c_void_p), len(seg)) == len(seg)
+        assert seg[-1] == lay.n_slots and np.all(np.diff(seg.astype(np.int64)) >= 0)
+        assert np.all(seg[:-1] % (1 << s) == 0)
+        want_bits = {}
+        n_real = 0
+        for b, term, ids in ox.iter_lists():
+            n = L.sg_host_index_get_list_slots(h, b, term, len(term), None, 0)
+            slots = np.zeros(n, dtype=np.uint32)
+            assert L.sg_host_index_get_list_slots(h, b, term, len(term), slots.ctypes.data_as(C.c_void_p), n) == n
+            assert np.all(np.diff(slots.astype(np.int64)) > 0)
+            assert np.all((slots >= seg[b]) & (slots < seg[b + 1]))
+            want_bits.setdefault(term, set()).update((slots >> s).tolist())
+            n_real += n
+        for term, buckets in want_bits.items():
+            row = np.zeros(lay.row_words, dtype=np.uint32)
+            assert L.sg_host_index_get_bitmap(h, term, len(term), row.ctypes.data_as(C.c_void_p), len(row)) == len(row)
+            got = set(np.flatnonzero(np.unpackbits(row.view(np.uint8), bitorder="little")).tolist())
+            assert got == buckets, term
+    finally:
+        L.sg_host_index_free(h)
+
+
+@pytest.mark.parametrize("shift", [None, 0, 3, 7, 12])
+def test_bitmap_rows_match_lists_on_cars(cars_lines, monkeypatch, shift):
+    check_bitmaps(CARS_DESCRIPTION, cars_lines[::3], monkeypatch, shift)
+
+
+def test_bitmap_rows_synthetic_auto_shift(monkeypatch):
+    rng = np.random.default_rng(11)
+    lens = rng.integers(8, 33, size=20000)
+    docs = ["".join(chr(97 + c) for c in rng.integers(0, 26, size=l)) for l in lens]
+    check_bitmaps(TEST_DESCRIPTION, docs, monkeypatch, None)
+
+
+def test_index_without_bitmaps_when_over_budget(monkeypatch):
+    monkeypatch.setenv("SG_BITMAP_MAX_MB", "0")
+    h = host_index(TEST_DESCRIPTION, COLLECTION)
+    try:
+        lay = _capi.SgIndexLayout()
+        assert _capi.lib().sg_host_index_get_layout(h, C.byref(lay)) == 0
+        assert lay.row_words == 0 and lay.engine == 0 and lay.bitmap_bytes == 0
+    finally:
+        _capi.lib().sg_host_index_free(h)
