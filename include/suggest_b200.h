@@ -155,6 +155,15 @@ int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *
                            uint32_t *d_stats, void *stream);
 
 /*
+ * Measurement aid: one sg_search_batch_device launch with CUDA events between its kernels on `stream`; synchronises.
+ * ms_out receives one duration per kernel (at most 4), names_out their comma-separated names.  Returns the number of
+ * kernels.  bench.py uses it for the per-kernel roofline; it is not part of the reference-facing path.
+ */
+int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
+                          uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream,
+                          float *ms_out, char *names_out, uint32_t names_cap);
+
+/*
  * Cross-shard reduce for record-id-range shards: for every query pick the k best of n_parts
  * per-shard results (layout [part][query][k] as an all-gather of sg_search_batch_device outputs
  * delivers them) under the same (score desc, id asc) order.  Device buffers.

@@ -302,7 +302,7 @@ int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, 
 
 int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
-                   uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0) {
+                   uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0, cudaEvent_t *stage_events = nullptr) {
     Geometry g{};
     int rc = SG_OK;
     if (!ix->bitmap_engine && (rc = geometry(ix, n_q, k, &g)) != SG_OK) return rc;
@@ -341,11 +341,11 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
         p.wt.win = (sg::WordRange *)(p.wt.word_thr + ((rows * ix->dev.row_words + 15) & ~(size_t)15));
         p.warp_smem = (uint32_t)sg::bitmap_warp_smem(k);
         if ((size_t)p.warp_smem * 8 > ix->smem_optin) return fail(SG_ERR_INVALID, "k too large for the shared-memory top-k");
-        SG_CUDA(sg::launch_bitmap_search(ix->dev, p, ix->sm_count, stream));
+        SG_CUDA(sg::launch_bitmap_search(ix->dev, p, ix->sm_count, stream, stage_events));
         g_launches.fetch_add(3, std::memory_order_relaxed);  // sg_window_kernel + sg_tokens_kernel + sg_bitmap_search_kernel
         return SG_OK;
     }
-    SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream));
+    SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream, stage_events));
     g_launches.fetch_add(2, std::memory_order_relaxed);  // sg_plan_kernel + sg_search_kernel
     return SG_OK;
 }
@@ -575,6 +575,40 @@ int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *
     cudaError_t fe = cudaFreeAsync(plans, (cudaStream_t)stream);
     if (rc == SG_OK && fe != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(fe));
     return rc;
+}
+
+int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
+                          uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream,
+                          float *ms_out, char *names_out, uint32_t names_cap) {
+    int rc = validate_search(ix, n_q, metric, alpha, k);
+    if (rc != SG_OK) return rc;
+    if (n_q == 0 || !ms_out) return fail(SG_ERR_INVALID, "empty batch or null output");
+    if (!d_q_off || !d_out_ids || !d_out_scores || !d_out_counts) return fail(SG_ERR_INVALID, "null buffer");
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (auto &e : ev) SG_CUDA(cudaEventCreate(&e));
+    const uint32_t slot = ix->work_rr.fetch_add(1, std::memory_order_relaxed) & (kWorkRing - 1);
+    void *plans = nullptr;
+    const size_t plan_bytes = ((size_t)n_q * ix->plan_stride + 255) & ~(size_t)255;
+    SG_CUDA(cudaMalloc(&plans, plan_bytes + ix->wtab_bytes));
+    rc = enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, nullptr,
+                        ix->work_ring + slot, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, st, 0, ev);
+    cudaError_t se = cudaStreamSynchronize(st);
+    const int n_stages = ix->bitmap_engine ? 3 : 2;
+    if (rc == SG_OK && se == cudaSuccess)
+        for (int i = 0; i < n_stages; i++) cudaEventElapsedTime(ms_out + i, ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    cudaFree(plans);
+    if (rc != SG_OK) return rc;
+    if (se != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(se));
+    if (names_out && names_cap) {
+        const char *names = ix->bitmap_engine ? "sg_window_kernel,sg_tokens_kernel,sg_bitmap_search_kernel" : "sg_plan_kernel,sg_search_kernel";
+        std::strncpy(names_out, names, names_cap - 1);
+        names_out[names_cap - 1] = 0;
+    }
+    return n_stages;
 }
 
 int sg_merge_topk_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *d_part_ids,

@@ -31,9 +31,33 @@ namespace {
 constexpr int kWindowThreads = 128;
 constexpr int kBitmapWarps = 8;            // warps per CTA of sg_bitmap_search_kernel
 constexpr int kResolveSlots = 1 << kMaxBucketShift;
-// per-warp shared memory: [row offset of every list (136 x 4) | term id of every list (128 x 4) | resolve counters (256 x 4) | top-k]
 constexpr uint32_t kRowSlots = kMaxQueryTokens + 8;  // padded to a multiple of 8 with the all-zero row
-constexpr uint32_t kBitmapWarpFixedSmem = kRowSlots * 4 + kMaxQueryTokens * 4 + kResolveSlots * 4;
+
+// Per-warp shared memory of sg_bitmap_search_kernel.  The count loop itself only reads `row`; everything else belongs to
+// the cold path (a bucket reached its threshold), which keeps its state here so that the hot loop's registers stay free.
+struct WarpSmem {
+    int32_t tk_len;                    // candidates in the top-k
+    int32_t cur_seg;                   // segment cursor: flagged buckets arrive in ascending order
+    int32_t size_a, n_lists;
+    uint32_t pad[12];
+    uint32_t flag[32];                 // per lane: buckets of its word that reached the threshold
+    uint32_t bias[32];                 // per lane: 2^M - T(word), what the planes started from
+    alignas(16) uint32_t row[kRowSlots];   // word offset of the bitmap row of every list
+    uint32_t term[kMaxQueryTokens];    // term id of every list
+    uint32_t cnt[kResolveSlots];       // bshift > 0: per-document counters of the bucket being resolved;
+                                       // bshift = 0: the planes of every lane, cnt[j * 32 + lane]
+};
+constexpr uint32_t kBitmapWarpFixedSmem = (uint32_t)sizeof(WarpSmem);
+static_assert(sizeof(WarpSmem) % 16 == 0, "top-k scores follow and need 8-byte alignment");
+
+// What the cold path needs of the kernel arguments, copied once per CTA (a noinline callee cannot take the address of
+// a kernel parameter without a local copy per thread).
+struct BlockConsts {
+    const uint32_t *postings, *list_off, *perm, *seg_start;
+    const uint8_t *seg_thr;   // WindowTables::seg_thr
+    uint32_t n_segments, bshift, id_base, k;
+    int32_t metric;
+};
 
 // carry-save adder: (h, l) = a + b + c per bit position; two LOP3
 __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32_t b, uint32_t c) {
@@ -42,118 +66,145 @@ __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32
     l = u ^ c;
 }
 
-// planes += x (one more list), rippling the carry up
-template <int M>
-__device__ __forceinline__ void add_one(uint32_t (&c)[M], uint32_t x) {
-#pragma unroll
-    for (int j = 0; j < M; j++) {
-        const uint32_t t = c[j] & x;
-        c[j] ^= x;
-        x = t;
-    }
-}
+__device__ __forceinline__ double *warp_tk_score(WarpSmem *ws) { return (double *)(ws + 1); }
+__device__ __forceinline__ uint32_t *warp_tk_id(WarpSmem *ws, uint32_t k) { return (uint32_t *)(warp_tk_score(ws) + k); }
 
-// bits whose M-plane count is >= T (T in 1..255, per lane)
-template <int M>
-__device__ __forceinline__ uint32_t planes_ge(const uint32_t (&c)[M], uint32_t T) {
-    uint32_t gt = 0u, eq = 0xFFFFFFFFu;
-#pragma unroll
-    for (int j = M - 1; j >= 0; j--) {
-        const uint32_t tj = 0u - ((T >> j) & 1u);
-        gt |= eq & c[j] & ~tj;
-        eq &= ~(c[j] ^ tj);
-    }
-    return (T >> M) ? 0u : (gt | eq);
-}
-
-template <int M>
-__device__ __forceinline__ int planes_count(const uint32_t (&c)[M], int bit) {
-    int n = 0;
-#pragma unroll
-    for (int j = 0; j < M; j++) n |= (int)((c[j] >> bit) & 1u) << j;
-    return n;
-}
-
-// Per-query, warp-uniform state of the search kernel.
-struct BitmapQuery {
+// A document (new id) of segment size_b with an exact overlap count >= T: score it and offer it to the warp's sorted
+// top-k (best first, Candidate.Less of pkg/suggest/collector.go:20-26).  All lanes call with identical arguments.
+__device__ void offer_candidate(const BlockConsts *bc, WarpSmem *ws, uint32_t new_id, int count, int size_b, int lane) {
+    const uint32_t id = __ldg(bc->perm + new_id);
+    // FirstKCollectorManager.Collect scores a position with -position (pkg/suggest/collector.go:104-106)
+    const double score = bc->metric == kAutocomplete ? -(double)(bc->id_base + id) : metric_score(bc->metric, count, ws->size_a, size_b);
     QueryCtx c;
-    int n_lists;
-    int cur_seg;       // segment cursor: flagged buckets arrive in ascending order
-    const uint8_t *seg_thr;  // row len(tokens) of WindowTables::seg_thr
-};
-
-// segment that owns `bucket` (ascending calls within a query): seg_start[B] <= bucket << bshift < seg_start[B + 1]
-__device__ __forceinline__ int segment_of(const DevIndex &ix, BitmapQuery &bq, uint32_t bucket) {
-    const uint32_t id = bucket << ix.bshift;
-    int B = bq.cur_seg;
-    if (__ldg(ix.seg_start + B + 1) <= id) {
-        int lo = B + 1, hi = (int)ix.n_segments - 1;  // first segment whose end is above id
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(ix.seg_start + mid + 1) <= id) lo = mid + 1; else hi = mid;
-        }
-        B = lo;
-        bq.cur_seg = B;
-    }
-    return B;
-}
-
-// A bucket of bshift > 0 whose list count reached its segment's threshold: count every document of the bucket exactly.
-// Lane l takes lists l, l + 32, ...: the (term, segment) posting list is searched for the bucket's id range and every
-// posting inside adds one to its document's counter; then the counters are compared with T and the survivors offered.
-__device__ __noinline__ void resolve_bucket_exact(const DevIndex &ix, BitmapQuery &bq, const uint32_t *s_term, uint32_t *s_cnt,
-                                                  uint32_t bucket, int B, int T, int lane) {
-    const uint32_t width = 1u << ix.bshift;
-    const uint32_t id_lo = bucket << ix.bshift, id_hi = id_lo + width;
-    for (uint32_t i = lane; i < width; i += 32) s_cnt[i] = 0u;
+    c.k = bc->k;
+    c.tk_len = ws->tk_len;
+    c.tk_score = warp_tk_score(ws);
+    c.tk_id = warp_tk_id(ws, bc->k);
+    topk_insert(c, score, id, lane);
     __syncwarp();
-    const uint32_t *__restrict__ postings = ix.postings;
-    const size_t stride = (size_t)ix.n_segments + 1;
-    for (int j = lane; j < bq.n_lists; j += 32) {
-        const uint32_t *o = ix.list_off + (size_t)s_term[j] * stride + B;
-        const uint32_t b = __ldg(o + 1);
-        uint32_t pos = lower_bound(postings, __ldg(o), b, id_lo);
-        for (; pos < b; pos++) {
-            const uint32_t x = __ldg(postings + pos);
-            if (x >= id_hi) break;
-            atomicAdd(s_cnt + (x - id_lo), 1u);
-        }
-    }
-    __syncwarp();
-    for (uint32_t base = 0; base < width; base += 32) {
-        const uint32_t v = base + lane < width ? s_cnt[base + lane] : 0u;
-        unsigned m = __ballot_sync(kFull, v >= (uint32_t)T);
-        while (m) {
-            const int i = __ffs(m) - 1;
-            m &= m - 1;
-            emit_candidate(ix, bq.c, id_lo + base + (uint32_t)i, (int)__shfl_sync(kFull, v, i), B, T, lane);
-        }
-    }
+    if (lane == 0) ws->tk_len = c.tk_len;
     __syncwarp();
 }
 
-// One tile of 32 bitmap words (lane l owns word w0 + l): add the words of all lists, compare, handle the hits.
+// Buckets that reached the threshold of their word in the tile starting at word w0 (ws->flag, per lane).  For every one:
+// find its segment and that segment's own threshold; bshift = 0: the planes give the overlap (ws->cnt, ws->bias);
+// bshift > 0: count every document of the bucket exactly - lane l takes lists l, l + 32, ..., searches the (term, segment)
+// posting list for the bucket's id range and adds one to the counter of every document found - then offer the survivors.
+__device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, uint32_t w0, int M, int lane) {
+    const uint32_t bshift = bc->bshift;
+    const uint8_t *seg_thr = bc->seg_thr + (size_t)ws->size_a * bc->n_segments;
+    const uint32_t *__restrict__ seg_start = bc->seg_start;
+    const int n_lists = ws->n_lists;
+    for (int src = 0; src < 32; src++) {
+        uint32_t f = ws->flag[src];
+        while (f) {
+            const int bit = __ffs(f) - 1;
+            f &= f - 1;
+            const uint32_t bucket = (w0 + (uint32_t)src) * 32u + (uint32_t)bit;
+            const uint32_t id_lo = bucket << bshift;
+            int B = ws->cur_seg;
+            if (__ldg(seg_start + B + 1) <= id_lo) {
+                int lo = B + 1, hi = (int)bc->n_segments - 1;  // first segment whose end is above id_lo
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(seg_start + mid + 1) <= id_lo) lo = mid + 1; else hi = mid;
+                }
+                B = lo;
+                __syncwarp();
+                if (lane == 0) ws->cur_seg = B;
+            }
+            const int T = (int)__ldg(seg_thr + B);
+            if (T == 0) continue;  // the word's threshold came from a neighbouring segment
+            if (bshift == 0) {
+                int count = (1 << M) - (int)ws->bias[src];  // the planes hold bias + overlap - 2^M
+                for (int j = 0; j < M; j++) count += (int)((ws->cnt[j * 32 + src] >> bit) & 1u) << j;
+                if (count >= T) offer_candidate(bc, ws, bucket, count, B, lane);
+                continue;
+            }
+            const uint32_t width = 1u << bshift, id_hi = id_lo + width;
+            for (uint32_t i = lane; i < width; i += 32) ws->cnt[i] = 0u;
+            __syncwarp();
+            const uint32_t *__restrict__ postings = bc->postings;
+            const size_t stride = (size_t)bc->n_segments + 1;
+            for (int j = lane; j < n_lists; j += 32) {
+                const uint32_t *o = bc->list_off + (size_t)ws->term[j] * stride + B;
+                const uint32_t e = __ldg(o + 1);
+                for (uint32_t pos = lower_bound(postings, __ldg(o), e, id_lo); pos < e; pos++) {
+                    const uint32_t x = __ldg(postings + pos);
+                    if (x >= id_hi) break;
+                    atomicAdd(ws->cnt + (x - id_lo), 1u);
+                }
+            }
+            __syncwarp();
+            for (uint32_t base = 0; base < width; base += 32) {
+                const uint32_t v = base + lane < width ? ws->cnt[base + lane] : 0u;
+                unsigned m = __ballot_sync(kFull, v >= (uint32_t)T);
+                while (m) {
+                    const int i = __ffs(m) - 1;
+                    m &= m - 1;
+                    offer_candidate(bc, ws, id_lo + base + (uint32_t)i, (int)__shfl_sync(kFull, v, i), B, lane);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// The count loop of one query.  The window is walked in tiles of 32 bitmap words (lane l owns word w0 + l of every
+// row); inside a tile the lists are taken in blocks of 8 (the tail is padded with the all-zero row): seven carry-save
+// adders turn the eight words into one carry of weight 8, which ripples into the planes above.  The planes start at
+// bias = 2^M - T(word), so "count >= T" is the carry out of the top plane (kept sticky in ov) and no comparison is needed.
+// Loads run one block ahead of the adders (xa / xb), across tile boundaries, so every warp keeps 8-16 independent
+// 128-byte row reads in flight.
+// Returns the first word of the first tile in which a bucket reached its threshold, with every lane's flags (and, for
+// bshift = 0, planes) saved in ws for handle_flags, or kInf when the window is done.  The caller resumes behind that
+// tile: the cold path is called from outside this loop so that its registers do not add to the loop's.
 template <int M>
-__device__ __forceinline__ void search_tile(const DevIndex &ix, BitmapQuery &bq, const uint32_t *s_row, const uint32_t *s_term,
-                                            uint32_t *s_cnt, const uint8_t *__restrict__ word_thr, uint32_t w0, WordRange win, int lane) {
-    const uint32_t W = w0 + (uint32_t)lane;
-    const uint32_t *__restrict__ bm = ix.bitmaps + W;
-    const uint32_t T_w = __ldg(word_thr + W);
-    uint32_t c[M];
+__device__ __forceinline__ uint32_t count_until_flag(const uint32_t *__restrict__ bitmaps, bool keep_planes, WarpSmem *ws,
+                                                     const uint8_t *__restrict__ word_thr, uint32_t w_begin, uint32_t win_hi,
+                                                     int n_lists, int lane) {
+    const uint32_t *s_row = ws->row;
+    const uint32_t n_blocks = ((uint32_t)n_lists + 7u) >> 3;
+    const uint32_t n_units = ((win_hi - w_begin + 31u) >> 5) * n_blocks;
+    // loader state: this lane's word of the tile being loaded, next block to load
+    const uint32_t *ld_ptr = bitmaps + w_begin + (uint32_t)lane;
+    asm volatile("" : "+l"(ld_ptr));  // opaque: row offsets are added to this pointer as 32-bit indices (one IMAD.WIDE per load)
+    uint32_t ld_block = 0;
+    // (macros, not lambdas over array references: the word registers must stay registers)
+#define SG_LOAD_BLOCK(R)                                                                                       \
+    do {                                                                                                      \
+        const uint4 r0_ = *(const uint4 *)(s_row + ld_block * 8u), r1_ = *(const uint4 *)(s_row + ld_block * 8u + 4u); \
+        R##0 = __ldg(ld_ptr + r0_.x);                                                                         \
+        R##1 = __ldg(ld_ptr + r0_.y);                                                                         \
+        R##2 = __ldg(ld_ptr + r0_.z);                                                                         \
+        R##3 = __ldg(ld_ptr + r0_.w);                                                                         \
+        R##4 = __ldg(ld_ptr + r1_.x);                                                                         \
+        R##5 = __ldg(ld_ptr + r1_.y);                                                                         \
+        R##6 = __ldg(ld_ptr + r1_.z);                                                                         \
+        R##7 = __ldg(ld_ptr + r1_.w);                                                                         \
+        if (++ld_block == n_blocks) {                                                                         \
+            ld_block = 0;                                                                                     \
+            ld_ptr += 32;                                                                                     \
+            asm volatile("" : "+l"(ld_ptr));                                                                  \
+        }                                                                                                     \
+    } while (0)
+    // adder state
+    uint32_t c[M], ov = 0u, bias, w0 = w_begin, cons_block = 0;
+    const uint8_t *thr_ptr = word_thr + w_begin + (uint32_t)lane;  // this lane's word of the tile being added
+    uint32_t tw_next;                                              // its threshold in the next tile, loaded a tile ahead
+    auto begin_tile = [&](uint32_t T_w) {
+        bias = (T_w >> M) ? 0u : (1u << M) - T_w;  // a threshold no count can reach: the planes never overflow
 #pragma unroll
-    for (int j = 0; j < M; j++) c[j] = 0u;
-    // lists in blocks of 8 (the tail is padded with the all-zero row): seven carry-save adders turn eight words into one
-    // carry of weight 8, which ripples into the planes above
-    for (int j0 = 0; j0 < bq.n_lists; j0 += 8) {
-        uint32_t x[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) x[i] = __ldg(bm + s_row[j0 + i]);
+        for (int j = 0; j < M; j++) c[j] = 0u - ((bias >> j) & 1u);
+        ov = 0u;
+    };
+    auto consume = [&](uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5, uint32_t x6, uint32_t x7) -> bool {
         uint32_t tA, tB, tC, tD, fA, fB, e;
-        csa(tA, c[0], c[0], x[0], x[1]);
-        csa(tB, c[0], c[0], x[2], x[3]);
+        csa(tA, c[0], c[0], x0, x1);
+        csa(tB, c[0], c[0], x2, x3);
         csa(fA, c[1], c[1], tA, tB);
-        csa(tC, c[0], c[0], x[4], x[5]);
-        csa(tD, c[0], c[0], x[6], x[7]);
+        csa(tC, c[0], c[0], x4, x5);
+        csa(tD, c[0], c[0], x6, x7);
         csa(fB, c[1], c[1], tC, tD);
         csa(e, c[2], c[2], fA, fB);
 #pragma unroll
@@ -162,30 +213,42 @@ __device__ __forceinline__ void search_tile(const DevIndex &ix, BitmapQuery &bq,
             c[j] ^= e;
             e = t;
         }
-    }
-    uint32_t flag = planes_ge<M>(c, T_w);
-    if (W < win.x || W >= win.y) flag = 0u;
-    unsigned bal;
-    while ((bal = __ballot_sync(kFull, flag != 0u)) != 0u) {
-        const int src = __ffs(bal) - 1;
-        uint32_t f = __shfl_sync(kFull, flag, src);
-        if (lane == src) flag = 0u;
-        uint32_t cs[M];
-        if (ix.bshift == 0) {
+        ov |= e;
+        if (++cons_block == n_blocks) {
+            if (__any_sync(kFull, ov != 0u)) {  // rare: hand the tile to the cold path through shared memory
+                ws->flag[lane] = ov;
+                ws->bias[lane] = bias;
+                if (keep_planes) {
 #pragma unroll
-            for (int j = 0; j < M; j++) cs[j] = __shfl_sync(kFull, c[j], src);
+                    for (int j = 0; j < M; j++) ws->cnt[j * 32 + lane] = c[j];
+                }
+                __syncwarp();
+                return true;
+            }
+            cons_block = 0;
+            w0 += 32;
+            thr_ptr += 32;
+            begin_tile(tw_next);
+            tw_next = w0 + 32u < win_hi ? __ldg(thr_ptr + 32) : 255u;
         }
-        while (f) {
-            const int bit = __ffs(f) - 1;
-            f &= f - 1;
-            const uint32_t bucket = (w0 + (uint32_t)src) * 32u + (uint32_t)bit;
-            const int B = segment_of(ix, bq, bucket);
-            const int T = (int)__ldg(bq.seg_thr + B);
-            if (T == 0) continue;  // the word's threshold came from a neighbouring segment
-            if (ix.bshift == 0) emit_candidate(ix, bq.c, bucket, planes_count<M>(cs, bit), B, T, lane);
-            else resolve_bucket_exact(ix, bq, s_term, s_cnt, bucket, B, T, lane);
-        }
+        return false;
+    };
+    uint32_t xa0, xa1, xa2, xa3, xa4, xa5, xa6, xa7, xb0, xb1, xb2, xb3, xb4, xb5, xb6, xb7;
+    xb0 = xb1 = xb2 = xb3 = xb4 = xb5 = xb6 = xb7 = 0u;
+    begin_tile(__ldg(thr_ptr));
+    tw_next = w0 + 32u < win_hi ? __ldg(thr_ptr + 32) : 255u;
+    SG_LOAD_BLOCK(xa);
+#pragma unroll 1
+    for (uint32_t u = 0;;) {
+        if (u + 1 < n_units) SG_LOAD_BLOCK(xb);
+        if (consume(xa0, xa1, xa2, xa3, xa4, xa5, xa6, xa7)) return w0;
+        if (++u == n_units) break;
+        if (u + 1 < n_units) SG_LOAD_BLOCK(xa);
+        if (consume(xb0, xb1, xb2, xb3, xb4, xb5, xb6, xb7)) return w0;
+        if (++u == n_units) break;
     }
+#undef SG_LOAD_BLOCK
+    return kInf;
 }
 
 }  // namespace
@@ -291,78 +354,87 @@ __global__ void __launch_bounds__(kPlanThreads) sg_tokens_kernel(const DevIndex 
 // ---------------------------------------------------------------------------------------------------------------
 // sg_bitmap_search_kernel: one warp per query, query numbers from a global counter.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBitmapWarps * 32) sg_bitmap_search_kernel(const DevIndex ix, const SearchParams p) {
+__global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(const DevIndex ix, const SearchParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ BlockConsts s_bc;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    uint8_t *wsm = smem + (size_t)warp * p.warp_smem;
-    uint32_t *s_row = (uint32_t *)wsm;                 // [136] word offset of the bitmap row of every list
-    uint32_t *s_term = s_row + kRowSlots;              // [128] term id of every list
-    uint32_t *s_cnt = s_term + kMaxQueryTokens;        // [256] per-document counters of the bucket being resolved
-    double *tk_score = (double *)(s_cnt + kResolveSlots);  // [k]
-    uint32_t *tk_id = (uint32_t *)(tk_score + p.k);    // [k]
+    if (threadIdx.x == 0) {
+        s_bc.postings = ix.postings;
+        s_bc.list_off = ix.list_off;
+        s_bc.perm = ix.perm;
+        s_bc.seg_start = ix.seg_start;
+        s_bc.seg_thr = p.wt.seg_thr;
+        s_bc.n_segments = ix.n_segments;
+        s_bc.bshift = ix.bshift;
+        s_bc.id_base = ix.id_base;
+        s_bc.k = p.k;
+        s_bc.metric = p.mode == 1 ? (int)kAutocomplete : p.metric;
+    }
+    __syncthreads();
+    WarpSmem *ws = (WarpSmem *)(smem + (size_t)warp * p.warp_smem);
+    const double *tk_score = warp_tk_score(ws);
+    const uint32_t *tk_id = warp_tk_id(ws, p.k);
     const uint32_t zero_row = ix.n_terms * ix.row_words;
 
-    for (;;) {
-        uint32_t q = 0;
-        if (lane == 0) q = atomicAdd(p.work_counter, 1u);
-        q = __shfl_sync(kFull, q, 0);
-        if (q >= p.n_q) break;
+    uint32_t q = 0;
+    if (lane == 0) q = atomicAdd(p.work_counter, 1u);
+    q = __shfl_sync(kFull, q, 0);
+    while (q < p.n_q) {
+        uint32_t q_next = 0;
+        if (lane == 0) q_next = atomicAdd(p.work_counter, 1u);  // the next query number arrives while this one is searched
 
         const uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
         const uint4 h0 = __ldg((const uint4 *)plan_base);  // TokenPlan
-        BitmapQuery bq;
-        bq.c.metric = p.mode == 1 ? (int)kAutocomplete : p.metric;
-        bq.c.alpha = p.alpha;
-        bq.c.k = p.k;
-        bq.c.tk_len = 0;
-        bq.c.tk_score = tk_score;
-        bq.c.tk_id = tk_id;
-        bq.c.size_a = (int)h0.y;
-        bq.c.b_lo = 0;
-        bq.c.b_hi = -1;
-        bq.n_lists = (int)h0.z;
-        bq.cur_seg = 0;
-        bq.seg_thr = p.wt.seg_thr + (size_t)bq.c.size_a * ix.n_segments;
         const bool unsupported = h0.x != 0u;
-        const WordRange win = p.wt.win[bq.c.size_a];
+        const int size_a = (int)h0.y, n_lists = (int)h0.z;
+        const WordRange win = p.wt.win[size_a];
+        int tk_len = 0;
 
-        if (bq.n_lists > 0 && win.y > win.x) {
-            const int n_pad = (bq.n_lists + 7) & ~7;
+        if (n_lists > 0 && win.y > win.x) {
+            if (lane == 0) { ws->tk_len = 0; ws->cur_seg = 0; ws->size_a = size_a; ws->n_lists = n_lists; }
+            const int n_pad = (n_lists + 7) & ~7;
             for (int j = lane; j < n_pad; j += 32) {
                 uint32_t row = zero_row;
-                if (j < bq.n_lists) {
+                if (j < n_lists) {
                     const uint32_t t = __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + j);
-                    s_term[j] = t;
+                    ws->term[j] = t;
                     row = t * ix.row_words;
                 }
-                s_row[j] = row;
+                ws->row[j] = row;
             }
             __syncwarp();
-            const uint8_t *word_thr = p.wt.word_thr + (size_t)bq.c.size_a * ix.row_words;
-            if (bq.n_lists < 32) {
-                for (uint32_t w0 = win.x & ~31u; w0 < win.y; w0 += 32) search_tile<5>(ix, bq, s_row, s_term, s_cnt, word_thr, w0, win, lane);
-            } else {
-                for (uint32_t w0 = win.x & ~31u; w0 < win.y; w0 += 32) search_tile<8>(ix, bq, s_row, s_term, s_cnt, word_thr, w0, win, lane);
+            const uint8_t *word_thr = p.wt.word_thr + (size_t)size_a * ix.row_words;
+            const bool keep_planes = ix.bshift == 0;
+            for (uint32_t w = win.x & ~31u; w < win.y;) {
+                const int M = n_lists < 32 ? 5 : 8;
+                const uint32_t wf = M == 5 ? count_until_flag<5>(ix.bitmaps, keep_planes, ws, word_thr, w, win.y, n_lists, lane)
+                                           : count_until_flag<8>(ix.bitmaps, keep_planes, ws, word_thr, w, win.y, n_lists, lane);
+                if (wf == kInf) break;
+                handle_flags(&s_bc, ws, wf, M, lane);
+                w = wf + 32u;
             }
+            __syncwarp();
+            tk_len = ws->tk_len;
         }
 
         // results: GetCandidates order, fixed stride k
         const size_t row = (size_t)q * p.k;
         for (uint32_t j = lane; j < p.k; j += 32) {
-            const bool has = (int)j < bq.c.tk_len;
+            const bool has = (int)j < tk_len;
             p.out_ids[row + j] = has ? ix.id_base + tk_id[j] : 0u;
             p.out_scores[row + j] = has ? tk_score[j] : 0.0;
         }
-        if (lane == 0) p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)bq.c.tk_len;
-        __syncwarp();
+        if (lane == 0) p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)tk_len;
+        q = __shfl_sync(kFull, q_next, 0);
     }
 }
 
 // ---------------- launcher (host) ----------------
 size_t bitmap_warp_smem(uint32_t k) { return ((size_t)kBitmapWarpFixedSmem + (size_t)k * 12u + 15u) & ~(size_t)15u; }
 
-cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, cudaStream_t stream) {
+cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, cudaStream_t stream,
+                                 cudaEvent_t *stage_events) {
     const size_t smem = (size_t)kBitmapWarps * p.warp_smem;
     cudaError_t e = cudaFuncSetAttribute(sg_bitmap_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -370,17 +442,21 @@ cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int 
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_bitmap_search_kernel, kBitmapWarps * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    if (stage_events) cudaEventRecord(stage_events[0], stream);
     sg_window_kernel<<<kWindowRows, kWindowThreads, 0, stream>>>(ix, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (stage_events) cudaEventRecord(stage_events[1], stream);
     const int tok_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
     sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (stage_events) cudaEventRecord(stage_events[2], stream);
     int blocks = sm_count * per_sm;
     const int need = (int)((p.n_q + kBitmapWarps - 1) / kBitmapWarps);
     if (blocks > need) blocks = need;
     sg_bitmap_search_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, p);
+    if (stage_events) cudaEventRecord(stage_events[3], stream);
     return cudaGetLastError();
 }
 

@@ -517,14 +517,17 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
 
 // ---------------- launchers (host) ----------------
 cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks, int warps_per_block, size_t smem_bytes,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, cudaEvent_t *stage_events) {
     cudaError_t e = cudaFuncSetAttribute(sg_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) return e;
     const int plan_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
+    if (stage_events) cudaEventRecord(stage_events[0], stream);
     sg_plan_kernel<<<plan_blocks < 148 * 8 ? plan_blocks : 148 * 8, kPlanThreads, 0, stream>>>(ix, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (stage_events) cudaEventRecord(stage_events[1], stream);
     sg_search_kernel<<<blocks, warps_per_block * 32, smem_bytes, stream>>>(ix, p);
+    if (stage_events) cudaEventRecord(stage_events[2], stream);
     return cudaGetLastError();
 }
 

@@ -6,11 +6,13 @@
 
 namespace sg {
 
+// stage_events (optional): n_kernels + 1 events recorded before, between and after the kernels of the launch
 cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks, int warps_per_block, size_t smem_bytes,
-                          cudaStream_t stream);
+                          cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
 // bitmap engine (sg_bitmap.cu): sg_window_kernel + sg_tokens_kernel + sg_bitmap_search_kernel; p.warp_smem = bitmap_warp_smem(k)
 size_t bitmap_warp_smem(uint32_t k);
-cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, cudaStream_t stream);
+cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, cudaStream_t stream,
+                                 cudaEvent_t *stage_events = nullptr);
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
                               const uint32_t *part_counts, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
                               int blocks, cudaStream_t stream);

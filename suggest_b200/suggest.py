@@ -223,6 +223,15 @@ class NGramIndex:
         _capi.check(rc)
 
 
+    def StageTimes(self, d_q_bytes, d_q_off, n_q, similarity, metric, topK, d_ids, d_scores, d_counts, stream=0):
+        """sg_search_stage_times: {kernel name: ms} of one device-resident launch (CUDA events between its kernels)."""
+        ms = (C.c_float * 4)()
+        names = C.create_string_buffer(256)
+        n = _capi.check(_capi.lib().sg_search_stage_times(self.handle, d_q_bytes, d_q_off, n_q, metric.code, float(similarity),
+                                                          int(topK), d_ids, d_scores, d_counts, stream or None, ms, names, 256))
+        return dict(zip(names.value.decode().split(","), [float(ms[i]) for i in range(n)]))
+
+
 class Builder:
     """suggest.Builder, pkg/suggest/ngram_index_builder.go:14-17"""
 

@@ -13,7 +13,7 @@ echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_bench.log 2>&1 ; echo "ncu1 rc=$?"
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:sg_search_kernel -s 2 -c 1 -f -o $OUT/prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-sg_bitmap_search_kernel} -s 2 -c 1 -f -o $OUT/prof \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1 ; echo "ncu2 rc=$?"
 ls -la $OUT
 fi
