@@ -32,14 +32,16 @@ constexpr int kWindowThreads = 128;
 constexpr int kBitmapWarps = 8;            // warps per CTA of sg_bitmap_search_kernel
 constexpr int kResolveSlots = 1 << kMaxBucketShift;
 constexpr uint32_t kRowSlots = kMaxQueryTokens + 8;  // padded to a multiple of 8 with the all-zero row
+constexpr uint32_t kTileWords = 32;        // bitmap words per tile: lane l owns word l
+constexpr int kSegCache = 256;             // segment starts kept in shared memory per CTA
 
-// Per-warp shared memory of sg_bitmap_search_kernel.  The count loop itself only reads `row`; everything else belongs to
-// the cold path (a bucket reached its threshold), which keeps its state here so that the hot loop's registers stay free.
+// Per-warp shared memory of sg_bitmap_search_kernel.  The count loop itself only reads `row`; everything
+// else belongs to the cold path (a bucket reached its threshold), which keeps its state here so that the hot loop's
+// registers stay free.
 struct WarpSmem {
     int32_t tk_len;                    // candidates in the top-k
-    int32_t cur_seg;                   // segment cursor: flagged buckets arrive in ascending order
     int32_t size_a, n_lists;
-    uint32_t pad[12];
+    uint32_t pad[13];
     uint32_t flag[32];                 // per lane: buckets of its word that reached the threshold
     uint32_t bias[32];                 // per lane: 2^M - T(word), what the planes started from
     alignas(16) uint32_t row[kRowSlots];   // word offset of the bitmap row of every list
@@ -57,6 +59,7 @@ struct BlockConsts {
     const uint8_t *seg_thr;   // WindowTables::seg_thr
     uint32_t n_segments, bshift, id_base, k;
     int32_t metric;
+    uint32_t seg_cache[kSegCache + 1];  // seg_start[0 .. min(S, kSegCache)]
 };
 
 // carry-save adder: (h, l) = a + b + c per bit position; two LOP3
@@ -86,33 +89,62 @@ __device__ void offer_candidate(const BlockConsts *bc, WarpSmem *ws, uint32_t ne
     __syncwarp();
 }
 
-// Buckets that reached the threshold of their word in the tile starting at word w0 (ws->flag, per lane).  For every one:
-// find its segment and that segment's own threshold; bshift = 0: the planes give the overlap (ws->cnt, ws->bias);
-// bshift > 0: count every document of the bucket exactly - lane l takes lists l, l + 32, ..., searches the (term, segment)
-// posting list for the bucket's id range and adds one to the counter of every document found - then offer the survivors.
+// segment that owns new id `id`: seg_start[B] <= id < seg_start[B + 1]
+__device__ __forceinline__ int segment_of_id(const BlockConsts *bc, uint32_t id) {
+    int lo = 0, hi = (int)bc->n_segments - 1;  // first segment whose end is above id
+    const int cached = min((int)bc->n_segments, kSegCache);
+    if (bc->seg_cache[cached] > id) {
+        hi = cached - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (bc->seg_cache[mid + 1] <= id) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    }
+    lo = cached;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(bc->seg_start + mid + 1) <= id) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// first position in [a, b) whose posting is >= x; four probes per step, so a list of 64 takes three dependent loads
+__device__ __forceinline__ uint32_t lower_bound4(const uint32_t *__restrict__ postings, uint32_t a, uint32_t b, uint32_t x) {
+    while (b - a > 4) {
+        const uint32_t q = (b - a) / 5 + 1;
+        const uint32_t p1 = a + q - 1, p2 = p1 + q, p3 = p2 + q, p4 = min(p3 + q, b - 1);
+        const uint32_t v1 = __ldg(postings + p1), v2 = __ldg(postings + p2), v3 = __ldg(postings + min(p3, b - 1)), v4 = __ldg(postings + p4);
+        if (v1 >= x) b = p1;
+        else if (v2 >= x) { a = p1 + 1; b = p2; }
+        else if (p3 >= b || v3 >= x) { a = p2 + 1; b = min(p3, b); }
+        else if (v4 >= x) { a = p3 + 1; b = p4; }
+        else a = p4 + 1;
+    }
+    while (a < b && __ldg(postings + a) < x) a++;
+    return a;
+}
+
+// Buckets that reached the threshold of their word (ws->flag, per lane) in the tile starting at word w0; lane l's flags
+// are about word w0 + l.  For every such bucket: find its segment and that segment's own threshold; bshift = 0:
+// the planes give the overlap (ws->cnt, ws->bias); bshift > 0: count every document of the bucket exactly - lane l takes
+// lists l, l + 32, ..., searches the (term, segment) posting list for the bucket's id range and adds one to the counter
+// of every document found - then offer the survivors to the top-k.
 __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, uint32_t w0, int M, int lane) {
     const uint32_t bshift = bc->bshift;
     const uint8_t *seg_thr = bc->seg_thr + (size_t)ws->size_a * bc->n_segments;
-    const uint32_t *__restrict__ seg_start = bc->seg_start;
     const int n_lists = ws->n_lists;
-    for (int src = 0; src < 32; src++) {
+    unsigned lanes = __ballot_sync(kFull, ws->flag[lane] != 0u);
+    while (lanes) {
+        const int src = __ffs(lanes) - 1;
+        lanes &= lanes - 1;
         uint32_t f = ws->flag[src];
         while (f) {
             const int bit = __ffs(f) - 1;
             f &= f - 1;
             const uint32_t bucket = (w0 + (uint32_t)src) * 32u + (uint32_t)bit;
             const uint32_t id_lo = bucket << bshift;
-            int B = ws->cur_seg;
-            if (__ldg(seg_start + B + 1) <= id_lo) {
-                int lo = B + 1, hi = (int)bc->n_segments - 1;  // first segment whose end is above id_lo
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (__ldg(seg_start + mid + 1) <= id_lo) lo = mid + 1; else hi = mid;
-                }
-                B = lo;
-                __syncwarp();
-                if (lane == 0) ws->cur_seg = B;
-            }
+            const int B = segment_of_id(bc, id_lo);
             const int T = (int)__ldg(seg_thr + B);
             if (T == 0) continue;  // the word's threshold came from a neighbouring segment
             if (bshift == 0) {
@@ -129,7 +161,7 @@ __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, u
             for (int j = lane; j < n_lists; j += 32) {
                 const uint32_t *o = bc->list_off + (size_t)ws->term[j] * stride + B;
                 const uint32_t e = __ldg(o + 1);
-                for (uint32_t pos = lower_bound(postings, __ldg(o), e, id_lo); pos < e; pos++) {
+                for (uint32_t pos = lower_bound4(postings, __ldg(o), e, id_lo); pos < e; pos++) {
                     const uint32_t x = __ldg(postings + pos);
                     if (x >= id_hi) break;
                     atomicAdd(ws->cnt + (x - id_lo), 1u);
@@ -151,92 +183,90 @@ __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, u
 }
 
 // The count loop of one query.  The window is walked in tiles of 32 bitmap words (lane l owns word w0 + l of every
-// row); inside a tile the lists are taken in blocks of 8 (the tail is padded with the all-zero row): seven carry-save
-// adders turn the eight words into one carry of weight 8, which ripples into the planes above.  The planes start at
-// bias = 2^M - T(word), so "count >= T" is the carry out of the top plane (kept sticky in ov) and no comparison is needed.
-// Loads run one block ahead of the adders (xa / xb), across tile boundaries, so every warp keeps 8-16 independent
-// 128-byte row reads in flight.
-// Returns the first word of the first tile in which a bucket reached its threshold, with every lane's flags (and, for
-// bshift = 0, planes) saved in ws for handle_flags, or kInf when the window is done.  The caller resumes behind that
-// tile: the cold path is called from outside this loop so that its registers do not add to the loop's.
+// row); inside a tile the lists are taken in blocks of 8.  Per block, seven carry-save adders turn the eight list words
+// into one carry of weight 8, which ripples into the planes above.  The planes start at bias = 2^M - T(word), so
+// "count >= T" is the carry out of the top plane (kept sticky in ov) and no comparison is needed.  Loads run one block
+// ahead of the adders (xa / xb), across tile boundaries, so every warp keeps 8-16 independent 128-byte row reads in
+// flight.  The last block of a tile may hold fewer than 8 lists: the missing words are zeros, not loads.
+// Returns the first word of the first tile in which a bucket reached its threshold, with the lane's flags, bias and
+// planes in ts, or kInf when the window is done.  The caller runs the cold path and resumes behind that tile: called
+// from outside this loop its registers do not add to the loop's.
 template <int M>
-__device__ __forceinline__ uint32_t count_until_flag(const uint32_t *__restrict__ bitmaps, bool keep_planes, WarpSmem *ws,
+struct TileState {
+    uint32_t c[M];   // planes of this lane's word
+    uint32_t ov, bias;
+};
+
+template <int M>
+__device__ __forceinline__ uint32_t count_until_flag(const uint32_t *__restrict__ bitmaps, const uint32_t *s_row,
                                                      const uint8_t *__restrict__ word_thr, uint32_t w_begin, uint32_t win_hi,
-                                                     int n_lists, int lane) {
-    const uint32_t *s_row = ws->row;
+                                                     int n_lists, int lane, TileState<M> &ts) {
     const uint32_t n_blocks = ((uint32_t)n_lists + 7u) >> 3;
-    const uint32_t n_units = ((win_hi - w_begin + 31u) >> 5) * n_blocks;
+    const uint32_t n_units = ((win_hi - w_begin + kTileWords - 1) / kTileWords) * n_blocks;
+    const uint32_t tail = (uint32_t)n_lists - (n_blocks - 1) * 8u;  // lists in the last block, 1..8
     // loader state: this lane's word of the tile being loaded, next block to load
     const uint32_t *ld_ptr = bitmaps + w_begin + (uint32_t)lane;
     asm volatile("" : "+l"(ld_ptr));  // opaque: row offsets are added to this pointer as 32-bit indices (one IMAD.WIDE per load)
     uint32_t ld_block = 0;
     // (macros, not lambdas over array references: the word registers must stay registers)
-#define SG_LOAD_BLOCK(R)                                                                                       \
+#define SG_LOAD_BLOCK(R)                                                                                      \
     do {                                                                                                      \
         const uint4 r0_ = *(const uint4 *)(s_row + ld_block * 8u), r1_ = *(const uint4 *)(s_row + ld_block * 8u + 4u); \
+        const uint32_t nv_ = ld_block + 1 == n_blocks ? tail : 8u;                                            \
         R##0 = __ldg(ld_ptr + r0_.x);                                                                         \
-        R##1 = __ldg(ld_ptr + r0_.y);                                                                         \
-        R##2 = __ldg(ld_ptr + r0_.z);                                                                         \
-        R##3 = __ldg(ld_ptr + r0_.w);                                                                         \
-        R##4 = __ldg(ld_ptr + r1_.x);                                                                         \
-        R##5 = __ldg(ld_ptr + r1_.y);                                                                         \
-        R##6 = __ldg(ld_ptr + r1_.z);                                                                         \
-        R##7 = __ldg(ld_ptr + r1_.w);                                                                         \
+        R##1 = nv_ > 1 ? __ldg(ld_ptr + r0_.y) : 0u;                                                          \
+        R##2 = nv_ > 2 ? __ldg(ld_ptr + r0_.z) : 0u;                                                          \
+        R##3 = nv_ > 3 ? __ldg(ld_ptr + r0_.w) : 0u;                                                          \
+        R##4 = nv_ > 4 ? __ldg(ld_ptr + r1_.x) : 0u;                                                          \
+        R##5 = nv_ > 5 ? __ldg(ld_ptr + r1_.y) : 0u;                                                          \
+        R##6 = nv_ > 6 ? __ldg(ld_ptr + r1_.z) : 0u;                                                          \
+        R##7 = nv_ > 7 ? __ldg(ld_ptr + r1_.w) : 0u;                                                          \
         if (++ld_block == n_blocks) {                                                                         \
             ld_block = 0;                                                                                     \
-            ld_ptr += 32;                                                                                     \
+            ld_ptr += kTileWords;                                                                             \
             asm volatile("" : "+l"(ld_ptr));                                                                  \
         }                                                                                                     \
     } while (0)
     // adder state
-    uint32_t c[M], ov = 0u, bias, w0 = w_begin, cons_block = 0;
-    const uint8_t *thr_ptr = word_thr + w_begin + (uint32_t)lane;  // this lane's word of the tile being added
-    uint32_t tw_next;                                              // its threshold in the next tile, loaded a tile ahead
+    uint32_t w0 = w_begin, cons_block = 0;
+    const uint8_t *thr_ptr = word_thr + w_begin + (uint32_t)lane;  // threshold of this lane's word of the tile being added
+    uint32_t tw_next;                                              // ... of the next tile, loaded a tile ahead
     auto begin_tile = [&](uint32_t T_w) {
-        bias = (T_w >> M) ? 0u : (1u << M) - T_w;  // a threshold no count can reach: the planes never overflow
+        ts.bias = (T_w >> M) ? 0u : (1u << M) - T_w;  // a threshold no count can reach: the planes never overflow
 #pragma unroll
-        for (int j = 0; j < M; j++) c[j] = 0u - ((bias >> j) & 1u);
-        ov = 0u;
+        for (int j = 0; j < M; j++) ts.c[j] = 0u - ((ts.bias >> j) & 1u);
+        ts.ov = 0u;
     };
     auto consume = [&](uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5, uint32_t x6, uint32_t x7) -> bool {
-        uint32_t tA, tB, tC, tD, fA, fB, e;
-        csa(tA, c[0], c[0], x0, x1);
-        csa(tB, c[0], c[0], x2, x3);
-        csa(fA, c[1], c[1], tA, tB);
-        csa(tC, c[0], c[0], x4, x5);
-        csa(tD, c[0], c[0], x6, x7);
-        csa(fB, c[1], c[1], tC, tD);
-        csa(e, c[2], c[2], fA, fB);
+        uint32_t h1, l1, h2, l2, h3, l3, h4, g1, m1, g2, e;
+        csa(h1, l1, x0, x1, x2);
+        csa(h2, l2, x3, x4, x5);
+        csa(h3, l3, x6, x7, ts.c[0]);
+        csa(h4, ts.c[0], l1, l2, l3);
+        csa(g1, m1, h1, h2, h3);
+        csa(g2, ts.c[1], m1, h4, ts.c[1]);
+        csa(e, ts.c[2], g1, g2, ts.c[2]);
 #pragma unroll
         for (int j = 3; j < M; j++) {
-            const uint32_t t = c[j] & e;
-            c[j] ^= e;
+            const uint32_t t = ts.c[j] & e;
+            ts.c[j] ^= e;
             e = t;
         }
-        ov |= e;
+        ts.ov |= e;
         if (++cons_block == n_blocks) {
-            if (__any_sync(kFull, ov != 0u)) {  // rare: hand the tile to the cold path through shared memory
-                ws->flag[lane] = ov;
-                ws->bias[lane] = bias;
-                if (keep_planes) {
-#pragma unroll
-                    for (int j = 0; j < M; j++) ws->cnt[j * 32 + lane] = c[j];
-                }
-                __syncwarp();
-                return true;
-            }
+            if (__any_sync(kFull, ts.ov != 0u)) return true;  // rare: the caller hands the tile to the cold path
             cons_block = 0;
-            w0 += 32;
-            thr_ptr += 32;
+            w0 += kTileWords;
+            thr_ptr += kTileWords;
             begin_tile(tw_next);
-            tw_next = w0 + 32u < win_hi ? __ldg(thr_ptr + 32) : 255u;
+            tw_next = w0 + kTileWords < win_hi ? __ldg(thr_ptr + kTileWords) : 255u;
         }
         return false;
     };
     uint32_t xa0, xa1, xa2, xa3, xa4, xa5, xa6, xa7, xb0, xb1, xb2, xb3, xb4, xb5, xb6, xb7;
     xb0 = xb1 = xb2 = xb3 = xb4 = xb5 = xb6 = xb7 = 0u;
     begin_tile(__ldg(thr_ptr));
-    tw_next = w0 + 32u < win_hi ? __ldg(thr_ptr + 32) : 255u;
+    tw_next = w0 + kTileWords < win_hi ? __ldg(thr_ptr + kTileWords) : 255u;
     SG_LOAD_BLOCK(xa);
 #pragma unroll 1
     for (uint32_t u = 0;;) {
@@ -249,6 +279,30 @@ __device__ __forceinline__ uint32_t count_until_flag(const uint32_t *__restrict_
     }
 #undef SG_LOAD_BLOCK
     return kInf;
+}
+
+// One query: count, and for every tile with a hit run the cold path.
+template <int M>
+__device__ __forceinline__ void search_query(const uint32_t *__restrict__ bitmaps, const BlockConsts *bc, WarpSmem *ws,
+                                             const uint8_t *__restrict__ word_thr, uint32_t win_lo, uint32_t win_hi, int n_lists,
+                                             int lane) {
+    const bool keep_planes = bc->bshift == 0;
+    for (uint32_t w = win_lo & ~(kTileWords - 1); w < win_hi;) {
+        TileState<M> ts;
+        const uint32_t wf = count_until_flag<M>(bitmaps, ws->row, word_thr, w, win_hi, n_lists, lane, ts);
+        if (wf == kInf) break;
+        // hand the tile over through shared memory
+        ws->flag[lane] = ts.ov;
+        ws->bias[lane] = ts.bias;
+        if (keep_planes) {
+#pragma unroll
+            for (int j = 0; j < M; j++) ws->cnt[j * 32 + lane] = ts.c[j];
+        }
+        __syncwarp();
+        handle_flags(bc, ws, wf, M, lane);
+        __syncwarp();
+        w = wf + kTileWords;
+    }
 }
 
 }  // namespace
@@ -323,7 +377,11 @@ __global__ void __launch_bounds__(kPlanThreads) sg_tokens_kernel(const DevIndex 
         uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
         uint32_t *plan_terms = (uint32_t *)(plan_base + kTokTermsOffset);
         for (int j = lane; j < n_lists; j += 32) plan_terms[j] = s_lterm[j];
-        if (lane == 0) *(uint4 *)plan_base = make_uint4(unsupported ? 1u : 0u, (uint32_t)size_a, (uint32_t)n_lists, 0u);
+        if (lane == 0) {
+            const WordRange win = p.wt.win[size_a];
+            ((uint4 *)plan_base)[0] = make_uint4(unsupported ? 1u : 0u, (uint32_t)size_a, (uint32_t)n_lists, 0u);
+            ((uint4 *)plan_base)[1] = make_uint4(win.x, win.y, 0u, 0u);
+        }
         if (p.stats != nullptr) {
             uint32_t st_postings = 0, st_lists = 0;
             const uint8_t *seg_thr = p.wt.seg_thr + (size_t)size_a * ix.n_segments;
@@ -371,6 +429,7 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(
         s_bc.k = p.k;
         s_bc.metric = p.mode == 1 ? (int)kAutocomplete : p.metric;
     }
+    for (uint32_t i = threadIdx.x; i <= min(ix.n_segments, (uint32_t)kSegCache); i += blockDim.x) s_bc.seg_cache[i] = ix.seg_start[i];
     __syncthreads();
     WarpSmem *ws = (WarpSmem *)(smem + (size_t)warp * p.warp_smem);
     const double *tk_score = warp_tk_score(ws);
@@ -385,14 +444,14 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(
         if (lane == 0) q_next = atomicAdd(p.work_counter, 1u);  // the next query number arrives while this one is searched
 
         const uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
-        const uint4 h0 = __ldg((const uint4 *)plan_base);  // TokenPlan
+        const uint4 h0 = __ldg((const uint4 *)plan_base), h1 = __ldg((const uint4 *)plan_base + 1);  // TokenPlan
         const bool unsupported = h0.x != 0u;
         const int size_a = (int)h0.y, n_lists = (int)h0.z;
-        const WordRange win = p.wt.win[size_a];
+        const WordRange win{h1.x, h1.y};
         int tk_len = 0;
 
         if (n_lists > 0 && win.y > win.x) {
-            if (lane == 0) { ws->tk_len = 0; ws->cur_seg = 0; ws->size_a = size_a; ws->n_lists = n_lists; }
+            if (lane == 0) { ws->tk_len = 0; ws->size_a = size_a; ws->n_lists = n_lists; }
             const int n_pad = (n_lists + 7) & ~7;
             for (int j = lane; j < n_pad; j += 32) {
                 uint32_t row = zero_row;
@@ -405,15 +464,8 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(
             }
             __syncwarp();
             const uint8_t *word_thr = p.wt.word_thr + (size_t)size_a * ix.row_words;
-            const bool keep_planes = ix.bshift == 0;
-            for (uint32_t w = win.x & ~31u; w < win.y;) {
-                const int M = n_lists < 32 ? 5 : 8;
-                const uint32_t wf = M == 5 ? count_until_flag<5>(ix.bitmaps, keep_planes, ws, word_thr, w, win.y, n_lists, lane)
-                                           : count_until_flag<8>(ix.bitmaps, keep_planes, ws, word_thr, w, win.y, n_lists, lane);
-                if (wf == kInf) break;
-                handle_flags(&s_bc, ws, wf, M, lane);
-                w = wf + 32u;
-            }
+            if (n_lists < 32) search_query<5>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
+            else search_query<8>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
             __syncwarp();
             tk_len = ws->tk_len;
         }

@@ -209,13 +209,22 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
         bool keep = i < n_win;
         // appendUnique, ngram_tokenizer.go:46-54: raw windows, first occurrence wins (hash first, runes on a hit)
         const uint32_t my_hash = keep ? s_hash[i] : 0u;
-        const int j_end = min(base + 31, n_win - 1);
-        for (int j = 0; j < j_end; j++) {
-            if (keep && j < i && s_hash[j] == my_hash) {
+        // windows of earlier groups of 32, then the windows of this group that share the hash (one MATCH instead of a loop)
+        for (int j = 0; j < base; j++) {
+            if (keep && s_hash[j] == my_hash) {
                 bool eq = true;
                 for (int cpos = 0; cpos < wlen; cpos++) eq &= s_runes[first + i + cpos] == s_runes[first + j + cpos];
                 keep = !eq;
             }
+        }
+        const unsigned long long tag = keep ? (unsigned long long)my_hash : (1ull << 32 | (unsigned)lane);
+        unsigned earlier = __match_any_sync(kFull, tag) & ((1u << lane) - 1u);
+        while (keep && earlier) {
+            const int j = base + __ffs(earlier) - 1;
+            earlier &= earlier - 1;
+            bool eq = true;
+            for (int cpos = 0; cpos < wlen; cpos++) eq &= s_runes[first + i + cpos] == s_runes[first + j + cpos];
+            keep = !eq;
         }
         uint32_t term = kNoTerm;
         if (keep) {

@@ -64,7 +64,7 @@ struct DevIndex {
     // ---- bucket bitmaps (sg_bitmap.cu) ----
     // Segment starts are aligned to 2^bshift new ids, so a bucket (2^bshift consecutive new ids) lies inside one
     // segment.  Row t holds one bit per bucket: set iff term t has a posting in that bucket.  Rows are row_words
-    // 32-bit words (a multiple of 32) apart; row n_terms is all zero (padding lists of a query).
+    // 32-bit words (a multiple of 64: whole tiles of the search kernel) apart; row n_terms is all zero (padding lists of a query).
     uint32_t n_ids;          // seg_start[S]: new ids including the alignment holes
     uint32_t bshift;         // log2(new ids per bucket), 0..kMaxBucketShift
     uint32_t row_words;      // 0: the index has no bitmaps (over the memory budget) and is searched by sg_search_kernel
@@ -86,14 +86,16 @@ constexpr uint32_t kPlanThrOffset = 32, kPlanRunsOffset = 32 + 256;
 constexpr uint32_t kPlanStride = kPlanRunsOffset + kMaxQueryTokens * 8;
 
 // Bitmap engine: one per query, written by sg_tokens_kernel and read by sg_bitmap_search_kernel:
-// kTokStride bytes = [TokenPlan (16) | term id of every list to open (128 x 4)]
+// kTokStride bytes = [TokenPlan (32) | term id of every list to open (128 x 4)]
 struct TokenPlan {
     uint32_t flags;      // 1: more than 128 n-grams (SG_ERR_QUERY_TOO_LONG)
     int32_t size_a;      // len(tokens), suggester.go:53
     int32_t n_lists;     // tokens that are terms of the index, with multiplicity
     int32_t reserved;
+    uint32_t win_lo, win_hi;  // WindowTables::win[size_a], copied so that the search kernel has it with the header
+    uint32_t reserved2[2];
 };
-constexpr uint32_t kTokTermsOffset = 16;
+constexpr uint32_t kTokTermsOffset = 32;
 constexpr uint32_t kTokStride = kTokTermsOffset + kMaxQueryTokens * 4;
 
 // Per call (metric, similarity, mode are per call): everything that depends on the query only through len(tokens).

@@ -51,7 +51,7 @@ std::string finish(HostIndex *ix, const std::vector<uint32_t> &doc_seg, const st
         for (uint32_t b = 0; b < S; b++) n = ((n + ((1ull << s) - 1)) >> s << s) + seg_count[b];
         return n;
     };
-    auto row_words_at = [&](uint32_t s) { return (((ids_at(s) + ((1ull << s) - 1)) >> s) + 1023) / 1024 * 32 + (ids_at(s) ? 0 : 32); };
+    auto row_words_at = [&](uint32_t s) { return (((ids_at(s) + ((1ull << s) - 1)) >> s) + 2047) / 2048 * 64 + (ids_at(s) ? 0 : 64); };  // whole 64-word tiles
     uint32_t bs = 0;
     if (ix->want_bshift >= 0) bs = std::min<uint32_t>((uint32_t)ix->want_bshift, kMaxBucketShift);
     else if (n_docs > 16384 && n_terms > 0 && !doc_terms.empty()) {

@@ -134,7 +134,7 @@ def check_bitmaps(desc, docs, monkeypatch, shift):
         s = lay.bucket_shift
         if shift is not None:
             assert s == min(shift, 8)
-        assert lay.row_words % 32 == 0 and lay.row_words * 32 >= -(-lay.n_slots // (1 << s))
+        assert lay.row_words % 64 == 0 and lay.row_words * 32 >= -(-lay.n_slots // (1 << s))
         seg = np.zeros(ox.segments + 1, dtype=np.uint32)
         assert L.sg_host_index_get_segments(h, seg.ctypes.data_as(C.c_void_p), len(seg)) == len(seg)
         assert seg[-1] == lay.n_slots and np.all(np.diff(seg.astype(np.int64)) >= 0)
