@@ -80,6 +80,17 @@ struct CallCtx {
 
 }  // namespace
 
+// Window tables (sg_device.h: WindowTables) depend on (metric, similarity, mode) only: the first few combinations an
+// index sees are kept in HBM and reused by every later call; `ready` orders other streams behind the kernel that fills them.
+struct WtabEntry {
+    bool used = false;
+    int metric = 0, mode = 0;
+    double alpha = 0.0;
+    uint8_t *tab = nullptr;
+    cudaEvent_t ready = nullptr;
+};
+constexpr int kWtabCache = 4;
+
 struct sg_index {
     sg::HostIndex host;  // posting arrays are dropped after the upload; the description stays
     sg::DevIndex dev{};
@@ -105,6 +116,7 @@ struct sg_index {
     bool bitmap_engine = false;          // searches run sg_bitmap_search_kernel (default when the bitmaps fit their budget)
     size_t plan_stride = sg::kPlanStride;
     size_t wtab_bytes = 0;               // window tables per launch
+    WtabEntry wtab_cache[kWtabCache];    // guarded by mu
 };
 
 namespace {
@@ -154,6 +166,9 @@ int finalize(sg_index *ix) {
     d.pad_code = h.text.pad_code;
     decode_runes(h.text.wrap_start, d.wrap_start, &d.n_wrap_start);
     decode_runes(h.text.wrap_end, d.wrap_end, &d.n_wrap_end);
+    d.wrap_ascii = 1;
+    for (int i = 0; i < d.n_wrap_start; i++) d.wrap_ascii &= d.wrap_start[i] < 128;
+    for (int i = 0; i < d.n_wrap_end; i++) d.wrap_ascii &= d.wrap_end[i] < 128;
     std::memcpy(d.ascii_code, h.text.ascii_code, sizeof(d.ascii_code));
     d.n_ranges = (int32_t)h.text.ranges.size();
     d.n_terms = (uint32_t)h.term_keys.size();
@@ -237,6 +252,10 @@ void destroy(sg_index *ix) {
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         delete c;
+    }
+    for (WtabEntry &w : ix->wtab_cache) {
+        if (w.tab) cudaFree(w.tab);
+        if (w.ready) cudaEventDestroy(w.ready);
     }
     for (void *p : ix->allocations) cudaFree(p);
     delete ix;
@@ -333,18 +352,50 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
     }
-    SG_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), stream));
     if (ix->bitmap_engine) {
         const size_t rows = sg::kWindowRows;
-        p.wt.seg_thr = d_wtab;
-        p.wt.word_thr = d_wtab + ((rows * ix->dev.n_segments + 15) & ~(size_t)15);
-        p.wt.win = (sg::WordRange *)(p.wt.word_thr + ((rows * ix->dev.row_words + 15) & ~(size_t)15));
+        auto point_tables = [&](uint8_t *tab) {
+            p.wt.seg_thr = tab;
+            p.wt.word_thr = tab + ((rows * ix->dev.n_segments + 15) & ~(size_t)15);
+            p.wt.win = (sg::WordRange *)(p.wt.word_thr + ((rows * ix->dev.row_words + 15) & ~(size_t)15));
+        };
         p.warp_smem = (uint32_t)sg::bitmap_warp_smem(k);
         if ((size_t)p.warp_smem * 8 > ix->smem_optin) return fail(SG_ERR_INVALID, "k too large for the shared-memory top-k");
-        SG_CUDA(sg::launch_bitmap_search(ix->dev, p, ix->sm_count, stream, stage_events));
-        g_launches.fetch_add(3, std::memory_order_relaxed);  // sg_window_kernel + sg_tokens_kernel + sg_bitmap_search_kernel
+        int per_sm = 0;
+        SG_CUDA(sg::bitmap_search_occupancy(ix->device, k, &per_sm));
+        // window tables: cached per (metric, similarity, mode); a measurement launch (stage_events) always computes them
+        bool run_window = true;
+        point_tables(d_wtab);
+        if (!stage_events) {
+            std::lock_guard<std::mutex> lk(ix->mu);
+            WtabEntry *hit = nullptr, *vacant = nullptr;
+            for (WtabEntry &w : ix->wtab_cache) {
+                if (w.used && w.metric == metric && w.mode == mode && w.alpha == alpha) { hit = &w; break; }
+                if (!w.used && !vacant) vacant = &w;
+            }
+            if (hit) {
+                point_tables(hit->tab);
+                SG_CUDA(cudaStreamWaitEvent(stream, hit->ready, 0));
+                run_window = false;
+            } else if (vacant) {
+                if (!vacant->tab) SG_CUDA(cudaMalloc((void **)&vacant->tab, ix->wtab_bytes));
+                if (!vacant->ready) SG_CUDA(cudaEventCreateWithFlags(&vacant->ready, cudaEventDisableTiming));
+                point_tables(vacant->tab);
+                SG_CUDA(sg::launch_window(ix->dev, p, stream));
+                SG_CUDA(cudaEventRecord(vacant->ready, stream));
+                g_launches.fetch_add(1, std::memory_order_relaxed);
+                vacant->metric = metric;
+                vacant->mode = mode;
+                vacant->alpha = alpha;
+                vacant->used = true;
+                run_window = false;
+            }
+        }
+        SG_CUDA(sg::launch_bitmap_search(ix->dev, p, ix->sm_count, per_sm, run_window, stream, stage_events));
+        g_launches.fetch_add(run_window ? 3 : 2, std::memory_order_relaxed);  // [sg_window_kernel +] sg_tokens_kernel + sg_bitmap_search_kernel
         return SG_OK;
     }
+    SG_CUDA(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), stream));
     SG_CUDA(sg::launch_search(ix->dev, p, g.blocks, g.warps, g.smem, stream, stage_events));
     g_launches.fetch_add(2, std::memory_order_relaxed);  // sg_plan_kernel + sg_search_kernel
     return SG_OK;
@@ -479,54 +530,61 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     const uint32_t total = q_off[n_q];
     if (total && !q_bytes) return fail(SG_ERR_INVALID, "null query bytes");
 
-    // strings.ToLower for queries holding non-ASCII bytes (the device lowers A-Z itself)
-    std::string low_bytes;
-    std::vector<uint32_t> low_off;
-    const char *src_bytes = q_bytes;
-    const uint32_t *src_off = q_off;
-    unsigned char high = 0;  // no early exit: the loop vectorises
-    for (uint32_t i = 0; i < total; i++) high |= (unsigned char)q_bytes[i];
-    const bool nonascii = (high & 0x80) != 0;
-    if (nonascii) {
-        low_off.resize((size_t)n_q + 1);
-        low_bytes.reserve(total + 16);
-        for (uint32_t q = 0; q < n_q; q++) {
-            low_off[q] = (uint32_t)low_bytes.size();
-            sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &low_bytes);
-        }
-        low_off[n_q] = (uint32_t)low_bytes.size();
-        src_bytes = low_bytes.data();
-        src_off = low_off.data();
-    }
-    const uint32_t src_total = src_off[n_q];
-
     DeviceGuard guard;
     SG_CUDA(guard.set(ix->device));
     CtxLease lease(ix);
     rc = lease.acquire();
     if (rc != SG_OK) return rc;
     CallCtx *c = lease.ctx;
-    SG_CUDA(c->q_bytes.reserve((size_t)src_total + 16));
-    SG_CUDA(c->q_off.reserve((size_t)n_q + 1));
+    uint32_t n_slices = (n_q + ix->slice_queries - 1) / ix->slice_queries;
+    if (n_slices > kMaxSlices) n_slices = kMaxSlices;
+    if (n_slices < 1) n_slices = 1;
+    SG_CUDA(c->q_bytes.reserve((size_t)total * 2 + 64 * (size_t)n_slices + 64));  // strings.ToLower can grow a slice by half
+    SG_CUDA(c->q_off.reserve((size_t)n_q + n_slices + 1));
     SG_CUDA(c->ids.reserve((size_t)n_q * k));
     SG_CUDA(c->scores.reserve((size_t)n_q * k));
     SG_CUDA(c->counts.reserve(n_q));
     SG_CUDA(c->work.reserve(kMaxSlices));
     SG_CUDA(c->plans.reserve((size_t)n_q * ix->plan_stride));
     SG_CUDA(c->wtab.reserve(ix->wtab_bytes * kMaxSlices));
-    // Slices of the batch go down two streams: the H2D / D2H copies of one slice overlap the kernel of the other.
-    // Offsets stay absolute, so a slice only copies its own byte range of the query text.
-    uint32_t n_slices = (n_q + ix->slice_queries - 1) / ix->slice_queries;
-    if (n_slices > kMaxSlices) n_slices = kMaxSlices;
-    if (n_slices < 1) n_slices = 1;
+    // Slices of the batch go down two streams: the H2D / D2H copies of one slice overlap the kernels of the other, and
+    // the host-side look at the next slice's bytes overlaps both.  A slice without non-ASCII bytes is copied straight
+    // from the caller's buffer (the device lowers A-Z itself); otherwise its queries go through strings.ToLower first.
+    std::vector<std::string> low_bytes(n_slices);
+    std::vector<std::vector<uint32_t>> low_off(n_slices);
+    size_t dev_cursor = 0;
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t lo = (uint32_t)((uint64_t)n_q * sl / n_slices), hi = (uint32_t)((uint64_t)n_q * (sl + 1) / n_slices);
         if (lo == hi) continue;
         cudaStream_t st = (sl & 1) ? c->stream2 : c->stream;
-        const uint32_t b0 = src_off[lo], b1 = src_off[hi];
-        if (b1 > b0) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p + b0, src_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(c->q_off.p + lo, src_off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p + lo, hi - lo, metric, alpha, k, c->ids.p + (size_t)lo * k,
+        const uint32_t b0 = q_off[lo], b1 = q_off[hi];
+        unsigned char high = 0;  // no early exit: the loop vectorises
+        for (uint32_t i = b0; i < b1; i++) high |= (unsigned char)q_bytes[i];
+        const char *src_bytes = q_bytes + b0;
+        const uint32_t *src_off = q_off + lo;
+        size_t n_bytes = b1 - b0;
+        char *region = c->q_bytes.p + dev_cursor;
+        const char *d_q_bytes = region - b0;  // offsets stay absolute; only [b0, b1) is ever addressed
+        if (high & 0x80) {
+            std::string &lb = low_bytes[sl];
+            std::vector<uint32_t> &lof = low_off[sl];
+            lof.resize((size_t)(hi - lo) + 1);
+            lb.reserve(n_bytes + n_bytes / 2 + 16);
+            for (uint32_t q = lo; q < hi; q++) {
+                lof[q - lo] = (uint32_t)lb.size();
+                sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &lb);
+            }
+            lof[hi - lo] = (uint32_t)lb.size();
+            src_bytes = lb.data();
+            src_off = lof.data();
+            n_bytes = lb.size();
+            d_q_bytes = region;
+        }
+        dev_cursor += (n_bytes + 63) & ~(size_t)63;
+        uint32_t *d_off = c->q_off.p + lo + sl;
+        if (n_bytes) SG_CUDA(cudaMemcpyAsync(region, src_bytes, n_bytes, cudaMemcpyHostToDevice, st));
+        SG_CUDA(cudaMemcpyAsync(d_off, src_off, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        rc = enqueue_search(ix, d_q_bytes, d_off, hi - lo, metric, alpha, k, c->ids.p + (size_t)lo * k,
                             c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl,
                             c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st, mode);
         if (rc != SG_OK) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }

@@ -21,6 +21,10 @@
 //   sg_window_kernel         per len(tokens) = 0..128: segment window, T(segment), T(bitmap word)   (tiny)
 //   sg_tokens_kernel         tokenise every query -> len(tokens), term ids
 //   sg_bitmap_search_kernel  count, compare, resolve, score, top-k
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "sg_common.cuh"
 #include "sg_kernels.h"
 
@@ -362,16 +366,20 @@ __global__ void __launch_bounds__(kWindowThreads) sg_window_kernel(const DevInde
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPlanThreads) sg_tokens_kernel(const DevIndex ix, const SearchParams p) {
     __shared__ __align__(16) uint32_t s_scratch[kPlanThreads / 32][kMaxRunes + 2 * kMaxQueryTokens];
+    __shared__ uint8_t s_ascii[128];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    if (threadIdx.x < 128) s_ascii[threadIdx.x] = ix.ascii_code[threadIdx.x];
+    __syncthreads();
     uint32_t *s_runes = s_scratch[warp];
     uint32_t *s_lterm = s_runes + kMaxRunes;
     uint32_t *s_hash = s_lterm + kMaxQueryTokens;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const size_t stride = (size_t)ix.n_segments + 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_counter = 0u;  // query counter of the search kernel behind this one
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < p.n_q; q += n_warps) {
         int size_a = 0, n_lists = 0;
-        const bool unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists);
+        const bool unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
         if (p.mode == 1 && n_lists < size_a) n_lists = 0;  // a query token that is in no list: nothing can hold them all
         if (unsupported) { size_a = 0; n_lists = 0; }
         uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
@@ -485,19 +493,46 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(
 // ---------------- launcher (host) ----------------
 size_t bitmap_warp_smem(uint32_t k) { return ((size_t)kBitmapWarpFixedSmem + (size_t)k * 12u + 15u) & ~(size_t)15u; }
 
-cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, cudaStream_t stream,
-                                 cudaEvent_t *stage_events) {
-    const size_t smem = (size_t)kBitmapWarps * p.warp_smem;
-    cudaError_t e = cudaFuncSetAttribute(sg_bitmap_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_bitmap_search_kernel, kBitmapWarps * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    if (stage_events) cudaEventRecord(stage_events[0], stream);
+// The dynamic shared-memory opt-in is a per-device attribute of the kernel, shared by every index and host thread of
+// the process: only ever raise it.  CTAs per SM are cached per (device, k).
+cudaError_t bitmap_search_occupancy(int device, uint32_t k, int *blocks_per_sm) {
+    static std::mutex mu;
+    static size_t opted_in[64] = {0};
+    static std::map<std::pair<int, uint32_t>, int> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    const size_t smem = (size_t)kBitmapWarps * bitmap_warp_smem(k);
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (smem > opted_in[device]) {
+        cudaError_t e = cudaFuncSetAttribute(sg_bitmap_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        opted_in[device] = smem;
+    }
+    auto it = cache.find({device, k});
+    if (it == cache.end()) {
+        int per_sm = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_bitmap_search_kernel, kBitmapWarps * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        it = cache.emplace(std::make_pair(device, k), per_sm).first;
+    }
+    *blocks_per_sm = it->second;
+    return cudaSuccess;
+}
+
+cudaError_t launch_window(const DevIndex &ix, const SearchParams &p, cudaStream_t stream) {
     sg_window_kernel<<<kWindowRows, kWindowThreads, 0, stream>>>(ix, p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, int per_sm, bool run_window,
+                                 cudaStream_t stream, cudaEvent_t *stage_events) {
+    const size_t smem = (size_t)kBitmapWarps * p.warp_smem;
+    cudaError_t e;
+    if (stage_events) cudaEventRecord(stage_events[0], stream);
+    if (run_window) {
+        e = launch_window(ix, p, stream);
+        if (e != cudaSuccess) return e;
+    }
     if (stage_events) cudaEventRecord(stage_events[1], stream);
     const int tok_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
     sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);

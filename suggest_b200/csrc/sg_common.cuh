@@ -135,14 +135,60 @@ __device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *
 // s_runes[kMaxRunes], s_lterm[kMaxQueryTokens] (out: term id of every token that is a term of the index, duplicates
 // after normalisation stay separate lists as in the reference), s_hash[kMaxQueryTokens] are per-warp shared scratch.
 // *size_a = len(tokens) (suggester.go:53).  Returns true if the query has more than kMaxQueryTokens n-grams.
+// s_ascii (optional): a shared-memory copy of ix.ascii_code, which enables the fast path below.
 __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchParams &p, uint32_t q, uint32_t *s_runes,
-                                               uint32_t *s_lterm, uint32_t *s_hash, int lane, int *size_a_out, int *n_lists_out) {
+                                               uint32_t *s_lterm, uint32_t *s_hash, int lane, int *size_a_out, int *n_lists_out,
+                                               const uint8_t *s_ascii = nullptr) {
     bool unsupported = false;
     int size_a = 0;
     const uint32_t qb = __ldg(p.q_off + q), qe = __ldg(p.q_off + q + 1);
     const uint32_t qlen = qe - qb;
     const uint8_t *qp = (const uint8_t *)p.q_bytes + qb;
     const int nws = ix.n_wrap_start, nwe = p.mode == 1 ? 0 : ix.n_wrap_end;  // NewAutocompleteTokenizer: no tail wrap
+    if (s_ascii != nullptr && ix.wrap_ascii && nws + qlen + nwe <= 32u) {
+        // Fast path, the common case: an all-ASCII text of at most 32 runes, one rune per lane.  Trim is a ballot, a raw
+        // n-gram window is at most 8 bytes, so first-occurrence dedupe (appendUnique, ngram_tokenizer.go:46-54) is one
+        // exact MATCH on the packed window; bytes = runes for the early-out of ngram_tokenizer.go:18.
+        const int nr = nws + (int)qlen + nwe;
+        uint32_t r = ' ';
+        if (lane < nws) r = ix.wrap_start[lane];
+        else if (lane < nws + (int)qlen) r = qp[lane - nws];
+        else if (lane < nr) r = ix.wrap_end[lane - nws - (int)qlen];
+        if (!__any_sync(kFull, r >= 0x80u)) {
+            if (r >= 'A' && r <= 'Z') r += 32;
+            s_runes[lane] = r;
+            __syncwarp();
+            const unsigned nonspace = __ballot_sync(kFull, lane < nr && r != ' ');
+            int n_lists = 0;
+            if (nonspace != 0u) {
+                const int f = __ffs(nonspace) - 1, R = 32 - __clz(nonspace) - f;
+                const int n_win = R >= ix.n ? R - ix.n + 1 : 0;
+                const bool active = lane < n_win;
+                unsigned long long raw = 1ull << 63 | (unsigned)lane;  // ASCII windows never set bit 63
+                uint64_t key = 0;
+                if (active) {
+                    raw = 0;
+                    for (int cpos = 0; cpos < ix.n; cpos++) {
+                        const uint32_t ch = s_runes[f + lane + cpos];
+                        raw |= (unsigned long long)ch << (8 * cpos);
+                        const uint32_t code = s_ascii[ch];
+                        key |= (uint64_t)(code ? code : ix.pad_code) << (ix.bits * cpos);
+                    }
+                }
+                const unsigned same = __match_any_sync(kFull, raw);  // every lane takes part: no short-circuit around it
+                const bool keep = active && (same & ((1u << lane) - 1u)) == 0u;
+                const uint32_t term = keep ? term_lookup(ix, key) : kNoTerm;
+                size_a = __popc(__ballot_sync(kFull, keep));
+                const unsigned tm = __ballot_sync(kFull, term != kNoTerm);
+                if (term != kNoTerm) s_lterm[__popc(tm & ((1u << lane) - 1u))] = term;
+                n_lists = __popc(tm);
+            }
+            __syncwarp();
+            *size_a_out = size_a;
+            *n_lists_out = n_lists;
+            return false;
+        }
+    }
     bool nonascii = false;
     for (uint32_t i = lane; i < qlen; i += 32) nonascii |= qp[i] >= 0x80;
     nonascii = __any_sync(kFull, nonascii);

@@ -41,6 +41,7 @@ struct DevIndex {
     int32_t bits;            // bits per symbol code inside a packed term key
     uint32_t pad_code;       // code written for a rune outside the alphabet (pkg/analysis/normalizer.go:29-33)
     int32_t n_wrap_start, n_wrap_end;
+    int32_t wrap_ascii;      // 1: every wrap rune is ASCII (the tokenizer's one-rune-per-lane fast path applies)
     uint32_t wrap_start[kMaxWrapRunes], wrap_end[kMaxWrapRunes];  // Wrap[0], Wrap[1] as lower-cased runes
     uint8_t ascii_code[128]; // 0 = not in the alphabet
     const RuneRange *ranges; // sorted, disjoint

@@ -11,8 +11,11 @@ cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks,
                           cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
 // bitmap engine (sg_bitmap.cu): sg_window_kernel + sg_tokens_kernel + sg_bitmap_search_kernel; p.warp_smem = bitmap_warp_smem(k)
 size_t bitmap_warp_smem(uint32_t k);
-cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, cudaStream_t stream,
-                                 cudaEvent_t *stage_events = nullptr);
+// opt in to the shared memory the kernel needs at this k (raised, never lowered) and how many CTAs fit an SM (cached)
+cudaError_t bitmap_search_occupancy(int device, uint32_t k, int *blocks_per_sm);
+cudaError_t launch_window(const DevIndex &ix, const SearchParams &p, cudaStream_t stream);  // sg_window_kernel alone (fills p.wt)
+cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, int blocks_per_sm, bool run_window,
+                                 cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
                               const uint32_t *part_counts, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
                               int blocks, cudaStream_t stream);
