@@ -34,6 +34,9 @@ namespace {
 
 constexpr int kWindowThreads = 128;
 constexpr int kBitmapWarps = 8;            // warps per CTA of sg_bitmap_search_kernel
+#ifndef SG_BITMAP_MIN_BLOCKS
+#define SG_BITMAP_MIN_BLOCKS 4          // CTAs per SM the register allocation aims at (64 registers per thread)
+#endif
 constexpr int kResolveSlots = 1 << kMaxBucketShift;
 constexpr uint32_t kRowSlots = kMaxQueryTokens + 8;  // padded to a multiple of 8 with the all-zero row
 constexpr uint32_t kTileWords = 32;        // bitmap words per tile: lane l owns word l
@@ -65,6 +68,14 @@ struct BlockConsts {
     int32_t metric;
     uint32_t seg_cache[kSegCache + 1];  // seg_start[0 .. min(S, kSegCache)]
 };
+
+// next query number.  atom.inc, not atom.add: around an add with a uniform address ptxas puts its warp-aggregation
+// shuffle, which waits for the result on the spot; here the result is wanted a whole query later.
+__device__ __forceinline__ uint32_t take_query(uint32_t *counter) {
+    uint32_t q;
+    asm volatile("atom.global.inc.u32 %0, [%1], 0xfffffffe;" : "=r"(q) : "l"(counter) : "memory");
+    return q;
+}
 
 // carry-save adder: (h, l) = a + b + c per bit position; two LOP3
 __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32_t b, uint32_t c) {
@@ -191,7 +202,7 @@ __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, u
 // into one carry of weight 8, which ripples into the planes above.  The planes start at bias = 2^M - T(word), so
 // "count >= T" is the carry out of the top plane (kept sticky in ov) and no comparison is needed.  Loads run one block
 // ahead of the adders (xa / xb), across tile boundaries, so every warp keeps 8-16 independent 128-byte row reads in
-// flight.  The last block of a tile may hold fewer than 8 lists: the missing words are zeros, not loads.
+// flight.  The last block of a tile is padded to 8 lists with the all-zero row (1 KB, L1 resident: branch-free loads).
 // Returns the first word of the first tile in which a bucket reached its threshold, with the lane's flags, bias and
 // planes in ts, or kInf when the window is done.  The caller runs the cold path and resumes behind that tile: called
 // from outside this loop its registers do not add to the loop's.
@@ -207,7 +218,6 @@ __device__ __forceinline__ uint32_t count_until_flag(const uint32_t *__restrict_
                                                      int n_lists, int lane, TileState<M> &ts) {
     const uint32_t n_blocks = ((uint32_t)n_lists + 7u) >> 3;
     const uint32_t n_units = ((win_hi - w_begin + kTileWords - 1) / kTileWords) * n_blocks;
-    const uint32_t tail = (uint32_t)n_lists - (n_blocks - 1) * 8u;  // lists in the last block, 1..8
     // loader state: this lane's word of the tile being loaded, next block to load
     const uint32_t *ld_ptr = bitmaps + w_begin + (uint32_t)lane;
     asm volatile("" : "+l"(ld_ptr));  // opaque: row offsets are added to this pointer as 32-bit indices (one IMAD.WIDE per load)
@@ -216,15 +226,14 @@ __device__ __forceinline__ uint32_t count_until_flag(const uint32_t *__restrict_
 #define SG_LOAD_BLOCK(R)                                                                                      \
     do {                                                                                                      \
         const uint4 r0_ = *(const uint4 *)(s_row + ld_block * 8u), r1_ = *(const uint4 *)(s_row + ld_block * 8u + 4u); \
-        const uint32_t nv_ = ld_block + 1 == n_blocks ? tail : 8u;                                            \
         R##0 = __ldg(ld_ptr + r0_.x);                                                                         \
-        R##1 = nv_ > 1 ? __ldg(ld_ptr + r0_.y) : 0u;                                                          \
-        R##2 = nv_ > 2 ? __ldg(ld_ptr + r0_.z) : 0u;                                                          \
-        R##3 = nv_ > 3 ? __ldg(ld_ptr + r0_.w) : 0u;                                                          \
-        R##4 = nv_ > 4 ? __ldg(ld_ptr + r1_.x) : 0u;                                                          \
-        R##5 = nv_ > 5 ? __ldg(ld_ptr + r1_.y) : 0u;                                                          \
-        R##6 = nv_ > 6 ? __ldg(ld_ptr + r1_.z) : 0u;                                                          \
-        R##7 = nv_ > 7 ? __ldg(ld_ptr + r1_.w) : 0u;                                                          \
+        R##1 = __ldg(ld_ptr + r0_.y);                                                                         \
+        R##2 = __ldg(ld_ptr + r0_.z);                                                                         \
+        R##3 = __ldg(ld_ptr + r0_.w);                                                                         \
+        R##4 = __ldg(ld_ptr + r1_.x);                                                                         \
+        R##5 = __ldg(ld_ptr + r1_.y);                                                                         \
+        R##6 = __ldg(ld_ptr + r1_.z);                                                                         \
+        R##7 = __ldg(ld_ptr + r1_.w);                                                                         \
         if (++ld_block == n_blocks) {                                                                         \
             ld_block = 0;                                                                                     \
             ld_ptr += kTileWords;                                                                             \
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(kPlanThreads) sg_tokens_kernel(const DevIndex 
 // ---------------------------------------------------------------------------------------------------------------
 // sg_bitmap_search_kernel: one warp per query, query numbers from a global counter.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(const DevIndex ix, const SearchParams p) {
+__global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bitmap_search_kernel(const DevIndex ix, const SearchParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ BlockConsts s_bc;
     const int lane = threadIdx.x & 31;
@@ -445,14 +454,15 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(
     const uint32_t zero_row = ix.n_terms * ix.row_words;
 
     uint32_t q = 0;
-    if (lane == 0) q = atomicAdd(p.work_counter, 1u);
+    if (lane == 0) q = take_query(p.work_counter);
     q = __shfl_sync(kFull, q, 0);
     while (q < p.n_q) {
-        uint32_t q_next = 0;
-        if (lane == 0) q_next = atomicAdd(p.work_counter, 1u);  // the next query number arrives while this one is searched
-
+        // the plan of this query: header and the first 32 term ids are requested before anything waits on them
         const uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
         const uint4 h0 = __ldg((const uint4 *)plan_base), h1 = __ldg((const uint4 *)plan_base + 1);  // TokenPlan
+        const uint32_t t0 = __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + lane);
+        uint32_t q_next = 0;
+        if (lane == 0) q_next = take_query(p.work_counter);  // the next query number travels together with the plan loads
         const bool unsupported = h0.x != 0u;
         const int size_a = (int)h0.y, n_lists = (int)h0.z;
         const WordRange win{h1.x, h1.y};
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, 4) sg_bitmap_search_kernel(
             for (int j = lane; j < n_pad; j += 32) {
                 uint32_t row = zero_row;
                 if (j < n_lists) {
-                    const uint32_t t = __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + j);
+                    const uint32_t t = j < 32 ? t0 : __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + j);
                     ws->term[j] = t;
                     row = t * ix.row_words;
                 }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """ncu report -> the text summary committed under profiles/ (run here, no GPU needed).
 
-usage: profile_summary.py <prof.ncu-rep> <out.md> [title]
+usage: profile_summary.py <prof.ncu-rep> <out.md> [title] [kernel name]
 """
 import csv
 import io
@@ -16,6 +16,8 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_lines  # noqa: E402
 
 KEYS = [
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "smsp__sass_inst_executed_op_local_ld.sum",
+    "smsp__sass_inst_executed_op_local_st.sum", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
     "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
     "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
@@ -37,11 +39,12 @@ KEYS = [
 def main():
     rep, out = sys.argv[1], sys.argv[2]
     title = sys.argv[3] if len(sys.argv) > 3 else os.path.basename(rep)
+    kernel = sys.argv[4] if len(sys.argv) > 4 else "sg_bitmap_search_kernel"
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     lines = [f"# {title}", "", f"source: `{rep}` (ncu --set full --clock-control none --import-source on; one launch of "
-             "sg_search_kernel = 65,536 queries of BASELINE.json config #2)", "", "| metric | unit | value |", "|---|---|---|"]
+             f"{kernel} = 65,536 queries of BASELINE.json config #2)", "", "| metric | unit | value |", "|---|---|---|"]
     vals = {}
     for k in KEYS:
         if k in hdr:
@@ -56,9 +59,8 @@ def main():
     old = sys.stdout
     sys.stdout = buf
     try:
-        ncu_lines.regions(src_csv, os.path.join(ROOT, "suggest_b200", "csrc", "sg_kernels.cu"), launches=max(1, len(rows) - 2))
-        print()
-        ncu_lines.main(src_csv, 25)
+        import ncu_top
+        ncu_top.main(src_csv, 65536, 32)
     finally:
         sys.stdout = old
     lines += ["", "## instructions and stall samples per phase / per source line", "", "```", buf.getvalue().rstrip(), "```"]
@@ -67,8 +69,12 @@ def main():
         unit = units[hdr.index("dram__bytes_read.sum")]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
         lines += ["", f"DRAM traffic per launch: {dram * scale / 1e6:.1f} MB (read + write)"]
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:  # noqa: BLE001
+            traffic = {}
         with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
-            json.dump({"sg_search_kernel_dram_bytes_per_launch": dram * scale, "source": os.path.basename(out)}, f)
+            json.dump(dict(traffic, **{f"{kernel}_dram_bytes_per_launch": dram * scale, f"{kernel}_source": os.path.basename(out)}), f, indent=1)
     except Exception as e:  # noqa: BLE001
         lines.append(f"(no dram figures: {e})")
     with open(out, "w") as f:
