@@ -42,8 +42,8 @@ std::string finish(HostIndex *ix, const std::vector<uint32_t> &doc_seg, const st
     if ((uint64_t)n_terms * (S + 1) > 0xFFFFFFF0ull) return "term x segment offset table exceeds 32 bits";
     if (doc_terms.size() > 0xFFFFFFF0ull) return "more than 2^32 postings";
     // Bucket width of the bitmaps: 2^bshift new ids per bit.  Small dictionaries get one bit per document (the bit
-    // count is then the overlap itself); otherwise aim at rows about 1/8 full, where some 2-3 of a query's 20 lists hit
-    // a bucket by chance and its thresholds (>= ~10) leave almost no bucket to resolve.
+    // count is then the overlap itself); otherwise aim at rows about 1/8 full for the terms queries use, where some 2-3
+    // of a query's 20 lists hit a bucket by chance and its thresholds (>= ~10) leave almost no bucket to resolve.
     std::vector<uint32_t> seg_count((size_t)S, 0);
     for (uint32_t d = 0; d < n_docs; d++) seg_count[doc_seg[d]]++;
     auto ids_at = [&](uint32_t s) {  // new ids once every segment start is aligned to 2^s
@@ -55,9 +55,21 @@ std::string finish(HostIndex *ix, const std::vector<uint32_t> &doc_seg, const st
     uint32_t bs = 0;
     if (ix->want_bshift >= 0) bs = std::min<uint32_t>((uint32_t)ix->want_bshift, kMaxBucketShift);
     else if (n_docs > 16384 && n_terms > 0 && !doc_terms.empty()) {
-        const double d0 = (double)doc_terms.size() / ((double)n_terms * (double)n_docs);
-        const double want = std::log2(0.125 / d0);
-        bs = want <= 0.0 ? 0u : std::min<uint32_t>((uint32_t)std::lround(want), kMaxBucketShift);
+        // A query's terms are drawn like the dictionary's own n-grams, so weigh every term by its number of postings f:
+        // W(s) = sum f * (1 - exp(-f * 2^s / n_docs)) / sum f is the fraction of buckets one list of a typical query hits
+        // at width 2^s.  Take the widest bucket that keeps W under 0.16 (uniform 1M-entry 3-gram dictionary: 2^7, W = 0.13);
+        // skewed dictionaries, whose frequent n-grams fill wide buckets, come out with narrow ones.
+        std::vector<uint32_t> freq(n_terms, 0);
+        for (uint32_t t : doc_terms) freq[t]++;
+        for (uint32_t s = 1; s <= kMaxBucketShift; s++) {
+            double num = 0.0, den = 0.0;
+            for (uint32_t f : freq) {
+                num += (double)f * (1.0 - std::exp(-(double)f * (double)(1u << s) / (double)n_docs));
+                den += (double)f;
+            }
+            if (num / den > 0.16) break;
+            bs = s;
+        }
     }
     while (bs < kMaxBucketShift && (n_terms + 1) * row_words_at(bs) * 4 > ix->bitmap_budget) bs++;
     const bool with_bitmaps = (n_terms + 1) * row_words_at(bs) * 4 <= ix->bitmap_budget && (n_terms + 1) * row_words_at(bs) < 0xFFFFFFF0ull;
