@@ -174,6 +174,18 @@ int sg_merge_topk_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k,
                          const double *d_part_scores, const uint32_t *d_part_counts, uint32_t *d_out_ids,
                          double *d_out_scores, uint32_t *d_out_counts, void *stream);
 
+/*
+ * The same pair with one packed block per shard, so that the exchange is a single all-gather:
+ * block = [scores: n_q * k doubles | ids: n_q * k uint32 | counts: n_q uint32], padded to sg_packed_rows_bytes(n_q, k).
+ * sg_search_batch_packed_device writes this shard's block; after an all-gather of the blocks ([part][block]),
+ * sg_merge_topk_packed_device picks the k best per query.
+ */
+uint64_t sg_packed_rows_bytes(uint32_t n_q, uint32_t k);
+int sg_search_batch_packed_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,
+                                  double alpha, uint32_t k, void *d_packed, void *stream);
+int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const void *d_parts, uint32_t *d_out_ids,
+                                double *d_out_scores, uint32_t *d_out_counts, void *stream);
+
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 uint64_t sg_kernel_launches(void);
 

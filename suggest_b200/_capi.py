@@ -51,6 +51,11 @@ SIGNATURES = {
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_char_p, C.c_uint32]),
     "sg_merge_topk_device": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sg_packed_rows_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+    "sg_search_batch_packed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
+                                                C.c_void_p, C.c_void_p]),
+    "sg_merge_topk_packed_device": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
     "sg_kernel_launches": (C.c_uint64, []),
     "sg_last_error": (C.c_char_p, []),
     "sg_version": (C.c_char_p, []),

@@ -681,7 +681,40 @@ int sg_merge_topk_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k,
     SG_CUDA(guard.set(device));
     int blocks = (int)((n_q + 7) / 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    SG_CUDA(sg::launch_merge_topk(n_parts, n_q, k, d_part_ids, d_part_scores, d_part_counts, d_out_ids, d_out_scores,
+    SG_CUDA(sg::launch_merge_topk(n_parts, n_q, k, d_part_ids, d_part_scores, d_part_counts, (size_t)n_q * k, (size_t)n_q * k, n_q,
+                                  d_out_ids, d_out_scores, d_out_counts, blocks, (cudaStream_t)stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SG_OK;
+}
+
+uint64_t sg_packed_rows_bytes(uint32_t n_q, uint32_t k) {
+    const uint64_t b = (uint64_t)n_q * k * 12 + (uint64_t)n_q * 4;
+    return (b + 15) & ~(uint64_t)15;
+}
+
+int sg_search_batch_packed_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,
+                                  double alpha, uint32_t k, void *d_packed, void *stream) {
+    if (!d_packed) return fail(SG_ERR_INVALID, "null buffer");
+    double *sc = (double *)d_packed;
+    uint32_t *ids = (uint32_t *)(sc + (size_t)n_q * k);
+    return sg_search_batch_device(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, ids, sc, ids + (size_t)n_q * k, nullptr, stream);
+}
+
+int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const void *d_parts, uint32_t *d_out_ids,
+                                double *d_out_scores, uint32_t *d_out_counts, void *stream) {
+    if (n_parts < 1 || n_parts > 32) return fail(SG_ERR_INVALID, "n_parts must be in 1..32");
+    if (k < 1 || k > SG_MAX_TOPK) return fail(SG_ERR_INVALID, "topK is invalid");
+    if (n_q == 0) return SG_OK;
+    if (!d_parts || !d_out_ids || !d_out_scores || !d_out_counts) return fail(SG_ERR_INVALID, "null buffer");
+    DeviceGuard guard;
+    SG_CUDA(guard.set(device));
+    const uint64_t stride = sg_packed_rows_bytes(n_q, k);
+    const double *sc = (const double *)d_parts;
+    const uint32_t *ids = (const uint32_t *)(sc + (size_t)n_q * k);
+    const uint32_t *cnt = ids + (size_t)n_q * k;
+    int blocks = (int)((n_q + 7) / 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    SG_CUDA(sg::launch_merge_topk(n_parts, n_q, k, ids, sc, cnt, stride / 4, stride / 8, stride / 4, d_out_ids, d_out_scores,
                                   d_out_counts, blocks, (cudaStream_t)stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return SG_OK;

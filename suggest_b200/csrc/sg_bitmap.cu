@@ -496,6 +496,7 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
             p.out_scores[row + j] = has ? tk_score[j] : 0.0;
         }
         if (lane == 0) p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)tk_len;
+        __syncwarp();  // every lane is done with this query's shared state before lane 0 resets it for the next
         q = __shfl_sync(kFull, q_next, 0);
     }
 }

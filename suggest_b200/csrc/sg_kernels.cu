@@ -476,8 +476,10 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
 }
 
 // k best of n_parts sorted lists per query, (score desc, id asc).  One warp per query, lane = part.
+// Part p's rows start stride_* elements behind part p - 1's (separate [part][query][k] arrays, or one packed block per part).
 __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *__restrict__ part_ids,
                                      const double *__restrict__ part_scores, const uint32_t *__restrict__ part_counts,
+                                     size_t stride_ids, size_t stride_scores, size_t stride_counts,
                                      uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -485,9 +487,11 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
         uint32_t cur = 0, cnt = 0;
         size_t row = 0;
         bool unsupported = false;
+        const uint32_t *my_ids = part_ids + (size_t)lane * stride_ids;
+        const double *my_scores = part_scores + (size_t)lane * stride_scores;
         if ((uint32_t)lane < n_parts) {
-            cnt = part_counts[(size_t)lane * n_q + q];
-            row = ((size_t)lane * n_q + q) * k;
+            cnt = part_counts[(size_t)lane * stride_counts + q];
+            row = (size_t)q * k;
             if (cnt == kCountUnsupported) { unsupported = true; cnt = 0; }
             if (cnt > k) cnt = k;
         }
@@ -495,8 +499,8 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
         uint32_t n_out = 0;
         for (; n_out < k; n_out++) {
             bool has = cur < cnt;
-            double s = has ? part_scores[row + cur] : 0.0;
-            uint32_t id = has ? part_ids[row + cur] : kInf;
+            double s = has ? my_scores[row + cur] : 0.0;
+            uint32_t id = has ? my_ids[row + cur] : kInf;
             int who = lane;
             for (int o = 16; o; o >>= 1) {
                 const bool oh = __shfl_xor_sync(kFull, has, o);
@@ -532,10 +536,10 @@ cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks,
 }
 
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
-                              const uint32_t *part_counts, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
-                              int blocks, cudaStream_t stream) {
-    sg_merge_topk_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, part_ids, part_scores, part_counts, out_ids,
-                                                     out_scores, out_counts);
+                              const uint32_t *part_counts, size_t stride_ids, size_t stride_scores, size_t stride_counts,
+                              uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream) {
+    sg_merge_topk_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, part_ids, part_scores, part_counts, stride_ids, stride_scores,
+                                                     stride_counts, out_ids, out_scores, out_counts);
     return cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@ cudaError_t launch_window(const DevIndex &ix, const SearchParams &p, cudaStream_
 cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, int blocks_per_sm, bool run_window,
                                  cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
-                              const uint32_t *part_counts, uint32_t *out_ids, double *out_scores, uint32_t *out_counts,
-                              int blocks, cudaStream_t stream);
+                              const uint32_t *part_counts, size_t stride_ids, size_t stride_scores, size_t stride_counts,
+                              uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream);
 
 }  // namespace sg

@@ -3,8 +3,8 @@
 The reference is a single process and has nothing like this.  A query's answer is the top-k of the union of
 the per-shard top-k lists, so: rank r indexes documents [lo_r, hi_r) with id_base = lo_r (returned ids stay
 global, which keeps the (score desc, id asc) order meaningful across shards), every rank searches the same
-query batch, the per-shard rows are all-gathered ([part][query][k], NCCL over NVLink) and sg_merge_topk_device
-re-selects k per query on every rank.
+query batch and writes its rows as one packed block (scores | ids | counts), the blocks are exchanged with ONE
+all-gather (NCCL over NVLink) and sg_merge_topk_packed_device re-selects k per query on every rank.
 """
 import numpy as np
 
@@ -36,31 +36,27 @@ class ShardedIndex:
         import torch
         key = (n_q, k, str(device))
         if self._buffers is None or self._buffers[0] != key:
-            w = self.world
-            self._buffers = (key, dict(
-                ids=torch.zeros(n_q * k, dtype=torch.int32, device=device), sc=torch.zeros(n_q * k, dtype=torch.float64, device=device),
-                cnt=torch.zeros(n_q, dtype=torch.int32, device=device),
-                g_ids=torch.zeros(w * n_q * k, dtype=torch.int32, device=device), g_sc=torch.zeros(w * n_q * k, dtype=torch.float64, device=device),
-                g_cnt=torch.zeros(w * n_q, dtype=torch.int32, device=device)))
+            nbytes = int(_capi.lib().sg_packed_rows_bytes(n_q, k))
+            self._buffers = (key, dict(mine=torch.zeros(nbytes, dtype=torch.uint8, device=device),
+                                       all=torch.zeros(self.world * nbytes, dtype=torch.uint8, device=device)))
         return self._buffers[1]
 
     def SuggestBatchDevice(self, d_q, d_off, n_q, similarity, metric, k, out_ids, out_scores, out_counts):
         """d_q / d_off / out_*: torch tensors on this rank's device.  Enqueued on torch's current stream."""
         import torch
         import torch.distributed as dist
-        b = self._alloc(n_q, k, d_q.device)
         stream = torch.cuda.current_stream().cuda_stream
-        self.index.SuggestBatchDevice(d_q.data_ptr(), d_off.data_ptr(), n_q, similarity, metric, k, b["ids"].data_ptr(),
-                                      b["sc"].data_ptr(), b["cnt"].data_ptr(), 0, stream)
         if self.world == 1:
-            out_ids.copy_(b["ids"]); out_scores.copy_(b["sc"]); out_counts.copy_(b["cnt"])
+            self.index.SuggestBatchDevice(d_q.data_ptr(), d_off.data_ptr(), n_q, similarity, metric, k, out_ids.data_ptr(),
+                                          out_scores.data_ptr(), out_counts.data_ptr(), 0, stream)
             return
-        dist.all_gather_into_tensor(b["g_ids"], b["ids"])
-        dist.all_gather_into_tensor(b["g_sc"], b["sc"])
-        dist.all_gather_into_tensor(b["g_cnt"], b["cnt"])
-        _capi.check(_capi.lib().sg_merge_topk_device(d_q.device.index, self.world, n_q, k, b["g_ids"].data_ptr(), b["g_sc"].data_ptr(),
-                                                     b["g_cnt"].data_ptr(), out_ids.data_ptr(), out_scores.data_ptr(),
-                                                     out_counts.data_ptr(), stream))
+        b = self._alloc(n_q, k, d_q.device)
+        L = _capi.lib()
+        _capi.check(L.sg_search_batch_packed_device(self.index.handle, d_q.data_ptr(), d_off.data_ptr(), n_q, metric.code,
+                                                    float(similarity), int(k), b["mine"].data_ptr(), stream or None))
+        dist.all_gather_into_tensor(b["all"], b["mine"])
+        _capi.check(L.sg_merge_topk_packed_device(d_q.device.index, self.world, n_q, k, b["all"].data_ptr(), out_ids.data_ptr(),
+                                                  out_scores.data_ptr(), out_counts.data_ptr(), stream or None))
 
 
 def merge_rows_reference(part_ids, part_scores, part_counts, k):

@@ -372,6 +372,34 @@ def test_shards_and_merge(cars_lines, cars_pair):
     got_ids = o_ids.cpu().numpy().astype(np.uint32).reshape(nq, k)
     assert np.array_equal(got_ids[mask], ids_o[mask])
     assert np.array_equal(o_sc.cpu().numpy().reshape(nq, k)[mask], sc_o[mask])
+    # the packed form used by suggest_b200/sharding.py: one block per shard, as one all-gather delivers them
+    L = _capi.lib()
+    data, off = pack_strings([O.to_lower(x) for x in q])  # device buffers: non-ASCII queries arrive lower-cased (suggest_b200.h)
+    d_q = torch.from_numpy(data).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int32)).to(dev)
+    nbytes = int(L.sg_packed_rows_bytes(nq, k))
+    blocks = torch.zeros(n_parts * nbytes, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    for i, sh in enumerate(shards):
+        _capi.check(L.sg_search_batch_packed_device(sh.handle, d_q.data_ptr(), d_off.data_ptr(), nq, S.JaccardMetric().code, 0.5, k,
+                                                    blocks.data_ptr() + i * nbytes, st))
+    torch.cuda.synchronize()
+    raw = blocks.cpu().numpy()
+    for i in range(n_parts):
+        blk = raw[i * nbytes:(i + 1) * nbytes]
+        b_sc = blk[:nq * k * 8].view(np.float64).reshape(nq, k)
+        b_ids = blk[nq * k * 8:nq * k * 12].view(np.uint32).reshape(nq, k)
+        b_cnt = blk[nq * k * 12:nq * k * 12 + nq * 4].view(np.uint32)
+        assert np.array_equal(b_cnt, cnt[i]) and np.array_equal(b_ids, ids[i]), i
+        bad = np.nonzero(b_sc != sc[i])
+        assert len(bad[0]) == 0, (i, bad[0][:5], bad[1][:5], b_sc[bad][:5], sc[i][bad][:5])
+    o_ids.zero_(); o_sc.zero_(); o_cnt.zero_()
+    _capi.check(L.sg_merge_topk_packed_device(0, n_parts, nq, k, blocks.data_ptr(), o_ids.data_ptr(), o_sc.data_ptr(),
+                                              o_cnt.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert np.array_equal(o_cnt.cpu().numpy().astype(np.uint32), n_o)
+    assert np.array_equal(o_ids.cpu().numpy().astype(np.uint32).reshape(nq, k)[mask], ids_o[mask])
+    assert np.array_equal(o_sc.cpu().numpy().reshape(nq, k)[mask], sc_o[mask])
 
 
 def test_concurrent_searches_on_one_handle(cars_pair, cars_lines):
