@@ -186,6 +186,34 @@ int sg_search_batch_packed_device(sg_index *ix, const char *d_q_bytes, const uin
 int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const void *d_parts, uint32_t *d_out_ids,
                                 double *d_out_scores, uint32_t *d_out_counts, void *stream);
 
+/*
+ * ---- language model and spellchecker (BASELINE.json config #5) ----
+ * sg_lm: the stupid-back-off n-gram model of pkg/lm in HBM.  Level i (0-based) holds the (i+1)-grams as the reference's
+ * packed arrays (pkg/lm/packed_array.go): values[] = word << 32 | count ordered by (context, word), containers[] =
+ * context << 32 | index of the context's first value.  Word ids are the ids of the vocabulary dictionary, which is also
+ * the dictionary of the suggest index.
+ *   sg_lm_create            NewNGramModel(indices)                pkg/lm/ngram_model.go:36-41
+ *   sg_lm_open              nGramModel.Load of the binary model   pkg/lm/ngram_model.go:126-160 (the trailing MPH table is not read)
+ *   sg_lm_score_batch       nGramModel.Score per n-gram           pkg/lm/ngram_model.go:44-64, calcScore :163-175
+ *   sg_lm_score_next_batch  nGramModel.Next(context) then ScorerNext.ScoreNext(candidate)   ngram_model.go:67-99, scorer_next.go:15-23;
+ *                           out_has_scorer[q] = 0 where Next returns a nil scorer (every candidate then scores -100)
+ *   sg_predict_batch        SpellChecker.Predict                  pkg/spellchecker/spellchecker.go:40-92, for queries already split
+ *                           into the last word (w_bytes / w_off) and the word ids of the context as languageModel.Next passes
+ *                           them to the model (language_model.go:103-115).  Rows of out_ids have stride k + 1 (the reference
+ *                           keeps k + 1 candidates when it has more than k, spellchecker.go:87-89).
+ * Host buffers throughout.
+ */
+typedef struct sg_lm sg_lm;
+int sg_lm_create(uint32_t order, const uint64_t *const *containers, const uint64_t *n_containers, const uint64_t *const *values,
+                 const uint64_t *n_values, const uint32_t *totals, int device, sg_lm **out);
+int sg_lm_open(const char *path, int device, sg_lm **out);
+void sg_lm_free(sg_lm *lm);
+int sg_lm_score_batch(sg_lm *lm, const uint32_t *ids, const uint32_t *off, uint32_t n, double *out_scores);
+int sg_lm_score_next_batch(sg_lm *lm, const uint32_t *ctx_ids, const uint32_t *ctx_off, uint32_t n_q, const uint32_t *cand_ids,
+                           const uint32_t *cand_off, double *out_scores, uint8_t *out_has_scorer);
+int sg_predict_batch(sg_index *ix, sg_lm *lm, const char *w_bytes, const uint32_t *w_off, const uint32_t *ctx_ids,
+                     const uint32_t *ctx_off, uint32_t n_q, double similarity, uint32_t k, uint32_t *out_ids, uint32_t *out_counts);
+
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 uint64_t sg_kernel_launches(void);
 

@@ -56,6 +56,13 @@ SIGNATURES = {
                                                 C.c_void_p, C.c_void_p]),
     "sg_merge_topk_packed_device": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),
+    "sg_lm_create": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "sg_lm_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "sg_lm_free": (None, [C.c_void_p]),
+    "sg_lm_score_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "sg_lm_score_next_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sg_predict_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
+                                   C.c_uint32, C.c_void_p, C.c_void_p]),
     "sg_kernel_launches": (C.c_uint64, []),
     "sg_last_error": (C.c_char_p, []),
     "sg_version": (C.c_char_p, []),

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -321,7 +322,8 @@ int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, 
 
 int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
-                   uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0, cudaEvent_t *stage_events = nullptr) {
+                   uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0, cudaEvent_t *stage_events = nullptr,
+                   const sg::LmContext *d_lm_ctx = nullptr) {
     Geometry g{};
     int rc = SG_OK;
     if (!ix->bitmap_engine && (rc = geometry(ix, n_q, k, &g)) != SG_OK) return rc;
@@ -342,6 +344,7 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.warp_smem = g.warp_smem;
     p.force_shift = ix->force_shift;
     p.mode = mode;
+    p.lm_ctx = d_lm_ctx;
     if (ix->l2_persist_bytes) {
         // keep the posting array resident in L2: query plans and result rows stream through the same cache
         cudaStreamAttrValue attr{};
@@ -717,6 +720,237 @@ int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint
     SG_CUDA(sg::launch_merge_topk(n_parts, n_q, k, ids, sc, cnt, stride / 4, stride / 8, stride / 4, d_out_ids, d_out_scores,
                                   d_out_counts, blocks, (cudaStream_t)stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SG_OK;
+}
+
+// ---------------- language model and spellchecker (pkg/lm, pkg/spellchecker) ----------------
+struct sg_lm {
+    sg::DevLm dev{};
+    int device = 0;
+    std::vector<void *> allocations;
+};
+
+static void lm_destroy(sg_lm *lm) {
+    if (!lm) return;
+    DeviceGuard guard;
+    guard.set(lm->device);
+    for (void *p : lm->allocations) cudaFree(p);
+    delete lm;
+}
+
+int sg_lm_create(uint32_t order, const uint64_t *const *containers, const uint64_t *n_containers, const uint64_t *const *values,
+                 const uint64_t *n_values, const uint32_t *totals, int device, sg_lm **out) {
+    if (!out || !containers || !n_containers || !values || !n_values || !totals) return fail(SG_ERR_INVALID, "null argument");
+    if (order < 1 || order > (uint32_t)sg::kMaxLmOrder) return fail(SG_ERR_UNSUPPORTED, "nGramOrder must be in 1..8");
+    int n_dev = 0;
+    SG_CUDA(cudaGetDeviceCount(&n_dev));
+    if (device < 0 || device >= n_dev) return fail(SG_ERR_INVALID, "no such CUDA device");
+    sg_lm *lm = new (std::nothrow) sg_lm();
+    if (!lm) return fail(SG_ERR_NOMEM, "out of host memory");
+    lm->device = device;
+    lm->dev.order = order;
+    DeviceGuard guard;
+    cudaError_t e = guard.set(device);
+    for (uint32_t i = 0; i < order && e == cudaSuccess; i++) {
+        if (n_containers[i] > 0xFFFFFFF0ull || n_values[i] > 0xFFFFFFF0ull) { lm_destroy(lm); return fail(SG_ERR_UNSUPPORTED, "level exceeds 2^32 entries"); }
+        lm->dev.n_containers[i] = (uint32_t)n_containers[i];
+        lm->dev.n_values[i] = (uint32_t)n_values[i];
+        lm->dev.totals[i] = totals[i];
+        for (int which = 0; which < 2 && e == cudaSuccess; which++) {
+            const uint64_t *src = which ? values[i] : containers[i];
+            const size_t n = which ? n_values[i] : n_containers[i];
+            void *d = nullptr;
+            e = cudaMalloc(&d, (n ? n : 1) * sizeof(uint64_t));
+            if (e != cudaSuccess) break;
+            lm->allocations.push_back(d);
+            if (n) e = cudaMemcpy(d, src, n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+            (which ? lm->dev.values[i] : lm->dev.containers[i]) = (const uint64_t *)d;
+        }
+    }
+    if (e != cudaSuccess) {
+        lm_destroy(lm);
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? SG_ERR_NOMEM : SG_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = lm;
+    return SG_OK;
+}
+
+int sg_lm_open(const char *path, int device, sg_lm **out) {
+    // nGramModel.Load, pkg/lm/ngram_model.go:126-160 + packedArray.Load, packed_array.go:124-160; whatever follows the model
+    // in the file (the MPH table, binary.go:47-49) is not read
+    if (!path || !out) return fail(SG_ERR_INVALID, "null argument");
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return fail(SG_ERR_IO, std::string("io: cannot open ") + path);
+    std::vector<unsigned char> data;
+    unsigned char buf[1 << 16];
+    for (size_t n; (n = std::fread(buf, 1, sizeof(buf), f)) > 0;) data.insert(data.end(), buf, buf + n);
+    std::fclose(f);
+    if (data.size() < 6 || std::memcmp(data.data(), "0.0.2", 5) != 0) return fail(SG_ERR_FORMAT, "Version mismatch, expected 0.0.2");
+    const uint32_t order = data[5];
+    if (order < 1 || order > (uint32_t)sg::kMaxLmOrder) return fail(SG_ERR_UNSUPPORTED, "nGramOrder must be in 1..8");
+    size_t p = 6;
+    std::vector<std::vector<uint64_t>> cont(order), vals(order);
+    std::vector<const uint64_t *> cp(order), vp(order);
+    std::vector<uint64_t> nc(order), nv(order);
+    std::vector<uint32_t> totals(order);
+    for (uint32_t i = 0; i < order; i++) {
+        unsigned long long cs = 0, vs = 0, total = 0;
+        size_t nl = p;
+        while (nl < data.size() && data[nl] != '\n') nl++;
+        if (nl >= data.size()) return fail(SG_ERR_FORMAT, "language model file is truncated");
+        std::string line((const char *)data.data() + p, nl - p);
+        if (std::sscanf(line.c_str(), "%llu %llu %llu", &cs, &vs, &total) != 3 || cs % 8 || vs % 8) return fail(SG_ERR_FORMAT, "bad level header");
+        p = nl + 1;
+        if (p + cs + vs > data.size()) return fail(SG_ERR_FORMAT, "language model file is truncated");
+        cont[i].resize(cs / 8);
+        vals[i].resize(vs / 8);
+        if (cs) std::memcpy(cont[i].data(), data.data() + p, cs);
+        if (vs) std::memcpy(vals[i].data(), data.data() + p + cs, vs);
+        p += cs + vs;
+        cp[i] = cont[i].data(); vp[i] = vals[i].data(); nc[i] = cont[i].size(); nv[i] = vals[i].size(); totals[i] = (uint32_t)total;
+    }
+    return sg_lm_create(order, cp.data(), nc.data(), vp.data(), nv.data(), totals.data(), device, out);
+}
+
+void sg_lm_free(sg_lm *lm) { lm_destroy(lm); }
+
+namespace {
+// small RAII device scratch for the LM entry points (they are host-buffer calls: copy in, run, copy out)
+struct Scratch {
+    std::vector<void *> ptrs;
+    cudaError_t get(void **p, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+};
+}  // namespace
+
+int sg_lm_score_batch(sg_lm *lm, const uint32_t *ids, const uint32_t *off, uint32_t n, double *out_scores) {
+    if (!lm || !off || !out_scores) return fail(SG_ERR_INVALID, "null argument");
+    if (n == 0) return SG_OK;
+    if (off[n] && !ids) return fail(SG_ERR_INVALID, "null ids");
+    DeviceGuard guard;
+    SG_CUDA(guard.set(lm->device));
+    Scratch s;
+    uint32_t *d_ids, *d_off;
+    double *d_out;
+    SG_CUDA(s.get((void **)&d_ids, (size_t)off[n] * 4));
+    SG_CUDA(s.get((void **)&d_off, ((size_t)n + 1) * 4));
+    SG_CUDA(s.get((void **)&d_out, (size_t)n * 8));
+    if (off[n]) SG_CUDA(cudaMemcpy(d_ids, ids, (size_t)off[n] * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_off, off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(sg::launch_lm_score(lm->dev, d_ids, d_off, n, d_out, nullptr));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    SG_CUDA(cudaMemcpy(out_scores, d_out, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return SG_OK;
+}
+
+int sg_lm_score_next_batch(sg_lm *lm, const uint32_t *ctx_ids, const uint32_t *ctx_off, uint32_t n_q, const uint32_t *cand_ids,
+                           const uint32_t *cand_off, double *out_scores, uint8_t *out_has_scorer) {
+    if (!lm || !ctx_off || !cand_off || !out_scores) return fail(SG_ERR_INVALID, "null argument");
+    if (n_q == 0) return SG_OK;
+    DeviceGuard guard;
+    SG_CUDA(guard.set(lm->device));
+    Scratch s;
+    uint32_t *d_ctx, *d_ctx_off, *d_cand, *d_cand_off;
+    double *d_out;
+    sg::LmContext *d_lc;
+    const size_t n_ctx = ctx_off[n_q], n_cand = cand_off[n_q];
+    SG_CUDA(s.get((void **)&d_ctx, n_ctx * 4));
+    SG_CUDA(s.get((void **)&d_ctx_off, ((size_t)n_q + 1) * 4));
+    SG_CUDA(s.get((void **)&d_cand, n_cand * 4));
+    SG_CUDA(s.get((void **)&d_cand_off, ((size_t)n_q + 1) * 4));
+    SG_CUDA(s.get((void **)&d_out, n_cand * 8));
+    SG_CUDA(s.get((void **)&d_lc, (size_t)n_q * sizeof(sg::LmContext)));
+    if (n_ctx) SG_CUDA(cudaMemcpy(d_ctx, ctx_ids, n_ctx * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_ctx_off, ctx_off, ((size_t)n_q + 1) * 4, cudaMemcpyHostToDevice));
+    if (n_cand) SG_CUDA(cudaMemcpy(d_cand, cand_ids, n_cand * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_cand_off, cand_off, ((size_t)n_q + 1) * 4, cudaMemcpyHostToDevice));
+    SG_CUDA(sg::launch_lm_context(lm->dev, d_ctx, d_ctx_off, n_q, d_lc, nullptr));
+    SG_CUDA(sg::launch_lm_score_next(d_lc, d_cand, d_cand_off, n_q, d_out, nullptr));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    if (n_cand) SG_CUDA(cudaMemcpy(out_scores, d_out, n_cand * 8, cudaMemcpyDeviceToHost));
+    if (out_has_scorer) {
+        std::vector<sg::LmContext> lc(n_q);
+        SG_CUDA(cudaMemcpy(lc.data(), d_lc, (size_t)n_q * sizeof(sg::LmContext), cudaMemcpyDeviceToHost));
+        for (uint32_t q = 0; q < n_q; q++) out_has_scorer[q] = (uint8_t)lc[q].valid;
+    }
+    return SG_OK;
+}
+
+int sg_predict_batch(sg_index *ix, sg_lm *lm, const char *w_bytes, const uint32_t *w_off, const uint32_t *ctx_ids,
+                     const uint32_t *ctx_off, uint32_t n_q, double similarity, uint32_t k, uint32_t *out_ids, uint32_t *out_counts) {
+    int rc = validate_search(ix, n_q, SG_COSINE, similarity, k);
+    if (rc != SG_OK) return rc;
+    if (!lm || !w_off || !ctx_off || !out_ids || !out_counts) return fail(SG_ERR_INVALID, "null argument");
+    if (n_q == 0) return SG_OK;
+    if (!ix->bitmap_engine) return fail(SG_ERR_UNSUPPORTED, "sg_predict_batch needs the bitmap engine");
+    if (lm->device != ix->device) return fail(SG_ERR_INVALID, "index and language model live on different devices");
+    // the last words: strings.ToLower for non-ASCII input, as sg_search_batch does
+    std::string low;
+    std::vector<uint32_t> low_off;
+    const char *src = w_bytes;
+    const uint32_t *src_off = w_off;
+    unsigned char high = 0;
+    for (uint32_t i = 0; i < w_off[n_q]; i++) high |= (unsigned char)w_bytes[i];
+    if (high & 0x80) {
+        low_off.resize((size_t)n_q + 1);
+        for (uint32_t q = 0; q < n_q; q++) {
+            low_off[q] = (uint32_t)low.size();
+            sg::to_lower((const uint8_t *)w_bytes + w_off[q], w_off[q + 1] - w_off[q], &low);
+        }
+        low_off[n_q] = (uint32_t)low.size();
+        src = low.data();
+        src_off = low_off.data();
+    }
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    CtxLease lease(ix);
+    rc = lease.acquire();
+    if (rc != SG_OK) return rc;
+    cudaStream_t st = lease.ctx->stream;
+    Scratch s;
+    char *d_w;
+    uint32_t *d_w_off, *d_ctx, *d_ctx_off, *d_ac_ids, *d_ac_cnt, *d_fz_ids, *d_fz_cnt, *d_out_ids, *d_out_cnt, *d_tmp, *d_work;
+    double *d_sc;
+    uint8_t *d_plans, *d_wtab;
+    sg::LmContext *d_lc;
+    const size_t n_ctx = ctx_off[n_q];
+    SG_CUDA(s.get((void **)&d_w, (size_t)src_off[n_q] + 16));
+    SG_CUDA(s.get((void **)&d_w_off, ((size_t)n_q + 1) * 4));
+    SG_CUDA(s.get((void **)&d_ctx, n_ctx * 4));
+    SG_CUDA(s.get((void **)&d_ctx_off, ((size_t)n_q + 1) * 4));
+    SG_CUDA(s.get((void **)&d_ac_ids, (size_t)n_q * k * 4));
+    SG_CUDA(s.get((void **)&d_ac_cnt, (size_t)n_q * 4));
+    SG_CUDA(s.get((void **)&d_fz_ids, (size_t)n_q * k * 4));
+    SG_CUDA(s.get((void **)&d_fz_cnt, (size_t)n_q * 4));
+    SG_CUDA(s.get((void **)&d_sc, (size_t)n_q * k * 8));
+    SG_CUDA(s.get((void **)&d_out_ids, (size_t)n_q * (k + 1) * 4));
+    SG_CUDA(s.get((void **)&d_out_cnt, (size_t)n_q * 4));
+    SG_CUDA(s.get((void **)&d_tmp, (size_t)n_q * 4 * k * 4));
+    SG_CUDA(s.get((void **)&d_work, 8));
+    SG_CUDA(s.get((void **)&d_plans, (size_t)n_q * ix->plan_stride));
+    SG_CUDA(s.get((void **)&d_wtab, ix->wtab_bytes));
+    SG_CUDA(s.get((void **)&d_lc, (size_t)n_q * sizeof(sg::LmContext)));
+    if (src_off[n_q]) SG_CUDA(cudaMemcpyAsync(d_w, src, src_off[n_q], cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(d_w_off, src_off, ((size_t)n_q + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n_ctx) SG_CUDA(cudaMemcpyAsync(d_ctx, ctx_ids, n_ctx * 4, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(d_ctx_off, ctx_off, ((size_t)n_q + 1) * 4, cudaMemcpyHostToDevice, st));
+    SG_CUDA(sg::launch_lm_context(lm->dev, d_ctx, d_ctx_off, n_q, d_lc, st));
+    // completions of the last word, the k best by the model (index.Autocomplete with the lm collector, spellchecker.go:58-60)
+    rc = enqueue_search(ix, d_w, d_w_off, n_q, SG_EXACT, 1.0, k, d_ac_ids, d_sc, d_ac_cnt, nullptr, d_work, d_plans, d_wtab, st, 1, nullptr, d_lc);
+    // fuzzy candidates (index.Suggest with CosineMetric, spellchecker.go:67-74); searched for every query, used where needed
+    if (rc == SG_OK)
+        rc = enqueue_search(ix, d_w, d_w_off, n_q, SG_COSINE, similarity, k, d_fz_ids, d_sc, d_fz_cnt, nullptr, d_work + 1, d_plans, d_wtab, st, 0);
+    if (rc != SG_OK) { cudaStreamSynchronize(st); return rc; }
+    SG_CUDA(sg::launch_predict_merge(d_lc, n_q, k, d_ac_ids, d_ac_cnt, d_fz_ids, d_fz_cnt, d_out_ids, d_out_cnt, d_tmp, st));
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    SG_CUDA(cudaMemcpyAsync(out_ids, d_out_ids, (size_t)n_q * (k + 1) * 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(out_counts, d_out_cnt, (size_t)n_q * 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
     return SG_OK;
 }
 

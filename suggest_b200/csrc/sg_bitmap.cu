@@ -48,7 +48,9 @@ constexpr int kSegCache = 256;             // segment starts kept in shared memo
 struct WarpSmem {
     int32_t tk_len;                    // candidates in the top-k
     int32_t size_a, n_lists;
-    uint32_t pad[13];
+    uint32_t lm_valid, lm_from, lm_to; // spellchecker completions: rank by the language model (LmContext of the query)
+    const uint64_t *lm_vals;
+    uint32_t pad[8];
     uint32_t flag[32];                 // per lane: buckets of its word that reached the threshold
     uint32_t bias[32];                 // per lane: 2^M - T(word), what the planes started from
     alignas(16) uint32_t row[kRowSlots];   // word offset of the bitmap row of every list
@@ -91,8 +93,24 @@ __device__ __forceinline__ uint32_t *warp_tk_id(WarpSmem *ws, uint32_t k) { retu
 // top-k (best first, Candidate.Less of pkg/suggest/collector.go:20-26).  All lanes call with identical arguments.
 __device__ void offer_candidate(const BlockConsts *bc, WarpSmem *ws, uint32_t new_id, int count, int size_b, int lane) {
     const uint32_t id = __ldg(bc->perm + new_id);
-    // FirstKCollectorManager.Collect scores a position with -position (pkg/suggest/collector.go:104-106)
-    const double score = bc->metric == kAutocomplete ? -(double)(bc->id_base + id) : metric_score(bc->metric, count, ws->size_a, size_b);
+    double score;
+    if (bc->metric != kAutocomplete) score = metric_score(bc->metric, count, ws->size_a, size_b);
+    else if (!ws->lm_valid) score = -(double)(bc->id_base + id);  // FirstKCollectorManager.Collect: -position (collector.go:104-106)
+    else {
+        // lmCollector (pkg/spellchecker/collector.go:61-78): ScoreNext(word) = log(count(context, word) / count(context)), or
+        // -100 for an unseen continuation; monotone in the count, which is what the queue is ordered by here
+        const uint64_t *__restrict__ v = ws->lm_vals;
+        const uint32_t word = bc->id_base + id;
+        uint32_t lo = ws->lm_from, hi = ws->lm_to;
+        const uint64_t target = (uint64_t)word << 32;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(v + mid) < target) lo = mid + 1; else hi = mid;
+        }
+        uint64_t hit = 0;
+        if (lo < ws->lm_to) hit = __ldg(v + lo);
+        score = (uint32_t)(hit >> 32) == word && lo < ws->lm_to ? (double)(uint32_t)hit : 0.0;
+    }
     QueryCtx c;
     c.k = bc->k;
     c.tk_len = ws->tk_len;
@@ -469,7 +487,19 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
         int tk_len = 0;
 
         if (n_lists > 0 && win.y > win.x) {
-            if (lane == 0) { ws->tk_len = 0; ws->size_a = size_a; ws->n_lists = n_lists; }
+            if (lane == 0) {
+                ws->tk_len = 0;
+                ws->size_a = size_a;
+                ws->n_lists = n_lists;
+                ws->lm_valid = 0u;
+                if (p.lm_ctx != nullptr && p.lm_ctx[q].valid) {
+                    const LmContext lc = p.lm_ctx[q];
+                    ws->lm_valid = 1u;
+                    ws->lm_from = lc.from;
+                    ws->lm_to = lc.to;
+                    ws->lm_vals = lc.vals;
+                }
+            }
             const int n_pad = (n_lists + 7) & ~7;
             for (int j = lane; j < n_pad; j += 32) {
                 uint32_t row = zero_row;

@@ -111,6 +111,26 @@ struct WindowTables {
 };
 constexpr uint32_t kWindowRows = kMaxQueryTokens + 1;
 
+// ---- n-gram language model (pkg/lm), sg_lm.cu ----
+constexpr int kMaxLmOrder = 8;
+constexpr uint32_t kLmInvalidContext = 0xFFFFFFFDu;   // InvalidContextOffset, pkg/lm/ngram_vector.go:31-35
+constexpr double kLmUnknownWordScore = -100.0;        // pkg/lm/ngram_model.go:24
+// Level i holds the (i+1)-grams: values[] = word << 32 | count ordered by (context, word), containers[] = context << 32 |
+// first value of that context; the context of an entry is the position of its prefix in level i-1 (pkg/lm/packed_array.go).
+struct DevLm {
+    uint32_t order;
+    uint32_t n_containers[kMaxLmOrder], n_values[kMaxLmOrder], totals[kMaxLmOrder];
+    const uint64_t *containers[kMaxLmOrder], *values[kMaxLmOrder];
+};
+// What nGramModel.Next(context) leaves for ScoreNext (pkg/lm/ngram_model.go:67-99, scorer_next.go:9-23): the values of the
+// context's continuations and the count of the context itself.  valid = 0: no scorer (unknown context or none given).
+struct LmContext {
+    const uint64_t *vals;   // values of the continuation level
+    uint32_t from, to;      // [from, to) = continuations of the context
+    uint32_t ctx_count;     // count of the full context (the denominator of ScoreNext)
+    uint32_t valid;
+};
+
 struct SearchParams {
     const char *q_bytes;
     const uint32_t *q_off;
@@ -129,6 +149,7 @@ struct SearchParams {
     int32_t force_shift;      // < 0: cost model picks the bucket width; otherwise log2(bucket width)
     int32_t mode;             // 0: Suggest; 1: Autocomplete (no tail wrap, every token required, lowest ids win)
     WindowTables wt;          // bitmap engine only
+    const LmContext *lm_ctx;  // mode 1 only, optional: rank the completions by the language model (spellchecker collector)
 };
 
 SG_HD static inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; host and device hash term keys with it

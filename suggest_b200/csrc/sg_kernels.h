@@ -20,4 +20,14 @@ cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const 
                               const uint32_t *part_counts, size_t stride_ids, size_t stride_scores, size_t stride_counts,
                               uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream);
 
+// language model (sg_lm.cu)
+cudaError_t launch_lm_context(const DevLm &lm, const uint32_t *ctx_ids, const uint32_t *ctx_off, uint32_t n_q, LmContext *out,
+                              cudaStream_t stream);
+cudaError_t launch_lm_score(const DevLm &lm, const uint32_t *ids, const uint32_t *off, uint32_t n, double *out, cudaStream_t stream);
+cudaError_t launch_lm_score_next(const LmContext *ctx, const uint32_t *cand_ids, const uint32_t *cand_off, uint32_t n_q, double *out,
+                                 cudaStream_t stream);
+cudaError_t launch_predict_merge(const LmContext *ctx, uint32_t n_q, uint32_t k, const uint32_t *ac_ids, const uint32_t *ac_cnt,
+                                 const uint32_t *fz_ids, const uint32_t *fz_cnt, uint32_t *out_ids, uint32_t *out_cnt, uint32_t *scratch,
+                                 cudaStream_t stream);
+
 }  // namespace sg

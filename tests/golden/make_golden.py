@@ -8,6 +8,9 @@ on-disk index checks:
   cars.hd, cars.dl pkg/suggest/testdata/db/cars.{hd,dl}    (index v5.1 written by the Go indexer)
   roaring_samples.npz  twelve roaring-bitmap posting lists (> 256 ids) cut out of db/words.dl together with
                    the ids a rebuild of words.dict gives for the same (segment, term)
+  lm/1-gm, 2-gm, 3-gm, test.lm   pkg/lm/testdata/fixtures (Google n-gram text of the "i am sam" corpus and the binary
+                   model the reference's build-lm wrote from it); the expected scores live in tests/test_lm_oracle.py with
+                   their pkg/lm/*_test.go line numbers
 No reference source code is copied.
 """
 import os
@@ -24,6 +27,9 @@ def main():
     shutil.copyfile(os.path.join(REF, "cars.dict"), os.path.join(HERE, "cars.dict"))
     for name in ("cars.hd", "cars.dl"):
         shutil.copyfile(os.path.join(REF, "db", name), os.path.join(HERE, name))
+    os.makedirs(os.path.join(HERE, "lm"), exist_ok=True)
+    for name in ("1-gm", "2-gm", "3-gm", "test.lm"):
+        shutil.copyfile(os.path.join("/root/reference/pkg/lm/testdata/fixtures", name), os.path.join(HERE, "lm", name))
     roaring_samples()
     print("fixtures refreshed")
 
