@@ -59,6 +59,44 @@ def read_unigram_words(text: str, binary_order=False) -> List[str]:
     return [w for w, _ in items]
 
 
+def levels_from_sentences(sentences: Sequence[Sequence[int]], order: int, start: int, end: int):
+    """The packed arrays of every level from word-id sentences: what lm's build path produces from a corpus — every
+    sentence wrapped in <S> ... </S>, all k-grams for k = 1..order counted (NGramBuilder.Build, pkg/lm/ngram_builder.go:21-42),
+    then filed under (context offset, word) like NGramVectorBuilder + CreatePackedArray (ngram_vector_builder.go:69-106,
+    packed_array.go:198-237).  Vectorised with numpy sorts instead of a count trie and red-black trees."""
+    lens = np.fromiter((len(s) + 2 for s in sentences), dtype=np.int64, count=len(sentences))
+    flat = np.empty(int(lens.sum()), dtype=np.uint64)
+    starts = np.zeros(len(sentences) + 1, dtype=np.int64)
+    starts[1:] = np.cumsum(lens)
+    flat[starts[:-1]] = start
+    flat[starts[1:] - 1] = end
+    body = np.ones(len(flat), dtype=bool)
+    body[starts[:-1]] = False
+    body[starts[1:] - 1] = False
+    flat[body] = np.fromiter((w for s in sentences for w in s), dtype=np.uint64, count=int(body.sum()))
+    sent_of = np.repeat(np.arange(len(sentences)), lens)
+    levels, prev_keys = [], None
+    ctx_of_pos = np.full(len(flat), InvalidContextOffset, dtype=np.uint64)  # context offset of the (k-1)-gram starting at pos
+    for k in range(1, order + 1):
+        n = len(flat) - k + 1
+        if n <= 0:
+            levels.append((np.zeros(0, np.uint64), np.zeros(0, np.uint64), 0))
+            continue
+        ok = sent_of[:n] == sent_of[k - 1:k - 1 + n]           # the k-gram stays inside one sentence
+        pos = np.flatnonzero(ok)
+        keys = ctx_of_pos[pos] << np.uint64(32) | flat[pos + k - 1]
+        uniq, inverse, counts = np.unique(keys, return_inverse=True, return_counts=True)
+        ctx = uniq >> np.uint64(32)
+        values = (uniq & np.uint64(0xFFFFFFFF)) << np.uint64(32) | (counts.astype(np.uint64) & np.uint64(0xFFFFFFFF))
+        first = np.ones(len(uniq), dtype=bool)
+        first[1:] = ctx[1:] != ctx[:-1]
+        containers = ctx[first] << np.uint64(32) | np.flatnonzero(first).astype(np.uint64)
+        levels.append((containers, values, int(counts.sum()) & 0xFFFFFFFF))
+        ctx_of_pos = np.full(len(flat), InvalidContextOffset, dtype=np.uint64)
+        ctx_of_pos[pos] = inverse.astype(np.uint64)            # offset of this k-gram in its level = context of the (k+1)-gram
+    return levels
+
+
 class NGramModel:
     """lm.NGramModel on the device."""
 

@@ -105,3 +105,27 @@ def test_word_tokenizer():
     has = lambda ch: ch.isalnum() or ch in "-."  # noqa: E731
     assert LM.word_tokenize("  I am, Sam!  green-eggs ", has) == ["i", "am", "sam", "green-eggs"]
     assert LM.word_tokenize("", has) == []
+
+
+def test_numpy_corpus_builder_equals_text_reader():
+    """suggest_b200.lm.levels_from_sentences (host-side build, no GPU) = count the corpus, write Google n-gram text, read it
+    back with the reference's reader rules"""
+    import numpy as np
+    from suggest_b200 import lm as P
+    rng = np.random.default_rng(3)
+    n_words = 50
+    sents = [[int(w) + 2 for w in rng.integers(0, n_words, size=int(rng.integers(1, 9)))] for _ in range(400)]
+    vocab = ["<S>", "</S>"] + [f"w{i}" for i in range(n_words)]
+    levels = P.levels_from_sentences(sents, 3, 0, 1)
+    counts = [dict() for _ in range(3)]
+    for s in sents:
+        seq = [0] + s + [1]
+        for k in range(1, 4):
+            for i in range(len(seq) - k + 1):
+                g = " ".join(vocab[w] for w in seq[i:i + k])
+                counts[k - 1][g] = counts[k - 1].get(g, 0) + 1
+    files = ["".join(f"{g}\t{c}\n" for g, c in lvl.items()) for lvl in counts]
+    ids = {w: i for i, w in enumerate(vocab)}
+    om = LM.read_google_ngrams(files, lambda w: ids.get(w, LM.UNKNOWN_WORD_ID))
+    for (c, v, t), ov in zip(levels, om.vectors):
+        assert [int(x) for x in c] == ov.containers and [int(x) for x in v] == ov.values and t == ov.total
