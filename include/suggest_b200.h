@@ -81,6 +81,8 @@ typedef struct {
  * the posting lists kept decoded in HBM as CSR instead of VB/skipping/roaring bytes.
  * Document i gets id id_base + i (pkg/dictionary/helpers.go:38-45: id = line number); id_base > 0
  * is for record-id-range shards.
+ * The build itself runs on the device (tokenise, sort, CSR, bitmaps: sg_gpubuild.cu) unless a document has more than 128
+ * n-grams or the text exceeds 4 GB, in which case the host build is used; SG_BUILD=host|gpu forces one of them.
  */
 int sg_index_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs,
                    uint32_t id_base, sg_index **out);
@@ -117,6 +119,8 @@ typedef struct {
     uint32_t bucket_shift;
     uint32_t row_words;      /* 32-bit words per bitmap row; 0: built without bitmaps */
     uint32_t engine;
+    uint32_t built_on_device; /* 1: sg_index_build ran the device build (sg_gpubuild.cu); 0: host build */
+    uint32_t reserved;
     uint64_t bitmap_bytes;
 } sg_index_layout;
 int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout);

@@ -29,7 +29,7 @@ class SgIndexInfo(C.Structure):
 
 class SgIndexLayout(C.Structure):
     _fields_ = [("n_slots", C.c_uint32), ("bucket_shift", C.c_uint32), ("row_words", C.c_uint32), ("engine", C.c_uint32),
-                ("bitmap_bytes", C.c_uint64)]
+                ("built_on_device", C.c_uint32), ("reserved", C.c_uint32), ("bitmap_bytes", C.c_uint64)]
 
 
 # every symbol include/suggest_b200.h declares, with its signature

@@ -118,6 +118,9 @@ struct sg_index {
     size_t plan_stride = sg::kPlanStride;
     size_t wtab_bytes = 0;               // window tables per launch
     WtabEntry wtab_cache[kWtabCache];    // guarded by mu
+    uint32_t n_terms = 0;
+    size_t persist_l2_max = 0, policy_window_max = 0;
+    bool built_on_device = false;
 };
 
 namespace {
@@ -151,8 +154,10 @@ int env_int(const char *name, int dflt) {
     return v && *v ? std::atoi(v) : dflt;
 }
 
-// host arrays -> HBM, fill the DevIndex view
-int finalize(sg_index *ix) {
+int finish_setup(sg_index *ix);
+
+// device properties and the tokenizer part of the DevIndex view (alphabet ranges go to HBM)
+int setup_text(sg_index *ix) {
     DeviceGuard guard;
     SG_CUDA(guard.set(ix->device));
     cudaDeviceProp prop;
@@ -160,6 +165,8 @@ int finalize(sg_index *ix) {
     if (prop.major < 10) return fail(SG_ERR_UNSUPPORTED, "libsuggest_b200 needs an sm_100 device, found " + std::string(prop.name));
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
+    ix->persist_l2_max = (size_t)prop.persistingL2CacheMaxSize;
+    ix->policy_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     sg::HostIndex &h = ix->host;
     sg::DevIndex &d = ix->dev;
     d.n = h.text.n;
@@ -172,13 +179,23 @@ int finalize(sg_index *ix) {
     for (int i = 0; i < d.n_wrap_end; i++) d.wrap_ascii &= d.wrap_end[i] < 128;
     std::memcpy(d.ascii_code, h.text.ascii_code, sizeof(d.ascii_code));
     d.n_ranges = (int32_t)h.text.ranges.size();
+    d.id_base = h.id_base;
+    return upload(ix, h.text.ranges, &d.ranges);
+}
+
+// host arrays -> HBM, fill the DevIndex view
+int finalize(sg_index *ix) {
+    int rc = setup_text(ix);
+    if (rc != SG_OK) return rc;
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    sg::HostIndex &h = ix->host;
+    sg::DevIndex &d = ix->dev;
     d.n_terms = (uint32_t)h.term_keys.size();
     d.term_mask = (uint32_t)h.ht_keys.size() - 1;
     d.n_segments = h.n_segments;
     d.n_docs = h.n_docs;
-    d.id_base = h.id_base;
-    int rc;
-    if ((rc = upload(ix, h.text.ranges, &d.ranges)) != SG_OK) return rc;
+    ix->n_terms = d.n_terms;
     if ((rc = upload(ix, h.ht_keys, &d.term_keys)) != SG_OK) return rc;
     if ((rc = upload(ix, h.ht_vals, &d.term_vals)) != SG_OK) return rc;
     if ((rc = upload(ix, h.seg_start, &d.seg_start)) != SG_OK) return rc;
@@ -193,6 +210,19 @@ int finalize(sg_index *ix) {
         if ((rc = upload(ix, h.bitmaps, &d.bitmaps)) != SG_OK) return rc;
         std::vector<uint32_t>().swap(h.bitmaps);
     }
+    std::vector<uint32_t>().swap(h.postings);
+    std::vector<uint32_t>().swap(h.list_off);
+    std::vector<uint32_t>().swap(h.perm);
+    std::vector<uint64_t>().swap(h.ht_keys);
+    std::vector<uint32_t>().swap(h.ht_vals);
+    return finish_setup(ix);
+}
+
+// engine choice, per-index scratch and the tuning knobs; the DevIndex view is complete
+int finish_setup(sg_index *ix) {
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    sg::HostIndex &h = ix->host;
     {
         const char *eng = std::getenv("SG_ENGINE");
         const bool want_scan = eng && std::strcmp(eng, "scancount") == 0;
@@ -209,11 +239,6 @@ int finalize(sg_index *ix) {
         ix->allocations.push_back(ring);
         ix->work_ring = (uint32_t *)ring;
     }
-    std::vector<uint32_t>().swap(h.postings);
-    std::vector<uint32_t>().swap(h.list_off);
-    std::vector<uint32_t>().swap(h.perm);
-    std::vector<uint64_t>().swap(h.ht_keys);
-    std::vector<uint32_t>().swap(h.ht_vals);
     // tuning knobs (documented in DESIGN.md); defaults are what bench.py measures
     int tb = env_int("SG_TBL_BYTES", kDefaultTblBytes);
     if (tb < 2048) tb = 2048;
@@ -228,11 +253,11 @@ int finalize(sg_index *ix) {
         }
     }
     if (env_int("SG_L2_PERSIST", 0)) {
-        size_t want = (size_t)prop.persistingL2CacheMaxSize;
+        size_t want = ix->persist_l2_max;
         const size_t bytes = ((size_t)h.n_postings + 8) * sizeof(uint32_t);
         if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             ix->l2_persist_bytes = want;
-            ix->l2_window_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+            ix->l2_window_bytes = bytes < ix->policy_window_max ? bytes : ix->policy_window_max;
             ix->l2_hit_ratio = bytes <= want ? 1.0f : (float)want / (float)bytes;
         }
     }
@@ -448,6 +473,48 @@ int sg_index_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *
     if (n_docs && (!doc_bytes || !doc_off)) { delete ix; return fail(SG_ERR_INVALID, "null documents"); }
     ix->host.id_base = id_base;
     static const uint64_t zero_off[1] = {0};
+    // SG_BUILD: "gpu" (device build or an error), "host", default: device build when the dictionary is eligible
+    const char *where = std::getenv("SG_BUILD");
+    const bool want_host = where && std::strcmp(where, "host") == 0, want_gpu = where && std::strcmp(where, "gpu") == 0;
+    if (!want_host && n_docs > 0) {
+        rc = setup_text(ix);
+        if (rc != SG_OK) { destroy(ix); return rc; }
+        sg::GpuBuilt b;
+        std::string err;
+        {
+            DeviceGuard guard;
+            cudaError_t e = guard.set(ix->device);
+            err = e != cudaSuccess ? std::string("cuda: ") + cudaGetErrorString(e)
+                                   : sg::gpu_build(ix->dev, doc_bytes, doc_off, n_docs, ix->host.want_bshift, ix->host.bitmap_budget, &b, &ix->allocations);
+        }
+        if (err.empty()) {
+            sg::DevIndex &d = ix->dev;
+            sg::HostIndex &h = ix->host;
+            d.term_keys = b.term_keys; d.term_vals = b.term_vals; d.term_mask = b.term_mask; d.n_terms = b.n_terms;
+            d.n_segments = b.n_segments; d.n_docs = n_docs; d.seg_start = b.seg_start; d.list_off = b.list_off;
+            d.postings = b.postings; d.perm = b.perm; d.n_ids = b.n_ids; d.bshift = b.bshift; d.row_words = b.row_words; d.bitmaps = b.bitmaps;
+            h.n_docs = n_docs; h.n_segments = b.n_segments; h.n_lists = b.n_lists; h.n_postings = b.n_postings;
+            h.n_ids = b.n_ids; h.bshift = b.bshift; h.row_words = b.row_words;
+            ix->n_terms = b.n_terms;
+            ix->device_bytes += b.device_bytes;
+            ix->built_on_device = true;
+            g_launches.fetch_add((uint64_t)b.kernel_launches, std::memory_order_relaxed);
+            rc = finish_setup(ix);
+            if (rc != SG_OK) { destroy(ix); return rc; }
+            *out = ix;
+            return SG_OK;
+        }
+        const bool fallback = err.rfind("fallback:", 0) == 0;
+        if (!fallback || want_gpu) { destroy(ix); cudaGetLastError(); return fail(fallback ? SG_ERR_UNSUPPORTED : SG_ERR_CUDA, err); }
+        // not eligible: release what the attempt left on the device and build on the host
+        {
+            DeviceGuard guard;
+            guard.set(ix->device);
+            for (void *p : ix->allocations) cudaFree(p);
+            ix->allocations.clear();
+            ix->device_bytes = 0;
+        }
+    }
     std::string err = sg::build_from_docs(&ix->host, doc_bytes, n_docs ? doc_off : zero_off, n_docs);
     if (!err.empty()) { delete ix; return fail(SG_ERR_UNSUPPORTED, err); }
     rc = finalize(ix);
@@ -505,7 +572,7 @@ int sg_index_get_info(const sg_index *ix, sg_index_info *info) {
     if (!ix || !info) return fail(SG_ERR_INVALID, "null argument");
     info->n_docs = ix->host.n_docs;
     info->n_segments = ix->host.n_segments;
-    info->n_terms = (uint32_t)ix->host.term_keys.size();
+    info->n_terms = ix->n_terms;
     info->n_lists = ix->host.n_lists;
     info->n_postings = ix->host.n_postings;
     info->device_bytes = ix->device_bytes;
@@ -520,7 +587,8 @@ int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout) {
     layout->bucket_shift = ix->host.bshift;
     layout->row_words = ix->host.row_words;
     layout->engine = ix->bitmap_engine ? 1u : 0u;
-    layout->bitmap_bytes = (uint64_t)(ix->host.term_keys.size() + 1) * ix->host.row_words * sizeof(uint32_t);
+    layout->built_on_device = ix->built_on_device ? 1u : 0u;
+    layout->bitmap_bytes = ix->host.row_words ? (uint64_t)(ix->n_terms + 1) * ix->host.row_words * sizeof(uint32_t) : 0;
     return SG_OK;
 }
 

@@ -136,9 +136,12 @@ __device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *
 // after normalisation stay separate lists as in the reference), s_hash[kMaxQueryTokens] are per-warp shared scratch.
 // *size_a = len(tokens) (suggester.go:53).  Returns true if the query has more than kMaxQueryTokens n-grams.
 // s_ascii (optional): a shared-memory copy of ix.ascii_code, which enables the fast path below.
+// kKeys = true (documents, sg_gpubuild.cu): no term lookup; the packed key of every token goes to s_keys[kMaxQueryTokens]
+// in token order and *n_lists_out = len(tokens).
+template <bool kKeys = false>
 __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchParams &p, uint32_t q, uint32_t *s_runes,
                                                uint32_t *s_lterm, uint32_t *s_hash, int lane, int *size_a_out, int *n_lists_out,
-                                               const uint8_t *s_ascii = nullptr) {
+                                               const uint8_t *s_ascii = nullptr, uint64_t *s_keys = nullptr) {
     bool unsupported = false;
     int size_a = 0;
     const uint32_t qb = __ldg(p.q_off + q), qe = __ldg(p.q_off + q + 1);
@@ -177,11 +180,17 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
                 }
                 const unsigned same = __match_any_sync(kFull, raw);  // every lane takes part: no short-circuit around it
                 const bool keep = active && (same & ((1u << lane) - 1u)) == 0u;
-                const uint32_t term = keep ? term_lookup(ix, key) : kNoTerm;
-                size_a = __popc(__ballot_sync(kFull, keep));
-                const unsigned tm = __ballot_sync(kFull, term != kNoTerm);
-                if (term != kNoTerm) s_lterm[__popc(tm & ((1u << lane) - 1u))] = term;
-                n_lists = __popc(tm);
+                const unsigned km = __ballot_sync(kFull, keep);
+                size_a = __popc(km);
+                if (kKeys) {
+                    if (keep) s_keys[__popc(km & ((1u << lane) - 1u))] = key;
+                    n_lists = size_a;
+                } else {
+                    const uint32_t term = keep ? term_lookup(ix, key) : kNoTerm;
+                    const unsigned tm = __ballot_sync(kFull, term != kNoTerm);
+                    if (term != kNoTerm) s_lterm[__popc(tm & ((1u << lane) - 1u))] = term;
+                    n_lists = __popc(tm);
+                }
             }
             __syncwarp();
             *size_a_out = size_a;
@@ -273,16 +282,22 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
             keep = !eq;
         }
         uint32_t term = kNoTerm;
+        uint64_t key = 0;
         if (keep) {
-            uint64_t key = 0;
             for (int cpos = 0; cpos < wlen; cpos++)
                 key |= (uint64_t)symbol_code(ix, s_runes[first + i + cpos]) << (ix.bits * cpos);
-            term = term_lookup(ix, key);
+            if (!kKeys) term = term_lookup(ix, key);
         }
-        size_a += __popc(__ballot_sync(kFull, keep));
-        const unsigned tm = __ballot_sync(kFull, term != kNoTerm);
-        if (term != kNoTerm) s_lterm[n_lists + __popc(tm & ((1u << lane) - 1u))] = term;
-        n_lists += __popc(tm);
+        const unsigned km = __ballot_sync(kFull, keep);
+        size_a += __popc(km);
+        if (kKeys) {
+            if (keep) s_keys[n_lists + __popc(km & ((1u << lane) - 1u))] = key;
+            n_lists += __popc(km);
+        } else {
+            const unsigned tm = __ballot_sync(kFull, term != kNoTerm);
+            if (term != kNoTerm) s_lterm[n_lists + __popc(tm & ((1u << lane) - 1u))] = term;
+            n_lists += __popc(tm);
+        }
     }
     __syncwarp();
 

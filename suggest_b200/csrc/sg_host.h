@@ -71,6 +71,25 @@ struct HostIndex {
     void build_hash();
 };
 
+// bucket width, bitmap row length and aligned segment starts from the segment sizes and the terms' posting counts
+std::string choose_layout(const std::vector<uint32_t> &seg_count, const std::vector<uint32_t> &freq, uint32_t n_docs, uint64_t n_postings,
+                          int want_bshift, uint64_t bitmap_budget, uint32_t *bshift, uint32_t *row_words, std::vector<uint32_t> *seg_start,
+                          uint32_t *n_ids);
+
+// Index built on the device (sg_gpubuild.cu): device pointers, owned by the caller's allocation list.
+struct GpuBuilt {
+    const uint64_t *term_keys = nullptr;
+    const uint32_t *term_vals = nullptr;
+    uint32_t term_mask = 0, n_terms = 0, n_segments = 0, n_ids = 0, bshift = 0, row_words = 0;
+    const uint32_t *seg_start = nullptr, *list_off = nullptr, *postings = nullptr, *perm = nullptr, *bitmaps = nullptr;
+    uint64_t n_postings = 0, n_lists = 0, device_bytes = 0;
+    int kernel_launches = 0;
+};
+// `text`: a DevIndex whose tokenizer fields (and `ranges`, already on the device) are set.  "" = built; "fallback: ..." =
+// not eligible (a document of more than 128 n-grams, more than 4 GB of text), build on the host instead; else a CUDA error.
+std::string gpu_build(const DevIndex &text, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs, int want_bshift,
+                      uint64_t bitmap_budget, GpuBuilt *out, std::vector<void *> *allocs);
+
 // suggest.Index (pkg/suggest/indexer.go:14-45) + index.Writer.AddDocument (pkg/index/indexer_writer.go:66-86)
 std::string build_from_docs(HostIndex *ix, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs);
 // already decoded (segment, term) lists, original ids ascending (duplicates inside a list are dropped)

@@ -28,6 +28,53 @@ void HostIndex::build_hash() {
     }
 }
 
+// Bucket width of the bitmaps (2^bshift slots per bit), row length, and the segment starts aligned to it.
+// Small dictionaries get one bit per document (the bit count is then the overlap itself).  Otherwise: a query's terms are
+// drawn like the dictionary's own n-grams, so weigh every term by its number of postings f; W(s) = sum f * (1 - exp(-f * 2^s
+// / n_docs)) / sum f is the fraction of buckets one list of a typical query hits at width 2^s.  Take the widest bucket that
+// keeps W under 0.16 (uniform 1M-entry 3-gram dictionary: 2^7, W = 0.13), where some 2-3 of a query's 20 lists hit a
+// bucket by chance and its thresholds (>= ~10) leave almost no bucket to resolve; skewed dictionaries, whose frequent
+// n-grams fill wide buckets, come out with narrow ones.  Shared by the host build and the device build (sg_gpubuild.cu).
+std::string choose_layout(const std::vector<uint32_t> &seg_count, const std::vector<uint32_t> &freq, uint32_t n_docs, uint64_t n_postings,
+                          int want_bshift, uint64_t bitmap_budget, uint32_t *bshift, uint32_t *row_words, std::vector<uint32_t> *seg_start,
+                          uint32_t *n_ids) {
+    const uint32_t S = (uint32_t)seg_count.size();
+    const size_t n_terms = freq.size();
+    auto ids_at = [&](uint32_t s) {  // slots once every segment start is aligned to 2^s
+        uint64_t n = 0;
+        for (uint32_t b = 0; b < S; b++) n = ((n + ((1ull << s) - 1)) >> s << s) + seg_count[b];
+        return n;
+    };
+    auto row_words_at = [&](uint32_t s) { return (((ids_at(s) + ((1ull << s) - 1)) >> s) + 2047) / 2048 * 64 + (ids_at(s) ? 0 : 64); };  // whole 64-word tiles
+    uint32_t bs = 0;
+    if (want_bshift >= 0) bs = std::min<uint32_t>((uint32_t)want_bshift, kMaxBucketShift);
+    else if (n_docs > 16384 && n_terms > 0 && n_postings > 0) {
+        for (uint32_t s = 1; s <= kMaxBucketShift; s++) {
+            double num = 0.0, den = 0.0;
+            for (uint32_t f : freq) {
+                num += (double)f * (1.0 - std::exp(-(double)f * (double)(1u << s) / (double)n_docs));
+                den += (double)f;
+            }
+            if (num / den > 0.16) break;
+            bs = s;
+        }
+    }
+    while (bs < kMaxBucketShift && (n_terms + 1) * row_words_at(bs) * 4 > bitmap_budget) bs++;
+    const bool with_bitmaps = (n_terms + 1) * row_words_at(bs) * 4 <= bitmap_budget && (n_terms + 1) * row_words_at(bs) < 0xFFFFFFF0ull;
+    if (ids_at(bs) > 0xFFFFFFF0ull) return "more than 2^32 document ids";
+    *bshift = bs;
+    *row_words = with_bitmaps ? (uint32_t)row_words_at(bs) : 0u;
+    // every segment starts at a multiple of the bucket width, so a bucket never holds documents of two segments
+    seg_start->assign((size_t)S + 1, 0);
+    for (uint32_t b = 0; b < S; b++) {
+        const uint64_t a = ((uint64_t)(*seg_start)[b] + ((1ull << bs) - 1)) >> bs << bs;
+        (*seg_start)[b] = (uint32_t)a;  // an empty segment moves with its successor's alignment
+        (*seg_start)[b + 1] = (uint32_t)(a + seg_count[b]);
+    }
+    *n_ids = (*seg_start)[S];
+    return "";
+}
+
 namespace {
 
 // Common tail: given per-document (segment, distinct term ids) produce the CSR arrays.
@@ -41,50 +88,16 @@ std::string finish(HostIndex *ix, const std::vector<uint32_t> &doc_seg, const st
     ix->n_segments = S;
     if ((uint64_t)n_terms * (S + 1) > 0xFFFFFFF0ull) return "term x segment offset table exceeds 32 bits";
     if (doc_terms.size() > 0xFFFFFFF0ull) return "more than 2^32 postings";
-    // Bucket width of the bitmaps: 2^bshift new ids per bit.  Small dictionaries get one bit per document (the bit
-    // count is then the overlap itself); otherwise aim at rows about 1/8 full for the terms queries use, where some 2-3
-    // of a query's 20 lists hit a bucket by chance and its thresholds (>= ~10) leave almost no bucket to resolve.
     std::vector<uint32_t> seg_count((size_t)S, 0);
     for (uint32_t d = 0; d < n_docs; d++) seg_count[doc_seg[d]]++;
-    auto ids_at = [&](uint32_t s) {  // new ids once every segment start is aligned to 2^s
-        uint64_t n = 0;
-        for (uint32_t b = 0; b < S; b++) n = ((n + ((1ull << s) - 1)) >> s << s) + seg_count[b];
-        return n;
-    };
-    auto row_words_at = [&](uint32_t s) { return (((ids_at(s) + ((1ull << s) - 1)) >> s) + 2047) / 2048 * 64 + (ids_at(s) ? 0 : 64); };  // whole 64-word tiles
-    uint32_t bs = 0;
-    if (ix->want_bshift >= 0) bs = std::min<uint32_t>((uint32_t)ix->want_bshift, kMaxBucketShift);
-    else if (n_docs > 16384 && n_terms > 0 && !doc_terms.empty()) {
-        // A query's terms are drawn like the dictionary's own n-grams, so weigh every term by its number of postings f:
-        // W(s) = sum f * (1 - exp(-f * 2^s / n_docs)) / sum f is the fraction of buckets one list of a typical query hits
-        // at width 2^s.  Take the widest bucket that keeps W under 0.16 (uniform 1M-entry 3-gram dictionary: 2^7, W = 0.13);
-        // skewed dictionaries, whose frequent n-grams fill wide buckets, come out with narrow ones.
-        std::vector<uint32_t> freq(n_terms, 0);
-        for (uint32_t t : doc_terms) freq[t]++;
-        for (uint32_t s = 1; s <= kMaxBucketShift; s++) {
-            double num = 0.0, den = 0.0;
-            for (uint32_t f : freq) {
-                num += (double)f * (1.0 - std::exp(-(double)f * (double)(1u << s) / (double)n_docs));
-                den += (double)f;
-            }
-            if (num / den > 0.16) break;
-            bs = s;
-        }
+    std::vector<uint32_t> freq(n_terms, 0);
+    for (uint32_t t : doc_terms) freq[t]++;
+    {
+        std::string err = choose_layout(seg_count, freq, n_docs, doc_terms.size(), ix->want_bshift, ix->bitmap_budget, &ix->bshift,
+                                        &ix->row_words, &ix->seg_start, &ix->n_ids);
+        if (!err.empty()) return err;
     }
-    while (bs < kMaxBucketShift && (n_terms + 1) * row_words_at(bs) * 4 > ix->bitmap_budget) bs++;
-    const bool with_bitmaps = (n_terms + 1) * row_words_at(bs) * 4 <= ix->bitmap_budget && (n_terms + 1) * row_words_at(bs) < 0xFFFFFFF0ull;
-    if (ids_at(bs) > 0xFFFFFFF0ull) return "more than 2^32 document ids";
-    ix->bshift = bs;
-    ix->row_words = with_bitmaps ? (uint32_t)row_words_at(bs) : 0u;
-    // renumber: counting sort of documents by segment keeps the original id order inside a segment; every segment
-    // starts at a multiple of the bucket width, so a bucket never holds documents of two segments
-    ix->seg_start.assign((size_t)S + 1, 0);
-    for (uint32_t b = 0; b < S; b++) {
-        const uint64_t a = ((uint64_t)ix->seg_start[b] + ((1ull << bs) - 1)) >> bs << bs;
-        ix->seg_start[b] = (uint32_t)a;  // an empty segment moves with its successor's alignment
-        ix->seg_start[b + 1] = (uint32_t)(a + seg_count[b]);
-    }
-    ix->n_ids = ix->seg_start[S];
+    const uint32_t bs = ix->bshift;
     ix->perm.assign(ix->n_ids, 0xFFFFFFFFu);
     {
         std::vector<uint32_t> cur(ix->seg_start.begin(), ix->seg_start.end() - 1);

@@ -537,3 +537,52 @@ def test_random_dictionaries(seed):
         assert_same(gx, ox, queries, metric, alpha, k, f"seed={seed} desc={desc} m={metric} a={alpha} k={k} env={env}")
     assert_same_autocomplete(gx, ox, queries[:60], int(rng.choice([1, 4, 20])), f"seed={seed} autocomplete")
     gx.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# device index build (sg_gpubuild.cu) against the host build (sg_index.cpp)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["cars", "synthetic3", "synthetic2", "synthetic4", "unicode"])
+def test_device_build_equals_host_build(cars_lines, case):
+    if case == "cars":
+        desc, docs, queries = CARS_DESCRIPTION, cars_lines, cars_lines[::5]
+    elif case == "unicode":
+        desc = TEST_DESCRIPTION
+        docs = ["Жигули", "жигули 2106", "Ёлка", "ёж", "İstanbul", "naïve café", "日本語", "abc", "", "a", "RAM RAM", b"bad\xff\xfe bytes"] * 3
+        queries = ["жигули", "ЁЛКА", "istanbul", "cafe", "ram ram", "日本", ""]
+    else:
+        n = int(case[-1])
+        desc = dict(TEST_DESCRIPTION, ngram_size=n)
+        docs, queries = synthetic(30000, 1500, seed=77)
+    host = build_gpu(desc, docs, dict(SG_BUILD="host"))
+    dev = build_gpu(desc, docs, dict(SG_BUILD="gpu"))
+    assert host.layout()["built_on_device"] == 0 and dev.layout()["built_on_device"] == 1
+    hi, di = host.info(), dev.info()
+    for key in ("n_docs", "n_segments", "n_terms", "n_lists", "n_postings"):
+        assert hi[key] == di[key], (key, hi[key], di[key])
+    hl, dl = host.layout(), dev.layout()
+    for key in ("n_slots", "bucket_shift", "row_words", "engine", "bitmap_bytes"):
+        assert hl[key] == dl[key], (key, hl[key], dl[key])
+    for metric, alpha, k in ((S.JaccardMetric(), 0.5, 10), (S.CosineMetric(), 0.3, 7), (S.OverlapMetric(), 0.8, 3)):
+        a = host.SuggestBatch(queries, alpha, metric, k)
+        b = dev.SuggestBatch(queries, alpha, metric, k)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    a = host.AutocompleteBatch([q[:3] for q in queries], 6)
+    b = dev.AutocompleteBatch([q[:3] for q in queries], 6)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    host.close()
+    dev.close()
+
+
+def test_device_build_falls_back_for_long_documents(cars_pair):
+    docs = ["short one", "x" * 300, "another short entry", "y" * 140 + " tail"]
+    gx = build_gpu(TEST_DESCRIPTION, docs)
+    assert gx.layout()["built_on_device"] == 0          # a document of more than 128 n-grams: host build
+    ox = O.OracleIndex(**{"ngram_size": 3, "wrap": ("$", "$"), "pad": "$", "alphabet": TEST_DESCRIPTION["alphabet"]}).add_docs(docs)
+    assert_same(gx, ox, ["short one", "another short", "x" * 40, "tail"], O.JACCARD, 0.3, 3)
+    gx.close()
+    with pytest.raises(_capi.SuggestError):
+        build_gpu(TEST_DESCRIPTION, docs, dict(SG_BUILD="gpu"))
+    assert cars_pair[0].layout()["built_on_device"] == 1  # the default build of the suite's dictionaries is the device build
