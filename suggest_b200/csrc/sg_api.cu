@@ -884,15 +884,18 @@ int sg_lm_open(const char *path, int device, sg_lm **out) {
 void sg_lm_free(sg_lm *lm) { lm_destroy(lm); }
 
 namespace {
-// small RAII device scratch for the LM entry points (they are host-buffer calls: copy in, run, copy out)
+// small RAII device scratch for the LM entry points (they are host-buffer calls: copy in, run, copy out); stream-ordered
+// allocations from the device's default pool, whose release threshold finish_setup() raises, so repeated calls reuse them
 struct Scratch {
+    cudaStream_t st = nullptr;
     std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t s = nullptr) : st(s) {}
     cudaError_t get(void **p, size_t bytes) {
-        cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, st);
         if (e == cudaSuccess) ptrs.push_back(*p);
         return e;
     }
-    ~Scratch() { for (void *p : ptrs) cudaFree(p); }
+    ~Scratch() { for (void *p : ptrs) cudaFreeAsync(p, st); }
 };
 }  // namespace
 
@@ -980,7 +983,7 @@ int sg_predict_batch(sg_index *ix, sg_lm *lm, const char *w_bytes, const uint32_
     rc = lease.acquire();
     if (rc != SG_OK) return rc;
     cudaStream_t st = lease.ctx->stream;
-    Scratch s;
+    Scratch s(st);
     char *d_w;
     uint32_t *d_w_off, *d_ctx, *d_ctx_off, *d_ac_ids, *d_ac_cnt, *d_fz_ids, *d_fz_cnt, *d_out_ids, *d_out_cnt, *d_tmp, *d_work;
     double *d_sc;

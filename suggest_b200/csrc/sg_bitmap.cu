@@ -89,28 +89,30 @@ __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32
 __device__ __forceinline__ double *warp_tk_score(WarpSmem *ws) { return (double *)(ws + 1); }
 __device__ __forceinline__ uint32_t *warp_tk_id(WarpSmem *ws, uint32_t k) { return (uint32_t *)(warp_tk_score(ws) + k); }
 
+// Score of a completion (Autocomplete collectors): FirstKCollectorManager.Collect scores a position with -position
+// (pkg/suggest/collector.go:104-106); the spellchecker's lmCollector (pkg/spellchecker/collector.go:61-78) with
+// ScoreNext(word) = log(count(context, word) / count(context)), or -100 for an unseen continuation - monotone in the count,
+// which is what the queue is ordered by here.  Per lane (no warp-wide operation inside).
+__device__ __forceinline__ double completion_score(const BlockConsts *bc, const WarpSmem *ws, uint32_t id) {
+    const uint32_t word = bc->id_base + id;
+    if (!ws->lm_valid) return -(double)word;
+    const uint64_t *__restrict__ v = ws->lm_vals;
+    uint32_t lo = ws->lm_from, hi = ws->lm_to;
+    const uint64_t target = (uint64_t)word << 32;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(v + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    uint64_t hit = 0;
+    if (lo < ws->lm_to) hit = __ldg(v + lo);
+    return (uint32_t)(hit >> 32) == word && lo < ws->lm_to ? (double)(uint32_t)hit : 0.0;
+}
+
 // A document (new id) of segment size_b with an exact overlap count >= T: score it and offer it to the warp's sorted
 // top-k (best first, Candidate.Less of pkg/suggest/collector.go:20-26).  All lanes call with identical arguments.
 __device__ void offer_candidate(const BlockConsts *bc, WarpSmem *ws, uint32_t new_id, int count, int size_b, int lane) {
     const uint32_t id = __ldg(bc->perm + new_id);
-    double score;
-    if (bc->metric != kAutocomplete) score = metric_score(bc->metric, count, ws->size_a, size_b);
-    else if (!ws->lm_valid) score = -(double)(bc->id_base + id);  // FirstKCollectorManager.Collect: -position (collector.go:104-106)
-    else {
-        // lmCollector (pkg/spellchecker/collector.go:61-78): ScoreNext(word) = log(count(context, word) / count(context)), or
-        // -100 for an unseen continuation; monotone in the count, which is what the queue is ordered by here
-        const uint64_t *__restrict__ v = ws->lm_vals;
-        const uint32_t word = bc->id_base + id;
-        uint32_t lo = ws->lm_from, hi = ws->lm_to;
-        const uint64_t target = (uint64_t)word << 32;
-        while (lo < hi) {
-            const uint32_t mid = lo + ((hi - lo) >> 1);
-            if (__ldg(v + mid) < target) lo = mid + 1; else hi = mid;
-        }
-        uint64_t hit = 0;
-        if (lo < ws->lm_to) hit = __ldg(v + lo);
-        score = (uint32_t)(hit >> 32) == word && lo < ws->lm_to ? (double)(uint32_t)hit : 0.0;
-    }
+    const double score = bc->metric != kAutocomplete ? metric_score(bc->metric, count, ws->size_a, size_b) : completion_score(bc, ws, id);
     QueryCtx c;
     c.k = bc->k;
     c.tk_len = ws->tk_len;
@@ -213,6 +215,67 @@ __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, u
             __syncwarp();
         }
     }
+}
+
+// Autocomplete with one or two n-grams (a two- or three-letter prefix): every document of the shorter posting run is a
+// candidate, thousands of them, and nearly every bucket of the bitmap would have to be resolved.  Walk the run instead:
+// lane l takes posting base + l, checks the other run by binary search, scores its document (language-model lookup or
+// -id) - all in parallel - and only what beats the current k-th goes through the warp-serial insert.
+// Segments len(tokens)..S-1 (pkg/suggest/autocomplete.go:47) are one contiguous run of each term's postings.
+__device__ __noinline__ void complete_from_lists(const BlockConsts *bc, WarpSmem *ws, int lane) {
+    const uint32_t S = bc->n_segments;
+    const uint32_t b_lo = (uint32_t)ws->size_a;
+    if (b_lo >= S) return;
+    const size_t stride = (size_t)S + 1;
+    const uint32_t *__restrict__ postings = bc->postings;
+    const uint32_t *o0 = bc->list_off + (size_t)ws->term[0] * stride;
+    uint32_t a_d = __ldg(o0 + b_lo), e_d = __ldg(o0 + S), a_o = 0, e_o = 0;
+    const bool two = ws->n_lists == 2;
+    if (two) {
+        const uint32_t *o1 = bc->list_off + (size_t)ws->term[1] * stride;
+        a_o = __ldg(o1 + b_lo);
+        e_o = __ldg(o1 + S);
+        if (e_o - a_o < e_d - a_d) {  // drive with the shorter run
+            const uint32_t ta = a_d, te = e_d;
+            a_d = a_o; e_d = e_o; a_o = ta; e_o = te;
+        }
+    }
+    QueryCtx c;
+    c.k = bc->k;
+    c.tk_len = ws->tk_len;
+    c.tk_score = warp_tk_score(ws);
+    c.tk_id = warp_tk_id(ws, bc->k);
+    for (uint32_t base = a_d; base < e_d; base += 32) {
+        const uint32_t i = base + (uint32_t)lane;
+        bool valid = i < e_d;
+        uint32_t id = 0;
+        double score = 0.0;
+        if (valid) {
+            const uint32_t x = __ldg(postings + i);
+            if (two) {
+                const uint32_t pos = lower_bound(postings, a_o, e_o, x);
+                valid = pos < e_o && __ldg(postings + pos) == x;
+            }
+            if (valid) {
+                id = __ldg(bc->perm + x);
+                score = completion_score(bc, ws, id);
+                if (c.tk_len == (int)c.k) {  // the k-th only improves: whatever fails against it now fails later too
+                    const double ws_ = c.tk_score[c.k - 1];
+                    const uint32_t wi = c.tk_id[c.k - 1];
+                    valid = score > ws_ || (score == ws_ && id < wi);
+                }
+            }
+        }
+        unsigned m = __ballot_sync(kFull, valid);
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            topk_insert(c, __shfl_sync(kFull, score, src), __shfl_sync(kFull, id, src), lane);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) ws->tk_len = c.tk_len;
+    __syncwarp();
 }
 
 // The count loop of one query.  The window is walked in tiles of 32 bitmap words (lane l owns word w0 + l of every
@@ -512,7 +575,8 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
             }
             __syncwarp();
             const uint8_t *word_thr = p.wt.word_thr + (size_t)size_a * ix.row_words;
-            if (n_lists < 32) search_query<5>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
+            if (p.mode == 1 && n_lists <= 2) complete_from_lists(&s_bc, ws, lane);
+            else if (n_lists < 32) search_query<5>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
             else search_query<8>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
             __syncwarp();
             tk_len = ws->tk_len;

@@ -31,10 +31,8 @@ void HostIndex::build_hash() {
 // Bucket width of the bitmaps (2^bshift slots per bit), row length, and the segment starts aligned to it.
 // Small dictionaries get one bit per document (the bit count is then the overlap itself).  Otherwise: a query's terms are
 // drawn like the dictionary's own n-grams, so weigh every term by its number of postings f; W(s) = sum f * (1 - exp(-f * 2^s
-// / n_docs)) / sum f is the fraction of buckets one list of a typical query hits at width 2^s.  Take the widest bucket that
-// keeps W under 0.16 (uniform 1M-entry 3-gram dictionary: 2^7, W = 0.13), where some 2-3 of a query's 20 lists hit a
-// bucket by chance and its thresholds (>= ~10) leave almost no bucket to resolve; skewed dictionaries, whose frequent
-// n-grams fill wide buckets, come out with narrow ones.  Shared by the host build and the device build (sg_gpubuild.cu).
+// / n_docs)) / sum f is the fraction of buckets one list of a typical query hits at width 2^s, and the width is the one
+// that minimises an estimate of the work per query (below).  Shared by the host build and the device build (sg_gpubuild.cu).
 std::string choose_layout(const std::vector<uint32_t> &seg_count, const std::vector<uint32_t> &freq, uint32_t n_docs, uint64_t n_postings,
                           int want_bshift, uint64_t bitmap_budget, uint32_t *bshift, uint32_t *row_words, std::vector<uint32_t> *seg_start,
                           uint32_t *n_ids) {
@@ -49,14 +47,25 @@ std::string choose_layout(const std::vector<uint32_t> &seg_count, const std::vec
     uint32_t bs = 0;
     if (want_bshift >= 0) bs = std::min<uint32_t>((uint32_t)want_bshift, kMaxBucketShift);
     else if (n_docs > 16384 && n_terms > 0 && n_postings > 0) {
-        for (uint32_t s = 1; s <= kMaxBucketShift; s++) {
+        // cost of a typical query at width 2^s, in warp instructions: adding the bitmap words of its ~c lists (c = mean
+        // n-grams per document) plus resolving the buckets that reach a threshold of ~0.55 c by chance (Poisson tail of
+        // "lists hitting a bucket", mean c * W(s)).  Uniform 1M-entry 3-gram dictionary: 2^7; the Zipf-lettered one and
+        // dictionaries of short words (low thresholds) come out narrower.
+        const double c = (double)n_postings / (double)n_docs;
+        const int T = std::max(2, (int)std::lround(0.55 * c));
+        double best = 0.0;
+        for (uint32_t s = 0; s <= kMaxBucketShift; s++) {
             double num = 0.0, den = 0.0;
             for (uint32_t f : freq) {
                 num += (double)f * (1.0 - std::exp(-(double)f * (double)(1u << s) / (double)n_docs));
                 den += (double)f;
             }
-            if (num / den > 0.16) break;
-            bs = s;
+            const double lam = c * num / den, buckets = (double)((ids_at(s) + ((1ull << s) - 1)) >> s);
+            double term = std::exp(-lam), tail = 1.0;  // P(Poisson(lam) >= T) = 1 - sum_{i<T} e^-lam lam^i / i!
+            for (int i = 0; i < T; i++) { tail -= term; term *= lam / (double)(i + 1); }
+            if (tail < 0.0) tail = 0.0;
+            const double cost = c * buckets * 0.0054 + buckets * tail * 600.0;
+            if (s == 0 || cost < best) { best = cost; bs = s; }
         }
     }
     while (bs < kMaxBucketShift && (n_terms + 1) * row_words_at(bs) * 4 > bitmap_budget) bs++;
