@@ -7,4 +7,4 @@ mkdir -p $OUT
 run() { timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N "$@"; }
 echo "== replicated x$N"; run --steps 20 --warmup 3 --no-cpu-baseline > $OUT/replicated_$N.json 2> $OUT/replicated_$N.err; cut -c1-260 $OUT/replicated_$N.json
 echo "== sharded 10M x$N"; run --steps 10 --warmup 3 --workload sharded --no-cpu-baseline > $OUT/sharded10m_$N.json 2> $OUT/sharded10m_$N.err; cut -c1-260 $OUT/sharded10m_$N.json
-tail -3 $OUT/*.err
+for f in $OUT/*.err; do tail -n 3 "$f"; done
