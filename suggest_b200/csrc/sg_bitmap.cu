@@ -34,6 +34,9 @@ namespace {
 
 constexpr int kWindowThreads = 128;
 constexpr int kBitmapWarps = 8;            // warps per CTA of sg_bitmap_search_kernel
+#ifndef SG_TOKENS_MIN_BLOCKS
+#define SG_TOKENS_MIN_BLOCKS 8          // CTAs per SM of sg_tokens_kernel the register allocation aims at (32 registers: its dependent loads want warps)
+#endif
 #ifndef SG_BITMAP_MIN_BLOCKS
 #define SG_BITMAP_MIN_BLOCKS 4          // CTAs per SM the register allocation aims at (64 registers per thread)
 #endif
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(kWindowThreads) sg_window_kernel(const DevInde
 // sg_tokens_kernel: the tokenizer chain for every query; one warp per query.  With p.stats it also counts the
 // admissible postings / lists of SURVEY.md section 8(d) (the algorithmic bytes of the roofline).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPlanThreads) sg_tokens_kernel(const DevIndex ix, const SearchParams p) {
+__global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_kernel(const DevIndex ix, const SearchParams p) {
     __shared__ __align__(16) uint32_t s_scratch[kPlanThreads / 32][kMaxRunes + 2 * kMaxQueryTokens];
     __shared__ uint8_t s_ascii[128];
     const int lane = threadIdx.x & 31;
