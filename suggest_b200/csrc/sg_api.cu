@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -624,6 +625,8 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     std::vector<std::string> low_bytes(n_slices);
     std::vector<std::vector<uint32_t>> low_off(n_slices);
     size_t dev_cursor = 0;
+    static const bool trace = env_int("SG_TRACE", 0) != 0;
+    const auto t_begin = std::chrono::steady_clock::now();
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t lo = (uint32_t)((uint64_t)n_q * sl / n_slices), hi = (uint32_t)((uint64_t)n_q * (sl + 1) / n_slices);
         if (lo == hi) continue;
@@ -665,8 +668,15 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
                                 cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(out_counts + lo, c->counts.p + lo, (size_t)(hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
+    const auto t_enqueued = std::chrono::steady_clock::now();
     SG_CUDA(cudaStreamSynchronize(c->stream));
     SG_CUDA(cudaStreamSynchronize(c->stream2));
+    if (trace) {
+        const auto t_done = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "sg_search_batch: %u queries, %u slices: enqueue %.1f us, wait %.1f us\n", n_q, n_slices,
+                     std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count(),
+                     std::chrono::duration<double, std::micro>(t_done - t_enqueued).count());
+    }
     for (uint32_t q = 0; q < n_q; q++)
         if (out_counts[q] == SG_COUNT_UNSUPPORTED)
             return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");
