@@ -12,6 +12,8 @@ no data-path collective; weak scaling).  `--workload sharded` runs config #4 ins
 split by record-id range, every rank searches the same batch, per-shard top-k is all-gathered (NCCL) and
 merged on the device.
 
+`--workload spellchecker` / `--workload autocomplete` run the SURVEY.md 8(f) rows (bench_spellchecker.py, bench_autocomplete.py).
+
 Prints ONE JSON line (rank 0).  `value` = queries/s with the batch resident in HBM, CUDA-event timed;
 `e2e` = the same through sg_search_batch with pinned host buffers (H2D + kernel + D2H per step);
 `roofline` = algorithmic bytes (SURVEY.md 8(d) formula, counted by the kernel's own stats pass) over
@@ -221,7 +223,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="replicated", choices=["replicated", "sharded"])
+    ap.add_argument("--workload", default="replicated", choices=["replicated", "sharded", "spellchecker", "autocomplete"])
     ap.add_argument("--docs", type=int, default=None, help="dictionary size (default 1M; sharded: 10M)")
     ap.add_argument("--metric", default="Jaccard", choices=["Jaccard", "Cosine", "Dice"])
     ap.add_argument("--ngram", type=int, default=3)
@@ -229,6 +231,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload in ("spellchecker", "autocomplete"):
+        # the "next" rows of SURVEY.md 8(f): BASELINE.json config #5 (bench_spellchecker.py) and Autocomplete
+        # (bench_autocomplete.py); single GPU, their own JSON line with a cpu_baseline from the oracle
+        sys.stdout = out_stream
+        if args.workload == "spellchecker":
+            import bench_spellchecker
+            return bench_spellchecker.main(["--steps", str(min(args.steps, 20)), "--warmup", str(args.warmup)]) or 0
+        import bench_autocomplete
+        return bench_autocomplete.main() or 0
     if args.impl == "reference":
         return run_reference(args, out_stream)
 

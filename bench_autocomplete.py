@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """NGramIndex.Autocomplete on the config #2 dictionary: 65,536 prefixes (the first 3-8 letters of random
 entries), limit 10, through sg_autocomplete_batch with host buffers.  Prints ONE JSON line with the oracle on a CPU sample.
-usage (GPU box): python tools/bench_autocomplete.py"""
+usage (GPU box): python bench.py --workload autocomplete"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 

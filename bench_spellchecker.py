@@ -6,7 +6,7 @@ would make), the share of each kernel, and the CPU oracle on a bounded sample wi
 Workload: vocabulary of 1,000,000 synthetic words (4-14 letters a-z, seed 12345), trigram model counted from 400,000
 synthetic sentences (Zipf word choice), 65,536 queries = two context words of a sentence + the next word cut to a prefix
 (half) or with one substituted letter (half); topK 5, similarity 0.5.
-usage (GPU box): python tools/bench_spellchecker.py [--steps K] [--queries N]"""
+usage (GPU box): python bench.py --workload spellchecker [--steps K] [--queries N]"""
 import argparse
 import json
 import os
@@ -15,11 +15,11 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--sentences", type=int, default=400_000)
     ap.add_argument("--queries", type=int, default=65536)
     ap.add_argument("--cpu-sample", type=int, default=300)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     import suggest_b200 as S
     from suggest_b200 import _capi
     from suggest_b200 import lm as P
