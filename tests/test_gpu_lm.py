@@ -187,3 +187,33 @@ def test_predict_matches_oracle(synthetic_lm):
     for q, row in zip(queries[:50], words_out):
         assert row == [vocab[d] for d in LM.predict(ox, olm, q, 5, 0.5, O.COSINE, O.CANONICAL)]
     index.close()
+
+
+@pytest.mark.parametrize("order", [1, 2, 4])
+def test_other_model_orders(order):
+    """unigram, bigram and 4-gram models: every level of the context chain, contexts that are too long or empty"""
+    words, sents = synthetic_corpus(300, 3000, 100 + order)
+    ids = {w: i + 2 for i, w in enumerate(words)}
+    id_sents = [[ids[w] for w in s] for s in sents]
+    levels = P.levels_from_sentences(id_sents, order, 0, 1)
+    model = P.NGramModel.from_levels(levels)
+    omodel = LM.NGramModel([LM.PackedArray([int(x) for x in c], [int(x) for x in v], t) for c, v, t in levels])
+    rng = np.random.default_rng(order)
+    grams = [[int(x) for x in rng.integers(0, len(words) + 2, size=int(rng.integers(1, order + 3)))] for _ in range(300)]
+    grams += [s[:order] for s in id_sents[:300]] + [[0] + s[:order - 1] for s in id_sents[:200] if order > 1]
+    got = model.ScoreBatch(grams)
+    for g, v in zip(grams, got):
+        assert close(v, omodel.score(g)), (order, g, v, omodel.score(g))
+    ctxs = [s[:int(rng.integers(0, order + 1))] for s in id_sents[300:700]]
+    cands = [[int(x) for x in rng.integers(0, len(words) + 2, size=5)] + s[:4] for s in id_sents[300:700]]
+    scores, has = model.ScoreNextBatch(ctxs, cands)
+    for c, cd, sc, h in zip(ctxs, cands, scores, has):
+        try:
+            nxt = omodel.next(c)
+        except ValueError:   # empty context, or as long as the model's order: the reference returns an error, no scorer here
+            nxt = None
+        assert h == (nxt is not None), (order, c)
+        for w, v in zip(cd, sc):
+            want = omodel.score_next(nxt, w) if nxt is not None else LM.UNKNOWN_WORD_SCORE
+            assert close(v, want), (order, c, w, v, want)
+    model.close()

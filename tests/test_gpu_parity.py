@@ -586,3 +586,33 @@ def test_device_build_falls_back_for_long_documents(cars_pair):
     with pytest.raises(_capi.SuggestError):
         build_gpu(TEST_DESCRIPTION, docs, dict(SG_BUILD="gpu"))
     assert cars_pair[0].layout()["built_on_device"] == 1  # the default build of the suite's dictionaries is the device build
+
+
+def test_long_documents_and_queries():
+    """40-126 n-grams per entry: the 8-plane adders (32 or more lists), many segments, k-th score ties; and entries of
+    more than 128 n-grams in the dictionary (host build, more than 256 segments) next to queries that are too long"""
+    rng = np.random.default_rng(404)
+    docs = ["".join(chr(97 + c) for c in rng.integers(0, 8, size=int(rng.integers(38, 125)))) for _ in range(3000)]
+    queries = []
+    for d in docs[::10]:
+        q = list(d)
+        for _ in range(int(rng.integers(0, 6))):
+            q[int(rng.integers(len(q)))] = chr(97 + int(rng.integers(0, 8)))
+        queries.append("".join(q)[:int(rng.integers(30, len(q) + 1))])
+    gx, ox = build_pair(TEST_DESCRIPTION, docs)
+    assert gx.layout()["built_on_device"] == 1
+    for metric, alpha, k in ((O.JACCARD, 0.5, 10), (O.COSINE, 0.35, 5), (O.DICE, 0.6, 3), (O.OVERLAP, 0.9, 4)):
+        n = assert_same(gx, ox, queries, metric, alpha, k, f"long m={metric} a={alpha}")
+        assert n.sum() > 0
+    assert_same_autocomplete(gx, ox, [q[:int(rng.integers(3, 60))] for q in queries[:80]], 5, "long autocomplete")
+    gx.close()
+    docs2 = docs[:500] + ["".join(chr(97 + c) for c in rng.integers(0, 26, size=int(rng.integers(150, 400)))) for _ in range(40)]
+    gx, ox = build_pair(TEST_DESCRIPTION, docs2)
+    assert gx.layout()["built_on_device"] == 0 and gx.info()["n_segments"] > 256
+    q2 = queries[:40] + [d[:100] for d in docs2[500:520]]
+    assert_same(gx, ox, q2, O.JACCARD, 0.3, 10, "long docs host build")
+    assert_same(gx, ox, q2, O.OVERLAP, 0.8, 10, "long docs host build overlap")
+    with pytest.raises(_capi.SuggestError) as e:
+        gx.SuggestBatch([docs2[-1][:200]], 0.5, S.JaccardMetric(), 3)
+    assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG
+    gx.close()
