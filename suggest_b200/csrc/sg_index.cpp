@@ -29,7 +29,7 @@ void HostIndex::build_hash() {
 }
 
 // Bucket width of the bitmaps (2^bshift slots per bit), row length, and the segment starts aligned to it.
-// Small dictionaries get one bit per document (the bit count is then the overlap itself).  Otherwise: a query's terms are
+// Dictionaries of up to ~3M postings get one bit per document (the bit count is then the overlap itself).  Otherwise: a query's terms are
 // drawn like the dictionary's own n-grams, so weigh every term by its number of postings f; W(s) = sum f * (1 - exp(-f * 2^s
 // / n_docs)) / sum f is the fraction of buckets one list of a typical query hits at width 2^s, and the width is the one
 // that minimises an estimate of the work per query (below).  Shared by the host build and the device build (sg_gpubuild.cu).
@@ -46,11 +46,11 @@ std::string choose_layout(const std::vector<uint32_t> &seg_count, const std::vec
     auto row_words_at = [&](uint32_t s) { return (((ids_at(s) + ((1ull << s) - 1)) >> s) + 2047) / 2048 * 64 + (ids_at(s) ? 0 : 64); };  // whole 64-word tiles
     uint32_t bs = 0;
     if (want_bshift >= 0) bs = std::min<uint32_t>((uint32_t)want_bshift, kMaxBucketShift);
-    else if (n_docs > 16384 && n_terms > 0 && n_postings > 0) {
-        // cost of a typical query at width 2^s, in warp instructions: adding the bitmap words of its ~c lists (c = mean
-        // n-grams per document) plus resolving the buckets that reach a threshold of ~0.55 c by chance (Poisson tail of
-        // "lists hitting a bucket", mean c * W(s)).  Uniform 1M-entry 3-gram dictionary: 2^7; the Zipf-lettered one and
-        // dictionaries of short words (low thresholds) come out narrower.
+    else if (n_docs > 0 && n_terms > 0 && n_postings > 0 && (double)n_postings * 0.0054 > 16000.0) {
+        // Up to ~3M postings one bit per document stays: a query then adds ~c * n_docs / 32 words (c = mean n-grams per
+        // document), which is cheap, and no bucket is ever resolved, whatever the metric and similarity ask for.  (Measured
+        // on the reference's 235,887-word list: equal to 4 documents per bit for Jaccard 0.5, twice as fast for Cosine /
+        // Dice 0.5 and Jaccard 0.3.)  Above that:
         const double c = (double)n_postings / (double)n_docs;
         const int T = std::max(2, (int)std::lround(0.55 * c));
         double best = 0.0;
