@@ -197,8 +197,12 @@ int finalize(sg_index *ix) {
     d.n_segments = h.n_segments;
     d.n_docs = h.n_docs;
     ix->n_terms = d.n_terms;
-    if ((rc = upload(ix, h.ht_keys, &d.term_keys)) != SG_OK) return rc;
-    if ((rc = upload(ix, h.ht_vals, &d.term_vals)) != SG_OK) return rc;
+    {
+        std::vector<uint4> table(h.ht_keys.size());
+        for (size_t i = 0; i < table.size(); i++)
+            table[i] = uint4{(unsigned)h.ht_keys[i], (unsigned)(h.ht_keys[i] >> 32), h.ht_vals[i], 0u};
+        if ((rc = upload(ix, table, &d.term_table)) != SG_OK) return rc;
+    }
     if ((rc = upload(ix, h.seg_start, &d.seg_start)) != SG_OK) return rc;
     if ((rc = upload(ix, h.list_off, &d.list_off)) != SG_OK) return rc;
     if ((rc = upload(ix, h.postings, &d.postings, 8)) != SG_OK) return rc;
@@ -491,7 +495,7 @@ int sg_index_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *
         if (err.empty()) {
             sg::DevIndex &d = ix->dev;
             sg::HostIndex &h = ix->host;
-            d.term_keys = b.term_keys; d.term_vals = b.term_vals; d.term_mask = b.term_mask; d.n_terms = b.n_terms;
+            d.term_table = b.term_table; d.term_mask = b.term_mask; d.n_terms = b.n_terms;
             d.n_segments = b.n_segments; d.n_docs = n_docs; d.seg_start = b.seg_start; d.list_off = b.list_off;
             d.postings = b.postings; d.perm = b.perm; d.n_ids = b.n_ids; d.bshift = b.bshift; d.row_words = b.row_words; d.bitmaps = b.bitmaps;
             h.n_docs = n_docs; h.n_segments = b.n_segments; h.n_lists = b.n_lists; h.n_postings = b.n_postings;

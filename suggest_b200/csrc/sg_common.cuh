@@ -93,8 +93,9 @@ __device__ __forceinline__ uint32_t symbol_code(const DevIndex &ix, uint32_t r) 
 __device__ __forceinline__ uint32_t term_lookup(const DevIndex &ix, uint64_t key) {
     uint32_t h = (uint32_t)mix64(key) & ix.term_mask;
     for (;;) {
-        uint64_t k = __ldg(ix.term_keys + h);
-        if (k == key) return __ldg(ix.term_vals + h);
+        const uint4 e = __ldg(ix.term_table + h);
+        const uint64_t k = (uint64_t)e.y << 32 | e.x;
+        if (k == key) return e.z;
         if (k == 0) return kNoTerm;
         h = (h + 1) & ix.term_mask;
     }

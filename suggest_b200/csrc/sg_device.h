@@ -6,6 +6,9 @@
 #define SG_HD __host__ __device__
 #else
 #define SG_HD
+struct alignas(16) uint4 {  // layout of CUDA's uint4 for the host-only translation units
+    unsigned int x, y, z, w;
+};
 #endif
 
 namespace sg {
@@ -46,9 +49,9 @@ struct DevIndex {
     uint8_t ascii_code[128]; // 0 = not in the alphabet
     const RuneRange *ranges; // sorted, disjoint
     int32_t n_ranges;
-    // ---- term dictionary: packed key -> term id, open addressing, key 0 = empty ----
-    const uint64_t *term_keys;
-    const uint32_t *term_vals;
+    // ---- term dictionary: packed key -> term id, open addressing, key 0 = empty; one 16-byte entry per slot
+    // {key lo, key hi, term id, 0} so that a probe is a single load ----
+    const uint4 *term_table;
     uint32_t term_mask;
     uint32_t n_terms;
     // ---- inverted index, CSR in HBM ----

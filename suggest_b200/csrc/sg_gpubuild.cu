@@ -89,15 +89,14 @@ __global__ void sg_hist_kernel(const uint32_t *__restrict__ card, uint32_t n, ui
 }
 
 // term hash table: same probing as term_lookup (sg_common.cuh) and HostIndex::build_hash
-__global__ void sg_hash_insert_kernel(const uint64_t *__restrict__ keys, uint32_t n_terms, unsigned long long *ht_keys, uint32_t *ht_vals,
-                                      uint32_t mask) {
+__global__ void sg_hash_insert_kernel(const uint64_t *__restrict__ keys, uint32_t n_terms, uint4 *table, uint32_t mask) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_terms) return;
     const uint64_t key = keys[t];
     uint32_t h = (uint32_t)mix64(key) & mask;
-    for (;;) {
-        const unsigned long long prev = atomicCAS(ht_keys + h, 0ull, (unsigned long long)key);
-        if (prev == 0ull) { ht_vals[h] = t; return; }
+    for (;;) {  // the key occupies the first 8 bytes of the 16-byte entry
+        const unsigned long long prev = atomicCAS((unsigned long long *)(table + h), 0ull, (unsigned long long)key);
+        if (prev == 0ull) { table[h].z = t; return; }
         h = (h + 1) & mask;
     }
 }
@@ -328,17 +327,13 @@ std::string gpu_build(const DevIndex &text, const char *doc_bytes, const uint64_
     // 6a. term hash table (needed by step 5)
     size_t cap = 16;
     while (cap < (size_t)n_terms * 2 + 2) cap <<= 1;
-    unsigned long long *d_ht_keys;
-    uint32_t *d_ht_vals;
-    GB_CUDA(keep((void **)&d_ht_keys, cap * 8));
-    GB_CUDA(keep((void **)&d_ht_vals, cap * 4));
-    GB_CUDA(cudaMemset(d_ht_keys, 0, cap * 8));
-    GB_CUDA(cudaMemset(d_ht_vals, 0xFF, cap * 4));
-    sg_hash_insert_kernel<<<grid1(n_terms), 256>>>(d_terms, n_terms, d_ht_keys, d_ht_vals, (uint32_t)cap - 1);
+    uint4 *d_table;
+    GB_CUDA(keep((void **)&d_table, cap * sizeof(uint4)));
+    GB_CUDA(cudaMemset(d_table, 0, cap * sizeof(uint4)));
+    sg_hash_insert_kernel<<<grid1(n_terms), 256>>>(d_terms, n_terms, d_table, (uint32_t)cap - 1);
     GB_CUDA(cudaGetLastError());
     DevIndex look = text;
-    look.term_keys = (const uint64_t *)d_ht_keys;
-    look.term_vals = d_ht_vals;
+    look.term_table = d_table;
     look.term_mask = (uint32_t)cap - 1;
 
     // 5. posting lists: (term << 32 | slot) sorted
@@ -374,8 +369,7 @@ std::string gpu_build(const DevIndex &text, const char *doc_bytes, const uint64_
     GB_CUDA(cudaMemcpy(&n_lists, d_n_lists, 8, cudaMemcpyDeviceToHost));
     GB_CUDA(cudaDeviceSynchronize());
 
-    out->term_keys = (const uint64_t *)d_ht_keys;
-    out->term_vals = d_ht_vals;
+    out->term_table = d_table;
     out->term_mask = (uint32_t)cap - 1;
     out->n_terms = n_terms;
     out->n_segments = S;
@@ -389,7 +383,7 @@ std::string gpu_build(const DevIndex &text, const char *doc_bytes, const uint64_
     out->bitmaps = d_bitmaps;
     out->n_postings = n_pairs;
     out->n_lists = n_lists;
-    out->device_bytes = cap * 12 + ((size_t)S + 1) * 4 + (size_t)n_ids * 4 + n_post_alloc * 4 + (size_t)n_terms * (S + 1) * 4 +
+    out->device_bytes = cap * 16 + ((size_t)S + 1) * 4 + (size_t)n_ids * 4 + n_post_alloc * 4 + (size_t)n_terms * (S + 1) * 4 +
                         (row_words ? ((size_t)n_terms + 1) * row_words * 4 : 0);
     out->kernel_launches = 11;
     return "";

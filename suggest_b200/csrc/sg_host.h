@@ -78,8 +78,7 @@ std::string choose_layout(const std::vector<uint32_t> &seg_count, const std::vec
 
 // Index built on the device (sg_gpubuild.cu): device pointers, owned by the caller's allocation list.
 struct GpuBuilt {
-    const uint64_t *term_keys = nullptr;
-    const uint32_t *term_vals = nullptr;
+    const uint4 *term_table = nullptr;
     uint32_t term_mask = 0, n_terms = 0, n_segments = 0, n_ids = 0, bshift = 0, row_words = 0;
     const uint32_t *seg_start = nullptr, *list_off = nullptr, *postings = nullptr, *perm = nullptr, *bitmaps = nullptr;
     uint64_t n_postings = 0, n_lists = 0, device_bytes = 0;
