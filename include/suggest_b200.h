@@ -133,6 +133,12 @@ int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout);
  *   (pkg/suggest/collector.go:117-191, topk.go).
  * HOST buffers; the call copies queries to the device, runs the kernels and copies results back.
  * q_off has n_q + 1 entries.  out_ids / out_scores hold n_q * k entries, out_counts n_q.
+ * Row q holds out_counts[q] <= k candidates in GetCandidates order (score descending, id ascending); the entries of a
+ * row at and behind out_counts[q] are unspecified (the Go shim slices a row by its count).
+ * If all three output buffers are page-locked memory the device can address (sg_pinned_alloc, cudaHostAlloc,
+ * cudaHostRegister) the search kernel stores the candidates straight into them while it runs: no staging copy in HBM,
+ * no device-to-host copy behind the kernel, and only the valid entries cross PCIe.  Pageable buffers (plain Go or
+ * malloc memory) go through staging and cudaMemcpyAsync.  SG_DIRECT_OUT=0 forces the staged path.
  * A single Suggest call is a batch of one.
  */
 int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
@@ -217,6 +223,15 @@ int sg_lm_score_next_batch(sg_lm *lm, const uint32_t *ctx_ids, const uint32_t *c
                            const uint32_t *cand_off, double *out_scores, uint8_t *out_has_scorer);
 int sg_predict_batch(sg_index *ix, sg_lm *lm, const char *w_bytes, const uint32_t *w_off, const uint32_t *ctx_ids,
                      const uint32_t *ctx_off, uint32_t n_q, double similarity, uint32_t k, uint32_t *out_ids, uint32_t *out_counts);
+
+/*
+ * Page-locked, device-addressable host memory for query and result buffers (a micro-batcher allocates its buffers once
+ * and reuses them for every sg_search_batch call).  sg_is_pinned: 1 if [p, p + bytes) is such memory - what
+ * sg_search_batch checks to pick the direct result path - else 0.  No counterpart in the reference (Go heap memory).
+ */
+int sg_pinned_alloc(uint64_t bytes, void **out);
+void sg_pinned_free(void *p);
+int sg_is_pinned(const void *p, uint64_t bytes);
 
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 uint64_t sg_kernel_launches(void);

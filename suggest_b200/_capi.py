@@ -63,6 +63,9 @@ SIGNATURES = {
     "sg_lm_score_next_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sg_predict_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_double,
                                    C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sg_pinned_alloc": (C.c_int, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "sg_pinned_free": (None, [C.c_void_p]),
+    "sg_is_pinned": (C.c_int, [C.c_void_p, C.c_uint64]),
     "sg_kernel_launches": (C.c_uint64, []),
     "sg_last_error": (C.c_char_p, []),
     "sg_version": (C.c_char_p, []),

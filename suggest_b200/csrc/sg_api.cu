@@ -73,6 +73,9 @@ struct DevBuf {
 struct CallCtx {
     cudaStream_t stream = nullptr;   // slices of one call alternate between the two streams so that the copies of
     cudaStream_t stream2 = nullptr;  // one slice overlap the kernel of the other
+    cudaStream_t copy_stream = nullptr;  // every H2D copy of a call: a slice's queries never queue behind another slice's kernels
+    cudaEvent_t h2d_done[kMaxSlices] = {};
+    uint32_t *too_long = nullptr;        // page-locked word the search kernel sets if a query has too many n-grams (direct result path)
     DevBuf<char> q_bytes;
     DevBuf<uint32_t> q_off, ids, counts, work;
     DevBuf<uint8_t> plans;   // per-query plans, sg_plan_kernel -> sg_search_kernel or sg_tokens_kernel -> sg_bitmap_search_kernel
@@ -110,6 +113,13 @@ struct sg_index {
     std::atomic<uint32_t> work_rr{0};
     uint32_t tbl_bytes = kDefaultTblBytes;
     uint32_t slice_queries = 16384;      // queries per pipelined slice of sg_search_batch
+    uint32_t direct_slice_queries = 0;   // ... when the result rows are written straight into page-locked caller buffers
+                                         // (SG_DIRECT_SLICE_QUERIES; 0: cut at direct_split)
+    std::vector<uint32_t> direct_split{25};  // percent of the batch where the slices end (SG_DIRECT_SPLIT="25"): a small first
+                                         // slice so that the kernels start early; the rest travels under its kernels.
+                                         // Every further slice costs more in launch gaps and kernel tails than it hides
+                                         // (measured: "25" 186 M q/s, "10,40" 184, "6,20,50" 187 / Cosine 140, 137, 132)
+    bool direct_out = true;              // SG_DIRECT_OUT=0: always stage the rows in HBM and copy them back
     size_t l2_persist_bytes = 0;         // persisting-L2 carve-out used for the posting array (0: none)
     size_t l2_window_bytes = 0;
     float l2_hit_ratio = 1.0f;
@@ -268,6 +278,21 @@ int finish_setup(sg_index *ix) {
     }
     int sq = env_int("SG_SLICE_QUERIES", 16384);
     ix->slice_queries = sq < 256 ? 256u : (uint32_t)sq;
+    sq = env_int("SG_DIRECT_SLICE_QUERIES", 0);
+    ix->direct_slice_queries = sq <= 0 ? 0u : sq < 256 ? 256u : (uint32_t)sq;
+    if (const char *sp = std::getenv("SG_DIRECT_SPLIT")) {
+        ix->direct_split.clear();
+        for (const char *c = sp; *c;) {
+            char *end = nullptr;
+            const long v = std::strtol(c, &end, 10);
+            if (end == c) break;
+            if (v > 0 && v < 100 && (ix->direct_split.empty() || (uint32_t)v > ix->direct_split.back()) && ix->direct_split.size() + 2 < kMaxSlices)
+                ix->direct_split.push_back((uint32_t)v);
+            c = *end == ',' ? end + 1 : end;
+            if (*end != ',' ) break;
+        }
+    }
+    ix->direct_out = env_int("SG_DIRECT_OUT", 1) != 0;
     ix->max_warps = env_int("SG_WARPS", kMaxWarps);
     if (ix->max_warps < 1) ix->max_warps = 1;
     if (ix->max_warps > kMaxWarps) ix->max_warps = kMaxWarps;
@@ -282,6 +307,9 @@ void destroy(sg_index *ix) {
         c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release(); c->wtab.release();
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        for (cudaEvent_t e : c->h2d_done) if (e) cudaEventDestroy(e);
+        if (c->too_long) cudaFreeHost(c->too_long);
         delete c;
     }
     for (WtabEntry &w : ix->wtab_cache) {
@@ -353,7 +381,7 @@ int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, 
 int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
                    uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0, cudaEvent_t *stage_events = nullptr,
-                   const sg::LmContext *d_lm_ctx = nullptr) {
+                   const sg::LmContext *d_lm_ctx = nullptr, int sparse_rows = 0, uint32_t *too_long_flag = nullptr) {
     Geometry g{};
     int rc = SG_OK;
     if (!ix->bitmap_engine && (rc = geometry(ix, n_q, k, &g)) != SG_OK) return rc;
@@ -375,6 +403,8 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.force_shift = ix->force_shift;
     p.mode = mode;
     p.lm_ctx = d_lm_ctx;
+    p.sparse_rows = sparse_rows;
+    p.too_long_flag = too_long_flag;
     if (ix->l2_persist_bytes) {
         // keep the posting array resident in L2: query plans and result rows stream through the same cache
         cudaStreamAttrValue attr{};
@@ -450,8 +480,15 @@ struct CtxLease {
         if (!ctx) return fail(SG_ERR_NOMEM, "out of host memory");
         cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+        for (cudaEvent_t &ev : ctx->h2d_done)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->too_long, sizeof(uint32_t), cudaHostAllocMapped);
         if (e != cudaSuccess) {
             if (ctx->stream) cudaStreamDestroy(ctx->stream);
+            if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+            if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+            for (cudaEvent_t ev : ctx->h2d_done) if (ev) cudaEventDestroy(ev);
             delete ctx;
             ctx = nullptr;
             return fail(SG_ERR_CUDA, cudaGetErrorString(e));
@@ -597,6 +634,34 @@ int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout) {
     return SG_OK;
 }
 
+// Device address of [p, p + bytes) if that is page-locked host memory the device can address (cudaHostAlloc,
+// cudaHostRegister, sg_pinned_alloc); nullptr for pageable memory.
+static void *mapped_host_range(const void *p, size_t bytes) {
+    if (!p || !bytes) return nullptr;
+    cudaPointerAttributes a{}, b{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess || cudaPointerGetAttributes(&b, (const char *)p + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a.type != cudaMemoryTypeHost || b.type != cudaMemoryTypeHost || !a.devicePointer || !b.devicePointer) return nullptr;
+    if ((const char *)b.devicePointer - (const char *)a.devicePointer != (ptrdiff_t)(bytes - 1)) return nullptr;  // two allocations
+    return a.devicePointer;
+}
+
+int sg_pinned_alloc(uint64_t bytes, void **out) {
+    if (!out) return fail(SG_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (bytes == 0) return SG_OK;
+    SG_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return SG_OK;
+}
+
+void sg_pinned_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int sg_is_pinned(const void *p, uint64_t bytes) { return mapped_host_range(p, (size_t)bytes) != nullptr ? 1 : 0; }
+
 static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
                              uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int mode) {
     int rc = validate_search(ix, n_q, metric, alpha, k);
@@ -612,14 +677,37 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     rc = lease.acquire();
     if (rc != SG_OK) return rc;
     CallCtx *c = lease.ctx;
-    uint32_t n_slices = (n_q + ix->slice_queries - 1) / ix->slice_queries;
-    if (n_slices > kMaxSlices) n_slices = kMaxSlices;
-    if (n_slices < 1) n_slices = 1;
+    // Result rows in page-locked caller buffers: the search kernel stores the valid entries of every row (and its count)
+    // straight into them over PCIe while it runs - no staging in HBM, no D2H copy behind the kernel, and therefore no
+    // need to cut the batch into small slices to overlap that copy.  Entries at and behind out_counts[q] are not written.
+    uint32_t *m_ids = nullptr, *m_counts = nullptr;
+    double *m_scores = nullptr;
+    if (ix->direct_out && ix->bitmap_engine) {
+        m_ids = (uint32_t *)mapped_host_range(out_ids, (size_t)n_q * k * sizeof(uint32_t));
+        m_scores = (double *)mapped_host_range(out_scores, (size_t)n_q * k * sizeof(double));
+        m_counts = (uint32_t *)mapped_host_range(out_counts, (size_t)n_q * sizeof(uint32_t));
+    }
+    const bool direct = m_ids && m_scores && m_counts;
+    std::vector<uint32_t> bounds{0u};  // slice sl = queries [bounds[sl], bounds[sl + 1])
+    if (direct && ix->direct_slice_queries == 0) {
+        if (n_q >= 16384)
+            for (uint32_t pc : ix->direct_split) bounds.push_back((uint32_t)((uint64_t)n_q * pc / 100));
+        bounds.push_back(n_q);
+    } else {
+        const uint32_t slice_q = direct ? ix->direct_slice_queries : ix->slice_queries;
+        uint32_t n = (n_q + slice_q - 1) / slice_q;
+        if (n > kMaxSlices) n = kMaxSlices;
+        if (n < 1) n = 1;
+        for (uint32_t sl = 1; sl <= n; sl++) bounds.push_back((uint32_t)((uint64_t)n_q * sl / n));
+    }
+    const uint32_t n_slices = (uint32_t)bounds.size() - 1;
     SG_CUDA(c->q_bytes.reserve((size_t)total * 2 + 64 * (size_t)n_slices + 64));  // strings.ToLower can grow a slice by half
     SG_CUDA(c->q_off.reserve((size_t)n_q + n_slices + 1));
-    SG_CUDA(c->ids.reserve((size_t)n_q * k));
-    SG_CUDA(c->scores.reserve((size_t)n_q * k));
-    SG_CUDA(c->counts.reserve(n_q));
+    if (!direct) {
+        SG_CUDA(c->ids.reserve((size_t)n_q * k));
+        SG_CUDA(c->scores.reserve((size_t)n_q * k));
+        SG_CUDA(c->counts.reserve(n_q));
+    }
     SG_CUDA(c->work.reserve(kMaxSlices));
     SG_CUDA(c->plans.reserve((size_t)n_q * ix->plan_stride));
     SG_CUDA(c->wtab.reserve(ix->wtab_bytes * kMaxSlices));
@@ -629,20 +717,43 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     std::vector<std::string> low_bytes(n_slices);
     std::vector<std::vector<uint32_t>> low_off(n_slices);
     size_t dev_cursor = 0;
-    static const bool trace = env_int("SG_TRACE", 0) != 0;
+    static const int trace = env_int("SG_TRACE", 0);
     const auto t_begin = std::chrono::steady_clock::now();
+    // SG_TRACE=2: device timeline of the slices (events before the H2D copies, before and behind the kernels, behind the D2H)
+    std::vector<cudaEvent_t> tev;
+    std::vector<double> t_host;
+    if (trace >= 2) {
+        tev.resize((size_t)n_slices * 4 + 1);
+        for (auto &e : tev) SG_CUDA(cudaEventCreate(&e));
+        SG_CUDA(cudaEventRecord(tev[(size_t)n_slices * 4], c->copy_stream));
+    }
+    cudaStream_t cs = c->copy_stream;
+    uint32_t *d_too_long = nullptr;
+    if (direct) {
+        *c->too_long = 0u;
+        SG_CUDA(cudaHostGetDevicePointer((void **)&d_too_long, c->too_long, 0));
+    }
     for (uint32_t sl = 0; sl < n_slices; sl++) {
-        const uint32_t lo = (uint32_t)((uint64_t)n_q * sl / n_slices), hi = (uint32_t)((uint64_t)n_q * (sl + 1) / n_slices);
+        const uint32_t lo = bounds[sl], hi = bounds[sl + 1];
         if (lo == hi) continue;
         cudaStream_t st = (sl & 1) ? c->stream2 : c->stream;
         const uint32_t b0 = q_off[lo], b1 = q_off[hi];
-        unsigned char high = 0;  // no early exit: the loop vectorises
-        for (uint32_t i = b0; i < b1; i++) high |= (unsigned char)q_bytes[i];
         const char *src_bytes = q_bytes + b0;
         const uint32_t *src_off = q_off + lo;
         size_t n_bytes = b1 - b0;
         char *region = c->q_bytes.p + dev_cursor;
         const char *d_q_bytes = region - b0;  // offsets stay absolute; only [b0, b1) is ever addressed
+        if (trace >= 2) {
+            t_host.push_back(std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count());
+            cudaEventRecord(tev[(size_t)sl * 4], cs);
+        }
+        // Queries travel on the copy stream, the kernels of the slice wait for its event: the copy of slice i + 1 runs
+        // under the kernels of slice i instead of queueing behind the kernels of slice i - 1 on its own stream.
+        // The copy starts before the host has looked at the bytes: nearly every slice is plain ASCII and goes as it is.
+        if (n_bytes) SG_CUDA(cudaMemcpyAsync(region, src_bytes, n_bytes, cudaMemcpyHostToDevice, cs));
+        const size_t n_raw = n_bytes;
+        unsigned char high = 0;  // no early exit: the loop vectorises
+        for (uint32_t i = b0; i < b1; i++) high |= (unsigned char)q_bytes[i];
         if (high & 0x80) {
             std::string &lb = low_bytes[sl];
             std::vector<uint32_t> &lof = low_off[sl];
@@ -657,30 +768,53 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
             src_off = lof.data();
             n_bytes = lb.size();
             d_q_bytes = region;
+            if (n_bytes) SG_CUDA(cudaMemcpyAsync(region, src_bytes, n_bytes, cudaMemcpyHostToDevice, cs));  // replaces the raw bytes
         }
-        dev_cursor += (n_bytes + 63) & ~(size_t)63;
+        dev_cursor += ((n_bytes > n_raw ? n_bytes : n_raw) + 63) & ~(size_t)63;
         uint32_t *d_off = c->q_off.p + lo + sl;
-        if (n_bytes) SG_CUDA(cudaMemcpyAsync(region, src_bytes, n_bytes, cudaMemcpyHostToDevice, st));
-        SG_CUDA(cudaMemcpyAsync(d_off, src_off, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        rc = enqueue_search(ix, d_q_bytes, d_off, hi - lo, metric, alpha, k, c->ids.p + (size_t)lo * k,
-                            c->scores.p + (size_t)lo * k, c->counts.p + lo, nullptr, c->work.p + sl,
-                            c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st, mode);
-        if (rc != SG_OK) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }
+        SG_CUDA(cudaMemcpyAsync(d_off, src_off, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+        if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 1], cs);
+        SG_CUDA(cudaEventRecord(c->h2d_done[sl], cs));
+        SG_CUDA(cudaStreamWaitEvent(st, c->h2d_done[sl], 0));
+        rc = enqueue_search(ix, d_q_bytes, d_off, hi - lo, metric, alpha, k, (direct ? m_ids : c->ids.p) + (size_t)lo * k,
+                            (direct ? m_scores : c->scores.p) + (size_t)lo * k, (direct ? m_counts : c->counts.p) + lo, nullptr,
+                            c->work.p + sl, c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st,
+                            mode, nullptr, nullptr, direct ? 1 : 0, direct ? d_too_long : nullptr);
+        if (rc != SG_OK) { cudaStreamSynchronize(cs); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }
+        if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 2], st);
+        if (direct) {
+            if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 3], st);
+            continue;
+        }
         SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, c->ids.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(out_scores + (size_t)lo * k, c->scores.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(double),
                                 cudaMemcpyDeviceToHost, st));
         SG_CUDA(cudaMemcpyAsync(out_counts + lo, c->counts.p + lo, (size_t)(hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 3], st);
     }
     const auto t_enqueued = std::chrono::steady_clock::now();
     SG_CUDA(cudaStreamSynchronize(c->stream));
     SG_CUDA(cudaStreamSynchronize(c->stream2));
+    SG_CUDA(cudaStreamSynchronize(cs));
     if (trace) {
         const auto t_done = std::chrono::steady_clock::now();
-        std::fprintf(stderr, "sg_search_batch: %u queries, %u slices: enqueue %.1f us, wait %.1f us\n", n_q, n_slices,
+        std::fprintf(stderr, "sg_search_batch: %u queries, %u slices%s: enqueue %.1f us, wait %.1f us\n", n_q, n_slices,
+                     direct ? " (rows stored into page-locked host memory)" : "",
                      std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count(),
                      std::chrono::duration<double, std::micro>(t_done - t_enqueued).count());
     }
+    if (trace >= 2) {
+        const cudaEvent_t e0 = tev[(size_t)n_slices * 4];
+        for (uint32_t sl = 0; sl < n_slices && sl < t_host.size(); sl++) {
+            float t[4] = {0, 0, 0, 0};
+            for (int i = 0; i < 4; i++) cudaEventElapsedTime(&t[i], e0, tev[(size_t)sl * 4 + i]);
+            std::fprintf(stderr, "  slice %u: host enqueue at %.1f us; device: h2d %.1f-%.1f us, kernels until %.1f us, rows on the host at %.1f us\n",
+                         sl, t_host[sl], t[0] * 1e3, t[1] * 1e3, t[2] * 1e3, t[3] * 1e3);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
+    if (direct && *(volatile uint32_t *)c->too_long == 0u) return SG_OK;  // the kernel saw no such query: nothing to look for
     for (uint32_t q = 0; q < n_q; q++)
         if (out_counts[q] == SG_COUNT_UNSUPPORTED)
             return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");

@@ -585,14 +585,19 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
             tk_len = ws->tk_len;
         }
 
-        // results: GetCandidates order, fixed stride k
+        // results: GetCandidates order, fixed stride k.  sparse_rows: the rows are the caller's page-locked host buffers
+        // (sg_search_batch) and every store crosses PCIe - only the valid entries are written
         const size_t row = (size_t)q * p.k;
-        for (uint32_t j = lane; j < p.k; j += 32) {
+        const uint32_t n_out = p.sparse_rows ? (uint32_t)tk_len : p.k;
+        for (uint32_t j = lane; j < n_out; j += 32) {
             const bool has = (int)j < tk_len;
             p.out_ids[row + j] = has ? ix.id_base + tk_id[j] : 0u;
             p.out_scores[row + j] = has ? tk_score[j] : 0.0;
         }
-        if (lane == 0) p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)tk_len;
+        if (lane == 0) {
+            p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)tk_len;
+            if (unsupported && p.too_long_flag != nullptr) *p.too_long_flag = 1u;
+        }
         __syncwarp();  // every lane is done with this query's shared state before lane 0 resets it for the next
         q = __shfl_sync(kFull, q_next, 0);
     }

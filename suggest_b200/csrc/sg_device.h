@@ -153,6 +153,8 @@ struct SearchParams {
     int32_t mode;             // 0: Suggest; 1: Autocomplete (no tail wrap, every token required, lowest ids win)
     WindowTables wt;          // bitmap engine only
     const LmContext *lm_ctx;  // mode 1 only, optional: rank the completions by the language model (spellchecker collector)
+    uint32_t *too_long_flag;  // optional: set to 1 if any query of the launch is reported as SG_COUNT_UNSUPPORTED
+    int32_t sparse_rows;      // 1: write only the out_counts[q] valid entries of a row (rows in page-locked host memory)
 };
 
 SG_HD static inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; host and device hash term keys with it

@@ -40,6 +40,41 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+class PinnedBuffers:
+    """Result buffers for SuggestBatch / AutocompleteBatch in page-locked memory (sg_pinned_alloc): the search kernel
+    stores the candidates straight into them, entries at and behind counts[q] are left as they were.  Pass `.out` as
+    the `out=` argument; the arrays are views of the allocation and die with this object."""
+
+    def __init__(self, n_q, k):
+        self._ptrs = []
+        self.ids = self._alloc((n_q, k), np.uint32)
+        self.scores = self._alloc((n_q, k), np.float64)
+        self.counts = self._alloc((n_q,), np.uint32)
+        self.out = (self.ids, self.scores, self.counts)
+
+    def _alloc(self, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _capi.check(_capi.lib().sg_pinned_alloc(max(n, 1), C.byref(p)))
+        self._ptrs.append(p.value)
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        a[...] = 0
+        return a
+
+    def close(self):
+        ptrs, self._ptrs = self._ptrs, []
+        self.ids = self.scores = self.counts = self.out = None
+        for p in ptrs:
+            _capi.lib().sg_pinned_free(p)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 @dataclass
 class IndexDescription:
     """suggest.IndexDescription, pkg/suggest/config.go:25-35"""
@@ -202,15 +237,18 @@ class NGramIndex:
         ids, scores, counts = self.AutocompleteBatch([query], limit)
         return [Candidate(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
 
-    def AutocompleteBatch(self, queries, limit, packed=None):
+    def AutocompleteBatch(self, queries, limit, packed=None, out=None):
         data, off = packed if packed is not None else pack_strings(queries)
         data = np.ascontiguousarray(data, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         n_q = len(off) - 1
         k = max(int(limit), 0)
-        ids = np.zeros((n_q, k), dtype=np.uint32)
-        scores = np.zeros((n_q, k), dtype=np.float64)
-        counts = np.zeros(n_q, dtype=np.uint32)
+        if out is None:
+            ids = np.zeros((n_q, k), dtype=np.uint32)
+            scores = np.zeros((n_q, k), dtype=np.float64)
+            counts = np.zeros(n_q, dtype=np.uint32)
+        else:
+            ids, scores, counts = out
         _capi.check(_capi.lib().sg_autocomplete_batch(self.handle, _ptr(data), _ptr(off), n_q, k, _ptr(ids), _ptr(scores),
                                                       _ptr(counts)))
         return ids, scores, counts

@@ -308,6 +308,12 @@ def test_invalid_arguments_and_too_long_query(cars_pair):
     with pytest.raises(S.SuggestError) as e:
         gx.SuggestBatch(["ok", "y" * 300], 0.5, S.JaccardMetric(), 5)
     assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG
+    buf = S.PinnedBuffers(3, 5)  # the direct result path learns of such a query from a flag the kernel sets
+    with pytest.raises(S.SuggestError) as e:
+        gx.SuggestBatch(["ok", "y" * 300, "Nissan March"], 0.5, S.JaccardMetric(), 5, out=buf.out)
+    assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG and buf.counts[1] == _capi.SG_COUNT_UNSUPPORTED and buf.counts[2] > 0
+    gx.SuggestBatch(["ok", "Nissan March"], 0.5, S.JaccardMetric(), 5, out=(buf.ids[:2], buf.scores[:2], buf.counts[:2]))  # and the flag is per call
+    buf.close()
     with pytest.raises(S.SuggestError):
         S.NewRAMBuilder(["a"], IndexDescription(NGramSize=3, Pad="")).Build()
 
@@ -456,6 +462,65 @@ def test_full_size_1m_jaccard():
     m2 = np.arange(k)[None, :] < n_o[:, None]
     assert np.array_equal(ids[sample][m2], ids_o[m2])
     assert np.array_equal(sc[sample][m2], sc_o[m2])
+
+
+# ---------------------------------------------------------------------------------------------------
+# result rows in page-locked caller buffers: the kernel stores the valid entries straight into host memory
+# ---------------------------------------------------------------------------------------------------
+def test_pinned_result_buffers(cars_pair, cars_lines, synth_pairs):
+    L = _capi.lib()
+    SENT_ID, SENT_SC = 0xDEADBEEF, -7.25
+    cases = [(cars_pair[0], cars_pair[1], cars_lines, O.COSINE, 0.5, 5), (cars_pair[0], cars_pair[1], cars_lines, O.JACCARD, 0.2, 40)]
+    gx3, ox3, queries3 = synth_pairs[3]
+    cases.append((gx3, ox3, queries3, O.JACCARD, 0.5, 10))
+    for gx, ox, queries, metric, alpha, k in cases:
+        buf = S.PinnedBuffers(len(queries), k)
+        assert L.sg_is_pinned(buf.ids.ctypes.data, buf.ids.nbytes) == 1 and L.sg_is_pinned(buf.scores.ctypes.data, buf.scores.nbytes) == 1
+        plain = np.zeros(16, dtype=np.uint32)
+        assert L.sg_is_pinned(plain.ctypes.data, plain.nbytes) == 0
+        buf.ids[...] = SENT_ID
+        buf.scores[...] = SENT_SC
+        buf.counts[...] = 0x55555555
+        ids, sc, n = gx.SuggestBatch(queries, alpha, METRICS[metric], k, out=buf.out)
+        ids_o, sc_o, n_o = ox.suggest_batch(queries, metric, alpha, k, O.CANONICAL, threads=8)
+        assert np.array_equal(n, n_o)
+        mask = np.arange(k)[None, :] < n_o[:, None]
+        assert np.array_equal(ids[mask], ids_o[mask]) and np.array_equal(sc[mask], sc_o[mask])
+        # the direct path writes nothing else: what lies behind a row's count is untouched
+        assert np.all(ids[~mask] == SENT_ID) and np.all(sc[~mask] == SENT_SC)
+        # the staged path (pageable buffers) returns the same candidates
+        ids_p, sc_p, n_p = gx.SuggestBatch(queries, alpha, METRICS[metric], k)
+        assert np.array_equal(n_p, n) and np.array_equal(ids_p[mask], ids[mask]) and np.array_equal(sc_p[mask], sc[mask])
+        # autocomplete through the same buffers
+        lim = min(k, 10)
+        buf2 = S.PinnedBuffers(len(queries), lim)
+        prefixes = [q[: max(3, len(q) // 2)] for q in queries]
+        a_ids, a_sc, a_n = gx.AutocompleteBatch(prefixes, lim, out=buf2.out)
+        b_ids, b_sc, b_n = gx.AutocompleteBatch(prefixes, lim)
+        m2 = np.arange(lim)[None, :] < b_n[:, None]
+        assert np.array_equal(a_n, b_n) and np.array_equal(a_ids[m2], b_ids[m2]) and np.array_equal(a_sc[m2], b_sc[m2])
+        buf.close()
+        buf2.close()
+    # a batch large enough for the default cut into unequal slices (SG_DIRECT_SPLIT): the same rows as query by query
+    big = (queries3 * 7)[:20000]
+    buf = S.PinnedBuffers(len(big), 10)
+    ids, sc, n = gx3.SuggestBatch(big, 0.5, METRICS[O.JACCARD], 10, out=buf.out)
+    ids_1, sc_1, n_1 = gx3.SuggestBatch(queries3, 0.5, METRICS[O.JACCARD], 10)
+    rep = np.arange(len(big)) % len(queries3)
+    mask = np.arange(10)[None, :] < n[:, None]
+    assert np.array_equal(n, n_1[rep]) and np.array_equal(ids[mask], ids_1[rep][mask]) and np.array_equal(sc[mask], sc_1[rep][mask])
+    buf.close()
+    # the batch cut into slices that alternate between two streams; and the scan-count engine, which stages its rows
+    docs, _ = synthetic(60000, 3000)
+    for env in (dict(SG_DIRECT_SLICE_QUERIES=300), dict(SG_DIRECT_SPLIT="3,5,50"), SCAN, dict(SG_DIRECT_OUT=0)):
+        gx = build_gpu(TEST_DESCRIPTION, docs, env)
+        buf = S.PinnedBuffers(len(queries3), 10)
+        ids, sc, n = gx.SuggestBatch(queries3, 0.5, METRICS[O.JACCARD], 10, out=buf.out)
+        ids_o, sc_o, n_o = ox3.suggest_batch(queries3, O.JACCARD, 0.5, 10, O.CANONICAL, threads=8)
+        mask = np.arange(10)[None, :] < n_o[:, None]
+        assert np.array_equal(n, n_o) and np.array_equal(ids[mask], ids_o[mask]) and np.array_equal(sc[mask], sc_o[mask]), env
+        buf.close()
+        gx.close()
 
 
 # ---------------------------------------------------------------------------------------------------
