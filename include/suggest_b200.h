@@ -154,6 +154,29 @@ int sg_autocomplete_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_o
                           uint32_t *out_ids, double *out_scores, uint32_t *out_counts);
 
 /*
+ * Every candidate of the T-occurrence count, for callers whose CollectorManager is not a FuzzyCollectorManager /
+ * FirstKCollectorManager or whose metric.Metric is not one of the five built-ins: what searcher.Search + the mergers hand
+ * to Collector.Collect (pkg/index/searcher.go:28-78, pkg/merger/collector.go:10-13, MergeCandidate = position + overlap,
+ * pkg/merger/list_merger.go:33-48) over every admissible segment of nGramSuggester.Suggest's window
+ * (pkg/suggest/suggester.go:53-78).  The Go shim replays them through factory().Create() / SetScorer / Collect /
+ * manager.Collect on the host, segment by segment in the reference's feed order (suggester.go:110-118).
+ *   thresholds == NULL: window and thresholds of the built-in `metric` at `alpha`, computed on the device as in
+ *                       sg_search_batch;
+ *   thresholds != NULL: [SG_MAX_QUERY_TOKENS + 1][n_segments] bytes tabulated by the caller from its own metric.Metric:
+ *                       thresholds[a * n_segments + B] = Threshold(alpha, a, B) for MinY(alpha, a) <= B <= MaxY(alpha, a),
+ *                       0 elsewhere (values above 255 as 255: never admissible, a <= 128).  `metric` / `alpha` are ignored.
+ *                       The library applies suggester.go:76 (T == 0, T > sizeB, T > sizeA: skip) and skips empty segments.
+ * Output: one entry per candidate in no particular order: out_query (number of the query in the batch), out_ids
+ * (document id), out_overlap (exact overlap count, rule 5 of SURVEY.md 8c), out_segment (sizeB).  *out_total is the
+ * number found; only the first min(cap, *out_total) are written - call again with a larger cap if it was exceeded.
+ * out_size_a[q] = len(tokens) of query q (the sizeA of Distance / Threshold).  HOST buffers.  Bitmap-engine indexes only
+ * (SG_ERR_UNSUPPORTED otherwise).
+ */
+int sg_candidates_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                        const uint8_t *thresholds, uint64_t cap, uint32_t *out_query, uint32_t *out_ids, uint32_t *out_overlap,
+                        uint32_t *out_segment, uint64_t *out_total, uint32_t *out_size_a);
+
+/*
  * Same, every buffer already resident on the index's device; enqueued on `stream` (a cudaStream_t,
  * NULL = default stream) without synchronising.  Queries must already be lower-cased if they hold
  * non-ASCII bytes (sg_search_batch does that on the host, strings.ToLower semantics).

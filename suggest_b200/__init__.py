@@ -4,11 +4,11 @@ The package is a thin host-side mirror of the reference's Go interfaces over the
 libsuggest_b200.so (include/suggest_b200.h).  Names follow the reference: pkg/suggest
 (IndexDescription, Builder, NGramIndex, Service, SearchConfig, Candidate, ResultItem) and pkg/metric.
 """
-from . import metric
+from . import collector, metric
 from .metric import CosineMetric, DiceMetric, ExactMetric, JaccardMetric, OverlapMetric
 from .suggest import (Candidate, IndexDescription, PinnedBuffers, NGramIndex, NewRAMBuilder, NewFSBuilder, NewSearchConfig, NewService,
                       ResultItem, SearchConfig, Service, SuggestError, pack_strings)
 
-__all__ = ["metric", "CosineMetric", "DiceMetric", "ExactMetric", "JaccardMetric", "OverlapMetric", "Candidate", "PinnedBuffers",
+__all__ = ["collector", "metric", "CosineMetric", "DiceMetric", "ExactMetric", "JaccardMetric", "OverlapMetric", "Candidate", "PinnedBuffers",
            "IndexDescription", "NGramIndex", "NewRAMBuilder", "NewFSBuilder", "NewSearchConfig", "NewService",
            "ResultItem", "SearchConfig", "Service", "SuggestError", "pack_strings"]

@@ -81,6 +81,8 @@ struct CallCtx {
     DevBuf<uint8_t> plans;   // per-query plans, sg_plan_kernel -> sg_search_kernel or sg_tokens_kernel -> sg_bitmap_search_kernel
     DevBuf<uint8_t> wtab;    // window tables of the bitmap engine, one set per slice
     DevBuf<double> scores;
+    DevBuf<uint32_t> cand;               // sg_candidates_batch: [query | id | overlap | segment] x cap, then the thresholds
+    DevBuf<unsigned long long> cand_total;
 };
 
 }  // namespace
@@ -304,7 +306,7 @@ void destroy(sg_index *ix) {
     DeviceGuard guard;
     guard.set(ix->device);
     for (CallCtx *c : ix->pool) {
-        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release(); c->wtab.release();
+        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release(); c->wtab.release(); c->cand.release(); c->cand_total.release();
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -350,6 +352,14 @@ int make_index(const sg_config *cfg, sg_index **out, sg_index **ixp) {
 
 struct Geometry { int blocks, warps; size_t smem; uint32_t warp_smem; };
 
+// sg_candidates_batch: device side of SearchParams::cand_* / custom_thr
+struct CollectArgs {
+    const uint8_t *d_thr;             // nullptr: thresholds of the built-in metric
+    unsigned long long *d_total;
+    unsigned long long cap;
+    uint32_t *d_query, *d_ids, *d_overlap, *d_segment;
+};
+
 int geometry(const sg_index *ix, uint32_t n_q, uint32_t k, Geometry *g) {
     uint32_t warp_smem = ix->tbl_bytes + sg::kWarpFixedSmem + k * 12u;  // layout: sg_search_kernel
     warp_smem = (warp_smem + 15u) & ~15u;
@@ -381,7 +391,8 @@ int validate_search(const sg_index *ix, uint32_t n_q, int metric, double alpha, 
 int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
                    uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0, cudaEvent_t *stage_events = nullptr,
-                   const sg::LmContext *d_lm_ctx = nullptr, int sparse_rows = 0, uint32_t *too_long_flag = nullptr) {
+                   const sg::LmContext *d_lm_ctx = nullptr, int sparse_rows = 0, uint32_t *too_long_flag = nullptr,
+                   const CollectArgs *collect = nullptr) {
     Geometry g{};
     int rc = SG_OK;
     if (!ix->bitmap_engine && (rc = geometry(ix, n_q, k, &g)) != SG_OK) return rc;
@@ -405,6 +416,16 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.lm_ctx = d_lm_ctx;
     p.sparse_rows = sparse_rows;
     p.too_long_flag = too_long_flag;
+    if (collect) {
+        if (!ix->bitmap_engine) return fail(SG_ERR_UNSUPPORTED, "sg_candidates_batch needs an index with bitmaps (engine 1)");
+        p.custom_thr = collect->d_thr;
+        p.cand_total = collect->d_total;
+        p.cand_cap = collect->cap;
+        p.cand_query = collect->d_query;
+        p.cand_ids = collect->d_ids;
+        p.cand_overlap = collect->d_overlap;
+        p.cand_segment = collect->d_segment;
+    }
     if (ix->l2_persist_bytes) {
         // keep the posting array resident in L2: query plans and result rows stream through the same cache
         cudaStreamAttrValue attr{};
@@ -429,7 +450,7 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
         // window tables: cached per (metric, similarity, mode); a measurement launch (stage_events) always computes them
         bool run_window = true;
         point_tables(d_wtab);
-        if (!stage_events) {
+        if (!stage_events && !(collect && collect->d_thr)) {  // a caller-tabulated metric has no key to cache under
             std::lock_guard<std::mutex> lk(ix->mu);
             WtabEntry *hit = nullptr, *vacant = nullptr;
             for (WtabEntry &w : ix->wtab_cache) {
@@ -829,6 +850,98 @@ int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, ui
 int sg_autocomplete_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, uint32_t limit,
                           uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
     return search_batch_impl(ix, q_bytes, q_off, n_q, SG_EXACT, 1.0, limit, out_ids, out_scores, out_counts, 1);
+}
+
+int sg_candidates_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                        const uint8_t *thresholds, uint64_t cap, uint32_t *out_query, uint32_t *out_ids, uint32_t *out_overlap,
+                        uint32_t *out_segment, uint64_t *out_total, uint32_t *out_size_a) {
+    if (!ix) return fail(SG_ERR_INVALID, "null index");
+    if (!out_total) return fail(SG_ERR_INVALID, "null out_total");
+    *out_total = 0;
+    if (!thresholds) {
+        int rc0 = validate_search(ix, n_q, metric, alpha, 1);
+        if (rc0 != SG_OK) return rc0;
+    } else {
+        metric = SG_JACCARD;  // unused: every threshold comes from the table
+        alpha = 1.0;
+    }
+    if (n_q == 0) return SG_OK;
+    if (!q_off || !out_size_a || (cap && (!out_query || !out_ids || !out_overlap || !out_segment))) return fail(SG_ERR_INVALID, "null buffer");
+    const uint32_t total_bytes = q_off[n_q];
+    if (total_bytes && !q_bytes) return fail(SG_ERR_INVALID, "null query bytes");
+
+    DeviceGuard guard;
+    SG_CUDA(guard.set(ix->device));
+    CtxLease lease(ix);
+    int rc = lease.acquire();
+    if (rc != SG_OK) return rc;
+    CallCtx *c = lease.ctx;
+    // queries: strings.ToLower on the host if any byte is not ASCII (the device lowers A-Z itself), as sg_search_batch does
+    std::string low;
+    std::vector<uint32_t> low_off;
+    const char *src_bytes = q_bytes;
+    const uint32_t *src_off = q_off;
+    size_t n_bytes = total_bytes;
+    unsigned char high = 0;
+    for (uint32_t i = 0; i < total_bytes; i++) high |= (unsigned char)q_bytes[i];
+    if (high & 0x80) {
+        low_off.resize((size_t)n_q + 1);
+        for (uint32_t q = 0; q < n_q; q++) {
+            low_off[q] = (uint32_t)low.size();
+            sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &low);
+        }
+        low_off[n_q] = (uint32_t)low.size();
+        src_bytes = low.data();
+        src_off = low_off.data();
+        n_bytes = low.size();
+    }
+    const size_t thr_bytes = thresholds ? (size_t)sg::kWindowRows * ix->dev.n_segments : 0;
+    const size_t thr_words = (thr_bytes + 3) / 4;
+    SG_CUDA(c->q_bytes.reserve(n_bytes + 64));
+    SG_CUDA(c->q_off.reserve((size_t)n_q + 1));
+    SG_CUDA(c->counts.reserve(n_q));
+    SG_CUDA(c->work.reserve(kMaxSlices));
+    SG_CUDA(c->plans.reserve((size_t)n_q * ix->plan_stride));
+    SG_CUDA(c->wtab.reserve(ix->wtab_bytes * kMaxSlices));
+    SG_CUDA(c->cand.reserve((size_t)cap * 4 + thr_words + 4));
+    SG_CUDA(c->cand_total.reserve(1));
+    cudaStream_t st = c->stream;
+    if (n_bytes) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p, src_bytes, n_bytes, cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemcpyAsync(c->q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SG_CUDA(cudaMemsetAsync(c->cand_total.p, 0, sizeof(unsigned long long), st));
+    CollectArgs ca{};
+    ca.d_total = c->cand_total.p;
+    ca.cap = cap;
+    ca.d_query = c->cand.p;
+    ca.d_ids = c->cand.p + cap;
+    ca.d_overlap = c->cand.p + 2 * cap;
+    ca.d_segment = c->cand.p + 3 * cap;
+    if (thresholds) {
+        uint8_t *d_thr = (uint8_t *)(c->cand.p + 4 * cap);
+        SG_CUDA(cudaMemcpyAsync(d_thr, thresholds, thr_bytes, cudaMemcpyHostToDevice, st));
+        ca.d_thr = d_thr;
+    }
+    // k = 1: the top-k of the search kernel stays empty in collect mode; rows are "sparse" so nothing of them is written
+    rc = enqueue_search(ix, c->q_bytes.p, c->q_off.p, n_q, metric, alpha, 1, nullptr, nullptr, c->counts.p, nullptr, c->work.p,
+                        c->plans.p, c->wtab.p, st, 0, nullptr, nullptr, 1, nullptr, &ca);
+    if (rc != SG_OK) { cudaStreamSynchronize(st); return rc; }
+    unsigned long long found = 0;
+    SG_CUDA(cudaMemcpyAsync(&found, c->cand_total.p, sizeof(found), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(out_size_a, c->counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    *out_total = found;
+    const size_t n_out = (size_t)(found < cap ? found : cap);
+    if (n_out) {
+        SG_CUDA(cudaMemcpyAsync(out_query, ca.d_query, n_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(out_ids, ca.d_ids, n_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(out_overlap, ca.d_overlap, n_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(out_segment, ca.d_segment, n_out * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaStreamSynchronize(st));
+    }
+    for (uint32_t q = 0; q < n_q; q++)
+        if (out_size_a[q] == SG_COUNT_UNSUPPORTED)
+            return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");
+    return SG_OK;
 }
 
 int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,

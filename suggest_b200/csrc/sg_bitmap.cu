@@ -53,7 +53,8 @@ struct WarpSmem {
     int32_t size_a, n_lists;
     uint32_t lm_valid, lm_from, lm_to; // spellchecker completions: rank by the language model (LmContext of the query)
     const uint64_t *lm_vals;
-    uint32_t pad[8];
+    uint32_t q;                        // number of the query inside the launch (collect mode)
+    uint32_t pad[7];
     uint32_t flag[32];                 // per lane: buckets of its word that reached the threshold
     uint32_t bias[32];                 // per lane: 2^M - T(word), what the planes started from
     alignas(16) uint32_t row[kRowSlots];   // word offset of the bitmap row of every list
@@ -71,6 +72,9 @@ struct BlockConsts {
     const uint8_t *seg_thr;   // WindowTables::seg_thr
     uint32_t n_segments, bshift, id_base, k;
     int32_t metric;
+    unsigned long long *cand_total;     // collect mode (sg_candidates_batch): SearchParams::cand_*
+    unsigned long long cand_cap;
+    uint32_t *cand_query, *cand_ids, *cand_overlap, *cand_segment;
     uint32_t seg_cache[kSegCache + 1];  // seg_start[0 .. min(S, kSegCache)]
 };
 
@@ -111,10 +115,28 @@ __device__ __forceinline__ double completion_score(const BlockConsts *bc, const 
     return (uint32_t)(hit >> 32) == word && lo < ws->lm_to ? (double)(uint32_t)hit : 0.0;
 }
 
+// Collect mode (sg_candidates_batch): what the mergers hand to Collector.Collect (pkg/merger/collector.go:10-13), appended
+// to the launch-wide list; scoring and selection are the caller's (a CollectorManager / metric.Metric of its own).
+// Out of line: its registers (a 64-bit atomic and four pointers) stay out of handle_flags and of the kernel around it.
+__device__ __noinline__ void collect_candidate(const BlockConsts *bc, uint32_t q, uint32_t id, int count, int size_b) {
+    const unsigned long long at = atomicAdd(bc->cand_total, 1ull);
+    if (at < bc->cand_cap) {
+        bc->cand_query[at] = q;
+        bc->cand_ids[at] = bc->id_base + id;
+        bc->cand_overlap[at] = (uint32_t)count;
+        bc->cand_segment[at] = (uint32_t)size_b;
+    }
+}
+
 // A document (new id) of segment size_b with an exact overlap count >= T: score it and offer it to the warp's sorted
 // top-k (best first, Candidate.Less of pkg/suggest/collector.go:20-26).  All lanes call with identical arguments.
+template <bool kCollect>
 __device__ void offer_candidate(const BlockConsts *bc, WarpSmem *ws, uint32_t new_id, int count, int size_b, int lane) {
     const uint32_t id = __ldg(bc->perm + new_id);
+    if (kCollect) {
+        if (lane == 0) collect_candidate(bc, ws->q, id, count, size_b);
+        return;
+    }
     const double score = bc->metric != kAutocomplete ? metric_score(bc->metric, count, ws->size_a, size_b) : completion_score(bc, ws, id);
     QueryCtx c;
     c.k = bc->k;
@@ -168,6 +190,7 @@ __device__ __forceinline__ uint32_t lower_bound4(const uint32_t *__restrict__ po
 // the planes give the overlap (ws->cnt, ws->bias); bshift > 0: count every document of the bucket exactly - lane l takes
 // lists l, l + 32, ..., searches the (term, segment) posting list for the bucket's id range and adds one to the counter
 // of every document found - then offer the survivors to the top-k.
+template <bool kCollect>
 __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, uint32_t w0, int M, int lane) {
     const uint32_t bshift = bc->bshift;
     const uint8_t *seg_thr = bc->seg_thr + (size_t)ws->size_a * bc->n_segments;
@@ -188,7 +211,7 @@ __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, u
             if (bshift == 0) {
                 int count = (1 << M) - (int)ws->bias[src];  // the planes hold bias + overlap - 2^M
                 for (int j = 0; j < M; j++) count += (int)((ws->cnt[j * 32 + src] >> bit) & 1u) << j;
-                if (count >= T) offer_candidate(bc, ws, bucket, count, B, lane);
+                if (count >= T) offer_candidate<kCollect>(bc, ws, bucket, count, B, lane);
                 continue;
             }
             const uint32_t width = 1u << bshift, id_hi = id_lo + width;
@@ -212,7 +235,7 @@ __device__ __noinline__ void handle_flags(const BlockConsts *bc, WarpSmem *ws, u
                 while (m) {
                     const int i = __ffs(m) - 1;
                     m &= m - 1;
-                    offer_candidate(bc, ws, id_lo + base + (uint32_t)i, (int)__shfl_sync(kFull, v, i), B, lane);
+                    offer_candidate<kCollect>(bc, ws, id_lo + base + (uint32_t)i, (int)__shfl_sync(kFull, v, i), B, lane);
                 }
             }
             __syncwarp();
@@ -379,7 +402,7 @@ __device__ __forceinline__ uint32_t count_until_flag(const uint32_t *__restrict_
 }
 
 // One query: count, and for every tile with a hit run the cold path.
-template <int M>
+template <int M, bool kCollect>
 __device__ __forceinline__ void search_query(const uint32_t *__restrict__ bitmaps, const BlockConsts *bc, WarpSmem *ws,
                                              const uint8_t *__restrict__ word_thr, uint32_t win_lo, uint32_t win_hi, int n_lists,
                                              int lane) {
@@ -396,7 +419,7 @@ __device__ __forceinline__ void search_query(const uint32_t *__restrict__ bitmap
             for (int j = 0; j < M; j++) ws->cnt[j * 32 + lane] = ts.c[j];
         }
         __syncwarp();
-        handle_flags(bc, ws, wf, M, lane);
+        handle_flags<kCollect>(bc, ws, wf, M, lane);
         __syncwarp();
         w = wf + kTileWords;
     }
@@ -421,10 +444,11 @@ __global__ void __launch_bounds__(kWindowThreads) sg_window_kernel(const DevInde
         b_max = metric_max_y(metric, p.alpha, a);
         if (b_max >= S) b_max = S - 1;
     }
+    if (p.custom_thr != nullptr) { b_min = 0; b_max = a > 0 ? S - 1 : -1; }  // the table is zero outside the caller's window
     for (int B = threadIdx.x; B < S; B += kWindowThreads) {
         int T = 0;
         if (B >= b_min && B <= b_max) {
-            T = metric_threshold(metric, p.alpha, a, B);
+            T = p.custom_thr != nullptr ? (int)p.custom_thr[(size_t)a * S + B] : metric_threshold(metric, p.alpha, a, B);
             if (!threshold_admits(T, a, B) || ix.seg_start[B + 1] <= ix.seg_start[B]) T = 0;
         }
         seg_thr[B] = (uint8_t)T;  // T <= a <= 128
@@ -513,7 +537,11 @@ __global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_
 // ---------------------------------------------------------------------------------------------------------------
 // sg_bitmap_search_kernel: one warp per query, query numbers from a global counter.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bitmap_search_kernel(const DevIndex ix, const SearchParams p) {
+// kCollect = true is sg_bitmap_collect_kernel (sg_candidates_batch): same count and resolve, every survivor appended to
+// the launch-wide candidate list instead of scored into a top-k.  A template so that the top-k kernel's code and register
+// allocation are exactly what they are without it.
+template <bool kCollect>
+__device__ __forceinline__ void bitmap_search_body(const DevIndex &ix, const SearchParams &p) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ BlockConsts s_bc;
     const int lane = threadIdx.x & 31;
@@ -529,6 +557,14 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
         s_bc.id_base = ix.id_base;
         s_bc.k = p.k;
         s_bc.metric = p.mode == 1 ? (int)kAutocomplete : p.metric;
+        if (kCollect) {
+            s_bc.cand_total = p.cand_total;
+            s_bc.cand_cap = p.cand_cap;
+            s_bc.cand_query = p.cand_query;
+            s_bc.cand_ids = p.cand_ids;
+            s_bc.cand_overlap = p.cand_overlap;
+            s_bc.cand_segment = p.cand_segment;
+        }
     }
     for (uint32_t i = threadIdx.x; i <= min(ix.n_segments, (uint32_t)kSegCache); i += blockDim.x) s_bc.seg_cache[i] = ix.seg_start[i];
     __syncthreads();
@@ -557,6 +593,7 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
                 ws->tk_len = 0;
                 ws->size_a = size_a;
                 ws->n_lists = n_lists;
+                if (kCollect) ws->q = q;
                 ws->lm_valid = 0u;
                 if (p.lm_ctx != nullptr && p.lm_ctx[q].valid) {
                     const LmContext lc = p.lm_ctx[q];
@@ -579,8 +616,8 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
             __syncwarp();
             const uint8_t *word_thr = p.wt.word_thr + (size_t)size_a * ix.row_words;
             if (p.mode == 1 && n_lists <= 2) complete_from_lists(&s_bc, ws, lane);
-            else if (n_lists < 32) search_query<5>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
-            else search_query<8>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
+            else if (n_lists < 32) search_query<5, kCollect>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
+            else search_query<8, kCollect>(ix.bitmaps, &s_bc, ws, word_thr, win.x, win.y, n_lists, lane);
             __syncwarp();
             tk_len = ws->tk_len;
         }
@@ -595,12 +632,24 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
             p.out_scores[row + j] = has ? tk_score[j] : 0.0;
         }
         if (lane == 0) {
-            p.out_counts[q] = unsupported ? kCountUnsupported : (uint32_t)tk_len;
+            // collect mode reports len(tokens): the caller's Distance(inter, sizeA, sizeB) needs it
+            // (re-read from the plan: keeping size_a live across the search costs the count loop a register)
+            uint32_t n_report = (uint32_t)tk_len;
+            if (kCollect) n_report = __ldg((const uint32_t *)(p.plans + (size_t)q * kTokStride) + 1);
+            p.out_counts[q] = unsupported ? kCountUnsupported : n_report;
             if (unsupported && p.too_long_flag != nullptr) *p.too_long_flag = 1u;
         }
         __syncwarp();  // every lane is done with this query's shared state before lane 0 resets it for the next
         q = __shfl_sync(kFull, q_next, 0);
     }
+}
+
+__global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bitmap_search_kernel(const DevIndex ix, const SearchParams p) {
+    bitmap_search_body<false>(ix, p);
+}
+
+__global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bitmap_collect_kernel(const DevIndex ix, const SearchParams p) {
+    bitmap_search_body<true>(ix, p);
 }
 
 // ---------------- launcher (host) ----------------
@@ -655,7 +704,8 @@ cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int 
     int blocks = sm_count * per_sm;
     const int need = (int)((p.n_q + kBitmapWarps - 1) / kBitmapWarps);
     if (blocks > need) blocks = need;
-    sg_bitmap_search_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, p);
+    if (p.cand_total != nullptr) sg_bitmap_collect_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, p);  // k = 1: under 48 KB, no opt-in
+    else sg_bitmap_search_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, p);
     if (stage_events) cudaEventRecord(stage_events[3], stream);
     return cudaGetLastError();
 }

@@ -155,6 +155,12 @@ struct SearchParams {
     const LmContext *lm_ctx;  // mode 1 only, optional: rank the completions by the language model (spellchecker collector)
     uint32_t *too_long_flag;  // optional: set to 1 if any query of the launch is reported as SG_COUNT_UNSUPPORTED
     int32_t sparse_rows;      // 1: write only the out_counts[q] valid entries of a row (rows in page-locked host memory)
+    // ---- sg_candidates_batch (bitmap engine): every candidate of the T-occurrence count instead of a top-k ----
+    const uint8_t *custom_thr;        // optional [129][S]: Threshold(alpha, a, B) tabulated by the caller for a metric.Metric that
+                                      // is not built in (0 outside [MinY, MaxY]); replaces metric / alpha in sg_window_kernel
+    unsigned long long *cand_total;   // non-null: collect mode; candidates found so far (may exceed cand_cap)
+    unsigned long long cand_cap;      // entries the four arrays below hold
+    uint32_t *cand_query, *cand_ids, *cand_overlap, *cand_segment;  // MergeCandidate (pkg/merger/list_merger.go:33-48) + its query and segment
 };
 
 SG_HD static inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; host and device hash term keys with it

@@ -15,7 +15,9 @@ from typing import List, Sequence
 import numpy as np
 
 from . import _capi
+from . import collector as _col
 from ._capi import SuggestError
+from .collector import Candidate
 from .metric import Metric
 
 RAMDriver = "RAM"
@@ -119,13 +121,6 @@ def ReadConfigs(config_path):
 
 
 @dataclass
-class Candidate:
-    """suggest.Candidate, pkg/suggest/collector.go:12-17"""
-    Key: int
-    Score: float
-
-
-@dataclass
 class ResultItem:
     """suggest.ResultItem, pkg/suggest/service.go:11-16"""
     Score: float
@@ -205,10 +200,68 @@ class NGramIndex:
 
     # -- Suggester ------------------------------------------------------------------------------
     def Suggest(self, query, similarity, metric, topK) -> List[Candidate]:
-        """nGramSuggester.Suggest (pkg/suggest/suggester.go:46-131) with a FuzzyCollectorManager(topK)."""
-        ids, scores, counts = self.SuggestBatch([query], similarity, metric, topK)
-        n = int(counts[0])
-        return [Candidate(int(ids[0, i]), float(scores[0, i])) for i in range(n)]
+        """nGramSuggester.Suggest (pkg/suggest/suggester.go:46-131).  `topK` is a number - FuzzyCollectorManager(topK), the
+        reference's newFuzzyCollectorManager - or a CollectorManagerFactory as in the Go signature."""
+        return self.SuggestMany([query], similarity, metric, topK)[0]
+
+    def SuggestMany(self, queries, similarity, metric, topK) -> List[List[Candidate]]:
+        """Suggest for a list of queries, as lists of Candidate.  A built-in metric with a FuzzyCollectorManager runs
+        sg_search_batch (top-k on the device).  Anything else - a metric.Metric of the caller's own, or another
+        CollectorManager - gets every candidate of the T-occurrence count from sg_candidates_batch and is driven on the
+        host the way suggester.go:66-108 drives it (the two interface wrinkles)."""
+        factory = topK if callable(topK) else None
+        k = None if factory else int(topK)
+        if factory is not None:
+            probe = factory()
+            if type(probe) is _col.FuzzyCollectorManager:
+                k, factory = probe.topK, None
+        if factory is None and metric.code is not None:
+            ids, scores, counts = self.SuggestBatch(queries, similarity, metric, k)
+            return [[Candidate(int(ids[q, i]), float(scores[q, i])) for i in range(int(counts[q]))] for q in range(len(queries))]
+        if factory is None:
+            factory = _col.NewFuzzyCollectorManager(k)
+        cq, cid, cov, cseg, size_a = self.CandidatesBatch(queries, similarity, metric)
+        order = np.lexsort((cid, cseg, cq))  # per query, per segment, ids ascending: the order the mergers emit
+        cq, cid, cov, cseg = cq[order], cid[order], cov[order], cseg[order]
+        starts = np.searchsorted(cq, np.arange(len(queries) + 1))
+        S = self.info()["n_segments"]
+        out = []
+        for q in range(len(queries)):
+            lo, hi = int(starts[q]), int(starts[q + 1])
+            by_segment = {}
+            for i in range(lo, hi):
+                by_segment.setdefault(int(cseg[i]), []).append(_col.MergeCandidate(int(cid[i]), int(cov[i])))
+            out.append(_replay(factory(), metric, float(similarity), int(size_a[q]), S, by_segment))
+        return out
+
+    def CandidatesBatch(self, queries, similarity, metric, packed=None, cap=None):
+        """sg_candidates_batch: every (query, document, overlap, segment) with overlap >= Threshold over the admissible
+        segments, in no particular order, plus len(tokens) per query.  A metric without a device code is tabulated here
+        (Threshold over its [MinY, MaxY] window for every len(tokens) up to 128) and passed as a byte table."""
+        data, off = packed if packed is not None else pack_strings(queries)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        n_q = len(off) - 1
+        table = None
+        if metric.code is None:
+            S = self.info()["n_segments"]
+            table = np.zeros((_capi.SG_MAX_QUERY_TOKENS + 1, S), dtype=np.uint8)
+            for a in range(1, _capi.SG_MAX_QUERY_TOKENS + 1):
+                for B in range(max(int(metric.MinY(similarity, a)), 0), min(int(metric.MaxY(similarity, a)), S - 1) + 1):
+                    table[a, B] = min(max(int(metric.Threshold(similarity, a, B)), 0), 255)
+        cap = int(cap) if cap is not None else max(4 * n_q, 1024)
+        size_a = np.zeros(n_q, dtype=np.uint32)
+        while True:
+            bufs = [np.zeros(cap, dtype=np.uint32) for _ in range(4)]
+            total = C.c_uint64(0)
+            rc = _capi.lib().sg_candidates_batch(self.handle, _ptr(data), _ptr(off), n_q, metric.code if table is None else 0,
+                                                 float(similarity), _ptr(table), cap, *[_ptr(b) for b in bufs], C.byref(total),
+                                                 _ptr(size_a))
+            _capi.check(rc)
+            if total.value <= cap:
+                n = int(total.value)
+                return bufs[0][:n], bufs[1][:n], bufs[2][:n], bufs[3][:n], size_a
+            cap = int(total.value)
 
     def SuggestBatch(self, queries, similarity, metric, topK, packed=None, out=None):
         """Batched Suggest through sg_search_batch (host buffers).
@@ -268,6 +321,40 @@ class NGramIndex:
         n = _capi.check(_capi.lib().sg_search_stage_times(self.handle, d_q_bytes, d_q_off, n_q, metric.code, float(similarity),
                                                           int(topK), d_ids, d_scores, d_counts, stream or None, ms, names, 256))
         return dict(zip(names.value.decode().split(","), [float(ms[i]) for i in range(n)]))
+
+
+def _replay(manager, metric, similarity, sizeA, n_segments, by_segment):
+    """The host half of nGramSuggester.Suggest for a CollectorManager of the caller's own (suggester.go:46-131): segments
+    in the reference's feed order sizeA, sizeA+1, sizeA-1, ... (:110-118; its five workers make the order of the
+    manager.Collect calls nondeterministic, here it is the feed order), per admissible segment Create / SetScorer /
+    Collect* / manager.Collect.  ErrCollectionTerminated ends a segment as it does inside the mergers
+    (pkg/merger/cp_merge.go:109-111).  Thresholds below 1 skip the segment."""
+    if sizeA == 0:
+        return []  # suggester.go:49-51
+    bMin, bMax = int(metric.MinY(similarity, sizeA)), min(int(metric.MaxY(similarity, sizeA)), n_segments - 1)
+    i, j = sizeA, sizeA + 1
+    feed = []
+    while i >= bMin or j <= bMax:
+        if i >= bMin:
+            feed.append(i)
+        if j <= bMax:
+            feed.append(j)
+        i, j = i - 1, j + 1
+    for sizeB in feed:
+        if sizeB < 0 or sizeB >= n_segments:
+            continue  # indices.Get(sizeB) == nil
+        T = int(metric.Threshold(similarity, sizeA, sizeB))
+        if T <= 0 or T > sizeB or T > sizeA:
+            continue
+        c = manager.Create()
+        c.SetScorer(_col.NewMetricScorer(metric, sizeA, sizeB))
+        try:
+            for cand in by_segment.get(sizeB, ()):
+                c.Collect(cand)
+        except _col.ErrCollectionTerminated:
+            pass
+        manager.Collect(c)
+    return manager.GetCandidates()
 
 
 class Builder:
