@@ -152,6 +152,36 @@ class NGramIndex {
         return out;
     }
 
+    // What the mergers hand to Collector.Collect (pkg/merger/collector.go:10-13) over every admissible segment, for a
+    // CollectorManager other than the fuzzy / first-k ones or a metric.Metric that is not built in: sg_candidates_batch.
+    // `thresholds` = nullptr: the built-in metric m; otherwise [129][n_segments] bytes tabulated from the caller's metric.
+    struct MergeCandidate {  // pkg/merger/list_merger.go:33-48, plus the query and the segment (sizeB) it came from
+        uint32_t Query, Position, Overlap, Segment;
+    };
+    std::vector<MergeCandidate> Candidates(const std::vector<std::string> &queries, double similarity, metric::Metric m,
+                                           std::vector<uint32_t> *sizeA = nullptr, const uint8_t *thresholds = nullptr) const {
+        std::string bytes;
+        std::vector<uint32_t> off(1, 0);
+        for (const auto &q : queries) {
+            bytes += q;
+            off.push_back((uint32_t)bytes.size());
+        }
+        const size_t n = queries.size();
+        std::vector<uint32_t> size_a(n + 1);
+        uint64_t cap = 4 * n + 1024, total = 0;
+        for (;;) {
+            std::vector<uint32_t> q(cap), id(cap), ov(cap), seg(cap);
+            int rc = sg_candidates_batch(h_, bytes.data(), off.data(), (uint32_t)n, m.code(), similarity, thresholds, cap, q.data(),
+                                         id.data(), ov.data(), seg.data(), &total, size_a.data());
+            if (rc != SG_OK) throw Error(rc, sg_last_error());
+            if (total > cap) { cap = total; continue; }  // found more than the buffers hold: once more with the reported size
+            std::vector<MergeCandidate> out(total);
+            for (uint64_t i = 0; i < total; i++) out[i] = MergeCandidate{q[i], id[i], ov[i], seg[i]};
+            if (sizeA) sizeA->assign(size_a.begin(), size_a.begin() + n);
+            return out;
+        }
+    }
+
     sg_index_info Info() const {
         sg_index_info info{};
         sg_index_get_info(h_, &info);

@@ -30,6 +30,18 @@ int main(int argc, char **argv) {
         auto ac = index->Autocomplete("Niss", 5);
         CHECK(ac.size() == 5);
         for (uint32_t i = 0; i < 5; i++) CHECK(ac[i].Key == i);
+        // every candidate of the T-occurrence count: the two returned above are among them with the overlaps their scores imply
+        std::vector<uint32_t> size_a;
+        auto all = index->Candidates({"Nissan ma"}, 0.5, metric::JaccardMetric(), &size_a);
+        CHECK(size_a.size() == 1 && size_a[0] == 9);
+        int seen = 0;
+        for (const auto &c : all) {
+            CHECK(c.Query == 0 && c.Overlap >= 1 && c.Overlap <= 9);
+            const double score = (double)c.Overlap / (double)(9 + c.Segment - c.Overlap);
+            CHECK(score >= 0.5);
+            if (c.Position == 2 || c.Position == 0) seen++;
+        }
+        CHECK(seen == 2);
     }
     {  // Example
         suggest::IndexDescription d;
