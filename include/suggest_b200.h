@@ -220,6 +220,28 @@ int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint
                                 double *d_out_scores, uint32_t *d_out_counts, void *stream);
 
 /*
+ * Record-id-range shards of one dictionary over the GPUs of a box, driven by ONE host process (the Go service cannot be
+ * one process per GPU).  No reference counterpart (single process, single index); SURVEY.md 8(e), BASELINE.json config #4.
+ * Shard s indexes documents [n_docs * s / n_shards, n_docs * (s + 1) / n_shards) on CUDA device devices[s] with id_base =
+ * its first document, so returned ids are the dictionary's and the (score desc, id asc) order of pkg/suggest/collector.go:20-26
+ * holds across shards.  A query's result is the k best of the per-shard top-k lists (FuzzyCollectorManager.Collect merging
+ * per-segment queues, collector.go:165-178, is the same reduction).
+ * sg_sharded_search_batch: HOST buffers as sg_search_batch.  The queries go to the first GPU once and from there to the
+ * others over NVLink; every shard searches on its own stream; the merge kernel on the first GPU reads the per-shard rows
+ * straight from the other GPUs' HBM (peer access; `peer_reads` of sg_sharded_get_info), or from peer copies of the blocks
+ * when peer access is not available (SG_SHARD_GATHER_COPY=1 forces that).  One call at a time per handle.
+ * devices may name the same GPU more than once (shards then share it).
+ */
+typedef struct sg_sharded sg_sharded;
+int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs, const int32_t *devices,
+                     uint32_t n_shards, sg_sharded **out);
+int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                            uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts);
+int sg_sharded_get_info(const sg_sharded *sx, uint32_t *n_shards, uint32_t *n_docs, int32_t *peer_reads);
+sg_index *sg_sharded_shard(const sg_sharded *sx, uint32_t shard);   /* borrowed: sg_index_get_info / _layout of one shard */
+void sg_sharded_free(sg_sharded *sx);
+
+/*
  * ---- language model and spellchecker (BASELINE.json config #5) ----
  * sg_lm: the stupid-back-off n-gram model of pkg/lm in HBM.  Level i (0-based) holds the (i+1)-grams as the reference's
  * packed arrays (pkg/lm/packed_array.go): values[] = word << 32 | count ordered by (context, word), containers[] =

@@ -58,6 +58,12 @@ SIGNATURES = {
                                                 C.c_void_p, C.c_void_p]),
     "sg_merge_topk_packed_device": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p]),
+    "sg_sharded_build": (C.c_int, [C.POINTER(SgConfig), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "sg_sharded_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sg_sharded_get_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
+    "sg_sharded_shard": (C.c_void_p, [C.c_void_p, C.c_uint32]),
+    "sg_sharded_free": (None, [C.c_void_p]),
     "sg_lm_create": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_lm_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_lm_free": (None, [C.c_void_p]),

@@ -1052,6 +1052,217 @@ int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint
     return SG_OK;
 }
 
+// ---------------- record-id-range shards over the GPUs of one box, one host process ----------------
+// What suggest_b200/sharding.py does with one process per GPU and an NCCL all-gather, for a host that is a single
+// process (the Go service): shard s is an sg_index on devices[s] with id_base = its first document; a call uploads the
+// queries once, hands them to the other GPUs over NVLink (peer copies), runs every shard's search concurrently on its
+// own stream, and the merge kernel on the first GPU reads the per-shard rows straight out of the other GPUs' HBM
+// (peer access) - the exchange is those loads.  Without peer access the blocks are peer-copied and merged locally.
+struct ShardCtx {
+    sg_index *ix = nullptr;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr;     // queries on this device / rows of this shard written
+    DevBuf<char> q_bytes;
+    DevBuf<uint32_t> q_off;
+    DevBuf<uint8_t> rows;            // packed block of this shard (sg_packed_rows_bytes)
+};
+
+struct sg_sharded {
+    std::vector<ShardCtx> shards;
+    std::mutex mu;                   // one search at a time per handle
+    bool peer_reads = false;         // every shard's HBM is addressable from shards[0].device
+    DevBuf<uint8_t> parts;           // copy path: the blocks of all shards, contiguous, on shards[0].device
+    DevBuf<uint32_t> out_ids, out_counts;
+    DevBuf<double> out_scores;
+    const void **d_ptrs = nullptr;   // peer path: block pointers, on shards[0].device
+    cudaEvent_t queries_up = nullptr;
+    uint32_t n_docs = 0;
+};
+
+static void sharded_destroy(sg_sharded *sx) {
+    if (!sx) return;
+    DeviceGuard guard;
+    if (!sx->shards.empty()) guard.set(sx->shards[0].device);  // remembers the caller's device; cudaSetDevice from here on
+    for (ShardCtx &sh : sx->shards) {
+        if (cudaSetDevice(sh.device) == cudaSuccess) {
+            if (sh.stream) { cudaStreamSynchronize(sh.stream); cudaStreamDestroy(sh.stream); }
+            if (sh.ready) cudaEventDestroy(sh.ready);
+            sh.q_bytes.release(); sh.q_off.release(); sh.rows.release();
+        }
+        if (sh.ix) sg_index_free(sh.ix);
+    }
+    if (!sx->shards.empty() && cudaSetDevice(sx->shards[0].device) == cudaSuccess) {
+        sx->parts.release(); sx->out_ids.release(); sx->out_counts.release(); sx->out_scores.release();
+        if (sx->d_ptrs) cudaFree((void *)sx->d_ptrs);
+        if (sx->queries_up) cudaEventDestroy(sx->queries_up);
+    }
+    delete sx;
+}
+
+int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs, const int32_t *devices,
+                     uint32_t n_shards, sg_sharded **out) {
+    if (!out) return fail(SG_ERR_INVALID, "null out");
+    *out = nullptr;
+    if (!cfg || !devices || (n_docs && !doc_off)) return fail(SG_ERR_INVALID, "null argument");
+    if (n_shards < 1 || n_shards > 32) return fail(SG_ERR_INVALID, "n_shards must be in 1..32");
+    sg_sharded *sx = new (std::nothrow) sg_sharded();
+    if (!sx) return fail(SG_ERR_NOMEM, "out of host memory");
+    sx->shards.resize(n_shards);
+    sx->n_docs = n_docs;
+    DeviceGuard guard;
+    guard.set(devices[0]);  // remembers the caller's device; cudaSetDevice from here on
+    std::vector<uint64_t> sub_off;
+    for (uint32_t s = 0; s < n_shards; s++) {
+        const uint32_t lo = (uint32_t)((uint64_t)n_docs * s / n_shards), hi = (uint32_t)((uint64_t)n_docs * (s + 1) / n_shards);
+        sub_off.resize((size_t)(hi - lo) + 1);
+        const uint64_t base = n_docs ? doc_off[lo] : 0;
+        for (uint32_t i = lo; i <= hi && n_docs; i++) sub_off[i - lo] = doc_off[i] - base;
+        if (!n_docs) sub_off[0] = 0;
+        sg_config c = *cfg;
+        c.device = devices[s];
+        ShardCtx &sh = sx->shards[s];
+        sh.device = devices[s];
+        int rc = sg_index_build(&c, doc_bytes ? doc_bytes + base : nullptr, sub_off.data(), hi - lo, lo, &sh.ix);
+        if (rc != SG_OK) { const std::string msg = g_err; sharded_destroy(sx); return fail(rc, "shard " + std::to_string(s) + ": " + msg); }
+        cudaError_t e = cudaSetDevice(sh.device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sh.ready, cudaEventDisableTiming);
+        if (e != cudaSuccess) { sharded_destroy(sx); return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    // peer access from the merging GPU to every other shard's GPU (NVLink / NVSwitch on a B200 box)
+    const int dev0 = sx->shards[0].device;
+    bool peer = env_int("SG_SHARD_GATHER_COPY", 0) == 0;
+    cudaError_t e = cudaSetDevice(dev0);
+    for (uint32_t s = 1; s < n_shards && peer && e == cudaSuccess; s++) {
+        const int d = sx->shards[s].device;
+        if (d == dev0) continue;
+        int can = 0;
+        e = cudaDeviceCanAccessPeer(&can, dev0, d);
+        if (e != cudaSuccess || !can) { peer = false; break; }
+        cudaError_t pe = cudaDeviceEnablePeerAccess(d, 0);
+        if (pe == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); pe = cudaSuccess; }
+        if (pe != cudaSuccess) { cudaGetLastError(); peer = false; }
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sx->queries_up, cudaEventDisableTiming);
+    if (e == cudaSuccess && peer) e = cudaMalloc((void **)&sx->d_ptrs, 32 * sizeof(void *));
+    if (e != cudaSuccess) { sharded_destroy(sx); return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
+    sx->peer_reads = peer;
+    *out = sx;
+    return SG_OK;
+}
+
+void sg_sharded_free(sg_sharded *sx) { sharded_destroy(sx); }
+
+int sg_sharded_get_info(const sg_sharded *sx, uint32_t *n_shards, uint32_t *n_docs, int32_t *peer_reads) {
+    if (!sx) return fail(SG_ERR_INVALID, "null handle");
+    if (n_shards) *n_shards = (uint32_t)sx->shards.size();
+    if (n_docs) *n_docs = sx->n_docs;
+    if (peer_reads) *peer_reads = sx->peer_reads ? 1 : 0;
+    return SG_OK;
+}
+
+sg_index *sg_sharded_shard(const sg_sharded *sx, uint32_t s) {
+    return sx && s < sx->shards.size() ? sx->shards[s].ix : nullptr;
+}
+
+int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                            uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+    if (!sx) return fail(SG_ERR_INVALID, "null handle");
+    int rc = validate_search(sx->shards[0].ix, n_q, metric, alpha, k);
+    if (rc != SG_OK) return rc;
+    if (n_q == 0) return SG_OK;
+    if (!q_off || !out_ids || !out_scores || !out_counts) return fail(SG_ERR_INVALID, "null buffer");
+    const uint32_t total_bytes = q_off[n_q];
+    if (total_bytes && !q_bytes) return fail(SG_ERR_INVALID, "null query bytes");
+    std::lock_guard<std::mutex> lock(sx->mu);
+    // strings.ToLower on the host if any byte is not ASCII, as sg_search_batch does
+    std::string low;
+    std::vector<uint32_t> low_off;
+    const char *src_bytes = q_bytes;
+    const uint32_t *src_off = q_off;
+    size_t n_bytes = total_bytes;
+    unsigned char high = 0;
+    for (uint32_t i = 0; i < total_bytes; i++) high |= (unsigned char)q_bytes[i];
+    if (high & 0x80) {
+        low_off.resize((size_t)n_q + 1);
+        for (uint32_t q = 0; q < n_q; q++) {
+            low_off[q] = (uint32_t)low.size();
+            sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &low);
+        }
+        low_off[n_q] = (uint32_t)low.size();
+        src_bytes = low.data();
+        src_off = low_off.data();
+        n_bytes = low.size();
+    }
+    const uint32_t n = (uint32_t)sx->shards.size();
+    const size_t block = (size_t)sg_packed_rows_bytes(n_q, k);
+    DeviceGuard guard;
+    ShardCtx &s0 = sx->shards[0];
+    // queries: host -> first GPU once, from there to the others over NVLink
+    SG_CUDA(guard.set(s0.device));
+    SG_CUDA(s0.q_bytes.reserve(n_bytes + 64));
+    SG_CUDA(s0.q_off.reserve((size_t)n_q + 1));
+    SG_CUDA(sx->out_ids.reserve((size_t)n_q * k));
+    SG_CUDA(sx->out_scores.reserve((size_t)n_q * k));
+    SG_CUDA(sx->out_counts.reserve(n_q));
+    if (!sx->peer_reads) SG_CUDA(sx->parts.reserve(block * n));
+    if (n_bytes) SG_CUDA(cudaMemcpyAsync(s0.q_bytes.p, src_bytes, n_bytes, cudaMemcpyHostToDevice, s0.stream));
+    SG_CUDA(cudaMemcpyAsync(s0.q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s0.stream));
+    SG_CUDA(cudaEventRecord(sx->queries_up, s0.stream));
+    const void *ptrs[32] = {nullptr};
+    for (uint32_t s = 0; s < n; s++) {
+        ShardCtx &sh = sx->shards[s];
+        SG_CUDA(cudaSetDevice(sh.device));
+        SG_CUDA(sh.rows.reserve(block));
+        const char *d_q = s0.q_bytes.p;
+        const uint32_t *d_off = s0.q_off.p;
+        if (s > 0 && sh.device != s0.device) {
+            SG_CUDA(sh.q_bytes.reserve(n_bytes + 64));
+            SG_CUDA(sh.q_off.reserve((size_t)n_q + 1));
+            SG_CUDA(cudaStreamWaitEvent(sh.stream, sx->queries_up, 0));
+            if (n_bytes) SG_CUDA(cudaMemcpyPeerAsync(sh.q_bytes.p, sh.device, s0.q_bytes.p, s0.device, n_bytes, sh.stream));
+            SG_CUDA(cudaMemcpyPeerAsync(sh.q_off.p, sh.device, s0.q_off.p, s0.device, ((size_t)n_q + 1) * sizeof(uint32_t), sh.stream));
+            d_q = sh.q_bytes.p;
+            d_off = sh.q_off.p;
+        } else if (s > 0) {
+            SG_CUDA(cudaStreamWaitEvent(sh.stream, sx->queries_up, 0));  // another shard on the first GPU reads its copy
+        }
+        rc = sg_search_batch_packed_device(sh.ix, d_q, d_off, n_q, metric, alpha, k, sh.rows.p, sh.stream);
+        if (rc != SG_OK) break;
+        if (!sx->peer_reads)
+            SG_CUDA(cudaMemcpyPeerAsync(sx->parts.p + (size_t)s * block, s0.device, sh.rows.p, sh.device, block, sh.stream));
+        ptrs[s] = sh.rows.p;
+        if (s > 0) SG_CUDA(cudaEventRecord(sh.ready, sh.stream));
+    }
+    if (rc != SG_OK) {
+        const std::string msg = g_err;
+        for (ShardCtx &sh : sx->shards) { cudaSetDevice(sh.device); cudaStreamSynchronize(sh.stream); }
+        return fail(rc, msg);
+    }
+    // merge on the first GPU behind every shard's search
+    SG_CUDA(cudaSetDevice(s0.device));
+    for (uint32_t s = 1; s < n; s++) SG_CUDA(cudaStreamWaitEvent(s0.stream, sx->shards[s].ready, 0));
+    int blocks = (int)((n_q + 7) / 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (sx->peer_reads) {
+        SG_CUDA(cudaMemcpyAsync((void *)sx->d_ptrs, ptrs, n * sizeof(void *), cudaMemcpyHostToDevice, s0.stream));
+        SG_CUDA(sg::launch_merge_topk_peer(n, n_q, k, sx->d_ptrs, sx->out_ids.p, sx->out_scores.p, sx->out_counts.p, blocks, s0.stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    } else {
+        rc = sg_merge_topk_packed_device(s0.device, n, n_q, k, sx->parts.p, sx->out_ids.p, sx->out_scores.p, sx->out_counts.p, s0.stream);
+        if (rc != SG_OK) { cudaStreamSynchronize(s0.stream); return rc; }
+    }
+    SG_CUDA(cudaMemcpyAsync(out_ids, sx->out_ids.p, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
+    SG_CUDA(cudaMemcpyAsync(out_scores, sx->out_scores.p, (size_t)n_q * k * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+    SG_CUDA(cudaMemcpyAsync(out_counts, sx->out_counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
+    SG_CUDA(cudaStreamSynchronize(s0.stream));
+    for (uint32_t q = 0; q < n_q; q++)
+        if (out_counts[q] == SG_COUNT_UNSUPPORTED)
+            return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");
+    return SG_OK;
+}
+
 // ---------------- language model and spellchecker (pkg/lm, pkg/spellchecker) ----------------
 struct sg_lm {
     sg::DevLm dev{};

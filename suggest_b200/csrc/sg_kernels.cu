@@ -519,6 +519,63 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
     }
 }
 
+// The same selection with one pointer per part instead of a stride: part p's packed block [scores | ids | counts] lives in
+// the HBM of the GPU that searched shard p and is read from there over NVLink peer access, only the entries that are
+// needed (a count per part, then the rows the butterfly actually consumes) - the gather of the shard exchange is these
+// loads, there is no copy of the blocks (sg_sharded_search_batch).
+__global__ void sg_merge_topk_peer_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k, const void *const *__restrict__ parts,
+                                          uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const double *my_scores = nullptr;
+    const uint32_t *my_ids = nullptr, *my_counts = nullptr;
+    if ((uint32_t)lane < n_parts) {
+        my_scores = (const double *)parts[lane];
+        my_ids = (const uint32_t *)(my_scores + (size_t)n_q * k);
+        my_counts = my_ids + (size_t)n_q * k;
+    }
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_q; q += warps) {
+        uint32_t cur = 0, cnt = 0;
+        const size_t row = (size_t)q * k;
+        bool unsupported = false;
+        if ((uint32_t)lane < n_parts) {
+            cnt = my_counts[q];
+            if (cnt == kCountUnsupported) { unsupported = true; cnt = 0; }
+            if (cnt > k) cnt = k;
+        }
+        unsupported = __any_sync(kFull, unsupported);
+        // head of this lane's list, fetched once per advance (a remote load each)
+        bool has = cur < cnt;
+        double s = has ? my_scores[row] : 0.0;
+        uint32_t id = has ? my_ids[row] : kInf;
+        uint32_t n_out = 0;
+        for (; n_out < k; n_out++) {
+            bool bh = has;
+            double bs = s;
+            uint32_t bi = id;
+            int who = lane;
+            for (int o = 16; o; o >>= 1) {
+                const bool oh = __shfl_xor_sync(kFull, bh, o);
+                const double os = __shfl_xor_sync(kFull, bs, o);
+                const uint32_t oi = __shfl_xor_sync(kFull, bi, o);
+                const int ow = __shfl_xor_sync(kFull, who, o);
+                const bool take = oh && (!bh || os > bs || (os == bs && (oi < bi || (oi == bi && ow < who))));
+                if (take) { bh = oh; bs = os; bi = oi; who = ow; }
+            }
+            if (!bh) break;
+            if (lane == 0) { out_ids[row + n_out] = bi; out_scores[row + n_out] = bs; }
+            if (lane == who) {
+                cur++;
+                has = cur < cnt;
+                s = has ? my_scores[row + cur] : 0.0;
+                id = has ? my_ids[row + cur] : kInf;
+            }
+        }
+        for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[row + j] = 0; out_scores[row + j] = 0.0; }
+        if (lane == 0) out_counts[q] = unsupported ? kCountUnsupported : n_out;
+    }
+}
+
 // ---------------- launchers (host) ----------------
 cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks, int warps_per_block, size_t smem_bytes,
                           cudaStream_t stream, cudaEvent_t *stage_events) {
@@ -540,6 +597,12 @@ cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const 
                               uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream) {
     sg_merge_topk_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, part_ids, part_scores, part_counts, stride_ids, stride_scores,
                                                      stride_counts, out_ids, out_scores, out_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_merge_topk_peer(uint32_t n_parts, uint32_t n_q, uint32_t k, const void *const *parts, uint32_t *out_ids,
+                                   double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream) {
+    sg_merge_topk_peer_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, parts, out_ids, out_scores, out_counts);
     return cudaGetLastError();
 }
 

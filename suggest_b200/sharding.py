@@ -59,6 +59,73 @@ class ShardedIndex:
                                                   out_scores.data_ptr(), out_counts.data_ptr(), stream or None))
 
 
+class ShardedNGramIndex:
+    """The same record-id-range shards driven by ONE process (sg_sharded_*): what a Go service, which cannot be one
+    process per GPU, calls.  `devices`: CUDA ordinal per shard (a GPU may hold several).  Suggest / SuggestBatch as
+    NGramIndex; the exchange is the merge kernel reading the other GPUs' rows over NVLink peer access."""
+
+    def __init__(self, dictionary, description, devices):
+        import ctypes as C
+        from .suggest import pack_strings
+        if isinstance(dictionary, tuple) and len(dictionary) == 2 and isinstance(dictionary[0], np.ndarray):
+            data, off = dictionary
+        else:
+            data, off = pack_strings(dictionary, np.uint64)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        cfg, keep = description.c_config()
+        h = C.c_void_p()
+        rc = _capi.lib().sg_sharded_build(C.byref(cfg), data.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), len(off) - 1,
+                                          dev.ctypes.data_as(C.c_void_p), len(dev), C.byref(h))
+        del keep
+        _capi.check(rc)
+        self._h = h
+
+    def info(self):
+        import ctypes as C
+        n, d, p = C.c_uint32(), C.c_uint32(), C.c_int32()
+        _capi.check(_capi.lib().sg_sharded_get_info(self._h, C.byref(n), C.byref(d), C.byref(p)))
+        return dict(n_shards=n.value, n_docs=d.value, peer_reads=p.value)
+
+    def shard_info(self, s):
+        import ctypes as C
+        info = _capi.SgIndexInfo()
+        _capi.check(_capi.lib().sg_index_get_info(C.c_void_p(_capi.lib().sg_sharded_shard(self._h, s)), C.byref(info)))
+        return {name: getattr(info, name) for name, _ in info._fields_}
+
+    def SuggestBatch(self, queries, similarity, metric, topK, packed=None):
+        import ctypes as C
+        from .suggest import pack_strings
+        data, off = packed if packed is not None else pack_strings(queries)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        n_q, k = len(off) - 1, max(int(topK), 0)
+        ids = np.zeros((n_q, k), dtype=np.uint32)
+        scores = np.zeros((n_q, k), dtype=np.float64)
+        counts = np.zeros(n_q, dtype=np.uint32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _capi.check(_capi.lib().sg_sharded_search_batch(self._h, p(data), p(off), n_q, metric.code, float(similarity), k, p(ids),
+                                                        p(scores), p(counts)))
+        return ids, scores, counts
+
+    def Suggest(self, query, similarity, metric, topK):
+        from .collector import Candidate
+        ids, scores, counts = self.SuggestBatch([query], similarity, metric, topK)
+        return [Candidate(int(ids[0, i]), float(scores[0, i])) for i in range(int(counts[0]))]
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _capi.lib().sg_sharded_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def merge_rows_reference(part_ids, part_scores, part_counts, k):
     """numpy statement of the merge order ([part][query][k] -> [query][k]); what sg_merge_topk_kernel computes.
     Used by the CPU tests of the sharding plan; never on the product path."""
