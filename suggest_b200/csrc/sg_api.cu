@@ -1097,6 +1097,7 @@ static void sharded_destroy(sg_sharded *sx) {
         if (sx->d_ptrs) cudaFree((void *)sx->d_ptrs);
         if (sx->queries_up) cudaEventDestroy(sx->queries_up);
     }
+    cudaGetLastError();  // a device that does not exist (failed build) must not leave its error for the next launch check
     delete sx;
 }
 
@@ -1111,7 +1112,7 @@ int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t
     sx->shards.resize(n_shards);
     sx->n_docs = n_docs;
     DeviceGuard guard;
-    guard.set(devices[0]);  // remembers the caller's device; cudaSetDevice from here on
+    if (guard.set(devices[0]) != cudaSuccess) cudaGetLastError();  // remembers the caller's device; sg_index_build reports a bad ordinal
     std::vector<uint64_t> sub_off;
     for (uint32_t s = 0; s < n_shards; s++) {
         const uint32_t lo = (uint32_t)((uint64_t)n_docs * s / n_shards), hi = (uint32_t)((uint64_t)n_docs * (s + 1) / n_shards);
@@ -1203,9 +1204,19 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
     SG_CUDA(guard.set(s0.device));
     SG_CUDA(s0.q_bytes.reserve(n_bytes + 64));
     SG_CUDA(s0.q_off.reserve((size_t)n_q + 1));
-    SG_CUDA(sx->out_ids.reserve((size_t)n_q * k));
-    SG_CUDA(sx->out_scores.reserve((size_t)n_q * k));
-    SG_CUDA(sx->out_counts.reserve(n_q));
+    // page-locked result buffers (sg_pinned_alloc): the merge kernel stores the valid entries straight into them
+    uint32_t *m_ids = (uint32_t *)mapped_host_range(out_ids, (size_t)n_q * k * sizeof(uint32_t));
+    double *m_scores = (double *)mapped_host_range(out_scores, (size_t)n_q * k * sizeof(double));
+    uint32_t *m_counts = (uint32_t *)mapped_host_range(out_counts, (size_t)n_q * sizeof(uint32_t));
+    const bool direct = m_ids && m_scores && m_counts;
+    if (!direct) {
+        SG_CUDA(sx->out_ids.reserve((size_t)n_q * k));
+        SG_CUDA(sx->out_scores.reserve((size_t)n_q * k));
+        SG_CUDA(sx->out_counts.reserve(n_q));
+        m_ids = sx->out_ids.p;
+        m_scores = sx->out_scores.p;
+        m_counts = sx->out_counts.p;
+    }
     if (!sx->peer_reads) SG_CUDA(sx->parts.reserve(block * n));
     if (n_bytes) SG_CUDA(cudaMemcpyAsync(s0.q_bytes.p, src_bytes, n_bytes, cudaMemcpyHostToDevice, s0.stream));
     SG_CUDA(cudaMemcpyAsync(s0.q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s0.stream));
@@ -1247,15 +1258,19 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (sx->peer_reads) {
         SG_CUDA(cudaMemcpyAsync((void *)sx->d_ptrs, ptrs, n * sizeof(void *), cudaMemcpyHostToDevice, s0.stream));
-        SG_CUDA(sg::launch_merge_topk_peer(n, n_q, k, sx->d_ptrs, sx->out_ids.p, sx->out_scores.p, sx->out_counts.p, blocks, s0.stream));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
+        SG_CUDA(sg::launch_merge_topk_peer(n, n_q, k, sx->d_ptrs, m_ids, m_scores, m_counts, blocks, s0.stream, direct ? 1 : 0));
     } else {
-        rc = sg_merge_topk_packed_device(s0.device, n, n_q, k, sx->parts.p, sx->out_ids.p, sx->out_scores.p, sx->out_counts.p, s0.stream);
-        if (rc != SG_OK) { cudaStreamSynchronize(s0.stream); return rc; }
+        const double *sc = (const double *)sx->parts.p;
+        const uint32_t *ids = (const uint32_t *)(sc + (size_t)n_q * k);
+        SG_CUDA(sg::launch_merge_topk(n, n_q, k, ids, sc, ids + (size_t)n_q * k, block / 4, block / 8, block / 4, m_ids, m_scores, m_counts,
+                                      blocks, s0.stream, direct ? 1 : 0));
     }
-    SG_CUDA(cudaMemcpyAsync(out_ids, sx->out_ids.p, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
-    SG_CUDA(cudaMemcpyAsync(out_scores, sx->out_scores.p, (size_t)n_q * k * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
-    SG_CUDA(cudaMemcpyAsync(out_counts, sx->out_counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!direct) {
+        SG_CUDA(cudaMemcpyAsync(out_ids, m_ids, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
+        SG_CUDA(cudaMemcpyAsync(out_scores, m_scores, (size_t)n_q * k * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
+        SG_CUDA(cudaMemcpyAsync(out_counts, m_counts, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
+    }
     SG_CUDA(cudaStreamSynchronize(s0.stream));
     for (uint32_t q = 0; q < n_q; q++)
         if (out_counts[q] == SG_COUNT_UNSUPPORTED)

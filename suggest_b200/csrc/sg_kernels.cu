@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(kMaxSearchThreads, 1) sg_search_kernel(const D
 __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *__restrict__ part_ids,
                                      const double *__restrict__ part_scores, const uint32_t *__restrict__ part_counts,
                                      size_t stride_ids, size_t stride_scores, size_t stride_counts,
-                                     uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+                                     uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int sparse) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_q; q += warps) {
@@ -514,7 +514,8 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
             if (lane == 0) { out_ids[(size_t)q * k + n_out] = id; out_scores[(size_t)q * k + n_out] = s; }
             if (lane == who) cur++;
         }
-        for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[(size_t)q * k + j] = 0; out_scores[(size_t)q * k + j] = 0.0; }
+        // sparse: the rows are page-locked host memory (every store crosses PCIe): only the valid entries are written
+        if (!sparse) for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[(size_t)q * k + j] = 0; out_scores[(size_t)q * k + j] = 0.0; }
         if (lane == 0) out_counts[q] = unsupported ? kCountUnsupported : n_out;
     }
 }
@@ -524,7 +525,7 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
 // needed (a count per part, then the rows the butterfly actually consumes) - the gather of the shard exchange is these
 // loads, there is no copy of the blocks (sg_sharded_search_batch).
 __global__ void sg_merge_topk_peer_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k, const void *const *__restrict__ parts,
-                                          uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
+                                          uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int sparse) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const double *my_scores = nullptr;
@@ -571,7 +572,7 @@ __global__ void sg_merge_topk_peer_kernel(uint32_t n_parts, uint32_t n_q, uint32
                 id = has ? my_ids[row + cur] : kInf;
             }
         }
-        for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[row + j] = 0; out_scores[row + j] = 0.0; }
+        if (!sparse) for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[row + j] = 0; out_scores[row + j] = 0.0; }
         if (lane == 0) out_counts[q] = unsupported ? kCountUnsupported : n_out;
     }
 }
@@ -594,15 +595,15 @@ cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks,
 
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
                               const uint32_t *part_counts, size_t stride_ids, size_t stride_scores, size_t stride_counts,
-                              uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream) {
+                              uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream, int sparse) {
     sg_merge_topk_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, part_ids, part_scores, part_counts, stride_ids, stride_scores,
-                                                     stride_counts, out_ids, out_scores, out_counts);
+                                                     stride_counts, out_ids, out_scores, out_counts, sparse);
     return cudaGetLastError();
 }
 
 cudaError_t launch_merge_topk_peer(uint32_t n_parts, uint32_t n_q, uint32_t k, const void *const *parts, uint32_t *out_ids,
-                                   double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream) {
-    sg_merge_topk_peer_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, parts, out_ids, out_scores, out_counts);
+                                   double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream, int sparse) {
+    sg_merge_topk_peer_kernel<<<blocks, 256, 0, stream>>>(n_parts, n_q, k, parts, out_ids, out_scores, out_counts, sparse);
     return cudaGetLastError();
 }
 

@@ -18,10 +18,11 @@ cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int 
                                  cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
                               const uint32_t *part_counts, size_t stride_ids, size_t stride_scores, size_t stride_counts,
-                              uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream);
+                              uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream,
+                              int sparse = 0);  // sparse: write only the valid entries of a row (rows in page-locked host memory)
 // parts: device array of n_parts pointers to packed blocks (sg_packed_rows_bytes), each in the HBM of its shard's GPU (peer access)
 cudaError_t launch_merge_topk_peer(uint32_t n_parts, uint32_t n_q, uint32_t k, const void *const *parts, uint32_t *out_ids,
-                                   double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream);
+                                   double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream, int sparse = 0);
 
 // language model (sg_lm.cu)
 cudaError_t launch_lm_context(const DevLm &lm, const uint32_t *ctx_ids, const uint32_t *ctx_off, uint32_t n_q, LmContext *out,

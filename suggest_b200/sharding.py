@@ -94,16 +94,20 @@ class ShardedNGramIndex:
         _capi.check(_capi.lib().sg_index_get_info(C.c_void_p(_capi.lib().sg_sharded_shard(self._h, s)), C.byref(info)))
         return {name: getattr(info, name) for name, _ in info._fields_}
 
-    def SuggestBatch(self, queries, similarity, metric, topK, packed=None):
+    def SuggestBatch(self, queries, similarity, metric, topK, packed=None, out=None):
+        """`out`: PinnedBuffers(n_q, k).out - the merge kernel then stores the valid entries straight into them."""
         import ctypes as C
         from .suggest import pack_strings
         data, off = packed if packed is not None else pack_strings(queries)
         data = np.ascontiguousarray(data, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         n_q, k = len(off) - 1, max(int(topK), 0)
-        ids = np.zeros((n_q, k), dtype=np.uint32)
-        scores = np.zeros((n_q, k), dtype=np.float64)
-        counts = np.zeros(n_q, dtype=np.uint32)
+        if out is None:
+            ids = np.zeros((n_q, k), dtype=np.uint32)
+            scores = np.zeros((n_q, k), dtype=np.float64)
+            counts = np.zeros(n_q, dtype=np.uint32)
+        else:
+            ids, scores, counts = out
         p = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
         _capi.check(_capi.lib().sg_sharded_search_batch(self._h, p(data), p(off), n_q, metric.code, float(similarity), k, p(ids),
                                                         p(scores), p(counts)))

@@ -66,6 +66,16 @@ def test_sharded_equals_unsharded_and_oracle(gather):
                 assert np.array_equal(a_ids[mask], o_ids[mask]), (devices, m)
                 assert np.array_equal(a_sc[mask], o_sc[mask]), (devices, m)
             assert (cnt > 0).mean() > 0.5
+        # page-locked result rows: the merge kernel stores the valid entries (and the counts) straight into them
+        pinned = S.PinnedBuffers(len(qo) - 1, 10)
+        pinned.ids[...] = 0xABABABAB
+        ids, sc, cnt = sx.SuggestBatch(None, 0.5, METRICS[O.JACCARD], 10, packed=(qb, qo), out=pinned.out)
+        ids1, sc1, cnt1 = single.SuggestBatch(None, 0.5, METRICS[O.JACCARD], 10, packed=(qb, qo))
+        mask = np.arange(10)[None, :] < cnt1[:, None]
+        assert np.array_equal(cnt, cnt1) and np.array_equal(ids[mask], ids1[mask]) and np.array_equal(sc[mask], sc1[mask])
+        assert np.all(ids[~mask] == 0xABABABAB)
+        del ids, sc, cnt
+        pinned.close()
         sx.close()
     single.close()
 

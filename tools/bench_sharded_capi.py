@@ -21,8 +21,7 @@ def main():
     n_gpus = torch.cuda.device_count()
     docs, (qb, qo), _ = synthetic_workload(n_docs, 65536)
     desc = IndexDescription(Name="bench", NGramSize=3)
-    for mode in ("peer", "copy"):
-        os.environ["SG_SHARD_GATHER_COPY"] = "1" if mode == "copy" else "0"
+XX
         t0 = time.perf_counter()
         sx = ShardedNGramIndex(docs, desc, list(range(n_gpus)))
         build_s = time.perf_counter() - t0
