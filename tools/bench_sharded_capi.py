@@ -21,18 +21,21 @@ def main():
     n_gpus = torch.cuda.device_count()
     docs, (qb, qo), _ = synthetic_workload(n_docs, 65536)
     desc = IndexDescription(Name="bench", NGramSize=3)
-XX
+    pinned = S.PinnedBuffers(65536, 10)
+    for mode, rows in (("peer", "page-locked"), ("peer", "pageable"), ("copy", "page-locked")):
+        os.environ["SG_SHARD_GATHER_COPY"] = "1" if mode == "copy" else "0"
         t0 = time.perf_counter()
         sx = ShardedNGramIndex(docs, desc, list(range(n_gpus)))
         build_s = time.perf_counter() - t0
+        out = pinned.out if rows == "page-locked" else None
         for _ in range(3):
-            ids, sc, cnt = sx.SuggestBatch(None, 0.5, S.JaccardMetric(), 10, packed=(qb, qo))
+            ids, sc, cnt = sx.SuggestBatch(None, 0.5, S.JaccardMetric(), 10, packed=(qb, qo), out=out)
         t0 = time.perf_counter()
         for _ in range(steps):
-            ids, sc, cnt = sx.SuggestBatch(None, 0.5, S.JaccardMetric(), 10, packed=(qb, qo))
+            ids, sc, cnt = sx.SuggestBatch(None, 0.5, S.JaccardMetric(), 10, packed=(qb, qo), out=out)
         dt = (time.perf_counter() - t0) / steps
         print(json.dumps({"workload": f"{n_docs}-entry dictionary, {n_gpus} record-id-range shards, one process (sg_sharded_search_batch, "
-                                      "host buffers in and out)", "gather": mode, "peer_reads": sx.info()["peer_reads"],
+                                      "host buffers in and out)", "gather": mode, "result_rows": rows, "peer_reads": sx.info()["peer_reads"],
                           "queries_per_s": 65536 / dt, "ms_per_batch": dt * 1e3, "n_gpus": n_gpus, "build_s": round(build_s, 2),
                           "queries_with_a_match": float((cnt > 0).mean()), "timing": "host wall clock around the call"}))
         sx.close()
