@@ -9,9 +9,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/suggest_b200.h"
@@ -1066,10 +1068,26 @@ struct ShardCtx {
     DevBuf<char> q_bytes;
     DevBuf<uint32_t> q_off;
     DevBuf<uint8_t> rows;            // packed block of this shard (sg_packed_rows_bytes)
+    // shards 1.. are enqueued by a worker thread each: ~12 runtime calls per shard, serial on one host thread they cost more
+    // than the search of a small shard takes (8 shards: the last one's kernels would start ~0.4 ms late)
+    std::thread worker;
+    std::mutex m;
+    std::condition_variable cv;
+    int state = 0;                   // 0 idle, 1 job posted, 2 job done, 3 exit
+    int rc = SG_OK;
+    std::string err;
+};
+
+struct ShardJob {                    // one sg_sharded_search_batch, as the shards see it
+    uint32_t n_q = 0, k = 0;
+    int metric = 0;
+    double alpha = 0.0;
+    size_t n_bytes = 0, block = 0;
 };
 
 struct sg_sharded {
-    std::vector<ShardCtx> shards;
+    std::deque<ShardCtx> shards;     // (deque: ShardCtx holds a mutex and a thread and is never moved)
+    ShardJob job;
     std::mutex mu;                   // one search at a time per handle
     bool peer_reads = false;         // every shard's HBM is addressable from shards[0].device
     DevBuf<uint8_t> parts;           // copy path: the blocks of all shards, contiguous, on shards[0].device
@@ -1082,6 +1100,12 @@ struct sg_sharded {
 
 static void sharded_destroy(sg_sharded *sx) {
     if (!sx) return;
+    for (ShardCtx &sh : sx->shards) {
+        if (!sh.worker.joinable()) continue;
+        { std::lock_guard<std::mutex> lk(sh.m); sh.state = 3; }
+        sh.cv.notify_all();
+        sh.worker.join();
+    }
     DeviceGuard guard;
     if (!sx->shards.empty()) guard.set(sx->shards[0].device);  // remembers the caller's device; cudaSetDevice from here on
     for (ShardCtx &sh : sx->shards) {
@@ -1101,6 +1125,52 @@ static void sharded_destroy(sg_sharded *sx) {
     delete sx;
 }
 
+// Everything shard s does for one call, enqueued on its stream: wait for the queries on the first GPU, fetch them over
+// NVLink, search, (copy path: push the rows to the first GPU,) record `ready`.  Runs on the shard's worker thread
+// (shard 0: on the caller's).  Errors come back through sh.rc / sh.err (sg_last_error is thread-local).
+static int shard_enqueue(sg_sharded *sx, uint32_t s) {
+    ShardCtx &sh = sx->shards[s];
+    ShardCtx &s0 = sx->shards[0];
+    const ShardJob &j = sx->job;
+    SG_CUDA(cudaSetDevice(sh.device));
+    SG_CUDA(sh.rows.reserve(j.block));
+    const char *d_q = s0.q_bytes.p;
+    const uint32_t *d_off = s0.q_off.p;
+    if (s > 0) SG_CUDA(cudaStreamWaitEvent(sh.stream, sx->queries_up, 0));
+    if (s > 0 && sh.device != s0.device) {
+        SG_CUDA(sh.q_bytes.reserve(j.n_bytes + 64));
+        SG_CUDA(sh.q_off.reserve((size_t)j.n_q + 1));
+        if (j.n_bytes) SG_CUDA(cudaMemcpyPeerAsync(sh.q_bytes.p, sh.device, s0.q_bytes.p, s0.device, j.n_bytes, sh.stream));
+        SG_CUDA(cudaMemcpyPeerAsync(sh.q_off.p, sh.device, s0.q_off.p, s0.device, ((size_t)j.n_q + 1) * sizeof(uint32_t), sh.stream));
+        d_q = sh.q_bytes.p;
+        d_off = sh.q_off.p;
+    }
+    int rc = sg_search_batch_packed_device(sh.ix, d_q, d_off, j.n_q, j.metric, j.alpha, j.k, sh.rows.p, sh.stream);
+    if (rc != SG_OK) return rc;
+    if (!sx->peer_reads)
+        SG_CUDA(cudaMemcpyPeerAsync(sx->parts.p + (size_t)s * j.block, s0.device, sh.rows.p, sh.device, j.block, sh.stream));
+    if (s > 0) SG_CUDA(cudaEventRecord(sh.ready, sh.stream));
+    return SG_OK;
+}
+
+static void shard_worker(sg_sharded *sx, uint32_t s) {
+    ShardCtx &sh = sx->shards[s];
+    cudaSetDevice(sh.device);
+    for (;;) {
+        std::unique_lock<std::mutex> lk(sh.m);
+        sh.cv.wait(lk, [&] { return sh.state == 1 || sh.state == 3; });
+        if (sh.state == 3) return;
+        lk.unlock();
+        const int rc = shard_enqueue(sx, s);
+        lk.lock();
+        sh.rc = rc;
+        sh.err = rc == SG_OK ? std::string() : g_err;
+        sh.state = 2;
+        lk.unlock();
+        sh.cv.notify_all();
+    }
+}
+
 int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs, const int32_t *devices,
                      uint32_t n_shards, sg_sharded **out) {
     if (!out) return fail(SG_ERR_INVALID, "null out");
@@ -1109,7 +1179,7 @@ int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t
     if (n_shards < 1 || n_shards > 32) return fail(SG_ERR_INVALID, "n_shards must be in 1..32");
     sg_sharded *sx = new (std::nothrow) sg_sharded();
     if (!sx) return fail(SG_ERR_NOMEM, "out of host memory");
-    sx->shards.resize(n_shards);
+    for (uint32_t s = 0; s < n_shards; s++) sx->shards.emplace_back();
     sx->n_docs = n_docs;
     DeviceGuard guard;
     if (guard.set(devices[0]) != cudaSuccess) cudaGetLastError();  // remembers the caller's device; sg_index_build reports a bad ordinal
@@ -1149,6 +1219,7 @@ int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t
     if (e == cudaSuccess && peer) e = cudaMalloc((void **)&sx->d_ptrs, 32 * sizeof(void *));
     if (e != cudaSuccess) { sharded_destroy(sx); return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
     sx->peer_reads = peer;
+    for (uint32_t s = 1; s < n_shards; s++) sx->shards[s].worker = std::thread(shard_worker, sx, s);
     *out = sx;
     return SG_OK;
 }
@@ -1221,33 +1292,30 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
     if (n_bytes) SG_CUDA(cudaMemcpyAsync(s0.q_bytes.p, src_bytes, n_bytes, cudaMemcpyHostToDevice, s0.stream));
     SG_CUDA(cudaMemcpyAsync(s0.q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s0.stream));
     SG_CUDA(cudaEventRecord(sx->queries_up, s0.stream));
-    const void *ptrs[32] = {nullptr};
-    for (uint32_t s = 0; s < n; s++) {
+    // every shard enqueues its own work: shards 1.. on their worker threads, shard 0 here
+    sx->job.n_q = n_q;
+    sx->job.k = k;
+    sx->job.metric = metric;
+    sx->job.alpha = alpha;
+    sx->job.n_bytes = n_bytes;
+    sx->job.block = block;
+    for (uint32_t s = 1; s < n; s++) {
         ShardCtx &sh = sx->shards[s];
-        SG_CUDA(cudaSetDevice(sh.device));
-        SG_CUDA(sh.rows.reserve(block));
-        const char *d_q = s0.q_bytes.p;
-        const uint32_t *d_off = s0.q_off.p;
-        if (s > 0 && sh.device != s0.device) {
-            SG_CUDA(sh.q_bytes.reserve(n_bytes + 64));
-            SG_CUDA(sh.q_off.reserve((size_t)n_q + 1));
-            SG_CUDA(cudaStreamWaitEvent(sh.stream, sx->queries_up, 0));
-            if (n_bytes) SG_CUDA(cudaMemcpyPeerAsync(sh.q_bytes.p, sh.device, s0.q_bytes.p, s0.device, n_bytes, sh.stream));
-            SG_CUDA(cudaMemcpyPeerAsync(sh.q_off.p, sh.device, s0.q_off.p, s0.device, ((size_t)n_q + 1) * sizeof(uint32_t), sh.stream));
-            d_q = sh.q_bytes.p;
-            d_off = sh.q_off.p;
-        } else if (s > 0) {
-            SG_CUDA(cudaStreamWaitEvent(sh.stream, sx->queries_up, 0));  // another shard on the first GPU reads its copy
-        }
-        rc = sg_search_batch_packed_device(sh.ix, d_q, d_off, n_q, metric, alpha, k, sh.rows.p, sh.stream);
-        if (rc != SG_OK) break;
-        if (!sx->peer_reads)
-            SG_CUDA(cudaMemcpyPeerAsync(sx->parts.p + (size_t)s * block, s0.device, sh.rows.p, sh.device, block, sh.stream));
-        ptrs[s] = sh.rows.p;
-        if (s > 0) SG_CUDA(cudaEventRecord(sh.ready, sh.stream));
+        { std::lock_guard<std::mutex> lk(sh.m); sh.state = 1; }
+        sh.cv.notify_all();
     }
+    rc = shard_enqueue(sx, 0);
+    std::string msg = rc == SG_OK ? std::string() : g_err;
+    for (uint32_t s = 1; s < n; s++) {
+        ShardCtx &sh = sx->shards[s];
+        std::unique_lock<std::mutex> lk(sh.m);
+        sh.cv.wait(lk, [&] { return sh.state == 2; });
+        sh.state = 0;
+        if (sh.rc != SG_OK && rc == SG_OK) { rc = sh.rc; msg = sh.err; }
+    }
+    const void *ptrs[32] = {nullptr};
+    for (uint32_t s = 0; s < n; s++) ptrs[s] = sx->shards[s].rows.p;
     if (rc != SG_OK) {
-        const std::string msg = g_err;
         for (ShardCtx &sh : sx->shards) { cudaSetDevice(sh.device); cudaStreamSynchronize(sh.stream); }
         return fail(rc, msg);
     }
