@@ -1216,7 +1216,7 @@ int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t
         if (pe != cudaSuccess) { cudaGetLastError(); peer = false; }
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sx->queries_up, cudaEventDisableTiming);
-    if (e == cudaSuccess && peer) e = cudaMalloc((void **)&sx->d_ptrs, 32 * sizeof(void *));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&sx->d_ptrs, 32 * sizeof(void *));
     if (e != cudaSuccess) { sharded_destroy(sx); return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
     sx->peer_reads = peer;
     for (uint32_t s = 1; s < n_shards; s++) sx->shards[s].worker = std::thread(shard_worker, sx, s);
@@ -1289,9 +1289,18 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
         m_counts = sx->out_counts.p;
     }
     if (!sx->peer_reads) SG_CUDA(sx->parts.reserve(block * n));
+    // SG_TRACE: timeline of the call on the first GPU (queries up | shards searched | merged) and the host's enqueue time
+    static const int trace = env_int("SG_TRACE", 0);
+    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (trace) {
+        for (auto &e : tev) SG_CUDA(cudaEventCreate(&e));
+        cudaEventRecord(tev[0], s0.stream);
+    }
     if (n_bytes) SG_CUDA(cudaMemcpyAsync(s0.q_bytes.p, src_bytes, n_bytes, cudaMemcpyHostToDevice, s0.stream));
     SG_CUDA(cudaMemcpyAsync(s0.q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s0.stream));
     SG_CUDA(cudaEventRecord(sx->queries_up, s0.stream));
+    if (trace) cudaEventRecord(tev[1], s0.stream);
     // every shard enqueues its own work: shards 1.. on their worker threads, shard 0 here
     sx->job.n_q = n_q;
     sx->job.k = k;
@@ -1324,22 +1333,32 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
     for (uint32_t s = 1; s < n; s++) SG_CUDA(cudaStreamWaitEvent(s0.stream, sx->shards[s].ready, 0));
     int blocks = (int)((n_q + 7) / 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    if (sx->peer_reads) {
-        SG_CUDA(cudaMemcpyAsync((void *)sx->d_ptrs, ptrs, n * sizeof(void *), cudaMemcpyHostToDevice, s0.stream));
-        SG_CUDA(sg::launch_merge_topk_peer(n, n_q, k, sx->d_ptrs, m_ids, m_scores, m_counts, blocks, s0.stream, direct ? 1 : 0));
-    } else {
-        const double *sc = (const double *)sx->parts.p;
-        const uint32_t *ids = (const uint32_t *)(sc + (size_t)n_q * k);
-        SG_CUDA(sg::launch_merge_topk(n, n_q, k, ids, sc, ids + (size_t)n_q * k, block / 4, block / 8, block / 4, m_ids, m_scores, m_counts,
-                                      blocks, s0.stream, direct ? 1 : 0));
-    }
+    if (trace) cudaEventRecord(tev[2], s0.stream);
+    // one kernel for both gathers: the pointers name the shards' own rows (peer reads) or their copies on this GPU
+    if (!sx->peer_reads) for (uint32_t s = 0; s < n; s++) ptrs[s] = sx->parts.p + (size_t)s * block;
+    SG_CUDA(cudaMemcpyAsync((void *)sx->d_ptrs, ptrs, n * sizeof(void *), cudaMemcpyHostToDevice, s0.stream));
+    blocks = (int)(((n_q + 31) / 32 + 7) / 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    SG_CUDA(sg::launch_merge_topk_peer(n, n_q, k, sx->d_ptrs, m_ids, m_scores, m_counts, blocks, s0.stream, direct ? 1 : 0));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (!direct) {
         SG_CUDA(cudaMemcpyAsync(out_ids, m_ids, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
         SG_CUDA(cudaMemcpyAsync(out_scores, m_scores, (size_t)n_q * k * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
         SG_CUDA(cudaMemcpyAsync(out_counts, m_counts, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
     }
+    if (trace) cudaEventRecord(tev[3], s0.stream);
+    const auto t_enqueued = std::chrono::steady_clock::now();
     SG_CUDA(cudaStreamSynchronize(s0.stream));
+    if (trace) {
+        float t[3] = {0, 0, 0};
+        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+        std::fprintf(stderr, "sg_sharded_search_batch: %u queries, %u shards (%s): host enqueue %.1f us, wait %.1f us; first GPU: queries up %.1f us, "
+                             "own search + waiting for the shards %.1f us, merge%s %.1f us\n", n_q, n, sx->peer_reads ? "peer reads" : "peer copies",
+                     std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count(),
+                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enqueued).count(), t[0] * 1e3, t[1] * 1e3,
+                     direct ? " into page-locked rows" : " + D2H", t[2] * 1e3);
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     for (uint32_t q = 0; q < n_q; q++)
         if (out_counts[q] == SG_COUNT_UNSUPPORTED)
             return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");

@@ -522,58 +522,73 @@ __global__ void sg_merge_topk_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k,
 
 // The same selection with one pointer per part instead of a stride: part p's packed block [scores | ids | counts] lives in
 // the HBM of the GPU that searched shard p and is read from there over NVLink peer access, only the entries that are
-// needed (a count per part, then the rows the butterfly actually consumes) - the gather of the shard exchange is these
-// loads, there is no copy of the blocks (sg_sharded_search_batch).
-__global__ void sg_merge_topk_peer_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k, const void *const *__restrict__ parts,
-                                          uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int sparse) {
+// needed - the gather of the shard exchange is these loads, there is no copy of the blocks (sg_sharded_search_batch).
+// A warp takes 32 consecutive queries at a time: the counts of a part for those queries are one coalesced 128-byte
+// (remote) load, staged in shared memory; the 32 result counts leave as one 128-byte store (one PCIe write when the rows
+// are page-locked host memory, instead of 32).  Within a query lane = part, as in sg_merge_topk_kernel.
+__global__ void __launch_bounds__(256) sg_merge_topk_peer_kernel(uint32_t n_parts, uint32_t n_q, uint32_t k, const void *const *__restrict__ parts,
+                                                                 uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int sparse) {
+    __shared__ uint32_t s_cnt[8][32][33];  // [warp][part][query of the chunk] (+1: conflict-free column reads)
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const double *my_scores = nullptr;
-    const uint32_t *my_ids = nullptr, *my_counts = nullptr;
+    const uint32_t *my_ids = nullptr;
     if ((uint32_t)lane < n_parts) {
         my_scores = (const double *)parts[lane];
         my_ids = (const uint32_t *)(my_scores + (size_t)n_q * k);
-        my_counts = my_ids + (size_t)n_q * k;
     }
-    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n_q; q += warps) {
-        uint32_t cur = 0, cnt = 0;
-        const size_t row = (size_t)q * k;
-        bool unsupported = false;
-        if ((uint32_t)lane < n_parts) {
-            cnt = my_counts[q];
-            if (cnt == kCountUnsupported) { unsupported = true; cnt = 0; }
+    const uint32_t n_chunks = (n_q + 31) >> 5;
+    for (uint32_t chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps) {
+        const uint32_t q0 = chunk << 5;
+        for (uint32_t p = 0; p < n_parts; p++) {
+            const uint32_t *cnts = (const uint32_t *)((const double *)parts[p] + (size_t)n_q * k) + (size_t)n_q * k;
+            s_cnt[warp][p][lane] = q0 + lane < n_q ? cnts[q0 + lane] : 0u;
+        }
+        __syncwarp();
+        uint32_t my_out = 0;
+        const uint32_t q_end = min(32u, n_q - q0);
+        for (uint32_t i = 0; i < q_end; i++) {
+            const size_t row = (size_t)(q0 + i) * k;
+            uint32_t cur = 0, cnt = (uint32_t)lane < n_parts ? s_cnt[warp][lane][i] : 0u;
+            bool unsupported = cnt == kCountUnsupported;
+            if (unsupported) cnt = 0;
             if (cnt > k) cnt = k;
-        }
-        unsupported = __any_sync(kFull, unsupported);
-        // head of this lane's list, fetched once per advance (a remote load each)
-        bool has = cur < cnt;
-        double s = has ? my_scores[row] : 0.0;
-        uint32_t id = has ? my_ids[row] : kInf;
-        uint32_t n_out = 0;
-        for (; n_out < k; n_out++) {
-            bool bh = has;
-            double bs = s;
-            uint32_t bi = id;
-            int who = lane;
-            for (int o = 16; o; o >>= 1) {
-                const bool oh = __shfl_xor_sync(kFull, bh, o);
-                const double os = __shfl_xor_sync(kFull, bs, o);
-                const uint32_t oi = __shfl_xor_sync(kFull, bi, o);
-                const int ow = __shfl_xor_sync(kFull, who, o);
-                const bool take = oh && (!bh || os > bs || (os == bs && (oi < bi || (oi == bi && ow < who))));
-                if (take) { bh = oh; bs = os; bi = oi; who = ow; }
+            unsupported = __any_sync(kFull, unsupported);
+            uint32_t n_out = 0;
+            if (__any_sync(kFull, cnt != 0u)) {
+                // head of this lane's list, fetched once per advance (a remote load each)
+                bool has = cur < cnt;
+                double s = has ? my_scores[row] : 0.0;
+                uint32_t id = has ? my_ids[row] : kInf;
+                for (; n_out < k; n_out++) {
+                    bool bh = has;
+                    double bs = s;
+                    uint32_t bi = id;
+                    int who = lane;
+                    for (int o = 16; o; o >>= 1) {
+                        const bool oh = __shfl_xor_sync(kFull, bh, o);
+                        const double os = __shfl_xor_sync(kFull, bs, o);
+                        const uint32_t oi = __shfl_xor_sync(kFull, bi, o);
+                        const int ow = __shfl_xor_sync(kFull, who, o);
+                        const bool take = oh && (!bh || os > bs || (os == bs && (oi < bi || (oi == bi && ow < who))));
+                        if (take) { bh = oh; bs = os; bi = oi; who = ow; }
+                    }
+                    if (!bh) break;
+                    if (lane == 0) { out_ids[row + n_out] = bi; out_scores[row + n_out] = bs; }
+                    if (lane == who) {
+                        cur++;
+                        has = cur < cnt;
+                        s = has ? my_scores[row + cur] : 0.0;
+                        id = has ? my_ids[row + cur] : kInf;
+                    }
+                }
             }
-            if (!bh) break;
-            if (lane == 0) { out_ids[row + n_out] = bi; out_scores[row + n_out] = bs; }
-            if (lane == who) {
-                cur++;
-                has = cur < cnt;
-                s = has ? my_scores[row + cur] : 0.0;
-                id = has ? my_ids[row + cur] : kInf;
-            }
+            if (!sparse) for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[row + j] = 0; out_scores[row + j] = 0.0; }
+            if ((uint32_t)lane == i) my_out = unsupported ? kCountUnsupported : n_out;
         }
-        if (!sparse) for (uint32_t j = n_out + lane; j < k; j += 32) { out_ids[row + j] = 0; out_scores[row + j] = 0.0; }
-        if (lane == 0) out_counts[q] = unsupported ? kCountUnsupported : n_out;
+        if (q0 + lane < n_q) out_counts[q0 + lane] = my_out;
+        __syncwarp();
     }
 }
 
