@@ -1060,14 +1060,18 @@ int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint
 // queries once, hands them to the other GPUs over NVLink (peer copies), runs every shard's search concurrently on its
 // own stream, and the merge kernel on the first GPU reads the per-shard rows straight out of the other GPUs' HBM
 // (peer access) - the exchange is those loads.  Without peer access the blocks are peer-copied and merged locally.
+// A batch is cut in two slices so that the merge of the first (its result rows cross PCIe entry by entry when they
+// are page-locked host memory: ~160 us for 65,536 queries) and the upload of the second run under the searches.
+constexpr uint32_t kShardSlices = 2;
+
 struct ShardCtx {
     sg_index *ix = nullptr;
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ready = nullptr;     // queries on this device / rows of this shard written
+    cudaEvent_t ready[kShardSlices] = {};  // rows of this shard written, per slice of the batch
     DevBuf<char> q_bytes;
     DevBuf<uint32_t> q_off;
-    DevBuf<uint8_t> rows;            // packed block of this shard (sg_packed_rows_bytes)
+    DevBuf<uint8_t> rows;            // packed blocks of this shard (sg_packed_rows_bytes), one per slice
     // shards 1.. are enqueued by a worker thread each: ~12 runtime calls per shard, serial on one host thread they cost more
     // than the search of a small shard takes (8 shards: the last one's kernels would start ~0.4 ms late)
     std::thread worker;
@@ -1078,11 +1082,15 @@ struct ShardCtx {
     std::string err;
 };
 
-struct ShardJob {                    // one sg_sharded_search_batch, as the shards see it
-    uint32_t n_q = 0, k = 0;
+struct ShardJob {                    // one slice of one sg_sharded_search_batch, as the shards see it
+    uint32_t k = 0;
     int metric = 0;
     double alpha = 0.0;
-    size_t n_bytes = 0, block = 0;
+    uint32_t slice = 0;
+    uint32_t lo = 0, hi = 0;         // queries [lo, hi)
+    size_t b0 = 0, b1 = 0;           // their bytes (offsets stay absolute)
+    size_t rows_off = 0, block = 0;  // where the slice's packed block starts in ShardCtx::rows, and its size
+    size_t parts_off = 0;            // copy path: where the slice's blocks start in sg_sharded::parts
 };
 
 struct sg_sharded {
@@ -1093,8 +1101,9 @@ struct sg_sharded {
     DevBuf<uint8_t> parts;           // copy path: the blocks of all shards, contiguous, on shards[0].device
     DevBuf<uint32_t> out_ids, out_counts;
     DevBuf<double> out_scores;
-    const void **d_ptrs = nullptr;   // peer path: block pointers, on shards[0].device
-    cudaEvent_t queries_up = nullptr;
+    const void **d_ptrs = nullptr;   // block pointers for the merge kernel, 32 per slice, on shards[0].device
+    cudaEvent_t queries_up[kShardSlices] = {};
+    cudaStream_t copy_stream = nullptr, merge_stream = nullptr;  // on shards[0].device
     uint32_t n_docs = 0;
 };
 
@@ -1111,7 +1120,7 @@ static void sharded_destroy(sg_sharded *sx) {
     for (ShardCtx &sh : sx->shards) {
         if (cudaSetDevice(sh.device) == cudaSuccess) {
             if (sh.stream) { cudaStreamSynchronize(sh.stream); cudaStreamDestroy(sh.stream); }
-            if (sh.ready) cudaEventDestroy(sh.ready);
+            for (cudaEvent_t ev : sh.ready) if (ev) cudaEventDestroy(ev);
             sh.q_bytes.release(); sh.q_off.release(); sh.rows.release();
         }
         if (sh.ix) sg_index_free(sh.ix);
@@ -1119,7 +1128,9 @@ static void sharded_destroy(sg_sharded *sx) {
     if (!sx->shards.empty() && cudaSetDevice(sx->shards[0].device) == cudaSuccess) {
         sx->parts.release(); sx->out_ids.release(); sx->out_counts.release(); sx->out_scores.release();
         if (sx->d_ptrs) cudaFree((void *)sx->d_ptrs);
-        if (sx->queries_up) cudaEventDestroy(sx->queries_up);
+        for (cudaEvent_t ev : sx->queries_up) if (ev) cudaEventDestroy(ev);
+        if (sx->copy_stream) { cudaStreamSynchronize(sx->copy_stream); cudaStreamDestroy(sx->copy_stream); }
+        if (sx->merge_stream) { cudaStreamSynchronize(sx->merge_stream); cudaStreamDestroy(sx->merge_stream); }
     }
     cudaGetLastError();  // a device that does not exist (failed build) must not leave its error for the next launch check
     delete sx;
@@ -1132,24 +1143,23 @@ static int shard_enqueue(sg_sharded *sx, uint32_t s) {
     ShardCtx &sh = sx->shards[s];
     ShardCtx &s0 = sx->shards[0];
     const ShardJob &j = sx->job;
+    const uint32_t n = j.hi - j.lo;
     SG_CUDA(cudaSetDevice(sh.device));
-    SG_CUDA(sh.rows.reserve(j.block));
-    const char *d_q = s0.q_bytes.p;
-    const uint32_t *d_off = s0.q_off.p;
-    if (s > 0) SG_CUDA(cudaStreamWaitEvent(sh.stream, sx->queries_up, 0));
-    if (s > 0 && sh.device != s0.device) {
-        SG_CUDA(sh.q_bytes.reserve(j.n_bytes + 64));
-        SG_CUDA(sh.q_off.reserve((size_t)j.n_q + 1));
-        if (j.n_bytes) SG_CUDA(cudaMemcpyPeerAsync(sh.q_bytes.p, sh.device, s0.q_bytes.p, s0.device, j.n_bytes, sh.stream));
-        SG_CUDA(cudaMemcpyPeerAsync(sh.q_off.p, sh.device, s0.q_off.p, s0.device, ((size_t)j.n_q + 1) * sizeof(uint32_t), sh.stream));
+    const char *d_q = s0.q_bytes.p;                      // base pointer: the offsets of a slice stay absolute
+    const uint32_t *d_off = s0.q_off.p + j.lo + j.slice; // slice sl keeps its n + 1 offsets at lo + sl
+    SG_CUDA(cudaStreamWaitEvent(sh.stream, sx->queries_up[j.slice], 0));
+    if (sh.device != s0.device) {
+        if (j.b1 > j.b0) SG_CUDA(cudaMemcpyPeerAsync(sh.q_bytes.p + j.b0, sh.device, s0.q_bytes.p + j.b0, s0.device, j.b1 - j.b0, sh.stream));
+        SG_CUDA(cudaMemcpyPeerAsync(sh.q_off.p + j.lo + j.slice, sh.device, d_off, s0.device, ((size_t)n + 1) * sizeof(uint32_t), sh.stream));
         d_q = sh.q_bytes.p;
-        d_off = sh.q_off.p;
+        d_off = sh.q_off.p + j.lo + j.slice;
     }
-    int rc = sg_search_batch_packed_device(sh.ix, d_q, d_off, j.n_q, j.metric, j.alpha, j.k, sh.rows.p, sh.stream);
+    uint8_t *rows = sh.rows.p + j.rows_off;
+    int rc = sg_search_batch_packed_device(sh.ix, d_q, d_off, n, j.metric, j.alpha, j.k, rows, sh.stream);
     if (rc != SG_OK) return rc;
     if (!sx->peer_reads)
-        SG_CUDA(cudaMemcpyPeerAsync(sx->parts.p + (size_t)s * j.block, s0.device, sh.rows.p, sh.device, j.block, sh.stream));
-    if (s > 0) SG_CUDA(cudaEventRecord(sh.ready, sh.stream));
+        SG_CUDA(cudaMemcpyPeerAsync(sx->parts.p + j.parts_off + (size_t)s * j.block, s0.device, rows, sh.device, j.block, sh.stream));
+    SG_CUDA(cudaEventRecord(sh.ready[j.slice], sh.stream));
     return SG_OK;
 }
 
@@ -1198,7 +1208,8 @@ int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t
         if (rc != SG_OK) { const std::string msg = g_err; sharded_destroy(sx); return fail(rc, "shard " + std::to_string(s) + ": " + msg); }
         cudaError_t e = cudaSetDevice(sh.device);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sh.ready, cudaEventDisableTiming);
+        for (cudaEvent_t &ev : sh.ready)
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         if (e != cudaSuccess) { sharded_destroy(sx); return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
     }
     // peer access from the merging GPU to every other shard's GPU (NVLink / NVSwitch on a B200 box)
@@ -1215,8 +1226,11 @@ int sg_sharded_build(const sg_config *cfg, const char *doc_bytes, const uint64_t
         if (pe == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); pe = cudaSuccess; }
         if (pe != cudaSuccess) { cudaGetLastError(); peer = false; }
     }
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sx->queries_up, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&sx->d_ptrs, 32 * sizeof(void *));
+    for (cudaEvent_t &ev : sx->queries_up)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sx->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sx->merge_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&sx->d_ptrs, 32 * kShardSlices * sizeof(void *));
     if (e != cudaSuccess) { sharded_destroy(sx); return fail(SG_ERR_CUDA, cudaGetErrorString(e)); }
     sx->peer_reads = peer;
     for (uint32_t s = 1; s < n_shards; s++) sx->shards[s].worker = std::thread(shard_worker, sx, s);
@@ -1268,13 +1282,18 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
         n_bytes = low.size();
     }
     const uint32_t n = (uint32_t)sx->shards.size();
-    const size_t block = (size_t)sg_packed_rows_bytes(n_q, k);
     DeviceGuard guard;
     ShardCtx &s0 = sx->shards[0];
-    // queries: host -> first GPU once, from there to the others over NVLink
     SG_CUDA(guard.set(s0.device));
-    SG_CUDA(s0.q_bytes.reserve(n_bytes + 64));
-    SG_CUDA(s0.q_off.reserve((size_t)n_q + 1));
+    // slices of the batch: [0, split) and [split, n_q)
+    static const int split_pc = env_int("SG_SHARD_SPLIT", 50);
+    uint32_t bounds[kShardSlices + 1] = {0, n_q, n_q};
+    if (n_q >= 16384 && split_pc > 0 && split_pc < 100) bounds[1] = (uint32_t)((uint64_t)n_q * split_pc / 100);
+    size_t rows_off[kShardSlices + 1] = {0}, blocks_[kShardSlices] = {0};
+    for (uint32_t sl = 0; sl < kShardSlices; sl++) {
+        blocks_[sl] = bounds[sl + 1] > bounds[sl] ? (size_t)sg_packed_rows_bytes(bounds[sl + 1] - bounds[sl], k) : 0;
+        rows_off[sl + 1] = rows_off[sl] + blocks_[sl];
+    }
     // page-locked result buffers (sg_pinned_alloc): the merge kernel stores the valid entries straight into them
     uint32_t *m_ids = (uint32_t *)mapped_host_range(out_ids, (size_t)n_q * k * sizeof(uint32_t));
     double *m_scores = (double *)mapped_host_range(out_scores, (size_t)n_q * k * sizeof(double));
@@ -1288,75 +1307,102 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
         m_scores = sx->out_scores.p;
         m_counts = sx->out_counts.p;
     }
-    if (!sx->peer_reads) SG_CUDA(sx->parts.reserve(block * n));
-    // SG_TRACE: timeline of the call on the first GPU (queries up | shards searched | merged) and the host's enqueue time
+    // every buffer a worker touches is sized here, before any job is posted
+    for (uint32_t s = 0; s < n; s++) {
+        ShardCtx &sh = sx->shards[s];
+        SG_CUDA(cudaSetDevice(sh.device));
+        SG_CUDA(sh.rows.reserve(rows_off[kShardSlices]));
+        if (s == 0 || sh.device != s0.device) {
+            SG_CUDA(sh.q_bytes.reserve(n_bytes + 64));
+            SG_CUDA(sh.q_off.reserve((size_t)n_q + kShardSlices + 1));
+        }
+    }
+    SG_CUDA(cudaSetDevice(s0.device));
+    if (!sx->peer_reads) SG_CUDA(sx->parts.reserve(rows_off[kShardSlices] * n));
+    // SG_TRACE: timeline of the call on the first GPU and the host's enqueue time
     static const int trace = env_int("SG_TRACE", 0);
-    cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t tev[2 + 2 * kShardSlices] = {};
     const auto t_begin = std::chrono::steady_clock::now();
     if (trace) {
         for (auto &e : tev) SG_CUDA(cudaEventCreate(&e));
-        cudaEventRecord(tev[0], s0.stream);
+        cudaEventRecord(tev[0], sx->copy_stream);
     }
-    if (n_bytes) SG_CUDA(cudaMemcpyAsync(s0.q_bytes.p, src_bytes, n_bytes, cudaMemcpyHostToDevice, s0.stream));
-    SG_CUDA(cudaMemcpyAsync(s0.q_off.p, src_off, ((size_t)n_q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s0.stream));
-    SG_CUDA(cudaEventRecord(sx->queries_up, s0.stream));
-    if (trace) cudaEventRecord(tev[1], s0.stream);
-    // every shard enqueues its own work: shards 1.. on their worker threads, shard 0 here
-    sx->job.n_q = n_q;
-    sx->job.k = k;
-    sx->job.metric = metric;
-    sx->job.alpha = alpha;
-    sx->job.n_bytes = n_bytes;
-    sx->job.block = block;
-    for (uint32_t s = 1; s < n; s++) {
-        ShardCtx &sh = sx->shards[s];
-        { std::lock_guard<std::mutex> lk(sh.m); sh.state = 1; }
-        sh.cv.notify_all();
+    const void *ptrs[32 * kShardSlices] = {nullptr};
+    std::string msg;
+    for (uint32_t sl = 0; sl < kShardSlices && rc == SG_OK; sl++) {
+        const uint32_t lo = bounds[sl], hi = bounds[sl + 1];
+        if (hi == lo) continue;
+        const size_t b0 = src_off[lo], b1 = src_off[hi];
+        // queries of the slice: host -> first GPU on its copy stream (the second slice travels under the first one's search)
+        if (b1 > b0) SG_CUDA(cudaMemcpyAsync(s0.q_bytes.p + b0, src_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, sx->copy_stream));
+        SG_CUDA(cudaMemcpyAsync(s0.q_off.p + lo + sl, src_off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                sx->copy_stream));
+        SG_CUDA(cudaEventRecord(sx->queries_up[sl], sx->copy_stream));
+        // every shard enqueues its own work: shards 1.. on their worker threads, shard 0 here
+        ShardJob &j = sx->job;
+        j.k = k; j.metric = metric; j.alpha = alpha; j.slice = sl; j.lo = lo; j.hi = hi; j.b0 = b0; j.b1 = b1;
+        j.rows_off = rows_off[sl]; j.block = blocks_[sl]; j.parts_off = rows_off[sl] * n;
+        for (uint32_t s = 1; s < n; s++) {
+            ShardCtx &sh = sx->shards[s];
+            { std::lock_guard<std::mutex> lk(sh.m); sh.state = 1; }
+            sh.cv.notify_all();
+        }
+        rc = shard_enqueue(sx, 0);
+        if (rc != SG_OK) msg = g_err;
+        for (uint32_t s = 1; s < n; s++) {
+            ShardCtx &sh = sx->shards[s];
+            std::unique_lock<std::mutex> lk(sh.m);
+            sh.cv.wait(lk, [&] { return sh.state == 2; });
+            sh.state = 0;
+            if (sh.rc != SG_OK && rc == SG_OK) { rc = sh.rc; msg = sh.err; }
+        }
+        if (rc != SG_OK) break;
+        // merge of the slice on the first GPU's merge stream, behind every shard's search of it; the pointers name the
+        // shards' own rows (peer reads) or their copies on this GPU
+        SG_CUDA(cudaSetDevice(s0.device));
+        for (uint32_t s = 0; s < n; s++) {
+            SG_CUDA(cudaStreamWaitEvent(sx->merge_stream, sx->shards[s].ready[sl], 0));
+            ptrs[32 * sl + s] = sx->peer_reads ? (const void *)(sx->shards[s].rows.p + rows_off[sl])
+                                               : (const void *)(sx->parts.p + rows_off[sl] * n + (size_t)s * blocks_[sl]);
+        }
+        if (trace) cudaEventRecord(tev[1 + 2 * sl], sx->merge_stream);
+        SG_CUDA(cudaMemcpyAsync((void *)(sx->d_ptrs + 32 * sl), ptrs + 32 * sl, n * sizeof(void *), cudaMemcpyHostToDevice, sx->merge_stream));
+        int blocks = (int)(((hi - lo + 31) / 32 + 7) / 8);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        SG_CUDA(sg::launch_merge_topk_peer(n, hi - lo, k, sx->d_ptrs + 32 * sl, m_ids + (size_t)lo * k, m_scores + (size_t)lo * k, m_counts + lo,
+                                           blocks, sx->merge_stream, direct ? 1 : 0));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (!direct) {
+            SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, m_ids + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                    sx->merge_stream));
+            SG_CUDA(cudaMemcpyAsync(out_scores + (size_t)lo * k, m_scores + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(double),
+                                    cudaMemcpyDeviceToHost, sx->merge_stream));
+            SG_CUDA(cudaMemcpyAsync(out_counts + lo, m_counts + lo, (size_t)(hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, sx->merge_stream));
+        }
+        if (trace) cudaEventRecord(tev[2 + 2 * sl], sx->merge_stream);
     }
-    rc = shard_enqueue(sx, 0);
-    std::string msg = rc == SG_OK ? std::string() : g_err;
-    for (uint32_t s = 1; s < n; s++) {
-        ShardCtx &sh = sx->shards[s];
-        std::unique_lock<std::mutex> lk(sh.m);
-        sh.cv.wait(lk, [&] { return sh.state == 2; });
-        sh.state = 0;
-        if (sh.rc != SG_OK && rc == SG_OK) { rc = sh.rc; msg = sh.err; }
-    }
-    const void *ptrs[32] = {nullptr};
-    for (uint32_t s = 0; s < n; s++) ptrs[s] = sx->shards[s].rows.p;
     if (rc != SG_OK) {
         for (ShardCtx &sh : sx->shards) { cudaSetDevice(sh.device); cudaStreamSynchronize(sh.stream); }
+        cudaSetDevice(s0.device);
+        cudaStreamSynchronize(sx->copy_stream);
+        cudaStreamSynchronize(sx->merge_stream);
         return fail(rc, msg);
     }
-    // merge on the first GPU behind every shard's search
-    SG_CUDA(cudaSetDevice(s0.device));
-    for (uint32_t s = 1; s < n; s++) SG_CUDA(cudaStreamWaitEvent(s0.stream, sx->shards[s].ready, 0));
-    int blocks = (int)((n_q + 7) / 8);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    if (trace) cudaEventRecord(tev[2], s0.stream);
-    // one kernel for both gathers: the pointers name the shards' own rows (peer reads) or their copies on this GPU
-    if (!sx->peer_reads) for (uint32_t s = 0; s < n; s++) ptrs[s] = sx->parts.p + (size_t)s * block;
-    SG_CUDA(cudaMemcpyAsync((void *)sx->d_ptrs, ptrs, n * sizeof(void *), cudaMemcpyHostToDevice, s0.stream));
-    blocks = (int)(((n_q + 31) / 32 + 7) / 8);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    SG_CUDA(sg::launch_merge_topk_peer(n, n_q, k, sx->d_ptrs, m_ids, m_scores, m_counts, blocks, s0.stream, direct ? 1 : 0));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (!direct) {
-        SG_CUDA(cudaMemcpyAsync(out_ids, m_ids, (size_t)n_q * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
-        SG_CUDA(cudaMemcpyAsync(out_scores, m_scores, (size_t)n_q * k * sizeof(double), cudaMemcpyDeviceToHost, s0.stream));
-        SG_CUDA(cudaMemcpyAsync(out_counts, m_counts, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, s0.stream));
-    }
-    if (trace) cudaEventRecord(tev[3], s0.stream);
     const auto t_enqueued = std::chrono::steady_clock::now();
-    SG_CUDA(cudaStreamSynchronize(s0.stream));
+    SG_CUDA(cudaStreamSynchronize(sx->merge_stream));   // behind every shard's stream (events) and the copy stream
     if (trace) {
-        float t[3] = {0, 0, 0};
-        for (int i = 0; i < 3; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
-        std::fprintf(stderr, "sg_sharded_search_batch: %u queries, %u shards (%s): host enqueue %.1f us, wait %.1f us; first GPU: queries up %.1f us, "
-                             "own search + waiting for the shards %.1f us, merge%s %.1f us\n", n_q, n, sx->peer_reads ? "peer reads" : "peer copies",
+        std::fprintf(stderr, "sg_sharded_search_batch: %u queries, %u shards (%s), rows %s: host enqueue %.1f us, wait %.1f us; first GPU, us from the start:",
+                     n_q, n, sx->peer_reads ? "peer reads" : "peer copies", direct ? "page-locked" : "staged + D2H",
                      std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count(),
-                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enqueued).count(), t[0] * 1e3, t[1] * 1e3,
-                     direct ? " into page-locked rows" : " + D2H", t[2] * 1e3);
+                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enqueued).count());
+        for (uint32_t sl = 0; sl < kShardSlices; sl++) {
+            if (bounds[sl + 1] == bounds[sl]) continue;
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, tev[0], tev[1 + 2 * sl]);
+            cudaEventElapsedTime(&t1, tev[0], tev[2 + 2 * sl]);
+            std::fprintf(stderr, " slice %u searched by all at %.1f, merged at %.1f;", sl, t0 * 1e3, t1 * 1e3);
+        }
+        std::fprintf(stderr, "\n");
         for (auto &e : tev) cudaEventDestroy(e);
     }
     for (uint32_t q = 0; q < n_q; q++)
