@@ -1,4 +1,5 @@
 //go:build cgo
+// +build cgo
 
 // b200.go - the one file a maintainer adds to github.com/suggest-go/suggest/pkg/suggest to serve NGramIndex from
 // libsuggest_b200.so (include/suggest_b200.h).  It lives in package suggest because topKQueue.topK and
@@ -50,7 +51,7 @@ func (b *b200Builder) config() (C.sg_config, func()) {
 	d := b.description
 	n := len(d.Alphabet)
 	pa := (**C.char)(C.malloc(C.size_t(n+1) * C.size_t(unsafe.Sizeof(uintptr(0)))))
-	alphabet := unsafe.Slice(pa, n+1)
+	alphabet := (*[1 << 20]*C.char)(unsafe.Pointer(pa))[: n+1 : n+1] // go.mod says go 1.13: no unsafe.Slice
 	for i, a := range d.Alphabet {
 		alphabet[i] = C.CString(a)
 	}
