@@ -487,6 +487,33 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     return SG_OK;
 }
 
+// A whole batch as the device wants it: the caller's bytes if they are all ASCII (the kernels lower A-Z themselves), else
+// every query through strings.ToLower on the host (Go's tables, sg_text.cpp) with rebuilt offsets.  sg_search_batch does
+// the same per slice.
+struct LoweredQueries {
+    std::string low;
+    std::vector<uint32_t> low_off;
+    const char *bytes;
+    const uint32_t *off;
+    size_t n_bytes;
+    LoweredQueries(const char *q_bytes, const uint32_t *q_off, uint32_t n_q) : bytes(q_bytes), off(q_off), n_bytes(q_off[n_q]) {
+        unsigned char high = 0;  // no early exit: the loop vectorises
+        for (size_t i = 0; i < n_bytes; i++) high |= (unsigned char)q_bytes[i];
+        if (!(high & 0x80)) return;
+        low_off.resize((size_t)n_q + 1);
+        for (uint32_t q = 0; q < n_q; q++) {
+            low_off[q] = (uint32_t)low.size();
+            sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &low);
+        }
+        low_off[n_q] = (uint32_t)low.size();
+        bytes = low.data();
+        off = low_off.data();
+        n_bytes = low.size();
+    }
+    LoweredQueries(const LoweredQueries &) = delete;
+    LoweredQueries &operator=(const LoweredQueries &) = delete;
+};
+
 struct CtxLease {
     sg_index *ix;
     CallCtx *ctx = nullptr;
@@ -878,25 +905,10 @@ int sg_candidates_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off
     int rc = lease.acquire();
     if (rc != SG_OK) return rc;
     CallCtx *c = lease.ctx;
-    // queries: strings.ToLower on the host if any byte is not ASCII (the device lowers A-Z itself), as sg_search_batch does
-    std::string low;
-    std::vector<uint32_t> low_off;
-    const char *src_bytes = q_bytes;
-    const uint32_t *src_off = q_off;
-    size_t n_bytes = total_bytes;
-    unsigned char high = 0;
-    for (uint32_t i = 0; i < total_bytes; i++) high |= (unsigned char)q_bytes[i];
-    if (high & 0x80) {
-        low_off.resize((size_t)n_q + 1);
-        for (uint32_t q = 0; q < n_q; q++) {
-            low_off[q] = (uint32_t)low.size();
-            sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &low);
-        }
-        low_off[n_q] = (uint32_t)low.size();
-        src_bytes = low.data();
-        src_off = low_off.data();
-        n_bytes = low.size();
-    }
+    LoweredQueries lq(q_bytes, q_off, n_q);
+    const char *src_bytes = lq.bytes;
+    const uint32_t *src_off = lq.off;
+    const size_t n_bytes = lq.n_bytes;
     const size_t thr_bytes = thresholds ? (size_t)sg::kWindowRows * ix->dev.n_segments : 0;
     const size_t thr_words = (thr_bytes + 3) / 4;
     SG_CUDA(c->q_bytes.reserve(n_bytes + 64));
@@ -1262,25 +1274,10 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
     const uint32_t total_bytes = q_off[n_q];
     if (total_bytes && !q_bytes) return fail(SG_ERR_INVALID, "null query bytes");
     std::lock_guard<std::mutex> lock(sx->mu);
-    // strings.ToLower on the host if any byte is not ASCII, as sg_search_batch does
-    std::string low;
-    std::vector<uint32_t> low_off;
-    const char *src_bytes = q_bytes;
-    const uint32_t *src_off = q_off;
-    size_t n_bytes = total_bytes;
-    unsigned char high = 0;
-    for (uint32_t i = 0; i < total_bytes; i++) high |= (unsigned char)q_bytes[i];
-    if (high & 0x80) {
-        low_off.resize((size_t)n_q + 1);
-        for (uint32_t q = 0; q < n_q; q++) {
-            low_off[q] = (uint32_t)low.size();
-            sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &low);
-        }
-        low_off[n_q] = (uint32_t)low.size();
-        src_bytes = low.data();
-        src_off = low_off.data();
-        n_bytes = low.size();
-    }
+    LoweredQueries lq(q_bytes, q_off, n_q);
+    const char *src_bytes = lq.bytes;
+    const uint32_t *src_off = lq.off;
+    const size_t n_bytes = lq.n_bytes;
     const uint32_t n = (uint32_t)sx->shards.size();
     DeviceGuard guard;
     ShardCtx &s0 = sx->shards[0];

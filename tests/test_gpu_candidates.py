@@ -136,7 +136,7 @@ class Containment(Metric):
 
 def test_custom_metric_equals_builtin(cars_lines):
     gx, ox = build_pair(CARS_DESCRIPTION, cars_lines)
-    queries = perturbed(cars_lines, 150, 5) + ["", "Nissan March", "RAM RAM"]
+    queries = perturbed(cars_lines, 150, 5) + ["", "Nissan March", "RAM RAM", "Nissan МАРЧ", "ЖИГУЛИ 2107"]  # non-ASCII: host ToLower
     for k in (1, 5, 40):
         want = gx.SuggestMany(queries, 0.5, S.JaccardMetric(), k)
         got = gx.SuggestMany(queries, 0.5, MyJaccard(), k)
