@@ -1,3 +1,6 @@
+//go:build cgo
+// +build cgo
+
 // b200_bench_test.go - times the reference's own Suggest path (and, built with cgo, the B200 index) on the workload
 // bench.py measures: BASELINE.json config #2, exported by `python tools/export_workload.py DIR`.
 // Goes next to b200.go in github.com/suggest-go/suggest/pkg/suggest.  NOT RUN in this repository's build image (no Go
