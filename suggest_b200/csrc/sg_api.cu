@@ -751,7 +751,8 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         for (uint32_t sl = 1; sl <= n; sl++) bounds.push_back((uint32_t)((uint64_t)n_q * sl / n));
     }
     const uint32_t n_slices = (uint32_t)bounds.size() - 1;
-    SG_CUDA(c->q_bytes.reserve((size_t)total * 2 + 64 * (size_t)n_slices + 64));  // strings.ToLower can grow a slice by half
+    // strings.ToLower maps every invalid UTF-8 byte to U+FFFD (1 -> 3 bytes), so a slice can triple (sg_text.cpp: to_lower)
+    SG_CUDA(c->q_bytes.reserve((size_t)total * 3 + 64 * (size_t)n_slices + 64));
     SG_CUDA(c->q_off.reserve((size_t)n_q + n_slices + 1));
     if (!direct) {
         SG_CUDA(c->ids.reserve((size_t)n_q * k));
@@ -783,6 +784,9 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         *c->too_long = 0u;
         SG_CUDA(cudaHostGetDevicePointer((void **)&d_too_long, c->too_long, 0));
     }
+    // Everything enqueued for the call; any failure leaves through the one cleanup path behind it (the streams are drained
+    // before the caller's buffers are handed back: kernels and copies of earlier slices may still be writing them).
+    auto enqueue_slices = [&]() -> int {
     for (uint32_t sl = 0; sl < n_slices; sl++) {
         const uint32_t lo = bounds[sl], hi = bounds[sl + 1];
         if (lo == hi) continue;
@@ -830,7 +834,7 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
                             (direct ? m_scores : c->scores.p) + (size_t)lo * k, (direct ? m_counts : c->counts.p) + lo, nullptr,
                             c->work.p + sl, c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st,
                             mode, nullptr, nullptr, direct ? 1 : 0, direct ? d_too_long : nullptr);
-        if (rc != SG_OK) { cudaStreamSynchronize(cs); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); return rc; }
+        if (rc != SG_OK) return rc;
         if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 2], st);
         if (direct) {
             if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 3], st);
@@ -843,10 +847,19 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         SG_CUDA(cudaMemcpyAsync(out_counts + lo, c->counts.p + lo, (size_t)(hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 3], st);
     }
+    return SG_OK;
+    };
+    rc = enqueue_slices();
     const auto t_enqueued = std::chrono::steady_clock::now();
-    SG_CUDA(cudaStreamSynchronize(c->stream));
-    SG_CUDA(cudaStreamSynchronize(c->stream2));
-    SG_CUDA(cudaStreamSynchronize(cs));
+    {
+        const cudaError_t e1 = cudaStreamSynchronize(c->stream), e2 = cudaStreamSynchronize(c->stream2), e3 = cudaStreamSynchronize(cs);
+        const cudaError_t e = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3;
+        if (rc == SG_OK && e != cudaSuccess) { cudaGetLastError(); rc = fail(SG_ERR_CUDA, std::string("sg_search_batch: ") + cudaGetErrorString(e)); }
+    }
+    if (rc != SG_OK) {
+        for (auto &e : tev) cudaEventDestroy(e);
+        return rc;
+    }
     if (trace) {
         const auto t_done = std::chrono::steady_clock::now();
         std::fprintf(stderr, "sg_search_batch: %u queries, %u slices%s: enqueue %.1f us, wait %.1f us\n", n_q, n_slices,
@@ -1326,6 +1339,8 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
     }
     const void *ptrs[32 * kShardSlices] = {nullptr};
     std::string msg;
+    // one cleanup path: a failure anywhere in here (CUDA call or shard) drains every stream below before returning
+    auto enqueue_slices = [&]() -> int {
     for (uint32_t sl = 0; sl < kShardSlices && rc == SG_OK; sl++) {
         const uint32_t lo = bounds[sl], hi = bounds[sl + 1];
         if (hi == lo) continue;
@@ -1378,11 +1393,18 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
         }
         if (trace) cudaEventRecord(tev[2 + 2 * sl], sx->merge_stream);
     }
+    return rc;
+    };
+    {
+        const int rc2 = enqueue_slices();
+        if (rc == SG_OK && rc2 != SG_OK) { rc = rc2; msg = g_err; }  // a CUDA call of the loop itself
+    }
     if (rc != SG_OK) {
         for (ShardCtx &sh : sx->shards) { cudaSetDevice(sh.device); cudaStreamSynchronize(sh.stream); }
         cudaSetDevice(s0.device);
         cudaStreamSynchronize(sx->copy_stream);
         cudaStreamSynchronize(sx->merge_stream);
+        if (trace) for (auto &e : tev) if (e) cudaEventDestroy(e);
         return fail(rc, msg);
     }
     const auto t_enqueued = std::chrono::steady_clock::now();
@@ -1487,7 +1509,7 @@ int sg_lm_open(const char *path, int device, sg_lm **out) {
         std::string line((const char *)data.data() + p, nl - p);
         if (std::sscanf(line.c_str(), "%llu %llu %llu", &cs, &vs, &total) != 3 || cs % 8 || vs % 8) return fail(SG_ERR_FORMAT, "bad level header");
         p = nl + 1;
-        if (p + cs + vs > data.size()) return fail(SG_ERR_FORMAT, "language model file is truncated");
+        if (p > data.size() || cs > data.size() - p || vs > data.size() - p - cs) return fail(SG_ERR_FORMAT, "language model file is truncated");
         cont[i].resize(cs / 8);
         vals[i].resize(vs / 8);
         if (cs) std::memcpy(cont[i].data(), data.data() + p, cs);

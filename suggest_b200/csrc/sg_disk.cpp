@@ -77,7 +77,7 @@ std::string parse_header(const std::vector<uint8_t> &hd, uint32_t *indices, std:
     size_t end = 0;
     for (;;) {
         uint64_t len = c.gob_uint();
-        if (!c.ok || len == 0 || c.i + len > hd.size()) return "corrupt gob header";
+        if (!c.ok || len == 0 || c.i > hd.size() || len > hd.size() - c.i) return "corrupt gob header";  // no sum of a length from the file: it could wrap
         end = c.i + (size_t)len;
         int64_t tid = c.gob_int();
         if (!c.ok) return "corrupt gob header";
@@ -93,7 +93,7 @@ std::string parse_header(const std::vector<uint8_t> &hd, uint32_t *indices, std:
         field += (int)d;
         if (field == 0) {
             uint64_t n = c.gob_uint();
-            if (!c.ok || c.i + n > hd.size()) return "corrupt gob header";
+            if (!c.ok || c.i > hd.size() || n > hd.size() - c.i) return "corrupt gob header";
             version.assign((const char *)hd.data() + c.i, (size_t)n);
             c.i += (size_t)n;
         } else if (field == 1) {
@@ -112,7 +112,7 @@ std::string parse_header(const std::vector<uint8_t> &hd, uint32_t *indices, std:
                     f += (int)d2;
                     if (f == 0) {
                         uint64_t n = c.gob_uint();
-                        if (!c.ok || c.i + n > hd.size()) return "corrupt gob header";
+                        if (!c.ok || c.i > hd.size() || n > hd.size() - c.i) return "corrupt gob header";
                         td.term.assign((const char *)hd.data() + c.i, (size_t)n);
                         c.i += (size_t)n;
                     } else {

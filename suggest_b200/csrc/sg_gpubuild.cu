@@ -78,6 +78,14 @@ __global__ void __launch_bounds__(kDocThreads) sg_doc_tokens_kernel(const DevInd
     }
 }
 
+// 64-bit sum of per-document key counts: the 32-bit exclusive scan below wraps silently past 2^32 pairs
+__global__ void sg_sum64_kernel(const uint32_t *__restrict__ a, uint32_t n, unsigned long long *out) {
+    unsigned long long s = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += a[i];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
 __global__ void sg_iota_kernel(uint32_t *a, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) a[i] = i;
@@ -239,6 +247,15 @@ std::string gpu_build(const DevIndex &text, const char *doc_bytes, const uint64_
         cub_bytes = need;
         return cudaSuccess;
     };
+    {   // the pair count in 64 bits first: offsets, CUB's int counts and every buffer below assume it fits 2^31
+        unsigned long long *d_total = nullptr, total = 0;
+        GB_CUDA(tmp.get(&d_total, 1));
+        GB_CUDA(cudaMemset(d_total, 0, sizeof(unsigned long long)));
+        sg_sum64_kernel<<<296, 256>>>(d_nkeys, n_docs, d_total);
+        GB_CUDA(cudaGetLastError());
+        GB_CUDA(cudaMemcpy(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost));
+        if (total > 0x7FFFFFF0ull) return "fallback: more than 2^31 postings";
+    }
     size_t need = 0;
     GB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, d_nkeys, d_key_off, (int)n_docs + 1));
     GB_CUDA(cub_reserve(need));

@@ -24,6 +24,8 @@
 //      (pkg/suggest/collector.go:20-26).
 //
 // sg_merge_topk_kernel: k best of the per-shard top-k lists for record-id-range shards.
+#include <mutex>
+
 #include "sg_common.cuh"
 #include "sg_kernels.h"
 
@@ -595,8 +597,23 @@ __global__ void __launch_bounds__(256) sg_merge_topk_peer_kernel(uint32_t n_part
 // ---------------- launchers (host) ----------------
 cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks, int warps_per_block, size_t smem_bytes,
                           cudaStream_t stream, cudaEvent_t *stage_events) {
-    cudaError_t e = cudaFuncSetAttribute(sg_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
+    // per-device attribute shared by every index and host thread of the process: only ever raise it (a thread with a
+    // smaller k must not lower it between another thread's set and its launch)
+    cudaError_t e = cudaSuccess;
+    {
+        static std::mutex mu;
+        static size_t opted_in[64] = {0};
+        int device = 0;
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return e;
+        if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem_bytes > opted_in[device]) {
+            e = cudaFuncSetAttribute(sg_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+            if (e != cudaSuccess) return e;
+            opted_in[device] = smem_bytes;
+        }
+    }
     const int plan_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
     if (stage_events) cudaEventRecord(stage_events[0], stream);
     sg_plan_kernel<<<plan_blocks < 148 * 8 ? plan_blocks : 148 * 8, kPlanThreads, 0, stream>>>(ix, p);

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import CARS_DESCRIPTION, GOLDEN, REFERENCE_TESTDATA
+from diskfmt import gob_header, roaring_blob
 from oracle import oracle
 from suggest_b200 import _capi
 
@@ -73,29 +74,6 @@ def test_roaring_samples_from_words_dl():
         assert np.array_equal(got, want), i
 
 
-def gob_uint(v):
-    if v < 128:
-        return bytes([v])
-    b = v.to_bytes((v.bit_length() + 7) // 8, "big")
-    return bytes([256 - len(b)]) + b
-
-
-def gob_header(terms, indices):
-    """header{Version, Indices, Terms} body as encoding/gob lays it out (type definitions omitted: the reader skips them)"""
-    body = gob_uint(1) + gob_uint(4) + b"v5.1" + gob_uint(1) + gob_uint(indices) + gob_uint(1) + gob_uint(len(terms))
-    for term, indice, size, pos, length in terms:
-        rec = gob_uint(1) + gob_uint(len(term)) + term
-        last = 0
-        for f, v in ((1, indice), (2, size), (3, pos), (4, length)):
-            if v:
-                rec += gob_uint(f - last) + gob_uint(v)
-                last = f
-        body += rec + gob_uint(0)
-    body += gob_uint(0)
-    msg = gob_uint(2 * 64) + body  # type id 64 as a gob int
-    return gob_uint(len(msg)) + msg
-
-
 def decode_single_list(blob, length, tmp=[0]):
     import tempfile
     d = tempfile.mkdtemp()
@@ -109,55 +87,6 @@ def decode_single_list(blob, length, tmp=[0]):
         return get_list(h, 3, b"abc")
     finally:
         _capi.lib().sg_host_index_free(h)
-
-
-def roaring_blob(values, runs=False):
-    """RoaringBitmap portable serialisation written from the published format description"""
-    values = np.unique(np.asarray(values, dtype=np.uint32))
-    keys = np.unique(values >> 16)
-    conts = [(int(k), (values[(values >> 16) == k] & 0xFFFF).astype(np.uint16)) for k in keys]
-    size = len(conts)
-    out = b""
-    run_flags = []
-    bodies = []
-    for k, lows in conts:
-        as_runs = []
-        start = prev = int(lows[0])
-        for v in lows[1:]:
-            v = int(v)
-            if v != prev + 1:
-                as_runs.append((start, prev - start))
-                start = v
-            prev = v
-        as_runs.append((start, prev - start))
-        use_run = runs and 2 + 4 * len(as_runs) < min(2 * len(lows), 8192)
-        run_flags.append(use_run)
-        if use_run:
-            bodies.append(struct.pack("<H", len(as_runs)) + b"".join(struct.pack("<HH", s, l) for s, l in as_runs))
-        elif len(lows) > 4096:
-            words = np.zeros(1024, dtype=np.uint64)
-            for v in lows:
-                words[int(v) >> 6] |= np.uint64(1) << np.uint64(int(v) & 63)
-            bodies.append(words.tobytes())
-        else:
-            bodies.append(lows.astype("<u2").tobytes())
-    if any(run_flags):
-        out += struct.pack("<I", 12347 | ((size - 1) << 16))
-        bm = bytearray((size + 7) // 8)
-        for i, f in enumerate(run_flags):
-            if f:
-                bm[i // 8] |= 1 << (i % 8)
-        out += bytes(bm)
-    else:
-        out += struct.pack("<II", 12346, size)
-    for (k, lows) in conts:
-        out += struct.pack("<HH", k, len(lows) - 1)
-    if not any(run_flags) or size >= 4:
-        pos = len(out) + 4 * size
-        for b in bodies:
-            out += struct.pack("<I", pos)
-            pos += len(b)
-    return out + b"".join(bodies)
 
 
 @pytest.mark.parametrize("runs", [False, True])
@@ -192,3 +121,16 @@ def test_bad_files_are_format_errors(tmp_path):
         assert rc == _capi.SG_ERR_FORMAT, content
     rc = _capi.lib().sg_host_index_open_disk(C.byref(cfg), b"/nonexistent.hd", str(dl).encode(), C.byref(h))
     assert rc == _capi.SG_ERR_IO
+
+
+def test_written_index_with_all_three_codecs(tmp_path):
+    """diskfmt.write_index (what tests/test_gpu_disk.py feeds sg_index_open_disk) reads back list by list"""
+    from diskfmt import write_index
+    from suggest_b200.workload import synthetic_dictionary, unpack
+    desc = dict(ngram_size=2, wrap=("$", "$"), pad="$", alphabet=("english", "$"))
+    data, off, _ = synthetic_dictionary(70000, seed=99, lo=4, hi=14, skew="zipf")
+    docs = unpack(data, off)
+    ox = oracle.OracleIndex(desc["ngram_size"], desc["wrap"], desc["pad"], desc["alphabet"]).add_docs(docs)
+    n_lists, n_roaring = write_index(ox, str(tmp_path), "synth")
+    assert n_roaring > 50
+    check_against_rebuild(desc, docs, str(tmp_path / "synth.hd"), str(tmp_path / "synth.dl"))
