@@ -5,20 +5,25 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
 
 Workload: 1,000,000 synthetic 8-32 character a-z strings, 3-gram index, Jaccard >= 0.5,
-k = 10, 65,536 queries per step (dictionary entries with two substituted characters).  A step is one
-pass of the whole path (tokenise -> posting fetch -> T-occurrence count -> score -> top-k) over one batch.
-With N > 1 every rank holds a replica of the 1M index and searches its own batch (independent queries,
-no data-path collective; weak scaling).  `--workload sharded` runs config #4 instead: the dictionary is
-split by record-id range, every rank searches the same batch, per-shard top-k is all-gathered (NCCL) and
-merged on the device.
+k = 10, batches of 65,536 queries (dictionary entries with two substituted characters).  One pass of the whole path
+(tokenise -> posting fetch -> T-occurrence count -> score -> top-k) over one batch takes ~0.25 ms on a B200, too short
+for a clock sampler to see, so a STEP is BATCHES_PER_STEP (128) such passes back to back over a ring of 8 different
+batches: ~30 ms per step, >= 0.5 s per timed region.  Queries/s is what is reported, as before.
+With N > 1 every rank holds a replica of the 1M index and searches its own batches (independent queries, no data-path
+collective; weak scaling).  Every run also measures, as extra objects of the same JSON line:
+  config4  BASELINE.json config #4: a 10M-entry dictionary split by record-id range over the N ranks, every rank searches
+           the same batch, per-shard top-k exchanged and merged by the fused peer-memory kernel (sg_exchange.cu) and,
+           for comparison, by NCCL all-gather + merge; a sample is checked against the oracle
+  config3  (N = 1) BASELINE.json config #3: Jaccard / Cosine / Dice x n in {2,3,4} on the same dictionary, plus the
+           Zipf-lettered variant; `min_qps_e2e` is the worst point
+`--workload sharded` prints config #4 as the main line; `--workload spellchecker|autocomplete` run the SURVEY.md 8(f) rows.
 
-`--workload spellchecker` / `--workload autocomplete` run the SURVEY.md 8(f) rows (bench_spellchecker.py, bench_autocomplete.py).
-
-Prints ONE JSON line (rank 0).  `value` = queries/s with the batch resident in HBM, CUDA-event timed;
-`e2e` = the same through sg_search_batch with pinned host buffers (H2D + kernel + D2H per step);
-`roofline` = algorithmic bytes (SURVEY.md 8(d) formula, counted by the kernel's own stats pass) over
-the kernel's event-timed duration against MEASURED_PEAKS.json; `cpu_baseline` = the oracle's
-line-faithful CPMerge path on the host cores over a bounded sample, which also checks the GPU results.
+Prints ONE JSON line (rank 0).  `value` = queries/s with the batches resident in HBM, CUDA-event timed;
+`e2e` = the same through sg_search_batch with pinned host buffers (H2D + kernels + result rows per call);
+`roofline` = algorithmic bytes (SURVEY.md 8(d) formula, counted by the kernel's own stats pass) over the dominant
+kernel's event-timed duration against MEASURED_PEAKS.json; `roofline_engine` = what the engine itself reads, against
+the measured L2 bandwidth; `cpu_baseline` = the oracle's line-faithful CPMerge path on the host cores over one whole
+batch, which also checks the GPU results.
 """
 import argparse
 import json
@@ -33,7 +38,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_DOCS = 1_000_000
-N_QUERIES = 65536
+N_QUERIES = 65536        # queries per batch (one call of the path)
+RING = 8                 # different batches a step cycles through
+BATCHES_PER_STEP = 128   # calls per step
 K = 10
 ALPHA = 0.5
 DESCRIPTION = dict(ngram_size=3, wrap=("$", "$"), pad="$", alphabet=("english", "russian", "numbers", "$"))
@@ -152,55 +159,77 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def oracle_index(docs):
+ORACLE_METRIC = {"Jaccard": 0, "Cosine": 1, "Dice": 2}
+
+
+def oracle_index(docs, ngram=3, commit=True):
     from oracle import oracle as O
-    ox = O.OracleIndex(DESCRIPTION["ngram_size"], DESCRIPTION["wrap"], DESCRIPTION["pad"], DESCRIPTION["alphabet"])
+    ox = O.OracleIndex(ngram, DESCRIPTION["wrap"], DESCRIPTION["pad"], DESCRIPTION["alphabet"])
     ox.add_packed(docs[0], docs[1])
-    ox.commit()  # VB / skipping(64) bytes, decoded lazily per Next() like the reference
+    if commit:
+        ox.commit()  # VB / skipping(64) bytes, decoded lazily per Next() like the reference
     return ox
 
 
-def oracle_run(ox, q_bytes, q_off, lo, hi, threads):
+def oracle_run(ox, q_bytes, q_off, lo, hi, threads, metric="Jaccard", faithful=True):
     """line-faithful reference path (CPMerge, lazy codecs, per-segment queues, dynamic alpha) on queries [lo, hi)"""
     from oracle import oracle as O
     off = q_off[lo:hi + 1].astype(np.uint64)
     data = q_bytes[int(off[0]):int(off[-1])]
     off = off - off[0]
     t0 = time.perf_counter()
-    res = ox.suggest_batch(None, O.JACCARD, ALPHA, K, O.FAITHFUL, O.CP_MERGE, threads=threads, packed=(data, off))
+    res = ox.suggest_batch(None, ORACLE_METRIC[metric], ALPHA, K, O.FAITHFUL if faithful else O.CANONICAL, O.CP_MERGE, threads=threads,
+                           packed=(data, off))
     return time.perf_counter() - t0, res
+
+
+def same_rows(o, ids, scores, counts, k=K):
+    """oracle rows (ids, scores, counts) against GPU rows of the same queries: counts, ids in order, scores bit-equal"""
+    o_ids, o_sc, o_cnt = o
+    n = len(o_cnt)
+    if not np.array_equal(o_cnt, np.asarray(counts[:n]).astype(np.uint32)):
+        return False
+    m = np.arange(k)[None, :] < o_cnt[:, None]
+    return bool(np.array_equal(o_ids[m], np.asarray(ids).reshape(-1, k)[:n][m].astype(np.uint32))
+                and np.array_equal(o_sc[m], np.asarray(scores).reshape(-1, k)[:n][m]))
+
+
+def common_config(metric="Jaccard", ngram=3, letters="uniform"):
+    """the part of `config` both arms print identically"""
+    return {"workload": "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10, 64K-query batch", "n_docs": N_DOCS,
+            "queries_per_batch": N_QUERIES, "k": K, "similarity": ALPHA, "metric": metric, "ngram": ngram, "letters": letters}
 
 
 def run_reference(args, out_stream):
     """--impl reference: the reference's own CPU implementation of the path.  No Go toolchain exists in this image,
-    so this is the oracle's line-faithful port (oracle/so_suggest.c FAITHFUL mode), all host threads."""
+    so this is the oracle's line-faithful port (oracle/so_suggest.c FAITHFUL mode), all host threads.  A step is one
+    whole 65,536-query batch of the workload (the b200 arm's step is 128 such batches)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from suggest_b200.workload import synthetic_workload
-    docs, (q_bytes, q_off), _ = synthetic_workload(N_DOCS, N_QUERIES)
-    ox = oracle_index(docs)
+    from suggest_b200.workload import synthetic_dictionary, synthetic_queries
+    d_bytes, d_off, rng = synthetic_dictionary(N_DOCS)
+    batches = [synthetic_queries(d_bytes, d_off, N_QUERIES, rng)[:2] for _ in range(2)]
+    ox = oracle_index((d_bytes, d_off))
     threads = host_threads()
-    sample = 8192
     for w in range(args.warmup):
-        oracle_run(ox, q_bytes, q_off, 0, min(sample, 2048), threads)
+        oracle_run(ox, batches[0][0], batches[0][1], 0, 4096, threads)
     total_t, total_q = 0.0, 0
     for s in range(args.steps):
-        lo = (s * sample) % N_QUERIES
-        hi = min(lo + sample, N_QUERIES)
-        dt, _ = oracle_run(ox, q_bytes, q_off, lo, hi, threads)
+        q_bytes, q_off = batches[s % len(batches)]
+        dt, _ = oracle_run(ox, q_bytes, q_off, 0, N_QUERIES, threads)
         total_t += dt
-        total_q += hi - lo
+        total_q += N_QUERIES
     qps = total_q / total_t
     line = {
         "impl": "reference", "metric": METRIC_NAME, "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total_t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10", "n_docs": N_DOCS,
-                   "queries_per_step": sample, "note": "each step is a bounded 8192-query sample of the 65536-query batch"},
+        "config": common_config(),
+        "run": {"batches_per_step": 1, "note": "a step is one whole 65,536-query batch"},
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} x {sample} queries, oracle FAITHFUL mode (CPMerge, lazy VB/skipping decode, "
-                                   "bounded heap), one query per thread"},
+                         "sample": f"{args.steps} x {N_QUERIES} queries (whole batches), oracle FAITHFUL mode (CPMerge, lazy VB/skipping "
+                                   "decode, bounded heap), one query per thread"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=out_stream, flush=True)
@@ -216,19 +245,339 @@ def claim_stdout():
     return real
 
 
+class Rig:
+    """process-wide state of a b200-arm run: torch, the device, the ranks"""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the Suggest path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        self.stream = torch.cuda.current_stream()
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_device(self, call, calls_per_step, steps, warmup, before_timed=None):
+        """CUDA events around every step (calls_per_step calls back to back on the launching stream), L2 flushed between
+        steps (untimed), barrier + synchronize on both sides, max over ranks.  -> ms per step"""
+        torch = self.torch
+        for _ in range(warmup):
+            for b in range(calls_per_step):
+                call(b)
+        self.barrier()
+        if before_timed:
+            before_timed()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s in range(steps):
+            self.flush.fill_(s & 0xFF)
+            ev[s][0].record()
+            for b in range(calls_per_step):
+                call(b)
+            ev[s][1].record()
+        self.barrier()
+        return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+
+    def time_host(self, call, calls_per_step, steps, warmup):
+        """end to end: every call returns with its results on the host.  Wall clock per rank around exactly the timed
+        calls (no barrier inside), max over ranks.  -> seconds for all steps"""
+        for _ in range(warmup):
+            for b in range(calls_per_step):
+                call(b)
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            for b in range(calls_per_step):
+                call(b)
+        dt = time.perf_counter() - t0
+        return self.max_over_ranks(dt)
+
+
+class Batches:
+    """RING query batches of one workload: resident in HBM (value) and in page-locked host memory (e2e), with result rows
+    on both sides"""
+
+    def __init__(self, rig, batches, k):
+        torch = rig.torch
+        self.k, self.n = k, len(batches)
+        self.raw = batches
+        self.dq = [torch.from_numpy(b[0]).to(rig.dev) for b in batches]
+        self.doff = [torch.from_numpy(b[1].astype(np.int32)).to(rig.dev) for b in batches]
+        nq = N_QUERIES
+        self.d_ids = [torch.zeros(nq * k, dtype=torch.int32, device=rig.dev) for _ in batches]
+        self.d_sc = [torch.zeros(nq * k, dtype=torch.float64, device=rig.dev) for _ in batches]
+        self.d_cnt = [torch.zeros(nq, dtype=torch.int32, device=rig.dev) for _ in batches]
+        self.hq = [torch.from_numpy(b[0]).pin_memory() for b in batches]
+        self.hoff = [torch.from_numpy(b[1].astype(np.int32)).pin_memory() for b in batches]
+        self.h_ids = [torch.zeros(nq * k, dtype=torch.int32).pin_memory() for _ in batches]
+        self.h_sc = [torch.zeros(nq * k, dtype=torch.float64).pin_memory() for _ in batches]
+        self.h_cnt = [torch.zeros(nq, dtype=torch.int32).pin_memory() for _ in batches]
+
+    def host_out(self, i):
+        nq, k = N_QUERIES, self.k
+        return (self.h_ids[i].numpy().view(np.uint32).reshape(nq, k), self.h_sc[i].numpy().reshape(nq, k), self.h_cnt[i].numpy().view(np.uint32))
+
+    def host_in(self, i):
+        return (self.hq[i].numpy(), self.hoff[i].numpy().view(np.uint32))
+
+    def h2d_bytes(self, i):
+        return int(self.raw[i][0].nbytes + 4 * (N_QUERIES + 1))
+
+
+def make_batches(d_bytes, d_off, rng, n):
+    from suggest_b200.workload import synthetic_queries
+    return [synthetic_queries(d_bytes, d_off, N_QUERIES, rng)[:2] for _ in range(n)]
+
+
+def l2_peak():
+    """measured L2 -> SM bandwidth of this pool's B200s (tools/microbench.cu l2read, profiles/r2_microbench.txt)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "l2_peak.json")) as f:
+            j = json.load(f)
+            return float(j["l2_read_gbs"]), j.get("how", "profiles/l2_peak.json")
+    except Exception:  # noqa: BLE001
+        return None, None
+
+
+def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard", ngram=3, letters="uniform", steps=None,
+                       warmup=None, calls_per_step=BATCHES_PER_STEP, ring=RING, with_stages=True):
+    """the headline measurement (and every config #3 point): one index on this rank, RING batches, value + e2e"""
+    from suggest_b200 import _capi
+    from suggest_b200.suggest import IndexDescription
+    torch = rig.torch
+    L = _capi.lib()
+    steps = steps or args.steps
+    warmup = args.warmup if warmup is None else warmup
+    metric = {"Jaccard": S.JaccardMetric(), "Cosine": S.CosineMetric(), "Dice": S.DiceMetric()}[metric_name]
+    description = IndexDescription(Name="bench", NGramSize=ngram, Alphabet=DESCRIPTION["alphabet"], Pad=DESCRIPTION["pad"],
+                                   Wrap=DESCRIPTION["wrap"], Device=rig.local)
+    t0 = time.perf_counter()
+    index = S.NewRAMBuilder((d_bytes, d_off), description).Build()
+    build_s = time.perf_counter() - t0
+    info, layout = index.info(), index.layout()
+    B = Batches(rig, make_batches(d_bytes, d_off, rng, ring), K)
+    nq = N_QUERIES
+    cs = rig.stream.cuda_stream
+
+    def call_device(b, stats=0):
+        i = b % B.n
+        index.SuggestBatchDevice(B.dq[i].data_ptr(), B.doff[i].data_ptr(), nq, ALPHA, metric, K, B.d_ids[i].data_ptr(),
+                                 B.d_sc[i].data_ptr(), B.d_cnt[i].data_ptr(), stats, cs)
+
+    def call_host(b):
+        i = b % B.n
+        index.SuggestBatch(None, ALPHA, metric, K, packed=B.host_in(i), out=B.host_out(i))
+
+    # algorithmic bytes and the engine's own reads, counted by the kernel's stats pass on batch 0 (untimed)
+    d_stats = torch.zeros(nq * 4, dtype=torch.int32, device=rig.dev)
+    call_device(0, d_stats.data_ptr())
+    torch.cuda.synchronize()
+    st = d_stats.cpu().numpy().astype(np.int64).reshape(-1, 4)
+    alg_bytes = int(4 * st[:, 0].sum() + 8 * st[:, 1].sum() + int(B.raw[0][1][-1]) + 12 * K * nq)
+    engine_bytes = int(4 * st[:, 2].sum())
+    del d_stats
+
+    mark = {}
+
+    def timed_region_starts():
+        mark["launches"], mark["t"] = L.sg_kernel_launches(), time.perf_counter()
+
+    ms_per_step = rig.time_device(call_device, calls_per_step, steps, warmup, timed_region_starts)
+    launches = L.sg_kernel_launches() - mark["launches"]   # kernels of this library launched inside the timed region
+    wall_timed = time.perf_counter() - mark["t"]
+    value = nq * calls_per_step * rig.world / (ms_per_step * 1e-3)
+    dev_rows = [(B.d_ids[i].cpu().numpy().copy(), B.d_sc[i].cpu().numpy().copy(), B.d_cnt[i].cpu().numpy().copy()) for i in range(B.n)]
+
+    stage_ms = {}
+    if with_stages:
+        # the kernels of one call alone: CUDA events between them on the launching stream, L2 flushed before every launch
+        n_runs = 20
+        for s in range(n_runs):
+            rig.flush.fill_(s & 0xFF)
+            for name, ms in index.StageTimes(B.dq[0].data_ptr(), B.doff[0].data_ptr(), nq, ALPHA, metric, K, B.d_ids[0].data_ptr(),
+                                             B.d_sc[0].data_ptr(), B.d_cnt[0].data_ptr(), cs).items():
+                stage_ms[name] = stage_ms.get(name, 0.0) + ms / n_runs
+
+    e2e_s = rig.time_host(call_host, calls_per_step, steps, warmup)
+    e2e_value = nq * calls_per_step * steps * rig.world / e2e_s
+    same = all(np.array_equal(B.h_cnt[i].numpy(), dev_rows[i][2]) and
+               np.array_equal(B.h_ids[i].numpy().reshape(nq, K)[np.arange(K)[None, :] < dev_rows[i][2][:, None]],
+                              dev_rows[i][0].reshape(nq, K)[np.arange(K)[None, :] < dev_rows[i][2][:, None]]) for i in range(B.n))
+    direct = (layout["engine"] == 1 and os.environ.get("SG_DIRECT_OUT", "1") != "0"
+              and all(L.sg_is_pinned(t.data_ptr(), t.numel() * t.element_size()) == 1 for t in (B.h_ids[0], B.h_sc[0], B.h_cnt[0])))
+    counts0 = dev_rows[0][2].astype(np.int64)
+    h2d = B.h2d_bytes(0) * calls_per_step
+    d2h = int(nq * 4 + 12 * int(counts0.clip(0, K).sum())) if direct else int(nq * K * 12 + nq * 4)
+    out = dict(index=index, batches=B, dev_rows=dev_rows, info=info, layout=layout, build_s=build_s, ms_per_step=ms_per_step,
+               value=value, e2e_value=e2e_value, e2e_s=e2e_s, host_equals_device=bool(same), direct=direct, stage_ms=stage_ms,
+               alg_bytes=alg_bytes, engine_bytes=engine_bytes, h2d=h2d, d2h=d2h * calls_per_step, launches=int(launches),
+               calls_per_step=calls_per_step, steps=steps, match=float((counts0 > 0).mean()), wall_timed=wall_timed)
+    return out
+
+
+def measure_config3(rig, args, S, d_bytes, d_off):
+    """BASELINE.json config #3 (Cosine / Dice, n in {2,3,4}) and the Zipf-lettered variant of SURVEY.md 8(d): short runs of
+    every point through the same code as the headline; the worst end-to-end rate is surfaced"""
+    from suggest_b200.workload import synthetic_dictionary
+    points = []
+    z_bytes, z_off, z_rng = synthetic_dictionary(N_DOCS, skew="zipf")
+    plan = [(m, n, "uniform") for n in (2, 3, 4) for m in ("Jaccard", "Cosine", "Dice") if not (m == "Jaccard" and n == 3)]
+    plan += [(m, 3, "zipf") for m in ("Jaccard", "Cosine", "Dice")]
+    for metric_name, ngram, letters in plan:
+        data, off = (z_bytes, z_off) if letters == "zipf" else (d_bytes, d_off)
+        rng = np.random.default_rng(777 + ngram)
+        r = measure_replicated(rig, args, S, data, off, rng, metric_name, ngram, letters, steps=3, warmup=1, calls_per_step=4, ring=2,
+                               with_stages=False)
+        points.append({"metric": metric_name, "ngram": ngram, "letters": letters, "bucket_shift": int(r["layout"]["bucket_shift"]),
+                       "value": r["value"], "e2e": r["e2e_value"], "ms_per_batch": r["ms_per_step"] / r["calls_per_step"],
+                       "host_equals_device": r["host_equals_device"], "queries_with_a_match": r["match"]})
+        r["index"].close()
+    worst = min(points, key=lambda p: p["e2e"])
+    return {"points": points, "min_qps_e2e": worst["e2e"], "min_point": {k_: worst[k_] for k_ in ("metric", "ngram", "letters")},
+            "note": "3 steps x 4 batches of 65,536 queries per point, same dictionary (n-gram size and metric vary), plus Zipf letters"}
+
+
+def oracle_sharded_sample(d_bytes, d_off, q_bytes, q_off, n_sample, parts=10):
+    """oracle over a large dictionary, affordable: `parts` oracle indexes over record-id ranges built in parallel threads
+    (the C oracle releases the GIL), searched with the sample, rows merged under (score desc, id asc) - the reduction
+    tests/test_sharding_gloo.py pins to the oracle over the whole dictionary"""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    from suggest_b200.sharding import merge_rows_reference, shard_bounds, slice_packed
+    n_docs = len(d_off) - 1
+    off = q_off[:n_sample + 1].astype(np.uint64)
+    data = q_bytes[:int(off[-1])]
+
+    def one(bounds):
+        lo, hi = bounds
+        sub, sub_off = slice_packed(d_bytes, d_off, lo, hi)
+        ox = O.OracleIndex(DESCRIPTION["ngram_size"], DESCRIPTION["wrap"], DESCRIPTION["pad"], DESCRIPTION["alphabet"])
+        ox.add_packed(sub, sub_off)
+        ids, sc, cnt = ox.suggest_batch(None, O.JACCARD, ALPHA, K, O.CANONICAL, threads=2, packed=(data, off))
+        ox.close()
+        return ids + np.uint32(lo), sc, cnt
+
+    with ThreadPoolExecutor(max_workers=min(parts, max(host_threads() // 2, 1))) as ex:
+        rows = list(ex.map(one, shard_bounds(n_docs, parts)))
+    return merge_rows_reference(np.stack([r[0] for r in rows]), np.stack([r[1] for r in rows]), np.stack([r[2] for r in rows]), K)
+
+
+def measure_config4(rig, args, S, n_docs, steps, warmup, exchanges=("fused", "nccl"), calls_per_step=16, check=True):
+    """BASELINE.json config #4: n_docs entries split by record-id range over the ranks; every rank searches the same
+    batches; per-shard top-k exchanged + merged (fused peer-memory kernel / NCCL all-gather + merge)"""
+    from suggest_b200.sharding import ShardedIndex
+    from suggest_b200.suggest import IndexDescription
+    from suggest_b200.workload import synthetic_dictionary
+    torch = rig.torch
+    d_bytes, d_off, rng = synthetic_dictionary(n_docs)
+    description = IndexDescription(Name="bench4", NGramSize=DESCRIPTION["ngram_size"], Alphabet=DESCRIPTION["alphabet"],
+                                   Pad=DESCRIPTION["pad"], Wrap=DESCRIPTION["wrap"], Device=rig.local)
+    B = Batches(rig, make_batches(d_bytes, d_off, rng, 2), K)
+    nq = N_QUERIES
+    out = {"n_docs": n_docs, "n_shards": rig.world, "queries_per_batch": nq, "batches_per_step": calls_per_step, "steps": steps,
+           "unit": "queries/s", "exchange": {}}
+    t0 = time.perf_counter()
+    sx = ShardedIndex((d_bytes, d_off), description, rig.rank, rig.world, S.NewRAMBuilder, max_queries=nq, max_k=K, exchange="fused")
+    out["index_build_s"] = round(time.perf_counter() - t0, 2)
+    out["shard_postings"] = int(sx.index.info()["n_postings"])
+    out["bucket_shift"] = int(sx.index.layout()["bucket_shift"])
+    modes = [sx.exchange] if rig.world == 1 else [m for m in exchanges if not (m == "fused" and sx.exchange != "fused")]
+    if sx.exchange_note:
+        out["exchange_note"] = sx.exchange_note
+    oracle_rows = None
+    for mode in modes:
+        fused_handle = sx._ex
+        if mode == "nccl":
+            sx._ex = None  # the same shard through the NCCL all-gather + merge path
+
+        def call_device(b):
+            i = b % B.n
+            sx.SuggestBatchDevice(B.dq[i], B.doff[i], nq, ALPHA, S.JaccardMetric(), K, B.d_ids[i], B.d_sc[i], B.d_cnt[i])
+
+        def call_host(b):
+            i = b % B.n
+            B.dq[i].copy_(B.hq[i], non_blocking=True)
+            B.doff[i].copy_(B.hoff[i], non_blocking=True)
+            sx.SuggestBatchDevice(B.dq[i], B.doff[i], nq, ALPHA, S.JaccardMetric(), K, B.d_ids[i], B.d_sc[i], B.d_cnt[i])
+            B.h_ids[i].copy_(B.d_ids[i], non_blocking=True)
+            B.h_sc[i].copy_(B.d_sc[i], non_blocking=True)
+            B.h_cnt[i].copy_(B.d_cnt[i], non_blocking=True)
+            torch.cuda.synchronize()
+
+        ms = rig.time_device(call_device, calls_per_step, steps, warmup)
+        sx.check_exchange()
+        rows = (B.d_ids[0].cpu().numpy().copy(), B.d_sc[0].cpu().numpy().copy(), B.d_cnt[0].cpu().numpy().copy())
+        e2e_s = rig.time_host(call_host, calls_per_step, steps, warmup)
+        # where the step goes: local search alone (no exchange), CUDA events
+        search_ms = None
+        if rig.world > 1:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            rig.barrier()
+            ev0.record()
+            for b in range(calls_per_step):
+                i = b % B.n
+                sx.index.SuggestBatchDevice(B.dq[i].data_ptr(), B.doff[i].data_ptr(), nq, ALPHA, S.JaccardMetric(), K, B.d_ids[i].data_ptr(),
+                                            B.d_sc[i].data_ptr(), B.d_cnt[i].data_ptr(), 0, rig.stream.cuda_stream)
+            ev1.record()
+            torch.cuda.synchronize()
+            search_ms = rig.max_over_ranks(ev0.elapsed_time(ev1)) / calls_per_step
+        res = {"value": nq * calls_per_step / (ms * 1e-3), "ms_per_batch": ms / calls_per_step,
+               "e2e": nq * calls_per_step * steps / e2e_s,
+               "stage_ms": {"search": search_ms if search_ms is not None else ms / calls_per_step,
+                            "exchange_and_merge": (ms / calls_per_step - search_ms) if search_ms is not None else 0.0}}
+        if check:
+            n_sample = 4096
+            if rig.rank == 0:
+                if oracle_rows is None:
+                    oracle_rows = oracle_sharded_sample(d_bytes, d_off, B.raw[0][0], B.raw[0][1], n_sample)
+                res["gpu_results_identical"] = same_rows(oracle_rows, rows[0].reshape(nq, K)[:n_sample], rows[1].reshape(nq, K)[:n_sample],
+                                                         rows[2][:n_sample])
+                res["oracle_sample"] = f"first {n_sample} queries of batch 0, oracle CANONICAL over the whole dictionary (10 id-range parts merged)"
+            rig.barrier()
+        out["exchange"][mode] = res
+        sx._ex = fused_handle
+    best = max(out["exchange"], key=lambda m: out["exchange"][m]["value"])
+    out.update({"value": out["exchange"][best]["value"], "ms_per_batch": out["exchange"][best]["ms_per_batch"],
+                "e2e": out["exchange"][best]["e2e"], "stage_ms": out["exchange"][best]["stage_ms"], "best_exchange": best,
+                "gpu_results_identical": all(r.get("gpu_results_identical", True) for r in out["exchange"].values())})
+    sx.close()
+    return out
+
+
 def main():
     out_stream = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="replicated", choices=["replicated", "sharded", "spellchecker", "autocomplete"])
-    ap.add_argument("--docs", type=int, default=None, help="dictionary size (default 1M; sharded: 10M)")
+    ap.add_argument("--docs", type=int, default=None, help="dictionary size (default 1M; config #4: 10M)")
     ap.add_argument("--metric", default="Jaccard", choices=["Jaccard", "Cosine", "Dice"])
     ap.add_argument("--ngram", type=int, default=3)
     ap.add_argument("--data", default="uniform", choices=["uniform", "zipf"], help="letter distribution of the dictionary")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config3", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.workload in ("spellchecker", "autocomplete"):
@@ -243,225 +592,135 @@ def main():
     if args.impl == "reference":
         return run_reference(args, out_stream)
 
-    import torch
-    import torch.distributed as dist
     import suggest_b200 as S
-    from suggest_b200 import _capi
-    from suggest_b200.suggest import IndexDescription
-    from suggest_b200.workload import synthetic_dictionary, synthetic_queries
+    from suggest_b200.workload import synthetic_dictionary
+    rig = Rig()
+    rank, world = rig.rank, rig.world
+    headline = args.metric == "Jaccard" and args.ngram == 3 and args.data == "uniform" and not args.docs
+    sampler = ClockSampler(rig.local) if rank == 0 else None
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the Suggest path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    sharded = args.workload == "sharded"
-    n_docs = args.docs or (10_000_000 if sharded else N_DOCS)
-    metric = {"Jaccard": S.JaccardMetric(), "Cosine": S.CosineMetric(), "Dice": S.DiceMetric()}[args.metric]
-    desc = dict(DESCRIPTION, ngram_size=args.ngram)
-
-    # ---- data: identical dictionary on every rank; replicated mode gives every rank its own query batch ----
-    d_bytes, d_off, rng = synthetic_dictionary(n_docs, skew=None if args.data == "uniform" else args.data)
-    if not sharded and rank > 0:
-        rng = np.random.default_rng(12345 + 7919 * rank)
-    q_bytes, q_off, pick = synthetic_queries(d_bytes, d_off, N_QUERIES, rng)
-    description = IndexDescription(Name="bench", NGramSize=desc["ngram_size"], Alphabet=desc["alphabet"], Pad=desc["pad"],
-                                   Wrap=desc["wrap"], Device=local)
-    t0 = time.perf_counter()
-    sharded_index = None
-    if sharded:
-        from suggest_b200.sharding import ShardedIndex
-        sharded_index = ShardedIndex((d_bytes, d_off), description, rank, world, S.NewRAMBuilder)
-        index = sharded_index.index
-    else:
-        index = S.NewRAMBuilder((d_bytes, d_off), description).Build()
-    build_s = time.perf_counter() - t0
-    info = index.info()
-    L = _capi.lib()
-
-    # ---- device-resident buffers for `value`, pinned host buffers for `e2e` ----
-    nq = N_QUERIES
-    dq = torch.from_numpy(q_bytes).to(dev)
-    doff = torch.from_numpy(q_off.astype(np.int32)).to(dev)
-    d_ids = torch.zeros(nq * K, dtype=torch.int32, device=dev)
-    d_sc = torch.zeros(nq * K, dtype=torch.float64, device=dev)
-    d_cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
-    d_stats = torch.zeros(nq * 2, dtype=torch.int32, device=dev)
-    g_ids = None
-    m_ids = m_sc = m_cnt = None
-    if sharded and world > 1:
-        g_ids = True  # per-shard rows are all-gathered and merged (suggest_b200/sharding.py)
-        m_ids, m_sc, m_cnt = torch.zeros_like(d_ids), torch.zeros_like(d_sc), torch.zeros_like(d_cnt)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    stream = torch.cuda.current_stream()
-
-    def step_device(stats_ptr=0):
-        if g_ids is not None and not stats_ptr:  # config #4: local search, all-gather of per-shard top-k, merge on the device
-            sharded_index.SuggestBatchDevice(dq, doff, nq, ALPHA, metric, K, m_ids, m_sc, m_cnt)
-            return
-        index.SuggestBatchDevice(dq.data_ptr(), doff.data_ptr(), nq, ALPHA, metric, K, d_ids.data_ptr(), d_sc.data_ptr(),
-                                 d_cnt.data_ptr(), stats_ptr, stream.cuda_stream)
-
-    def barrier():
-        torch.cuda.synchronize()
+    if args.workload == "sharded":
+        c4 = measure_config4(rig, args, S, args.docs or 10_000_000, args.steps, args.warmup, calls_per_step=32)
+        clocks = sampler.stop() if sampler else None
+        if rank == 0:
+            line = {"metric": METRIC_NAME.replace("1M", f"{c4['n_docs'] // 1_000_000}M"), "value": c4["value"], "unit": "queries/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": c4["ms_per_batch"] * 32,
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bitmap words / f64 scores",
+                    "data": "synthetic", "config": {"workload": f"{c4['n_docs']}-entry dictionary sharded by record-id range over {world} GPU(s)"},
+                    "e2e": {"value": c4["e2e"], "unit": "queries/s"}, "config4": c4, "clocks": clocks}
+            print(json.dumps(line), file=out_stream, flush=True)
         if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+            rig.dist.barrier()
+            rig.dist.destroy_process_group()
+        return 0
 
-    # algorithmic bytes of one launch, counted by the kernel's stats pass (untimed)
-    step_device(d_stats.data_ptr())
-    torch.cuda.synchronize()
-    st = d_stats.cpu().numpy().astype(np.int64).reshape(-1, 2)
-    alg_bytes = int(4 * st[:, 0].sum() + 8 * st[:, 1].sum() + int(q_off[-1]) + 12 * K * nq)
-    first_counts = d_cnt.cpu().numpy().copy()
-    first_ids = d_ids.cpu().numpy().copy()
-
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None  # runs through both timed regions (device-resident and e2e)
-    launches0 = L.sg_kernel_launches()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.fill_(s & 0xFF)  # L2 flush between timed steps (untimed)
-        ev[s][0].record()
-        step_device()
-        ev[s][1].record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    launches = L.sg_kernel_launches() - launches0
-    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    total_ms = float(step_ms.sum())
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    queries_per_step = nq if sharded else nq * world
-    value = queries_per_step / (ms_per_step * 1e-3)
-
-    # the dominant kernel alone (roofline): CUDA events between the kernels of a launch, on the launching stream,
-    # L2 flushed before every launch like the timed steps above
-    stage_ms = {}
-    n_stage_runs = min(args.steps, 20)
-    for s in range(n_stage_runs):
-        flush.fill_(s & 0xFF)
-        for name, ms in index.StageTimes(dq.data_ptr(), doff.data_ptr(), nq, ALPHA, metric, K, d_ids.data_ptr(), d_sc.data_ptr(),
-                                         d_cnt.data_ptr(), stream.cuda_stream).items():
-            stage_ms[name] = stage_ms.get(name, 0.0) + ms / n_stage_runs
-    top_kernel = max(stage_ms, key=stage_ms.get)
-    kernel_ms = stage_ms[top_kernel]
-    layout = index.layout()
-
-    # ---- e2e: sg_search_batch, pinned host buffers, H2D + kernel + D2H inside the timed region ----
-    hq = torch.from_numpy(q_bytes).pin_memory()
-    hoff = torch.from_numpy(q_off.astype(np.int32)).pin_memory()
-    h_ids = torch.zeros(nq * K, dtype=torch.int32).pin_memory()
-    h_sc = torch.zeros(nq * K, dtype=torch.float64).pin_memory()
-    h_cnt = torch.zeros(nq, dtype=torch.int32).pin_memory()
-    out = (h_ids.numpy().view(np.uint32).reshape(nq, K), h_sc.numpy().reshape(nq, K), h_cnt.numpy().view(np.uint32))
-    packed = (hq.numpy(), hoff.numpy().view(np.uint32))
-
-    def step_e2e():
-        if g_ids is not None:  # queries from pinned host memory, merged rows back to the host
-            dq.copy_(hq, non_blocking=True)
-            doff.copy_(hoff, non_blocking=True)
-            sharded_index.SuggestBatchDevice(dq, doff, nq, ALPHA, metric, K, m_ids, m_sc, m_cnt)
-            h_ids.copy_(m_ids, non_blocking=True)
-            h_sc.copy_(m_sc, non_blocking=True)
-            h_cnt.copy_(m_cnt, non_blocking=True)
-            torch.cuda.synchronize()
-            return
-        index.SuggestBatch(None, ALPHA, metric, K, packed=packed, out=out)
-
-    for _ in range(args.warmup):
-        step_e2e()
-    barrier()
-    e0 = time.perf_counter()
-    for s in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - e0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = queries_per_step * args.steps / e2e_s
+    # ---- headline: identical dictionary on every rank, every rank its own query batches ----
+    d_bytes, d_off, rng = synthetic_dictionary(args.docs or N_DOCS, skew=None if args.data == "uniform" else args.data)
+    if rank > 0:
+        rng = np.random.default_rng(12345 + 7919 * rank)
+    r = measure_replicated(rig, args, S, d_bytes, d_off, rng, args.metric, args.ngram, args.data)
+    wall = r["wall_timed"]
     clocks = sampler.stop() if sampler else None
-    if g_ids is None:
-        assert np.array_equal(out[2].astype(np.int32), first_counts) and np.array_equal(h_ids.numpy(), first_ids), \
-            "host-buffer and device-buffer paths disagree"
-    h2d = int(q_bytes.nbytes + 4 * (nq + 1))
-    d2h = int(nq * K * 4 + nq * K * 8 + nq * 4)
-    # page-locked result buffers: sg_search_batch lets the kernel store the valid entries of every row (12 B each) and
-    # the counts straight into host memory; nothing is staged in HBM and no copy follows the kernel
-    direct = (g_ids is None and layout["engine"] == 1 and os.environ.get("SG_DIRECT_OUT", "1") != "0"
-              and all(L.sg_is_pinned(t.data_ptr(), t.numel() * t.element_size()) == 1 for t in (h_ids, h_sc, h_cnt)))
-    if direct:
-        d2h = int(nq * 4 + 12 * int(first_counts.astype(np.int64).clip(0, K).sum()))
+    index, B = r["index"], r["batches"]
+    nq = N_QUERIES
+
+    # ---- parity of the timed batches against the oracle (rank 0): every query of batch 0 at N = 1 (the cpu_baseline leg),
+    # a 4096-query sample at N > 1 ----
+    parity = None
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline and args.ngram == 3 and args.data == "uniform" and not args.docs:
+        ox = oracle_index((d_bytes, d_off))
+        threads = host_threads()
+        sample = nq if world == 1 else 4096
+        dt, o = oracle_run(ox, B.raw[0][0], B.raw[0][1], 0, sample, threads, args.metric)
+        ids0, sc0, cnt0 = r["dev_rows"][0]
+        parity = same_rows(o, ids0.view(np.uint32).reshape(nq, K)[:sample], B.host_out(0)[1][:sample], cnt0[:sample])
+        parity = parity and r["host_equals_device"]
+        if world == 1 and headline:
+            cpu_baseline = {"value": sample / dt, "unit": "queries/s", "cores": threads, "kind": "port",
+                            "sample": f"all {sample} queries of batch 0, oracle FAITHFUL mode (CPMerge, lazy VB/skipping decode, "
+                                      "bounded heap), one query per thread", "gpu_results_identical": bool(parity)}
+        ox.close()
+    if world > 1:
+        rig.barrier()
+
+    config3 = None
+    if world == 1 and headline and not args.no_config3:
+        config3 = measure_config3(rig, args, S, d_bytes, d_off)
+    config4 = None
+    if headline and not args.no_config4:
+        index.close()
+        del B
+        rig.torch.cuda.empty_cache()
+        config4 = measure_config4(rig, args, S, 10_000_000, steps=max(3, min(args.steps, 5)), warmup=2)
 
     if rank != 0:
         if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+            rig.dist.barrier()
+            rig.dist.destroy_process_group()
         return 0
 
     peak, peak_kind = measured_peak()
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    stage_ms = r["stage_ms"]
+    top_kernel = max(stage_ms, key=stage_ms.get)
+    kernel_ms = stage_ms[top_kernel]
+    achieved = r["alg_bytes"] / (kernel_ms * 1e-3) / 1e9
+    layout, info = r["layout"], r["info"]
+    l2_gbs, l2_how = l2_peak()
+    engine_gbs = r["engine_bytes"] / (kernel_ms * 1e-3) / 1e9
+    cfg = common_config(args.metric, args.ngram, args.data)
+    if args.docs:
+        cfg["n_docs"] = args.docs
     line = {
-        "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+        "metric": METRIC_NAME, "value": r["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32 bitmap words / f64 scores" if layout["engine"] == 1 else "u32 postings / u8 counters / f64 scores",
-        "data": "synthetic",
-        "config": {"workload": (f"{n_docs}-entry dictionary sharded by record-id range over {world} GPU(s), per-shard top-k + NCCL "
-                                "all-gather + merge" if sharded else "1M synthetic 8-32-char a-z strings, 3-gram, Jaccard 0.5, k=10, 64K-query batch"),
-                   "n_docs": n_docs, "queries_per_step_per_gpu": nq, "k": K, "similarity": ALPHA, "metric": args.metric,
-                   "ngram": args.ngram, "letters": args.data, "parallelism": ("record-id-range shards" if sharded else "replicated index, queries split"),
-                   "postings": int(info["n_postings"]), "index_bytes": int(info["device_bytes"]), "index_build_s": round(build_s, 2),
-                   "engine": "bitmap" if layout["engine"] == 1 else "scancount", "bucket_shift": int(layout["bucket_shift"]),
-                   "bitmap_bytes": int(layout["bitmap_bytes"]),
-                   "l2": "flushed between timed steps (256 MiB write, untimed); inside a step the index is re-read ~58x "
-                         "and stays L2-resident, which is the steady state of this workload"},
-        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "result_path": ("kernel stores into the caller's page-locked rows (valid entries + counts only)" if direct
+        "data": "synthetic", "config": cfg,
+        "run": {"batches_per_step": r["calls_per_step"], "queries_per_step_per_gpu": nq * r["calls_per_step"], "ring_of_batches": RING,
+                "parallelism": "replicated index, queries split", "postings": int(info["n_postings"]),
+                "index_bytes": int(info["device_bytes"]), "index_build_s": round(r["build_s"], 2),
+                "engine": "bitmap" if layout["engine"] == 1 else "scancount", "bucket_shift": int(layout["bucket_shift"]),
+                "bitmap_bytes": int(layout["bitmap_bytes"]),
+                "l2": "flushed between timed steps (256 MiB write, untimed); inside a step the index stays L2-resident, which "
+                      "is the steady state of this workload; the query batches cycle through a ring of 8"},
+        "e2e": {"value": r["e2e_value"], "unit": "queries/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "timing": "host wall clock per rank around the timed calls only, max over ranks",
+                "result_path": ("kernel stores into the caller's page-locked rows (valid entries + counts only)" if r["direct"]
                                 else "rows staged in HBM, cudaMemcpyAsync per slice")},
-        "gpu_launches": int(launches),
+        "gpu_launches": r["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(top_kernel), "peak_kind": peak_kind, "algorithmic_bytes_per_launch": alg_bytes,
-                     "algorithmic_bytes_per_query": alg_bytes / nq, "kernel": top_kernel, "kernel_ms": kernel_ms,
+                     "traffic": recorded_traffic(top_kernel), "traffic_source": recorded_traffic("source"),
+                     "peak_kind": peak_kind, "algorithmic_bytes_per_launch": r["alg_bytes"],
+                     "algorithmic_bytes_per_query": r["alg_bytes"] / nq, "kernel": top_kernel, "kernel_ms": kernel_ms,
                      "stage_ms": {k_: round(v, 5) for k_, v in stage_ms.items()},
-                     "note": ("algorithmic bytes = posting-list bytes of SURVEY.md 8(d) (implementation independent); the bitmap "
-                              "engine answers the same queries from per-term bucket bitmaps (~4-5x fewer bytes, L2 resident), "
-                              "so frac can exceed 1: it measures the path against a posting-list scan at HBM speed"
+                     "note": ("algorithmic bytes = posting-list bytes of SURVEY.md 8(d) (implementation independent).  The bitmap "
+                              "engine answers the same queries from per-term bucket bitmaps that stay in L2, so this is NOT a "
+                              "fraction of a hardware limit and can exceed 1; roofline_engine is the hardware-side view"
                               if layout["engine"] == 1 else "posting lists are read once per query by sg_search_kernel")},
+        "roofline_engine": {"bound": "l2 / issue slots (bitmaps are L2-resident; see profiles/ ncu summary)",
+                            "engine_bytes_per_launch": r["engine_bytes"], "engine_bytes_per_query": r["engine_bytes"] / nq,
+                            "achieved": engine_gbs, "unit": "GB/s", "peak": l2_gbs, "peak_kind": l2_how,
+                            "frac": (engine_gbs / l2_gbs) if l2_gbs else None,
+                            "note": "bitmap words the count reads (whole 32-word tiles x lists padded to 8) x 4 B over the dominant "
+                                    "kernel's duration, against the measured L2 -> SM read bandwidth"},
         "clocks": clocks, "wall_s_timed_region": wall,
-        "results": {"queries_with_a_match": float((first_counts > 0).mean())},
+        "results": {"queries_with_a_match": r["match"], "host_rows_equal_device_rows": r["host_equals_device"]},
     }
-
-    if world == 1 and not args.no_cpu_baseline and not sharded and args.metric == "Jaccard" and args.ngram == 3 and args.data == "uniform":
-        ox = oracle_index((d_bytes, d_off))
-        threads = host_threads()
-        sample = N_QUERIES  # the whole batch: about a second on 16 cores, and every GPU result of the step is checked
-        dt, (o_ids, o_sc, o_cnt) = oracle_run(ox, q_bytes, q_off, 0, sample, threads)
-        ok = bool(np.array_equal(o_cnt, first_counts[:sample].astype(np.uint32)))
-        m = np.arange(K)[None, :] < o_cnt[:, None]
-        ok = ok and bool(np.array_equal(o_ids[m], first_ids.view(np.uint32).reshape(nq, K)[:sample][m]))
-        ok = ok and bool(np.array_equal(o_sc[m], out[1][:sample][m]))
-        line["cpu_baseline"] = {"value": sample / dt, "unit": "queries/s", "cores": threads, "kind": "port",
-                                "sample": f"all {sample} queries of the batch, oracle FAITHFUL mode (CPMerge, lazy VB/skipping "
-                                          "decode, bounded heap), one query per thread", "gpu_results_identical": ok}
-        if not ok:
-            line["parity_error"] = "GPU results differ from the oracle on the cpu_baseline sample"
+    if parity is not None:
+        line["gpu_results_identical"] = bool(parity)
+        if not parity:
+            line["parity_error"] = "GPU results differ from the oracle"
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    if config3:
+        line["config3"] = config3
+        line["config3_min_qps"] = config3["min_qps_e2e"]
+    if config4:
+        line["config4"] = config4
     print(json.dumps(line), file=out_stream, flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        rig.dist.barrier()
+        rig.dist.destroy_process_group()
     return 0
 
 

@@ -180,8 +180,8 @@ int sg_candidates_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off
  * Same, every buffer already resident on the index's device; enqueued on `stream` (a cudaStream_t,
  * NULL = default stream) without synchronising.  Queries must already be lower-cased if they hold
  * non-ASCII bytes (sg_search_batch does that on the host, strings.ToLower semantics).
- * d_stats may be NULL; otherwise it receives per query {admissible postings, admissible lists}
- *  as two uint32.
+ * d_stats may be NULL; otherwise (16-byte aligned, 4 uint32 per query) it receives {admissible postings, admissible
+ * lists} of SURVEY.md section 8(d), the 32-bit words the engine itself reads for the count, and 0.
  */
 int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,
                            double alpha, uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts,
@@ -240,6 +240,32 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
 int sg_sharded_get_info(const sg_sharded *sx, uint32_t *n_shards, uint32_t *n_docs, int32_t *peer_reads);
 sg_index *sg_sharded_shard(const sg_sharded *sx, uint32_t shard);   /* borrowed: sg_index_get_info / _layout of one shard */
 void sg_sharded_free(sg_sharded *sx);
+
+/*
+ * The same shards with ONE PROCESS PER GPU (torch.distributed / MPI ranks): the exchange of the per-shard top-k and the merge
+ * as one kernel over NVLink peer memory (sg_exchange.cu).  No reference counterpart; replaces "NCCL all-gather + merge" of
+ * BASELINE.json config #4 (kept as SG_SHARD_EXCHANGE=nccl in suggest_b200/sharding.py).
+ * Every rank creates an exchange (a region of its HBM: flags, its shard's rows, the merged rows), publishes the region's
+ * CUDA IPC handle (SG_EXCHANGE_HANDLE_BYTES) to the others by whatever transport the host has, and connects with the
+ * handles of all ranks in rank order.  sg_exchange_search is collective: every rank calls it with the same batch in device
+ * memory, in the same order.  Rank r searches its shard, then merges queries [n_q * r / world, n_q * (r + 1) / world) from
+ * all shards' rows (peer loads, valid entries only) and stores the winners into the merged rows of every rank (peer stores);
+ * two flag barriers inside the kernel order the steps.  On return (stream order) d_out_* (optional) or sg_exchange_result
+ * hold the k best of the whole dictionary for every query, on every rank; entries behind a row's count are unspecified.
+ * max_queries / max_k must be the same on every rank.  sg_exchange_status: SG_OK, or an error if a barrier timed out
+ * (a rank did not arrive within ~4 s).
+ */
+#define SG_EXCHANGE_HANDLE_BYTES 64
+typedef struct sg_exchange sg_exchange;
+int sg_exchange_create(int device, uint32_t rank, uint32_t world, uint32_t max_queries, uint32_t max_k, sg_exchange **out);
+int sg_exchange_handle(sg_exchange *ex, void *handle_out);
+int sg_exchange_connect(sg_exchange *ex, const void *handles);
+int sg_exchange_search(sg_exchange *ex, sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,
+                       double alpha, uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream);
+int sg_exchange_result(sg_exchange *ex, uint32_t n_q, uint32_t k, const uint32_t **d_ids, const double **d_scores,
+                       const uint32_t **d_counts);
+int sg_exchange_status(sg_exchange *ex, void *stream);
+void sg_exchange_free(sg_exchange *ex);
 
 /*
  * ---- language model and spellchecker (BASELINE.json config #5) ----

@@ -14,6 +14,7 @@ SG_ERR_INVALID, SG_ERR_UNSUPPORTED, SG_ERR_CUDA, SG_ERR_NOMEM, SG_ERR_QUERY_TOO_
 SG_JACCARD, SG_COSINE, SG_DICE, SG_OVERLAP, SG_EXACT = range(5)
 SG_MAX_QUERY_TOKENS = 128
 SG_MAX_TOPK = 1024
+SG_EXCHANGE_HANDLE_BYTES = 64
 SG_COUNT_UNSUPPORTED = 0xFFFFFFFF
 
 
@@ -64,6 +65,14 @@ SIGNATURES = {
     "sg_sharded_get_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int32)]),
     "sg_sharded_shard": (C.c_void_p, [C.c_void_p, C.c_uint32]),
     "sg_sharded_free": (None, [C.c_void_p]),
+    "sg_exchange_create": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "sg_exchange_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sg_exchange_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sg_exchange_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sg_exchange_result": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "sg_exchange_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sg_exchange_free": (None, [C.c_void_p]),
     "sg_lm_create": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_lm_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_lm_free": (None, [C.c_void_p]),

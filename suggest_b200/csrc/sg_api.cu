@@ -34,6 +34,13 @@ int fail(int code, const std::string &msg) {
     return code;
 }
 
+}  // namespace
+
+// the other translation units of the library report through the same thread-local message (sg_last_error)
+int sg_internal_fail(int code, const std::string &msg) { return fail(code, msg); }
+
+namespace {
+
 #define SG_CUDA(expr)                                                                          \
     do {                                                                                       \
         cudaError_t e__ = (expr);                                                              \

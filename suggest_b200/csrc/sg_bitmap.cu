@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(kWindowThreads) sg_window_kernel(const DevInde
 
 // ---------------------------------------------------------------------------------------------------------------
 // sg_tokens_kernel: the tokenizer chain for every query; one warp per query.  With p.stats it also counts the
-// admissible postings / lists of SURVEY.md section 8(d) (the algorithmic bytes of the roofline).
+// admissible postings / lists of SURVEY.md section 8(d) (the algorithmic bytes of the roofline) and the bitmap words the
+// engine reads for the count: 16 bytes per query {postings, lists, bitmap words, 0}.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_kernel(const DevIndex ix, const SearchParams p) {
     __shared__ __align__(16) uint32_t s_scratch[kPlanThreads / 32][kMaxRunes + 2 * kMaxQueryTokens];
@@ -528,7 +529,12 @@ __global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_
             }
             st_postings = __reduce_add_sync(kFull, st_postings);
             st_lists = __reduce_add_sync(kFull, st_lists);
-            if (lane == 0) { p.stats[2 * q] = st_postings; p.stats[2 * q + 1] = st_lists; }
+            if (lane == 0) {
+                // what the bitmap engine itself reads for the count: every (padded) list's words of the window, whole tiles
+                const WordRange win = p.wt.win[size_a];
+                const uint32_t tiles = n_lists > 0 && win.y > win.x ? (win.y - (win.x & ~(kTileWords - 1)) + kTileWords - 1) / kTileWords : 0u;
+                ((uint4 *)p.stats)[q] = make_uint4(st_postings, st_lists, tiles * kTileWords * (uint32_t)((n_lists + 7) & ~7), 0u);
+            }
         }
         __syncwarp();
     }

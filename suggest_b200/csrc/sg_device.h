@@ -144,7 +144,7 @@ struct SearchParams {
     uint32_t *out_ids;
     double *out_scores;
     uint32_t *out_counts;
-    uint32_t *stats;          // optional: {admissible postings, admissible lists} per query
+    uint32_t *stats;          // optional, 16-byte aligned: {admissible postings, admissible lists, 32-bit words the engine reads for the count, 0} per query
     uint32_t *work_counter;   // zeroed before launch
     uint8_t *plans;           // n_q * kPlanStride bytes of scratch
     uint32_t tbl_bytes;       // per-warp count table size (power of two)

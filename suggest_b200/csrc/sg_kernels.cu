@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kPlanThreads) sg_plan_kernel(const DevIndex ix
             plan->b_hi = c.b_hi;
             plan->n_lists = n_lists;
             plan->shift = shift;
-            if (p.stats != nullptr) { p.stats[2 * q] = st_postings; p.stats[2 * q + 1] = st_lists; }
+            if (p.stats != nullptr) ((uint4 *)p.stats)[q] = make_uint4(st_postings, st_lists, st_postings, 0u);  // this engine reads the postings themselves
         }
         __syncwarp();
     }

@@ -3,8 +3,10 @@
 The reference is a single process and has nothing like this.  A query's answer is the top-k of the union of
 the per-shard top-k lists, so: rank r indexes documents [lo_r, hi_r) with id_base = lo_r (returned ids stay
 global, which keeps the (score desc, id asc) order meaningful across shards), every rank searches the same
-query batch and writes its rows as one packed block (scores | ids | counts), the blocks are exchanged with ONE
-all-gather (NCCL over NVLink) and sg_merge_topk_packed_device re-selects k per query on every rank.
+query batch and writes its rows as one packed block (scores | ids | counts); the exchange and the merge are one
+kernel per rank over NVLink peer memory (sg_exchange.cu: rank r merges 1/world of the queries from all shards' rows
+and stores the winners into every rank's result), or - SG_SHARD_EXCHANGE=nccl - ONE all-gather of the blocks (NCCL)
+and sg_merge_topk_packed_device re-selecting k per query on every rank.
 """
 import numpy as np
 
@@ -23,14 +25,48 @@ def slice_packed(data, off, lo, hi):
 
 
 class ShardedIndex:
-    """One rank's shard plus the cross-shard reduce.  Needs torch.distributed initialised with the nccl backend."""
+    """One rank's shard plus the cross-shard reduce.  Needs torch.distributed initialised (any backend: it only carries
+    the 64-byte IPC handles of the exchange regions at construction; the nccl backend is needed for exchange="nccl").
 
-    def __init__(self, dictionary, description, rank, world, builder_factory):
+    exchange="fused" (default; SG_SHARD_EXCHANGE overrides): sg_exchange_* - the per-shard rows stay in the HBM of the GPU
+    that wrote them, ONE kernel per rank merges that rank's 1/world of the queries reading the other shards' rows over
+    NVLink peer memory and stores the winners into every rank's result (sg_exchange.cu).
+    exchange="nccl": one NCCL all-gather of the full fixed-stride blocks + sg_merge_topk_packed_device of every query on
+    every rank (round 1; also what is used when CUDA IPC is not available)."""
+
+    def __init__(self, dictionary, description, rank, world, builder_factory, max_queries=65536, max_k=16, exchange=None):
+        import os
         data, off = dictionary
         self.rank, self.world = rank, world
         self.lo, self.hi = shard_bounds(len(off) - 1, world)[rank]
         self.index = builder_factory(slice_packed(data, off, self.lo, self.hi), description, self.lo).Build()
         self._buffers = None
+        self._ex = None
+        self.exchange = exchange or os.environ.get("SG_SHARD_EXCHANGE", "fused")
+        self.exchange_note = ""
+        if world > 1 and self.exchange == "fused":
+            self._connect(description.Device, max_queries, max_k)
+
+    def _connect(self, device, max_queries, max_k):
+        import ctypes as C
+        import torch.distributed as dist
+        L = _capi.lib()
+        h = C.c_void_p()
+        _capi.check(L.sg_exchange_create(int(device), self.rank, self.world, int(max_queries), int(max_k), C.byref(h)))
+        mine = C.create_string_buffer(_capi.SG_EXCHANGE_HANDLE_BYTES)
+        _capi.check(L.sg_exchange_handle(h, mine))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine.raw)
+        rc = L.sg_exchange_connect(h, b"".join(handles))
+        ok = [None] * self.world
+        dist.all_gather_object(ok, int(rc))
+        if any(r != 0 for r in ok):  # collective decision: every rank takes the same path
+            self.exchange_note = "CUDA IPC unavailable (%s): NCCL all-gather path" % (L.sg_last_error() or b"").decode()
+            L.sg_exchange_free(h)
+            self.exchange = "nccl"
+            return
+        self._ex = h
+        self._max = (int(max_queries), int(max_k))
 
     def _alloc(self, n_q, k, device):
         import torch
@@ -42,7 +78,7 @@ class ShardedIndex:
         return self._buffers[1]
 
     def SuggestBatchDevice(self, d_q, d_off, n_q, similarity, metric, k, out_ids, out_scores, out_counts):
-        """d_q / d_off / out_*: torch tensors on this rank's device.  Enqueued on torch's current stream."""
+        """d_q / d_off / out_*: torch tensors on this rank's device.  Enqueued on torch's current stream.  Collective."""
         import torch
         import torch.distributed as dist
         stream = torch.cuda.current_stream().cuda_stream
@@ -50,13 +86,30 @@ class ShardedIndex:
             self.index.SuggestBatchDevice(d_q.data_ptr(), d_off.data_ptr(), n_q, similarity, metric, k, out_ids.data_ptr(),
                                           out_scores.data_ptr(), out_counts.data_ptr(), 0, stream)
             return
-        b = self._alloc(n_q, k, d_q.device)
         L = _capi.lib()
+        if self._ex is not None and n_q <= self._max[0] and k <= self._max[1]:
+            _capi.check(L.sg_exchange_search(self._ex, self.index.handle, d_q.data_ptr(), d_off.data_ptr(), n_q, metric.code,
+                                             float(similarity), int(k), out_ids.data_ptr(), out_scores.data_ptr(),
+                                             out_counts.data_ptr(), stream or None))
+            return
+        b = self._alloc(n_q, k, d_q.device)
         _capi.check(L.sg_search_batch_packed_device(self.index.handle, d_q.data_ptr(), d_off.data_ptr(), n_q, metric.code,
                                                     float(similarity), int(k), b["mine"].data_ptr(), stream or None))
         dist.all_gather_into_tensor(b["all"], b["mine"])
         _capi.check(L.sg_merge_topk_packed_device(d_q.device.index, self.world, n_q, k, b["all"].data_ptr(), out_ids.data_ptr(),
                                                   out_scores.data_ptr(), out_counts.data_ptr(), stream or None))
+
+    def check_exchange(self):
+        """SG_OK, or raises if a barrier of the fused exchange timed out (synchronises the current stream)"""
+        import torch
+        if self._ex is not None:
+            _capi.check(_capi.lib().sg_exchange_status(self._ex, torch.cuda.current_stream().cuda_stream or None))
+
+    def close(self):
+        if self._ex is not None:
+            _capi.lib().sg_exchange_free(self._ex)
+            self._ex = None
+        self.index.close()
 
 
 class ShardedNGramIndex:

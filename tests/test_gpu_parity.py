@@ -233,18 +233,19 @@ def test_synthetic_stats_match_oracle(synth_pairs):
     d_ids = torch.zeros(len(q) * k, dtype=torch.int32, device=dev)
     d_sc = torch.zeros(len(q) * k, dtype=torch.float64, device=dev)
     d_cnt = torch.zeros(len(q), dtype=torch.int32, device=dev)
-    d_st = torch.zeros(len(q) * 2, dtype=torch.int32, device=dev)
+    d_st = torch.zeros(len(q) * 4, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     gx.SuggestBatchDevice(d_q.data_ptr(), d_off.data_ptr(), len(q), 0.5, S.JaccardMetric(), k, d_ids.data_ptr(),
                           d_sc.data_ptr(), d_cnt.data_ptr(), d_st.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
-    st = d_st.cpu().numpy().reshape(-1, 2)
+    st = d_st.cpu().numpy().reshape(-1, 4)
     ids_o, sc_o, n_o = ox.suggest_batch(q, O.JACCARD, 0.5, k, O.CANONICAL, threads=4)
     assert np.array_equal(d_cnt.cpu().numpy().astype(np.uint32), n_o)
     assert np.array_equal(d_ids.cpu().numpy().astype(np.uint32).reshape(-1, k), ids_o)
     for i, query in enumerate(q):
         want = ox.query_stats(query, O.JACCARD, 0.5)
         assert (int(st[i, 0]), int(st[i, 1])) == (want["postings"], want["lists"]), (i, query)
+        assert int(st[i, 3]) == 0
 
 
 # ---------------------------------------------------------------------------------------------------
