@@ -120,7 +120,8 @@ typedef struct {
     uint32_t row_words;      /* 32-bit words per bitmap row; 0: built without bitmaps */
     uint32_t engine;
     uint32_t built_on_device; /* 1: sg_index_build ran the device build (sg_gpubuild.cu); 0: host build */
-    uint32_t reserved;
+    uint32_t pipeline;       /* engine 1 only: 1 = Suggest runs the count -> resolve pipeline (sg_count_kernel, sg_resolve_kernel over the
+                                exact level, sg_fine.cu); 0 = sg_bitmap_search_kernel alone (SG_PIPELINE=classic, or the level did not fit) */
     uint64_t bitmap_bytes;
 } sg_index_layout;
 int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout);
@@ -189,7 +190,7 @@ int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *
 
 /*
  * Measurement aid: one sg_search_batch_device launch with CUDA events between its kernels on `stream`; synchronises.
- * ms_out receives one duration per kernel (at most 4), names_out their comma-separated names.  Returns the number of
+ * ms_out receives one duration per kernel (at most 8), names_out their comma-separated names.  Returns the number of
  * kernels.  bench.py uses it for the per-kernel roofline; it is not part of the reference-facing path.
  */
 int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
@@ -266,6 +267,32 @@ int sg_exchange_result(sg_exchange *ex, uint32_t n_q, uint32_t k, const uint32_t
                        const uint32_t **d_counts);
 int sg_exchange_status(sg_exchange *ex, void *stream);
 void sg_exchange_free(sg_exchange *ex);
+
+/*
+ * ---- single-query callers: a micro-batcher in front of sg_search_batch ----
+ * Replaces nothing of the reference and serves its calling pattern: Service.Suggest is called with ONE query per goroutine
+ * (internal/suggest/api/suggest_handler.go:42-76, cmd/suggest/cmd/eval.go:60, pkg/spellchecker/spellchecker.go:67).
+ * sg_suggest_one blocks the calling thread until its row is there; any number of host threads may call it at once.
+ * Their queries are coalesced by one worker thread into sg_search_batch calls over page-locked buffers the batcher owns:
+ * a batch closes when it holds max_batch queries, when its oldest query has waited max_wait_us, or - under load - as soon
+ * as the previous batch has returned.  Queries of one batch share (metric, similarity); k is per query (<= max_k).
+ * out_ids / out_scores: room for k entries; *out_count receives the number of candidates ((score desc, id asc) order).
+ * Errors are per query (SG_ERR_QUERY_TOO_LONG for one query does not fail its batch mates).
+ * sg_batcher_free serves what is queued, then stops the worker; the index must outlive the batcher.
+ */
+typedef struct sg_batcher sg_batcher;
+typedef struct {
+    uint64_t batches;        /* sg_search_batch calls so far */
+    uint64_t queries;        /* queries served so far */
+    uint32_t largest_batch;
+    uint32_t max_batch, max_wait_us;
+    uint32_t reserved;
+} sg_batcher_stats;
+int sg_batcher_create(sg_index *ix, uint32_t max_batch, uint32_t max_wait_us, uint32_t max_k, sg_batcher **out);
+int sg_suggest_one(sg_batcher *b, const char *query, uint32_t len, int metric, double alpha, uint32_t k, uint32_t *out_ids,
+                   double *out_scores, uint32_t *out_count);
+int sg_batcher_get_stats(const sg_batcher *b, sg_batcher_stats *stats);
+void sg_batcher_free(sg_batcher *b);
 
 /*
  * ---- language model and spellchecker (BASELINE.json config #5) ----

@@ -24,6 +24,7 @@ import (
 	"reflect"
 	"runtime"
 	"sort"
+	"sync"
 	"unsafe"
 
 	"github.com/suggest-go/suggest/pkg/dictionary"
@@ -100,11 +101,65 @@ func (b *b200Builder) Build() (NGramIndex, error) {
 		}
 	}
 	ix := &b200Index{handle: handle}
-	runtime.SetFinalizer(ix, func(i *b200Index) { C.sg_index_free(i.handle) }) // as index_reader.go:49-51 does for mmaps
+	// Service.Suggest is called with one query per goroutine (internal/suggest/api/suggest_handler.go:56): the batcher
+	// coalesces those calls into sg_search_batch calls over page-locked buffers of its own
+	if rc := C.sg_batcher_create(handle, batcherMaxBatch, batcherMaxWaitUs, batcherMaxK, &ix.batcher); rc != 0 {
+		C.sg_index_free(handle)
+		return nil, lastError()
+	}
+	runtime.SetFinalizer(ix, func(i *b200Index) { // as index_reader.go:49-51 does for mmaps
+		C.sg_batcher_free(i.batcher)
+		C.sg_index_free(i.handle)
+	})
 	return NewNGramIndex(ix, ix), nil
 }
 
-type b200Index struct{ handle *C.sg_index }
+const (
+	batcherMaxBatch  = 16384
+	batcherMaxWaitUs = 100
+	batcherMaxK      = 256
+)
+
+type b200Index struct {
+	handle  *C.sg_index
+	batcher *C.sg_batcher
+}
+
+// pinnedRows are page-locked result rows (sg_pinned_alloc): sg_search_batch lets the kernel store straight into them,
+// which a Go-heap slice (pageable) cannot offer.  Pooled, so that a batch call costs no cudaHostAlloc.
+type pinnedRows struct {
+	n, k   int
+	ids    unsafe.Pointer
+	scores unsafe.Pointer
+	counts unsafe.Pointer
+}
+
+var pinnedPool sync.Pool
+
+func getPinnedRows(n, k int) (*pinnedRows, error) {
+	if v := pinnedPool.Get(); v != nil {
+		r := v.(*pinnedRows)
+		if r.n >= n && r.n*r.k >= n*k {
+			return r, nil
+		}
+		r.free()
+	}
+	r := &pinnedRows{n: n, k: k}
+	if C.sg_pinned_alloc(C.uint64_t(n*k*4), &r.ids) != 0 || C.sg_pinned_alloc(C.uint64_t(n*k*8), &r.scores) != 0 ||
+		C.sg_pinned_alloc(C.uint64_t(n*4), &r.counts) != 0 {
+		r.free()
+		return nil, lastError()
+	}
+	runtime.SetFinalizer(r, func(r *pinnedRows) { r.free() })
+	return r, nil
+}
+
+func (r *pinnedRows) free() {
+	C.sg_pinned_free(r.ids)
+	C.sg_pinned_free(r.scores)
+	C.sg_pinned_free(r.counts)
+	r.ids, r.scores, r.counts = nil, nil, nil
+}
 
 func bytesPtr(b []byte) *C.char {
 	if len(b) == 0 {
@@ -153,8 +208,27 @@ func rowsToCandidates(n, k int, ids []C.uint32_t, scores []C.double, counts []C.
 	return out
 }
 
-// Suggest implements Suggester (suggester.go:46-131); a batch of one.
+// Suggest implements Suggester (suggester.go:46-131).  The fuzzy top-k with a built-in metric goes through the batcher:
+// concurrent callers (one goroutine per HTTP request) share sg_search_batch calls; everything else is a batch of one.
 func (ix *b200Index) Suggest(query string, similarity float64, m metric.Metric, factory CollectorManagerFactory) ([]Candidate, error) {
+	if fuzzy, ok := factory().(*FuzzyCollectorManager); ok {
+		if queue, ok := fuzzy.globalQueue.(*topKQueue); ok && queue.topK > 0 && queue.topK <= batcherMaxK {
+			if code, known := metricCode(m); known {
+				k := queue.topK
+				ids := make([]C.uint32_t, k)
+				scores := make([]C.double, k)
+				var count C.uint32_t
+				q := []byte(query)
+				rc := C.sg_suggest_one(ix.batcher, bytesPtr(q), C.uint32_t(len(q)), code, C.double(similarity), C.uint32_t(k),
+					&ids[0], &scores[0], &count)
+				runtime.KeepAlive(ix)
+				if rc != 0 {
+					return nil, lastError()
+				}
+				return rowsToCandidates(1, k, ids, scores, []C.uint32_t{count})[0], nil
+			}
+		}
+	}
 	res, err := ix.SuggestBatch([]string{query}, similarity, m, factory)
 	if err != nil {
 		return nil, err
@@ -180,16 +254,22 @@ func (ix *b200Index) SuggestBatch(queries []string, similarity float64, m metric
 	if n == 0 || k <= 0 {
 		return make([][]Candidate, n), nil
 	}
-	ids := make([]C.uint32_t, n*k)
-	scores := make([]C.double, n*k)
-	counts := make([]C.uint32_t, n)
+	// page-locked rows from the pool: the kernel stores the valid entries of every row straight into them
+	rows, err := getPinnedRows(n, k)
+	if err != nil {
+		return nil, err
+	}
+	defer pinnedPool.Put(rows)
+	ids := (*[1 << 28]C.uint32_t)(rows.ids)[: n*k : n*k]
+	scores := (*[1 << 27]C.double)(rows.scores)[: n*k : n*k]
+	counts := (*[1 << 28]C.uint32_t)(rows.counts)[:n:n]
 	rc := C.sg_search_batch(ix.handle, bytesPtr(bytes), &offsets[0], C.uint32_t(n), code, C.double(similarity), C.uint32_t(k),
 		&ids[0], &scores[0], &counts[0])
 	runtime.KeepAlive(ix)
 	if rc != 0 {
 		return nil, lastError()
 	}
-	return rowsToCandidates(n, k, ids, scores, counts), nil
+	return rowsToCandidates(n, k, ids, scores, counts), nil // copies the valid entries out of the pooled rows
 }
 
 // Autocomplete implements Autocomplete (autocomplete.go:40-77).  FirstKCollectorManager(limit) runs on the device

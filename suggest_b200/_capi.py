@@ -28,9 +28,14 @@ class SgIndexInfo(C.Structure):
                 ("n_postings", C.c_uint64), ("device_bytes", C.c_uint64), ("id_base", C.c_uint32), ("device", C.c_int32)]
 
 
+class SgBatcherStats(C.Structure):
+    _fields_ = [("batches", C.c_uint64), ("queries", C.c_uint64), ("largest_batch", C.c_uint32), ("max_batch", C.c_uint32),
+                ("max_wait_us", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 class SgIndexLayout(C.Structure):
     _fields_ = [("n_slots", C.c_uint32), ("bucket_shift", C.c_uint32), ("row_words", C.c_uint32), ("engine", C.c_uint32),
-                ("built_on_device", C.c_uint32), ("reserved", C.c_uint32), ("bitmap_bytes", C.c_uint64)]
+                ("built_on_device", C.c_uint32), ("pipeline", C.c_uint32), ("bitmap_bytes", C.c_uint64)]
 
 
 # every symbol include/suggest_b200.h declares, with its signature
@@ -73,6 +78,11 @@ SIGNATURES = {
     "sg_exchange_result": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "sg_exchange_status": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sg_exchange_free": (None, [C.c_void_p]),
+    "sg_batcher_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "sg_suggest_one": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32, C.c_void_p, C.c_void_p,
+                                 C.POINTER(C.c_uint32)]),
+    "sg_batcher_get_stats": (C.c_int, [C.c_void_p, C.POINTER(SgBatcherStats)]),
+    "sg_batcher_free": (None, [C.c_void_p]),
     "sg_lm_create": (C.c_int, [C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_lm_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "sg_lm_free": (None, [C.c_void_p]),

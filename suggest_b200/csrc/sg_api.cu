@@ -143,6 +143,8 @@ struct sg_index {
     uint32_t n_terms = 0;
     size_t persist_l2_max = 0, policy_window_max = 0;
     bool built_on_device = false;
+    bool lean_pipeline = false;          // Suggest top-k runs sg_count_kernel -> sg_resolve_kernel (the exact level is built, or one bit per document)
+    std::string fine_note;               // why the exact level was not built, if it was not
 };
 
 namespace {
@@ -256,12 +258,33 @@ int finish_setup(sg_index *ix) {
         ix->bitmap_engine = h.row_words != 0 && !want_scan;
         if (eng && std::strcmp(eng, "bitmap") == 0 && !ix->bitmap_engine) return fail(SG_ERR_NOMEM, "the bucket bitmaps do not fit their memory budget");
         ix->plan_stride = ix->bitmap_engine ? sg::kTokStride : sg::kPlanStride;
+        if (ix->bitmap_engine) {
+            // the exact level under the bitmaps (sg_fine.cu) and with it the count -> resolve pipeline; SG_PIPELINE=classic keeps
+            // every search on sg_bitmap_search_kernel
+            const char *pl = std::getenv("SG_PIPELINE");
+            const bool classic = pl && std::strcmp(pl, "classic") == 0;
+            if (pl && *pl && !classic && std::strcmp(pl, "lean") != 0) return fail(SG_ERR_INVALID, "SG_PIPELINE must be lean or classic");
+            if (!classic) {
+                size_t free_b = 0, total_b = 0;
+                uint64_t budget = 1ull << 62;
+                if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = free_b / 2;
+                const int mb = env_int("SG_FINE_MAX_MB", -1);
+                if (mb >= 0) budget = (uint64_t)mb << 20;
+                const std::string err = sg::build_fine_level(&ix->dev, h.n_postings, budget, &ix->allocations, &ix->device_bytes);
+                if (err.rfind("skip:", 0) == 0) ix->fine_note = err;
+                else if (!err.empty()) return fail(SG_ERR_CUDA, "exact level: " + err);
+                ix->lean_pipeline = ix->dev.bshift == 0 || ix->dev.fine != nullptr;
+                if (pl && std::strcmp(pl, "lean") == 0 && !ix->lean_pipeline) return fail(SG_ERR_NOMEM, ix->fine_note);
+                g_launches.fetch_add(ix->dev.fine ? 2 : 0, std::memory_order_relaxed);
+            }
+            if (ix->lean_pipeline) ix->plan_stride = (sg::kTokStride + sg::kLeanScratchPerQuery + 16 + 15) & ~(size_t)15;  // + the alignment gap behind the plans
+        }
         const size_t rows = sg::kWindowRows;
         ix->wtab_bytes = ((rows * h.n_segments + 15) & ~(size_t)15) + ((rows * h.row_words + 15) & ~(size_t)15) + rows * sizeof(sg::WordRange);
     }
     {
         void *ring = nullptr;
-        SG_CUDA(cudaMalloc(&ring, kWorkRing * sizeof(uint32_t)));
+        SG_CUDA(cudaMalloc(&ring, (size_t)kWorkRing * sg::kWorkWords * sizeof(uint32_t)));
         ix->allocations.push_back(ring);
         ix->work_ring = (uint32_t *)ring;
     }
@@ -484,6 +507,21 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
                 run_window = false;
             }
         }
+        if (ix->lean_pipeline && mode == 0 && !collect && !d_lm_ctx) {
+            // scratch of the pipeline behind the plans: [plans n_q x kTokStride | flags | nodes | pending | head]
+            uint8_t *at = d_plans + (((size_t)n_q * sg::kTokStride + 15) & ~(size_t)15);
+            p.lean_flags = (uint4 *)at;
+            at += (size_t)n_q * sg::kFlagsPerQuery * sizeof(uint4);
+            p.lean_nodes = (uint4 *)at;  // (the nodes' scores follow them: sg_bitmap.cu select_survivors)
+            at += (size_t)n_q * sg::kNodesPerQuery * (sizeof(uint4) + sizeof(double));
+            p.lean_pending = (uint32_t *)at;
+            p.lean_head = p.lean_pending + n_q;
+            int count_per_sm = 0, resolve_per_sm = 0;
+            SG_CUDA(sg::lean_occupancy(ix->device, k, &count_per_sm, &resolve_per_sm));
+            SG_CUDA(sg::launch_lean_search(ix->dev, p, ix->sm_count, count_per_sm, resolve_per_sm, per_sm, run_window, stream, stage_events));
+            g_launches.fetch_add(run_window ? 5 : 4, std::memory_order_relaxed);  // [window +] tokens + count + resolve + fallback search
+            return SG_OK;
+        }
         SG_CUDA(sg::launch_bitmap_search(ix->dev, p, ix->sm_count, per_sm, run_window, stream, stage_events));
         g_launches.fetch_add(run_window ? 3 : 2, std::memory_order_relaxed);  // [sg_window_kernel +] sg_tokens_kernel + sg_bitmap_search_kernel
         return SG_OK;
@@ -687,6 +725,7 @@ int sg_index_get_layout(const sg_index *ix, sg_index_layout *layout) {
     layout->row_words = ix->host.row_words;
     layout->engine = ix->bitmap_engine ? 1u : 0u;
     layout->built_on_device = ix->built_on_device ? 1u : 0u;
+    layout->pipeline = ix->lean_pipeline ? 1u : 0u;
     layout->bitmap_bytes = ix->host.row_words ? (uint64_t)(ix->n_terms + 1) * ix->host.row_words * sizeof(uint32_t) : 0;
     return SG_OK;
 }
@@ -764,9 +803,9 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     if (!direct) {
         SG_CUDA(c->ids.reserve((size_t)n_q * k));
         SG_CUDA(c->scores.reserve((size_t)n_q * k));
-        SG_CUDA(c->counts.reserve(n_q));
     }
-    SG_CUDA(c->work.reserve(kMaxSlices));
+    SG_CUDA(c->counts.reserve(n_q));  // direct rows too: counts are staged (one copy per slice instead of a PCIe write per query)
+    SG_CUDA(c->work.reserve((size_t)kMaxSlices * sg::kWorkWords));
     SG_CUDA(c->plans.reserve((size_t)n_q * ix->plan_stride));
     SG_CUDA(c->wtab.reserve(ix->wtab_bytes * kMaxSlices));
     // Slices of the batch go down two streams: the H2D / D2H copies of one slice overlap the kernels of the other, and
@@ -838,12 +877,16 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         SG_CUDA(cudaEventRecord(c->h2d_done[sl], cs));
         SG_CUDA(cudaStreamWaitEvent(st, c->h2d_done[sl], 0));
         rc = enqueue_search(ix, d_q_bytes, d_off, hi - lo, metric, alpha, k, (direct ? m_ids : c->ids.p) + (size_t)lo * k,
-                            (direct ? m_scores : c->scores.p) + (size_t)lo * k, (direct ? m_counts : c->counts.p) + lo, nullptr,
-                            c->work.p + sl, c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st,
+                            (direct ? m_scores : c->scores.p) + (size_t)lo * k, c->counts.p + lo, nullptr,
+                            c->work.p + (size_t)sl * sg::kWorkWords, c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st,
                             mode, nullptr, nullptr, direct ? 1 : 0, direct ? d_too_long : nullptr);
         if (rc != SG_OK) return rc;
         if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 2], st);
         if (direct) {
+            // The valid entries of the rows were stored by the kernels while they ran.  The counts are not: 65,536 four-byte
+            // stores over PCIe cost more than the kernels of the batch take (the link moves ~0.75 G writes per second whatever
+            // their size), one copy of the slice's counts is ~10 us.
+            SG_CUDA(cudaMemcpyAsync(out_counts + lo, c->counts.p + lo, (size_t)(hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 3], st);
             continue;
         }
@@ -934,7 +977,7 @@ int sg_candidates_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off
     SG_CUDA(c->q_bytes.reserve(n_bytes + 64));
     SG_CUDA(c->q_off.reserve((size_t)n_q + 1));
     SG_CUDA(c->counts.reserve(n_q));
-    SG_CUDA(c->work.reserve(kMaxSlices));
+    SG_CUDA(c->work.reserve((size_t)kMaxSlices * sg::kWorkWords));
     SG_CUDA(c->plans.reserve((size_t)n_q * ix->plan_stride));
     SG_CUDA(c->wtab.reserve(ix->wtab_bytes * kMaxSlices));
     SG_CUDA(c->cand.reserve((size_t)cap * 4 + thr_words + 4));
@@ -995,7 +1038,7 @@ int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *
     const size_t plan_bytes = ((size_t)n_q * ix->plan_stride + 255) & ~(size_t)255;
     SG_CUDA(cudaMallocAsync(&plans, plan_bytes + ix->wtab_bytes, (cudaStream_t)stream));
     rc = enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, d_stats,
-                        ix->work_ring + slot, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, (cudaStream_t)stream);
+                        ix->work_ring + (size_t)slot * sg::kWorkWords, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, (cudaStream_t)stream);
     cudaError_t fe = cudaFreeAsync(plans, (cudaStream_t)stream);
     if (rc == SG_OK && fe != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(fe));
     return rc;
@@ -1011,16 +1054,22 @@ int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d
     DeviceGuard guard;
     SG_CUDA(guard.set(ix->device));
     cudaStream_t st = (cudaStream_t)stream;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (auto &e : ev) SG_CUDA(cudaEventCreate(&e));
     const uint32_t slot = ix->work_rr.fetch_add(1, std::memory_order_relaxed) & (kWorkRing - 1);
     void *plans = nullptr;
     const size_t plan_bytes = ((size_t)n_q * ix->plan_stride + 255) & ~(size_t)255;
     SG_CUDA(cudaMalloc(&plans, plan_bytes + ix->wtab_bytes));
     rc = enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, nullptr,
-                        ix->work_ring + slot, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, st, 0, ev);
+                        ix->work_ring + (size_t)slot * sg::kWorkWords, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, st, 0, ev);
     cudaError_t se = cudaStreamSynchronize(st);
-    const int n_stages = ix->bitmap_engine ? 3 : 2;
+    if (env_int("SG_TRACE", 0) >= 1 && ix->bitmap_engine && se == cudaSuccess) {  // counters of the launch (sg_device.h: kWork*)
+        uint32_t w[sg::kWorkWords] = {0};
+        cudaMemcpy(w, ix->work_ring + (size_t)slot * sg::kWorkWords, sizeof(w), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "sg_search_stage_times: %u queries: flagged bitmap words %u, survivor nodes %u, dirty %u, fallback queries taken %u\n", n_q,
+                     w[sg::kWorkFlagCursor], w[sg::kWorkNodeCursor], w[sg::kWorkDirtyAny], w[sg::kWorkFallbackQuery]);
+    }
+    const int n_stages = !ix->bitmap_engine ? 2 : ix->lean_pipeline ? 5 : 3;
     if (rc == SG_OK && se == cudaSuccess)
         for (int i = 0; i < n_stages; i++) cudaEventElapsedTime(ms_out + i, ev[i], ev[i + 1]);
     for (auto &e : ev) cudaEventDestroy(e);
@@ -1028,7 +1077,9 @@ int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d
     if (rc != SG_OK) return rc;
     if (se != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(se));
     if (names_out && names_cap) {
-        const char *names = ix->bitmap_engine ? "sg_window_kernel,sg_tokens_kernel,sg_bitmap_search_kernel" : "sg_plan_kernel,sg_search_kernel";
+        const char *names = !ix->bitmap_engine ? "sg_plan_kernel,sg_search_kernel"
+                            : ix->lean_pipeline ? "sg_window_kernel,sg_tokens_kernel,sg_count_kernel,sg_resolve_kernel,sg_bitmap_search_kernel"
+                                                : "sg_window_kernel,sg_tokens_kernel,sg_bitmap_search_kernel";
         std::strncpy(names_out, names, names_cap - 1);
         names_out[names_cap - 1] = 0;
     }
@@ -1648,7 +1699,7 @@ int sg_predict_batch(sg_index *ix, sg_lm *lm, const char *w_bytes, const uint32_
     SG_CUDA(s.get((void **)&d_out_ids, (size_t)n_q * (k + 1) * 4));
     SG_CUDA(s.get((void **)&d_out_cnt, (size_t)n_q * 4));
     SG_CUDA(s.get((void **)&d_tmp, (size_t)n_q * 4 * k * 4));
-    SG_CUDA(s.get((void **)&d_work, 8));
+    SG_CUDA(s.get((void **)&d_work, 2 * sg::kWorkWords * sizeof(uint32_t)));
     SG_CUDA(s.get((void **)&d_plans, (size_t)n_q * ix->plan_stride));
     SG_CUDA(s.get((void **)&d_wtab, ix->wtab_bytes));
     SG_CUDA(s.get((void **)&d_lc, (size_t)n_q * sizeof(sg::LmContext)));
@@ -1661,7 +1712,7 @@ int sg_predict_batch(sg_index *ix, sg_lm *lm, const char *w_bytes, const uint32_
     rc = enqueue_search(ix, d_w, d_w_off, n_q, SG_EXACT, 1.0, k, d_ac_ids, d_sc, d_ac_cnt, nullptr, d_work, d_plans, d_wtab, st, 1, nullptr, d_lc);
     // fuzzy candidates (index.Suggest with CosineMetric, spellchecker.go:67-74); searched for every query, used where needed
     if (rc == SG_OK)
-        rc = enqueue_search(ix, d_w, d_w_off, n_q, SG_COSINE, similarity, k, d_fz_ids, d_sc, d_fz_cnt, nullptr, d_work + 1, d_plans, d_wtab, st, 0);
+        rc = enqueue_search(ix, d_w, d_w_off, n_q, SG_COSINE, similarity, k, d_fz_ids, d_sc, d_fz_cnt, nullptr, d_work + sg::kWorkWords, d_plans, d_wtab, st, 0);
     if (rc != SG_OK) { cudaStreamSynchronize(st); return rc; }
     SG_CUDA(sg::launch_predict_merge(d_lc, n_q, k, d_ac_ids, d_ac_cnt, d_fz_ids, d_fz_cnt, d_out_ids, d_out_cnt, d_tmp, st));
     g_launches.fetch_add(2, std::memory_order_relaxed);

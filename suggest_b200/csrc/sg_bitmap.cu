@@ -44,6 +44,7 @@ constexpr int kResolveSlots = 1 << kMaxBucketShift;
 constexpr uint32_t kRowSlots = kMaxQueryTokens + 8;  // padded to a multiple of 8 with the all-zero row
 constexpr uint32_t kTileWords = 32;        // bitmap words per tile: lane l owns word l
 constexpr int kSegCache = 256;             // segment starts kept in shared memory per CTA
+constexpr int kResolveThreads = 128;       // sg_resolve_kernel: one thread per flagged bitmap word
 
 // Per-warp shared memory of sg_bitmap_search_kernel.  The count loop itself only reads `row`; everything
 // else belongs to the cold path (a bucket reached its threshold), which keeps its state here so that the hot loop's
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_
     uint32_t *s_hash = s_lterm + kMaxQueryTokens;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const size_t stride = (size_t)ix.n_segments + 1;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *p.work_counter = 0u;  // query counter of the search kernel behind this one
+    if (blockIdx.x == 0 && threadIdx.x < kWorkWords) p.work_counter[threadIdx.x] = 0u;  // counters of the kernels behind this one
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < p.n_q; q += n_warps) {
         int size_a = 0, n_lists = 0;
         const bool unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
@@ -578,9 +579,11 @@ __device__ __forceinline__ void bitmap_search_body(const DevIndex &ix, const Sea
     const double *tk_score = warp_tk_score(ws);
     const uint32_t *tk_id = warp_tk_id(ws, p.k);
     const uint32_t zero_row = ix.n_terms * ix.row_words;
+    // behind the count -> resolve pipeline this kernel answers only the queries that ran out of scratch there (kPlanDirty)
+    uint32_t *const counter = p.work_counter + (p.only_dirty ? kWorkFallbackQuery : kWorkQuery);
 
     uint32_t q = 0;
-    if (lane == 0) q = take_query(p.work_counter);
+    if (lane == 0) q = take_query(counter);
     q = __shfl_sync(kFull, q, 0);
     while (q < p.n_q) {
         // the plan of this query: header and the first 32 term ids are requested before anything waits on them
@@ -588,8 +591,12 @@ __device__ __forceinline__ void bitmap_search_body(const DevIndex &ix, const Sea
         const uint4 h0 = __ldg((const uint4 *)plan_base), h1 = __ldg((const uint4 *)plan_base + 1);  // TokenPlan
         const uint32_t t0 = __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + lane);
         uint32_t q_next = 0;
-        if (lane == 0) q_next = take_query(p.work_counter);  // the next query number travels together with the plan loads
-        const bool unsupported = h0.x != 0u;
+        if (lane == 0) q_next = take_query(counter);  // the next query number travels together with the plan loads
+        if (p.only_dirty && !(h0.x & kPlanDirty)) {
+            q = __shfl_sync(kFull, q_next, 0);
+            continue;
+        }
+        const bool unsupported = (h0.x & 1u) != 0u;
         const int size_a = (int)h0.y, n_lists = (int)h0.z;
         const WordRange win{h1.x, h1.y};
         int tk_len = 0;
@@ -651,6 +658,7 @@ __device__ __forceinline__ void bitmap_search_body(const DevIndex &ix, const Sea
 }
 
 __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bitmap_search_kernel(const DevIndex ix, const SearchParams p) {
+    if (p.only_dirty && ((const volatile uint32_t *)p.work_counter)[kWorkDirtyAny] == 0u) return;  // the usual case: nothing to redo
     bitmap_search_body<false>(ix, p);
 }
 
@@ -658,32 +666,465 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
     bitmap_search_body<true>(ix, p);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// The count -> resolve pipeline (Suggest top-k on an index with the exact level, sg_fine.cu): the same bit-sliced count
+// as above, but a bucket that reaches its threshold is not resolved by the warp that found it.  sg_count_kernel only
+// counts and appends {query, bitmap word, flagged buckets} to a launch-wide list; sg_resolve_kernel takes one flagged
+// word per warp - so the resolves of a query with thousands of flagged buckets (frequent n-grams, low thresholds) spread
+// over the whole GPU instead of serialising one warp - counts the bucket's documents exactly from the pairs' bits
+// (DevIndex::rank4 / fine: two loads per list, no posting-list search), links the survivors to their query, and the
+// warp that resolves the LAST flagged word of a query scores its survivors, selects the k best and writes the row.
+// A query without a flagged word is finished by sg_count_kernel itself.  If a launch runs out of scratch the queries
+// concerned are marked kPlanDirty and answered by sg_bitmap_search_kernel (only_dirty) behind the pipeline.
+// ---------------------------------------------------------------------------------------------------------------
+#ifndef SG_COUNT_MIN_BLOCKS
+#define SG_COUNT_MIN_BLOCKS 4           // CTAs per SM the register allocation of sg_count_kernel aims at (64 registers: two sets of
+                                        // eight 8-byte row words in flight plus 2 x M planes)
+#endif
+
+// The same count with every lane owning TWO adjacent words of a 64-word tile: row reads are 8-byte loads (LDG.64, 256
+// bytes per warp-load).  A B200 SM issues 4-byte warp-loads at a rate that caps L2 -> SM traffic near 9.5 TB/s chip-wide;
+// with 8-byte loads the same cache delivers ~17 TB/s (tools/l2bench.cu, profiles/l2_peak.json), and the count of
+// config #2 is bound by exactly that.  Used by sg_count_kernel.
+constexpr uint32_t kTileWords2 = 64;
+template <int M>
+struct TileState2 {
+    uint32_t c[M][2];   // planes of this lane's two words
+    uint32_t ov[2], bias[2];
+};
+
+template <int M>
+__device__ __forceinline__ uint32_t count_until_flag2(const uint32_t *__restrict__ bitmaps, const uint32_t *s_row,
+                                                      const uint8_t *__restrict__ word_thr, uint32_t w_begin, uint32_t win_hi,
+                                                      int n_lists, int lane, TileState2<M> &ts) {
+    const uint32_t n_blocks = ((uint32_t)n_lists + 7u) >> 3;
+    const uint32_t n_units = ((win_hi - w_begin + kTileWords2 - 1) / kTileWords2) * n_blocks;
+    const uint32_t *ld_ptr = bitmaps + w_begin + 2u * (uint32_t)lane;
+    asm volatile("" : "+l"(ld_ptr));  // opaque: row offsets are added to this pointer as 32-bit indices (one IMAD.WIDE per load)
+    uint32_t ld_block = 0;
+#define SG_LOAD_BLOCK2(R)                                                                                     \
+    do {                                                                                                      \
+        const uint4 r0_ = *(const uint4 *)(s_row + ld_block * 8u), r1_ = *(const uint4 *)(s_row + ld_block * 8u + 4u); \
+        R##0 = __ldg((const uint2 *)(ld_ptr + r0_.x));                                                        \
+        R##1 = __ldg((const uint2 *)(ld_ptr + r0_.y));                                                        \
+        R##2 = __ldg((const uint2 *)(ld_ptr + r0_.z));                                                        \
+        R##3 = __ldg((const uint2 *)(ld_ptr + r0_.w));                                                        \
+        R##4 = __ldg((const uint2 *)(ld_ptr + r1_.x));                                                        \
+        R##5 = __ldg((const uint2 *)(ld_ptr + r1_.y));                                                        \
+        R##6 = __ldg((const uint2 *)(ld_ptr + r1_.z));                                                        \
+        R##7 = __ldg((const uint2 *)(ld_ptr + r1_.w));                                                        \
+        if (++ld_block == n_blocks) {                                                                         \
+            ld_block = 0;                                                                                     \
+            ld_ptr += kTileWords2;                                                                            \
+            asm volatile("" : "+l"(ld_ptr));                                                                  \
+        }                                                                                                     \
+    } while (0)
+    uint32_t w0 = w_begin, cons_block = 0;
+    const uint8_t *thr_ptr = word_thr + w_begin + 2u * (uint32_t)lane;  // thresholds of this lane's two words (one 16-bit load)
+    uint32_t tw_next;
+    auto begin_tile = [&](uint32_t T_pair) {
+#pragma unroll
+        for (int x = 0; x < 2; x++) {
+            const uint32_t T_w = (T_pair >> (8 * x)) & 0xFFu;
+            ts.bias[x] = (T_w >> M) ? 0u : (1u << M) - T_w;  // a threshold no count can reach: the planes never overflow
+#pragma unroll
+            for (int j = 0; j < M; j++) ts.c[j][x] = 0u - ((ts.bias[x] >> j) & 1u);
+            ts.ov[x] = 0u;
+        }
+    };
+    auto add8 = [&](int x, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5, uint32_t x6, uint32_t x7) {
+        uint32_t h1, l1, h2, l2, h3, l3, h4, g1, m1, g2, e;
+        csa(h1, l1, x0, x1, x2);
+        csa(h2, l2, x3, x4, x5);
+        csa(h3, l3, x6, x7, ts.c[0][x]);
+        csa(h4, ts.c[0][x], l1, l2, l3);
+        csa(g1, m1, h1, h2, h3);
+        csa(g2, ts.c[1][x], m1, h4, ts.c[1][x]);
+        csa(e, ts.c[2][x], g1, g2, ts.c[2][x]);
+#pragma unroll
+        for (int j = 3; j < M; j++) {
+            const uint32_t t = ts.c[j][x] & e;
+            ts.c[j][x] ^= e;
+            e = t;
+        }
+        ts.ov[x] |= e;
+    };
+    auto consume = [&](uint2 x0, uint2 x1, uint2 x2, uint2 x3, uint2 x4, uint2 x5, uint2 x6, uint2 x7) -> bool {
+        add8(0, x0.x, x1.x, x2.x, x3.x, x4.x, x5.x, x6.x, x7.x);
+        add8(1, x0.y, x1.y, x2.y, x3.y, x4.y, x5.y, x6.y, x7.y);
+        if (++cons_block == n_blocks) {
+            if (__any_sync(kFull, (ts.ov[0] | ts.ov[1]) != 0u)) return true;  // rare: the caller records the flagged words
+            cons_block = 0;
+            w0 += kTileWords2;
+            thr_ptr += kTileWords2;
+            begin_tile(tw_next);
+            tw_next = w0 + kTileWords2 < win_hi ? (uint32_t)__ldg((const uint16_t *)(thr_ptr + kTileWords2)) : 0xFFFFu;
+        }
+        return false;
+    };
+    uint2 xa0, xa1, xa2, xa3, xa4, xa5, xa6, xa7, xb0, xb1, xb2, xb3, xb4, xb5, xb6, xb7;
+    xb0 = xb1 = xb2 = xb3 = xb4 = xb5 = xb6 = xb7 = make_uint2(0u, 0u);
+    begin_tile((uint32_t)__ldg((const uint16_t *)thr_ptr));
+    tw_next = w0 + kTileWords2 < win_hi ? (uint32_t)__ldg((const uint16_t *)(thr_ptr + kTileWords2)) : 0xFFFFu;
+    SG_LOAD_BLOCK2(xa);
+#pragma unroll 1
+    for (uint32_t u = 0;;) {
+        if (u + 1 < n_units) SG_LOAD_BLOCK2(xb);
+        if (consume(xa0, xa1, xa2, xa3, xa4, xa5, xa6, xa7)) return w0;
+        if (++u == n_units) break;
+        if (u + 1 < n_units) SG_LOAD_BLOCK2(xa);
+        if (consume(xb0, xb1, xb2, xb3, xb4, xb5, xb6, xb7)) return w0;
+        if (++u == n_units) break;
+    }
+#undef SG_LOAD_BLOCK2
+    return kInf;
+}
+
+
+template <int M>
+__device__ __forceinline__ uint32_t count_and_flag(const DevIndex &ix, const SearchParams &p, const uint32_t *s_row,
+                                                   const uint8_t *__restrict__ word_thr, uint32_t win_lo, uint32_t win_hi, int n_lists,
+                                                   uint32_t q, int lane, bool &dirty) {
+    const uint32_t cap = p.n_q * kFlagsPerQuery;
+    uint32_t n_entries = 0;
+    for (uint32_t w = win_lo & ~(kTileWords2 - 1); w < win_hi;) {
+        TileState2<M> ts;
+        const uint32_t wf = count_until_flag2<M>(ix.bitmaps, s_row, word_thr, w, win_hi, n_lists, lane, ts);
+        if (wf == kInf) break;
+        const unsigned m0 = __ballot_sync(kFull, ts.ov[0] != 0u), m1 = __ballot_sync(kFull, ts.ov[1] != 0u);
+        const uint32_t n0 = (uint32_t)__popc(m0), n = n0 + (uint32_t)__popc(m1);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(p.work_counter + kWorkFlagCursor, n);
+        base = __shfl_sync(kFull, base, 0);
+        if (base + n <= cap) {
+            const unsigned below = (1u << lane) - 1u;
+            if (ts.ov[0] != 0u) p.lean_flags[base + (uint32_t)__popc(m0 & below)] = make_uint4(q, wf + 2u * (uint32_t)lane, ts.ov[0], 0u);
+            if (ts.ov[1] != 0u) p.lean_flags[base + n0 + (uint32_t)__popc(m1 & below)] = make_uint4(q, wf + 2u * (uint32_t)lane + 1u, ts.ov[1], 0u);
+            n_entries += n;
+        } else {
+            dirty = true;
+        }
+        w = wf + kTileWords2;
+    }
+    return n_entries;
+}
+
+__global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_count_kernel(const DevIndex ix, const SearchParams p) {
+    __shared__ __align__(16) uint32_t s_rows[kBitmapWarps][kRowSlots];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    uint32_t *row = s_rows[warp];
+    const uint32_t zero_row = ix.n_terms * ix.row_words;
+    uint32_t q = 0;
+    if (lane == 0) q = take_query(p.work_counter + kWorkQuery);
+    q = __shfl_sync(kFull, q, 0);
+    while (q < p.n_q) {
+        uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
+        const uint4 h0 = __ldg((const uint4 *)plan_base), h1 = __ldg((const uint4 *)plan_base + 1);  // TokenPlan
+        const uint32_t t0 = __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + lane);
+        uint32_t q_next = 0;
+        if (lane == 0) q_next = take_query(p.work_counter + kWorkQuery);
+        const bool unsupported = (h0.x & 1u) != 0u;
+        const int size_a = (int)h0.y, n_lists = (int)h0.z;
+        const WordRange win{h1.x, h1.y};
+        uint32_t n_entries = 0;
+        bool dirty = false;
+        if (n_lists > 0 && win.y > win.x) {
+            const int n_pad = (n_lists + 7) & ~7;
+            for (int j = lane; j < n_pad; j += 32) {
+                uint32_t r = zero_row;
+                if (j < n_lists) r = (j < 32 ? t0 : __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + j)) * ix.row_words;
+                row[j] = r;
+            }
+            __syncwarp();
+            const uint8_t *word_thr = p.wt.word_thr + (size_t)size_a * ix.row_words;
+            if (n_lists < 32) n_entries = count_and_flag<5>(ix, p, row, word_thr, win.x, win.y, n_lists, q, lane, dirty);
+            else n_entries = count_and_flag<8>(ix, p, row, word_thr, win.x, win.y, n_lists, q, lane, dirty);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            p.lean_head[q] = kNilNode;
+            p.lean_pending[q] = n_entries;
+            ((uint32_t *)plan_base)[6] = n_entries;  // TokenPlan::n_flagged
+            if (dirty) {
+                atomicOr((uint32_t *)plan_base, kPlanDirty);
+                p.work_counter[kWorkDirtyAny] = 1u;
+            }
+        }
+        if (n_entries == 0u && !dirty) {  // nothing reached its threshold: the answer is the empty row
+            if (!p.sparse_rows) {
+                const size_t r0 = (size_t)q * p.k;
+                for (uint32_t j = lane; j < p.k; j += 32) { p.out_ids[r0 + j] = 0u; p.out_scores[r0 + j] = 0.0; }
+            }
+            if (lane == 0) {
+                p.out_counts[q] = unsupported ? kCountUnsupported : 0u;
+                if (unsupported && p.too_long_flag != nullptr) *p.too_long_flag = 1u;
+            }
+        }
+        __syncwarp();
+        q = __shfl_sync(kFull, q_next, 0);
+    }
+}
+
+// ---- sg_resolve_kernel: one THREAD per flagged bitmap word ----
+// A flagged bucket is counted exactly by bit-sliced addition again, now over the documents of the bucket: the bits of a
+// (term, bucket) pair (DevIndex::fine, found through rank4 + popcounts: one 16-byte and one 4-byte load, then the pair's
+// bits) are added into 8 bit planes that start at 2^8 - T, so a document with overlap >= T is the carry out of the top
+// plane and its overlap is the planes' value + T.  128 documents at a time (four words per plane).  All of it is private to
+// the thread: no shared memory, no inter-lane traffic, ~70 warp instructions per flagged word instead of ~600 with a warp
+// per word, and the independent loads of 32 flagged words are in flight per warp.
+// Survivors: a query whose only flagged word (TokenPlan::n_flagged == 1, the usual case) holds one survivor is written
+// straight to its row.  Otherwise survivors are linked to the query ({slot, overlap | segment << 16, next, taken}), every
+// flagged word of the query "arrives" (atomicSub on lean_pending), and the thread that arrives last selects: pass 0
+// scores every survivor, then the best remaining one is taken k times ((score desc, id asc), Candidate.Less,
+// pkg/suggest/collector.go:20-26).  The list lives in L2 (.cg accesses): other SMs wrote it.
+__device__ __forceinline__ bool plan_is_dirty(const uint8_t *plan_base) { return (*(const volatile uint32_t *)plan_base & kPlanDirty) != 0u; }
+
+__device__ __forceinline__ void mark_dirty(const SearchParams &p, uint32_t q) {
+    atomicOr((uint32_t *)(p.plans + (size_t)q * kTokStride), kPlanDirty);
+    p.work_counter[kWorkDirtyAny] = 1u;
+}
+
+__device__ __forceinline__ void link_survivor(const SearchParams &p, uint32_t q, uint32_t slot, int count, int size_b) {
+    const uint32_t idx = atomicAdd(p.work_counter + kWorkNodeCursor, 1u);
+    if (idx < p.n_q * kNodesPerQuery) {
+        const uint32_t prev = atomicExch(p.lean_head + q, idx);
+        __stcg(p.lean_nodes + idx, make_uint4(slot, (uint32_t)count | (uint32_t)size_b << 16, prev, 0u));
+    } else {
+        mark_dirty(p, q);  // out of nodes: the fallback kernel answers this query
+    }
+}
+
+__device__ __forceinline__ void write_row_end(const DevIndex &ix, const SearchParams &p, uint32_t q, uint32_t n_out) {
+    if (!p.sparse_rows) {
+        const size_t row = (size_t)q * p.k;
+        for (uint32_t j = n_out; j < p.k; j++) { p.out_ids[row + j] = 0u; p.out_scores[row + j] = 0.0; }
+    }
+    p.out_counts[q] = n_out;  // (a query with too many n-grams has no lists and never gets here)
+}
+
+// every flagged word of query q is resolved and this thread arrived last: select the k best survivors
+__device__ __noinline__ void select_survivors(const DevIndex &ix, const SearchParams &p, uint32_t q, int size_a) {
+    double *node_score = (double *)(p.lean_nodes + (size_t)p.n_q * kNodesPerQuery);
+    for (uint32_t n = __ldcg(p.lean_head + q); n != kNilNode;) {  // pass 0: original id and score of every survivor
+        uint4 node = __ldcg(p.lean_nodes + n);
+        const uint32_t id = __ldg(ix.perm + node.x);
+        __stcg(node_score + n, metric_score(p.metric, (int)(node.y & 0xFFFFu), size_a, (int)(node.y >> 16)));
+        node.x = id;
+        node.w = 0u;
+        __stcg(p.lean_nodes + n, node);
+        n = node.z;
+    }
+    const size_t row = (size_t)q * p.k;
+    uint32_t n_out = 0;
+    for (; n_out < p.k; n_out++) {
+        uint32_t best = kNilNode, best_id = 0;
+        double best_score = 0.0;
+        for (uint32_t n = __ldcg(p.lean_head + q); n != kNilNode;) {
+            const uint4 node = __ldcg(p.lean_nodes + n);
+            if (node.w == 0u) {
+                const double sc = __ldcg(node_score + n);
+                if (best == kNilNode || sc > best_score || (sc == best_score && node.x < best_id)) { best = n; best_score = sc; best_id = node.x; }
+            }
+            n = node.z;
+        }
+        if (best == kNilNode) break;
+        __stcg(&p.lean_nodes[best].w, 1u);
+        p.out_ids[row + n_out] = ix.id_base + best_id;
+        p.out_scores[row + n_out] = best_score;
+    }
+    write_row_end(ix, p, q, n_out);
+}
+
+__global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIndex ix, const SearchParams p) {
+    __shared__ uint32_t s_seg[kSegCache + 1];
+    for (uint32_t i = threadIdx.x; i <= min(ix.n_segments, (uint32_t)kSegCache); i += blockDim.x) s_seg[i] = ix.seg_start[i];
+    __syncthreads();
+    const uint32_t bshift = ix.bshift, W = 1u << bshift;
+    const uint32_t n_entries = min(((const volatile uint32_t *)p.work_counter)[kWorkFlagCursor], p.n_q * kFlagsPerQuery);
+    const uint32_t n_threads = gridDim.x * blockDim.x;
+    const int S = (int)ix.n_segments, cached = min(S, kSegCache);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += n_threads) {
+        const uint4 f = __ldg(p.lean_flags + e);
+        const uint32_t q = f.x, w = f.y;
+        uint32_t mask = f.z;
+        const uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
+        const uint4 h0 = __ldg((const uint4 *)plan_base);  // len(tokens), list count: never change (the flags word may)
+        const uint32_t n_flagged = __ldcg((const uint32_t *)plan_base + 6);  // written by sg_count_kernel
+        const int size_a = (int)h0.y, n_lists = (int)h0.z;
+        if (plan_is_dirty(plan_base)) continue;  // answered by the fallback kernel; nobody waits for this word
+        const uint32_t *terms = (const uint32_t *)(plan_base + kTokTermsOffset);
+        const uint8_t *seg_thr = p.wt.seg_thr + (size_t)size_a * ix.n_segments;
+        const bool sole = n_flagged == 1u;
+        // the first survivor stays in registers: usually it is the only one
+        uint32_t n_surv = 0, s_slot = 0;
+        int s_count = 0, s_b = 0;
+        auto survivor = [&](uint32_t slot, int count, int B) {
+            if (n_surv == 0) { s_slot = slot; s_count = count; s_b = B; }
+            else {
+                if (n_surv == 1) link_survivor(p, q, s_slot, s_count, s_b);
+                link_survivor(p, q, slot, count, B);
+            }
+            n_surv++;
+        };
+        while (mask) {
+            const uint32_t bit = (uint32_t)__ffs(mask) - 1u;
+            mask &= mask - 1u;
+            const uint32_t bucket = w * 32u + bit;
+            const uint32_t id_lo = bucket << bshift;
+            int B;
+            {   // segment that owns the bucket: seg_start[B] <= id_lo < seg_start[B + 1]
+                int lo = 0, hi = S - 1;
+                if (s_seg[cached] > id_lo) {
+                    hi = cached - 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_seg[mid + 1] <= id_lo) lo = mid + 1; else hi = mid; }
+                } else {
+                    lo = cached;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(ix.seg_start + mid + 1) <= id_lo) lo = mid + 1; else hi = mid; }
+                }
+                B = lo;
+            }
+            const int T = (int)__ldg(seg_thr + B);
+            if (T == 0) continue;  // the word's threshold came from a neighbouring segment
+            if (bshift == 0u) {   // one bit per document: the overlap is the number of lists with the bit
+                int count = 0;
+                for (int j = 0; j < n_lists; j++) count += (int)((__ldg(ix.bitmaps + (size_t)__ldg(terms + j) * ix.row_words + w) >> bit) & 1u);
+                if (count >= T) survivor(bucket, count, B);
+                continue;
+            }
+            const uint32_t chunk_bits = W < 128u ? W : 128u;      // documents counted per pass
+            const uint32_t chunk_words = chunk_bits < 32u ? 1u : chunk_bits >> 5;
+            for (uint32_t c0 = 0; c0 < W; c0 += 128u) {
+                uint32_t pl[8][4], ov[4];
+                const uint32_t bias = 256u - (uint32_t)T;
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    ov[x] = 0u;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) pl[j][x] = 0u - ((bias >> j) & 1u);
+                }
+                for (int j0 = 0; j0 < n_lists; j0 += 4) {
+                    uint4 grp[4];
+                    uint32_t rk[4], in[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        grp[u] = make_uint4(0u, 0u, 0u, 0u);
+                        rk[u] = 0u;
+                        in[u] = 0u;
+                        if (j0 + u < n_lists) {
+                            const size_t at = (size_t)__ldg(terms + j0 + u) * ix.row_words + w;
+                            grp[u] = __ldg((const uint4 *)(ix.bitmaps + (at & ~(size_t)3)));
+                            rk[u] = __ldg(ix.rank4 + (at >> 2));
+                            in[u] = (uint32_t)(at & 3);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t rw = in[u] == 0 ? grp[u].x : in[u] == 1 ? grp[u].y : in[u] == 2 ? grp[u].z : grp[u].w;
+                        if (!((rw >> bit) & 1u)) continue;
+                        uint32_t pair = rk[u] + (uint32_t)__popc(rw & ((1u << bit) - 1u));
+                        if (in[u] > 0) pair += (uint32_t)__popc(grp[u].x);
+                        if (in[u] > 1) pair += (uint32_t)__popc(grp[u].y);
+                        if (in[u] > 2) pair += (uint32_t)__popc(grp[u].z);
+                        const uint64_t bitpos = ((uint64_t)pair << bshift) + c0;
+                        uint32_t m[4] = {0u, 0u, 0u, 0u};
+                        if (chunk_bits == 128u) {
+                            const uint4 v = __ldg((const uint4 *)(ix.fine + (bitpos >> 5)));
+                            m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+                        } else if (chunk_bits == 64u) {
+                            const uint2 v = __ldg((const uint2 *)(ix.fine + (bitpos >> 5)));
+                            m[0] = v.x; m[1] = v.y;
+                        } else if (chunk_bits == 32u) {
+                            m[0] = __ldg(ix.fine + (bitpos >> 5));
+                        } else {
+                            m[0] = (__ldg(ix.fine + (bitpos >> 5)) >> (uint32_t)(bitpos & 31u)) & ((1u << chunk_bits) - 1u);
+                        }
+#pragma unroll
+                        for (int x = 0; x < 4; x++) {
+                            if ((uint32_t)x >= chunk_words) break;
+                            uint32_t carry = m[x];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const uint32_t t = pl[j][x] & carry;
+                                pl[j][x] ^= carry;
+                                carry = t;
+                            }
+                            ov[x] |= carry;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    uint32_t o = ov[x];
+                    while (o) {
+                        const uint32_t b = (uint32_t)__ffs(o) - 1u;
+                        o &= o - 1u;
+                        int count = T;  // the planes hold bias + overlap - 256 = overlap - T
+#pragma unroll
+                        for (int j = 0; j < 8; j++) count += (int)((pl[j][x] >> b) & 1u) << j;
+                        survivor(id_lo + c0 + 32u * (uint32_t)x + b, count, B);
+                    }
+                }
+            }
+        }
+        if (sole && n_surv <= 1u) {  // the whole answer of the query is known here: no list, no atomics
+            if (n_surv == 1u) {
+                const size_t row = (size_t)q * p.k;
+                p.out_ids[row] = ix.id_base + __ldg(ix.perm + s_slot);
+                p.out_scores[row] = metric_score(p.metric, s_count, size_a, s_b);
+            }
+            write_row_end(ix, p, q, n_surv);
+            continue;
+        }
+        if (n_surv == 1u) link_survivor(p, q, s_slot, s_count, s_b);
+        bool last = sole;
+        if (!sole) {
+            __threadfence();  // this thread's nodes are visible before its arrival is
+            last = atomicSub(p.lean_pending + q, 1u) == 1u;
+            if (last) __threadfence();
+        }
+        if (last && !plan_is_dirty(plan_base)) select_survivors(ix, p, q, size_a);
+    }
+}
+
 // ---------------- launcher (host) ----------------
 size_t bitmap_warp_smem(uint32_t k) { return ((size_t)kBitmapWarpFixedSmem + (size_t)k * 12u + 15u) & ~(size_t)15u; }
 
-// The dynamic shared-memory opt-in is a per-device attribute of the kernel, shared by every index and host thread of
-// the process: only ever raise it.  CTAs per SM are cached per (device, k).
-cudaError_t bitmap_search_occupancy(int device, uint32_t k, int *blocks_per_sm) {
+// The dynamic shared-memory opt-in is a per-device attribute of a kernel, shared by every index and host thread of
+// the process: only ever raise it.  CTAs per SM are cached per (kernel, device, k).
+static cudaError_t kernel_occupancy(const void *func, int which, int device, uint32_t k, size_t smem, int *blocks_per_sm) {
     static std::mutex mu;
-    static size_t opted_in[64] = {0};
-    static std::map<std::pair<int, uint32_t>, int> cache;
+    static size_t opted_in[3][64] = {{0}};
+    static std::map<std::pair<int, std::pair<int, uint32_t>>, int> cache;
     std::lock_guard<std::mutex> lock(mu);
-    const size_t smem = (size_t)kBitmapWarps * bitmap_warp_smem(k);
     if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
-    if (smem > opted_in[device]) {
-        cudaError_t e = cudaFuncSetAttribute(sg_bitmap_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > opted_in[which][device]) {
+        cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        opted_in[device] = smem;
+        opted_in[which][device] = smem;
     }
-    auto it = cache.find({device, k});
+    auto it = cache.find({which, {device, k}});
     if (it == cache.end()) {
         int per_sm = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sg_bitmap_search_kernel, kBitmapWarps * 32, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, func, kBitmapWarps * 32, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
-        it = cache.emplace(std::make_pair(device, k), per_sm).first;
+        it = cache.emplace(std::make_pair(which, std::make_pair(device, k)), per_sm).first;
     }
     *blocks_per_sm = it->second;
+    return cudaSuccess;
+}
+
+cudaError_t bitmap_search_occupancy(int device, uint32_t k, int *blocks_per_sm) {
+    return kernel_occupancy((const void *)sg_bitmap_search_kernel, 0, device, k, (size_t)kBitmapWarps * bitmap_warp_smem(k), blocks_per_sm);
+}
+
+cudaError_t lean_occupancy(int device, uint32_t k, int *count_per_sm, int *resolve_per_sm) {
+    (void)k;
+    cudaError_t e = kernel_occupancy((const void *)sg_count_kernel, 1, device, 0, 0, count_per_sm);
+    if (e != cudaSuccess) return e;
+    *resolve_per_sm = 8;  // CTAs of kResolveThreads per SM the grid is sized for (the kernel strides over the flagged words)
     return cudaSuccess;
 }
 
@@ -713,6 +1154,44 @@ cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int 
     if (p.cand_total != nullptr) sg_bitmap_collect_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, p);  // k = 1: under 48 KB, no opt-in
     else sg_bitmap_search_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, p);
     if (stage_events) cudaEventRecord(stage_events[3], stream);
+    return cudaGetLastError();
+}
+
+// sg_window_kernel (optional) + sg_tokens_kernel + sg_count_kernel + sg_resolve_kernel + sg_bitmap_search_kernel (only_dirty);
+// stage_events: 6 events around the five kernels
+cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm_count, int count_per_sm, int resolve_per_sm,
+                               int search_per_sm, bool run_window, cudaStream_t stream, cudaEvent_t *stage_events) {
+    const size_t smem = (size_t)kBitmapWarps * p.warp_smem;
+    cudaError_t e;
+    if (stage_events) cudaEventRecord(stage_events[0], stream);
+    if (run_window) {
+        e = launch_window(ix, p, stream);
+        if (e != cudaSuccess) return e;
+    }
+    if (stage_events) cudaEventRecord(stage_events[1], stream);
+    const int tok_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
+    sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (stage_events) cudaEventRecord(stage_events[2], stream);
+    const int need = (int)((p.n_q + kBitmapWarps - 1) / kBitmapWarps);
+    int blocks = sm_count * count_per_sm;
+    if (blocks > need) blocks = need;
+    sg_count_kernel<<<blocks, kBitmapWarps * 32, 0, stream>>>(ix, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (stage_events) cudaEventRecord(stage_events[3], stream);
+    blocks = sm_count * resolve_per_sm;
+    sg_resolve_kernel<<<blocks, kResolveThreads, 0, stream>>>(ix, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (stage_events) cudaEventRecord(stage_events[4], stream);
+    SearchParams pf = p;
+    pf.only_dirty = 1;
+    blocks = sm_count * search_per_sm;
+    if (blocks > need) blocks = need;
+    sg_bitmap_search_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, pf);
+    if (stage_events) cudaEventRecord(stage_events[5], stream);
     return cudaGetLastError();
 }
 

@@ -73,6 +73,14 @@ struct DevIndex {
     uint32_t bshift;         // log2(new ids per bucket), 0..kMaxBucketShift
     uint32_t row_words;      // 0: the index has no bitmaps (over the memory budget) and is searched by sg_search_kernel
     const uint32_t *bitmaps; // (n_terms + 1) * row_words
+    // ---- exact level under the bucket bitmaps (sg_fine.cu), read by sg_resolve_kernel ----
+    // Every set bit of the bitmaps is a (term, bucket) pair; pairs are numbered in (term, bucket) order.  rank4[g] = number
+    // of pairs before the g-th group of four bitmap words (groups never straddle rows: row_words is a multiple of 64), and
+    // fine holds, for pair p, one bit per document of the bucket (2^bshift bits at bit offset p << bshift): set iff the
+    // term has that document.  A flagged bucket is therefore resolved with one 16-byte load (the group) and one load of
+    // the pair's bits per list, without touching the posting lists.  nullptr: not built (bshift = 0 needs neither).
+    const uint32_t *rank4;
+    const uint32_t *fine;
 };
 
 // One per query, written by sg_plan_kernel and read by sg_search_kernel: kPlanStride bytes =
@@ -92,15 +100,27 @@ constexpr uint32_t kPlanStride = kPlanRunsOffset + kMaxQueryTokens * 8;
 // Bitmap engine: one per query, written by sg_tokens_kernel and read by sg_bitmap_search_kernel:
 // kTokStride bytes = [TokenPlan (32) | term id of every list to open (128 x 4)]
 struct TokenPlan {
-    uint32_t flags;      // 1: more than 128 n-grams (SG_ERR_QUERY_TOO_LONG)
+    uint32_t flags;      // bit 0: more than 128 n-grams (SG_ERR_QUERY_TOO_LONG); bit 1 (kPlanDirty): the count / resolve
+                         // pipeline ran out of scratch for this query, sg_bitmap_search_kernel answers it instead
     int32_t size_a;      // len(tokens), suggester.go:53
     int32_t n_lists;     // tokens that are terms of the index, with multiplicity
     int32_t reserved;
     uint32_t win_lo, win_hi;  // WindowTables::win[size_a], copied so that the search kernel has it with the header
-    uint32_t reserved2[2];
+    uint32_t n_flagged;       // count -> resolve pipeline: bitmap words of the query with a bucket at its threshold (sg_count_kernel)
+    uint32_t reserved2;
 };
 constexpr uint32_t kTokTermsOffset = 32;
 constexpr uint32_t kTokStride = kTokTermsOffset + kMaxQueryTokens * 4;
+constexpr uint32_t kPlanDirty = 2u;
+
+// ---- count -> resolve pipeline (sg_count_kernel, sg_resolve_kernel): scratch of one launch, sized per query ----
+// flagged bitmap words {query, word, buckets that reached their threshold, 0}: sg_count_kernel -> sg_resolve_kernel
+// survivors {slot, overlap | segment << 16, next node of the query, taken}, a linked list per query, + a score per node
+constexpr uint32_t kFlagsPerQuery = 32, kNodesPerQuery = 8;
+constexpr uint32_t kLeanScratchPerQuery = kFlagsPerQuery * 16 + kNodesPerQuery * (16 + 8) + 8;  // + pending[q], head[q]
+constexpr uint32_t kNilNode = 0xFFFFFFFFu;
+// counters of one launch, zeroed by sg_tokens_kernel: SearchParams::work_counter points at kWorkWords of them
+enum { kWorkQuery = 0, kWorkFallbackQuery = 1, kWorkFlagCursor = 2, kWorkNodeCursor = 3, kWorkDirtyAny = 4, kWorkWords = 8 };
 
 // Per call (metric, similarity, mode are per call): everything that depends on the query only through len(tokens).
 // Row a = len(tokens) in 0..kMaxQueryTokens.
@@ -145,7 +165,7 @@ struct SearchParams {
     double *out_scores;
     uint32_t *out_counts;
     uint32_t *stats;          // optional, 16-byte aligned: {admissible postings, admissible lists, 32-bit words the engine reads for the count, 0} per query
-    uint32_t *work_counter;   // zeroed before launch
+    uint32_t *work_counter;   // kWorkWords counters of the launch (bitmap engine: zeroed by sg_tokens_kernel; scan-count engine: word 0, zeroed before launch)
     uint8_t *plans;           // n_q * kPlanStride bytes of scratch
     uint32_t tbl_bytes;       // per-warp count table size (power of two)
     uint32_t warp_smem;       // bytes of shared memory owned by one warp
@@ -155,6 +175,12 @@ struct SearchParams {
     const LmContext *lm_ctx;  // mode 1 only, optional: rank the completions by the language model (spellchecker collector)
     uint32_t *too_long_flag;  // optional: set to 1 if any query of the launch is reported as SG_COUNT_UNSUPPORTED
     int32_t sparse_rows;      // 1: write only the out_counts[q] valid entries of a row (rows in page-locked host memory)
+    // ---- count -> resolve pipeline (bitmap engine, Suggest top-k) ----
+    uint4 *lean_flags;        // n_q * kFlagsPerQuery entries; nullptr: the launch runs sg_bitmap_search_kernel only
+    uint4 *lean_nodes;        // n_q * kNodesPerQuery entries
+    uint32_t *lean_pending;   // [n_q] flagged words of the query not yet resolved
+    uint32_t *lean_head;      // [n_q] first survivor node of the query, kNilNode: none
+    int32_t only_dirty;       // sg_bitmap_search_kernel: answer only the queries marked kPlanDirty (and exit at once if none is)
     // ---- sg_candidates_batch (bitmap engine): every candidate of the T-occurrence count instead of a top-k ----
     const uint8_t *custom_thr;        // optional [129][S]: Threshold(alpha, a, B) tabulated by the caller for a metric.Metric that
                                       // is not built in (0 outside [MinY, MaxY]); replaces metric / alpha in sg_window_kernel

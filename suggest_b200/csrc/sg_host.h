@@ -89,6 +89,11 @@ struct GpuBuilt {
 std::string gpu_build(const DevIndex &text, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs, int want_bshift,
                       uint64_t bitmap_budget, GpuBuilt *out, std::vector<void *> *allocs);
 
+// sg_fine.cu: adds the exact level under the bucket bitmaps (DevIndex::rank4 / fine) to an index already in HBM.
+// "" = built or not needed; "skip: ..." = over the budget (the index works without it); else a CUDA error text.
+std::string build_fine_level(DevIndex *ix, uint64_t n_postings, uint64_t budget_bytes, std::vector<void *> *allocs,
+                             uint64_t *device_bytes);
+
 // suggest.Index (pkg/suggest/indexer.go:14-45) + index.Writer.AddDocument (pkg/index/indexer_writer.go:66-86)
 std::string build_from_docs(HostIndex *ix, const char *doc_bytes, const uint64_t *doc_off, uint32_t n_docs);
 // already decoded (segment, term) lists, original ids ascending (duplicates inside a list are dropped)

@@ -140,7 +140,7 @@ int sg_host_index_get_layout(const sg_host_index *hi, sg_index_layout *layout) {
     layout->row_words = hi->h.row_words;
     layout->engine = hi->h.row_words != 0;
     layout->built_on_device = 0;
-    layout->reserved = 0;
+    layout->pipeline = 0;
     layout->bitmap_bytes = (uint64_t)hi->h.bitmaps.size() * sizeof(uint32_t);
     return SG_OK;
 }

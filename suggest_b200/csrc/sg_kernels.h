@@ -16,6 +16,11 @@ cudaError_t bitmap_search_occupancy(int device, uint32_t k, int *blocks_per_sm);
 cudaError_t launch_window(const DevIndex &ix, const SearchParams &p, cudaStream_t stream);  // sg_window_kernel alone (fills p.wt)
 cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, int blocks_per_sm, bool run_window,
                                  cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
+// count -> resolve pipeline (sg_count_kernel, sg_resolve_kernel, then sg_bitmap_search_kernel for the queries that ran out of
+// scratch); p.lean_* set; stage_events (optional): 6 events around the five kernels
+cudaError_t lean_occupancy(int device, uint32_t k, int *count_per_sm, int *resolve_per_sm);
+cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm_count, int count_per_sm, int resolve_per_sm,
+                               int search_per_sm, bool run_window, cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
                               const uint32_t *part_counts, size_t stride_ids, size_t stride_scores, size_t stride_counts,
                               uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream,

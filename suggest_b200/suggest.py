@@ -316,11 +316,52 @@ class NGramIndex:
 
     def StageTimes(self, d_q_bytes, d_q_off, n_q, similarity, metric, topK, d_ids, d_scores, d_counts, stream=0):
         """sg_search_stage_times: {kernel name: ms} of one device-resident launch (CUDA events between its kernels)."""
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 8)()
         names = C.create_string_buffer(256)
         n = _capi.check(_capi.lib().sg_search_stage_times(self.handle, d_q_bytes, d_q_off, n_q, metric.code, float(similarity),
                                                           int(topK), d_ids, d_scores, d_counts, stream or None, ms, names, 256))
         return dict(zip(names.value.decode().split(","), [float(ms[i]) for i in range(n)]))
+
+
+class Batcher:
+    """sg_batcher_*: the micro-batcher in front of sg_search_batch for callers that issue ONE query per thread, as the
+    reference's do (internal/suggest/api/suggest_handler.go:42-76: one goroutine per HTTP request).  Suggest blocks the
+    calling thread; any number of threads may call it concurrently (ctypes releases the GIL for the duration)."""
+
+    def __init__(self, index, max_batch=16384, max_wait_us=100, max_k=256):
+        self._index = index  # keeps the index alive: it must outlive the batcher
+        self._h = C.c_void_p()
+        _capi.check(_capi.lib().sg_batcher_create(index.handle, int(max_batch), int(max_wait_us), int(max_k), C.byref(self._h)))
+        self.max_k = int(max_k)
+
+    def Suggest(self, query, similarity, metric, topK) -> List[Candidate]:
+        q = _b(query)
+        k = int(topK)
+        ids = (C.c_uint32 * max(k, 1))()
+        scores = (C.c_double * max(k, 1))()
+        count = C.c_uint32(0)
+        _capi.check(_capi.lib().sg_suggest_one(self._h, q, len(q), metric.code, float(similarity), k, ids, scores, C.byref(count)))
+        return [Candidate(int(ids[i]), float(scores[i])) for i in range(count.value)]
+
+    def stats(self):
+        st = _capi.SgBatcherStats()
+        _capi.check(_capi.lib().sg_batcher_get_stats(self._h, C.byref(st)))
+        return {name: getattr(st, name) for name, _ in st._fields_ if name != "reserved"}
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            _capi.lib().sg_batcher_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def NewBatcher(index, max_batch=16384, max_wait_us=100, max_k=256):
+    return Batcher(index, max_batch, max_wait_us, max_k)
 
 
 def _replay(manager, metric, similarity, sizeA, n_segments, by_segment):
