@@ -456,6 +456,41 @@ def measure_config3(rig, args, S, d_bytes, d_off):
             "note": "3 steps x 4 batches of 65,536 queries per point, same dictionary (n-gram size and metric vary), plus Zipf letters"}
 
 
+def measure_single_query(d_bytes, d_off, q_bytes, q_off):
+    """The reference's calling pattern: ONE query per caller thread (internal/suggest/api/suggest_handler.go:56), through
+    the micro-batcher sg_suggest_one.  tools/batcher_load.cpp (C++ threads: Python threads would measure the GIL) builds
+    its own index of the same dictionary in a separate process."""
+    import struct
+    import tempfile
+    tool = os.path.join(ROOT, "tools", "batcher_load")
+    if not os.path.exists(tool):
+        try:
+            subprocess.check_call(["g++", "-O2", "-std=c++17", tool + ".cpp", "-I" + os.path.join(ROOT, "include"), "-L" + os.path.join(ROOT, "suggest_b200"),
+                                   "-lsuggest_b200", "-Wl,-rpath," + os.path.join(ROOT, "suggest_b200"), "-lpthread", "-o", tool])
+        except Exception as e:  # noqa: BLE001
+            return {"unavailable": f"tools/batcher_load could not be built: {e}"}
+    with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as f:
+        n_docs, n_q = len(d_off) - 1, len(q_off) - 1
+        f.write(struct.pack("<I", n_docs))
+        f.write(np.ascontiguousarray(d_off, dtype=np.uint64).tobytes())
+        f.write(np.ascontiguousarray(d_bytes, dtype=np.uint8).tobytes())
+        f.write(struct.pack("<I", n_q))
+        f.write(np.ascontiguousarray(q_off, dtype=np.uint32).tobytes())
+        f.write(np.ascontiguousarray(q_bytes, dtype=np.uint8).tobytes())
+        path = f.name
+    out = {"how": "tools/batcher_load.cpp: T threads x sg_suggest_one (k=10, Jaccard 0.5), max_batch 16384; latency per call on the caller's clock"}
+    try:
+        for name, threads, calls, wait_us in (("one_caller", 1, 2000, 0), ("callers_64", 64, 4000, 100), ("callers_512", 512, 2000, 100)):
+            r = subprocess.run([tool, path, str(threads), str(calls), "16384", str(wait_us)], capture_output=True, text=True, timeout=300)
+            if r.returncode != 0:
+                out[name] = {"error": (r.stderr or "")[-300:]}
+                continue
+            out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    finally:
+        os.unlink(path)
+    return out
+
+
 def oracle_sharded_sample(d_bytes, d_off, q_bytes, q_off, n_sample, parts=10):
     """oracle over a large dictionary, affordable: `parts` oracle indexes over record-id ranges built in parallel threads
     (the C oracle releases the GIL), searched with the sample, rows merged under (score desc, id asc) - the reduction
@@ -645,8 +680,13 @@ def main():
         rig.barrier()
 
     config3 = None
+    single_query = None
     if world == 1 and headline and not args.no_config3:
         config3 = measure_config3(rig, args, S, d_bytes, d_off)
+        try:
+            single_query = measure_single_query(d_bytes, d_off, B.raw[0][0], B.raw[0][1])
+        except Exception as e:  # noqa: BLE001
+            single_query = {"error": str(e)[:300]}
     config4 = None
     if headline and not args.no_config4:
         index.close()
@@ -715,6 +755,8 @@ def main():
     if config3:
         line["config3"] = config3
         line["config3_min_qps"] = config3["min_qps_e2e"]
+    if single_query:
+        line["single_query"] = single_query
     if config4:
         line["config4"] = config4
     print(json.dumps(line), file=out_stream, flush=True)

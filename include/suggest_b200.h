@@ -36,7 +36,8 @@ typedef enum {
     SG_ERR_UNSUPPORTED = -2,  /* description outside what the device tokenizer encodes (see sg_index_build) */
     SG_ERR_CUDA = -3,         /* CUDA runtime failure, message holds cudaGetErrorString */
     SG_ERR_NOMEM = -4,
-    SG_ERR_QUERY_TOO_LONG = -5, /* some query has more than SG_MAX_QUERY_TOKENS n-grams; its count is SG_COUNT_UNSUPPORTED */
+    SG_ERR_QUERY_TOO_LONG = -5, /* device-buffer entry points: some query has more than SG_MAX_QUERY_TOKENS n-grams, its count is
+                                   SG_COUNT_UNSUPPORTED.  Host-buffer entry points answer such queries (up to 65535 n-grams, topK <= 1024) */
     SG_ERR_IO = -6,
     SG_ERR_FORMAT = -7        /* on-disk index is not "v5.1" or is corrupt */
 } sg_status;
@@ -45,8 +46,12 @@ typedef enum {
 typedef enum { SG_JACCARD = 0, SG_COSINE = 1, SG_DICE = 2, SG_OVERLAP = 3, SG_EXACT = 4 } sg_metric;
 
 #define SG_MAX_NGRAM 8               /* pkg/analysis/ngram_tokenizer.go:3 (maxN) */
-#define SG_MAX_QUERY_TOKENS 128      /* per query; the reference saturates at 0xFFFF (pkg/merger/list_merger.go:9) */
-#define SG_MAX_TOPK 1024
+#define SG_MAX_QUERY_TOKENS 128      /* n-grams per query the batched kernels take; longer queries (the reference saturates at 0xFFFF,
+                                        pkg/merger/list_merger.go:9) are answered by sg_search_batch / sg_autocomplete_batch / sg_suggest_one
+                                        on a slower path of their own (host tokenization + sg_long_query_kernel) */
+#define SG_MAX_TOPK 16384            /* sg_search_batch / _device; above 1024 the per-warp top-k lives in HBM instead of shared memory.
+                                        The shard merges, sg_candidates' replay aside, the batcher and sg_predict_batch take k <= SG_MAX_TOPK_SHARED */
+#define SG_MAX_TOPK_SHARED 1024
 #define SG_COUNT_UNSUPPORTED 0xFFFFFFFFu
 
 /* suggest.IndexDescription, pkg/suggest/config.go:25-35 (tokenizer-relevant fields) */

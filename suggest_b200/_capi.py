@@ -13,7 +13,8 @@ SG_ERR_INVALID, SG_ERR_UNSUPPORTED, SG_ERR_CUDA, SG_ERR_NOMEM, SG_ERR_QUERY_TOO_
     -1, -2, -3, -4, -5, -6, -7
 SG_JACCARD, SG_COSINE, SG_DICE, SG_OVERLAP, SG_EXACT = range(5)
 SG_MAX_QUERY_TOKENS = 128
-SG_MAX_TOPK = 1024
+SG_MAX_TOPK = 16384
+SG_MAX_TOPK_SHARED = 1024
 SG_EXCHANGE_HANDLE_BYTES = 64
 SG_COUNT_UNSUPPORTED = 0xFFFFFFFF
 

@@ -26,6 +26,7 @@ thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
 constexpr uint32_t kWorkRing = 1024;
 constexpr uint32_t kMaxSlices = 16;        // sg_search_batch pipelines a batch in at most this many slices
+constexpr uint32_t kMaxChunks = 16;        // ... or, with page-locked rows, lets the queries arrive in at most this many chunks under one launch
 constexpr int kMaxWarps = sg::kMaxSearchThreads / 32;
 constexpr int kDefaultTblBytes = 8192;     // 16 warps per SM at k = 10; one pass covers 1M documents at 128 per bucket
 
@@ -84,7 +85,10 @@ struct CallCtx {
     cudaStream_t stream2 = nullptr;  // one slice overlap the kernel of the other
     cudaStream_t copy_stream = nullptr;  // every H2D copy of a call: a slice's queries never queue behind another slice's kernels
     cudaEvent_t h2d_done[kMaxSlices] = {};
-    uint32_t *too_long = nullptr;        // page-locked word the search kernel sets if a query has too many n-grams (direct result path)
+    uint32_t *too_long = nullptr;        // page-locked words: [0] set by the search kernel if a query has too many n-grams (direct result
+                                         // path); [8 .. 8 + kMaxChunks) the arrival counter values copied behind every chunk of queries
+    DevBuf<uint32_t> arrived;            // the arrival counter in HBM (SearchParams::arrived); only ever grows
+    uint32_t arrive_epoch = 0;
     DevBuf<char> q_bytes;
     DevBuf<uint32_t> q_off, ids, counts, work;
     DevBuf<uint8_t> plans;   // per-query plans, sg_plan_kernel -> sg_search_kernel or sg_tokens_kernel -> sg_bitmap_search_kernel
@@ -338,7 +342,7 @@ void destroy(sg_index *ix) {
     DeviceGuard guard;
     guard.set(ix->device);
     for (CallCtx *c : ix->pool) {
-        c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release(); c->wtab.release(); c->cand.release(); c->cand_total.release();
+        c->arrived.release(); c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release(); c->wtab.release(); c->cand.release(); c->cand_total.release();
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -384,6 +388,12 @@ int make_index(const sg_config *cfg, sg_index **out, sg_index **ixp) {
 
 struct Geometry { int blocks, warps; size_t smem; uint32_t warp_smem; };
 
+// sg_search_batch, page-locked rows: the queries arrive in chunks while the kernels run (SearchParams::arrived)
+struct ArriveArgs {
+    const uint32_t *d_arrived;
+    uint32_t base, chunk_queries;
+};
+
 // sg_candidates_batch: device side of SearchParams::cand_* / custom_thr
 struct CollectArgs {
     const uint8_t *d_thr;             // nullptr: thresholds of the built-in metric
@@ -424,7 +434,7 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
                    uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0, cudaEvent_t *stage_events = nullptr,
                    const sg::LmContext *d_lm_ctx = nullptr, int sparse_rows = 0, uint32_t *too_long_flag = nullptr,
-                   const CollectArgs *collect = nullptr) {
+                   const CollectArgs *collect = nullptr, const ArriveArgs *arrive = nullptr) {
     Geometry g{};
     int rc = SG_OK;
     if (!ix->bitmap_engine && (rc = geometry(ix, n_q, k, &g)) != SG_OK) return rc;
@@ -448,6 +458,13 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.lm_ctx = d_lm_ctx;
     p.sparse_rows = sparse_rows;
     p.too_long_flag = too_long_flag;
+    if (arrive) {
+        p.arrived = arrive->d_arrived;
+        p.arrive_base = arrive->base;
+        p.chunk_queries = arrive->chunk_queries;
+    }
+    static const int resolve_debug = env_int("SG_RESOLVE_DEBUG", 0);
+    p.debug = (uint32_t)resolve_debug;
     if (collect) {
         if (!ix->bitmap_engine) return fail(SG_ERR_UNSUPPORTED, "sg_candidates_batch needs an index with bitmaps (engine 1)");
         p.custom_thr = collect->d_thr;
@@ -479,6 +496,20 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
         if ((size_t)p.warp_smem * 8 > ix->smem_optin) return fail(SG_ERR_INVALID, "k too large for the shared-memory top-k");
         int per_sm = 0;
         SG_CUDA(sg::bitmap_search_occupancy(ix->device, k, &per_sm));
+        // k above kSmemTopK: the per-warp sorted top-k lives in HBM, one slice per warp of the launch (stream-ordered scratch,
+        // freed behind the kernels); such calls run sg_bitmap_search_kernel alone
+        void *tk_scratch = nullptr;
+        if (k > sg::kSmemTopK) {
+            int blocks = ix->sm_count * per_sm;
+            const int need = (int)((n_q + 7) / 8);
+            if (blocks > need) blocks = need;
+            SG_CUDA(cudaMallocAsync(&tk_scratch, (size_t)blocks * 8 * (((size_t)k * 12 + 15) & ~(size_t)15), stream));  // 16-byte aligned slices
+            p.tk_global = (uint8_t *)tk_scratch;
+        }
+        struct TkFree {
+            void *p; cudaStream_t st;
+            ~TkFree() { if (p) cudaFreeAsync(p, st); }
+        } tk_free{tk_scratch, stream};
         // window tables: cached per (metric, similarity, mode); a measurement launch (stage_events) always computes them
         bool run_window = true;
         point_tables(d_wtab);
@@ -507,19 +538,22 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
                 run_window = false;
             }
         }
-        if (ix->lean_pipeline && mode == 0 && !collect && !d_lm_ctx) {
+        if (ix->lean_pipeline && mode == 0 && !collect && !d_lm_ctx && k <= sg::kSmemTopK) {
             // scratch of the pipeline behind the plans: [plans n_q x kTokStride | flags | nodes | pending | head]
             uint8_t *at = d_plans + (((size_t)n_q * sg::kTokStride + 15) & ~(size_t)15);
             p.lean_flags = (uint4 *)at;
             at += (size_t)n_q * sg::kFlagsPerQuery * sizeof(uint4);
-            p.lean_nodes = (uint4 *)at;  // (the nodes' scores follow them: sg_bitmap.cu select_survivors)
-            at += (size_t)n_q * sg::kNodesPerQuery * (sizeof(uint4) + sizeof(double));
+            p.lean_nodes = (uint4 *)at;
+            at += (size_t)n_q * sg::kNodesPerQuery * sizeof(uint4);
             p.lean_pending = (uint32_t *)at;
             p.lean_head = p.lean_pending + n_q;
             int count_per_sm = 0, resolve_per_sm = 0;
             SG_CUDA(sg::lean_occupancy(ix->device, k, &count_per_sm, &resolve_per_sm));
-            SG_CUDA(sg::launch_lean_search(ix->dev, p, ix->sm_count, count_per_sm, resolve_per_sm, per_sm, run_window, stream, stage_events));
-            g_launches.fetch_add(run_window ? 5 : 4, std::memory_order_relaxed);  // [window +] tokens + count + resolve + fallback search
+            static const bool want_fused = env_int("SG_FUSED_TOKENS", 1) != 0;
+            const bool fused = want_fused && d_stats == nullptr;  // the stats pass lives in sg_tokens_kernel
+            if (fused) SG_CUDA(cudaMemsetAsync(d_work, 0, sg::kWorkWords * sizeof(uint32_t), stream));
+            SG_CUDA(sg::launch_lean_search(ix->dev, p, ix->sm_count, count_per_sm, resolve_per_sm, per_sm, run_window, fused, stream, stage_events));
+            g_launches.fetch_add((run_window ? 4 : 3) + (fused ? 0 : 1), std::memory_order_relaxed);  // [window +] [tokens +] count + resolve + fallback search
             return SG_OK;
         }
         SG_CUDA(sg::launch_bitmap_search(ix->dev, p, ix->sm_count, per_sm, run_window, stream, stage_events));
@@ -578,7 +612,7 @@ struct CtxLease {
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
         for (cudaEvent_t &ev : ctx->h2d_done)
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->too_long, sizeof(uint32_t), cudaHostAllocMapped);
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&ctx->too_long, 64 * sizeof(uint32_t), cudaHostAllocMapped);
         if (e != cudaSuccess) {
             if (ctx->stream) cudaStreamDestroy(ctx->stream);
             if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -758,6 +792,177 @@ void sg_pinned_free(void *p) {
 
 int sg_is_pinned(const void *p, uint64_t bytes) { return mapped_host_range(p, (size_t)bytes) != nullptr ? 1 : 0; }
 
+// Queries the batched kernels refused (more than 128 n-grams: count SG_COUNT_UNSUPPORTED) are answered here, after the
+// batch: host tokenization (the index build's chain, sg_text.cpp), one warp per query on the device (sg_long.cu).  The
+// reference has no such limit (pkg/merger/list_merger.go:9 saturates overlaps at 0xFFFF).  Synchronous, rare.
+static int answer_long_queries(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha, uint32_t k,
+                               uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int mode) {
+    std::vector<uint32_t> which;
+    for (uint32_t q = 0; q < n_q; q++)
+        if (out_counts[q] == SG_COUNT_UNSUPPORTED) which.push_back(q);
+    if (which.empty()) return SG_OK;
+    if (k > sg::kSmemTopK) return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(which[0]) + " has more than 128 n-grams (not served with topK above 1024)");
+    sg::TextConfig text = ix->host.text;
+    if (mode == 1) text.wrap_end.clear();  // NewAutocompleteTokenizer: no tail wrap (pkg/suggest/tokenizer.go:23-34)
+    std::vector<uint64_t> keys, all_keys;
+    std::vector<uint32_t> key_off{0u};
+    sg::TokenScratch scratch;
+    for (uint32_t q : which) {
+        sg::tokenize_keys(text, (const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &keys, &scratch);
+        if (keys.size() > 0xFFFFu) return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 65535 n-grams");
+        all_keys.insert(all_keys.end(), keys.begin(), keys.end());
+        key_off.push_back((uint32_t)all_keys.size());
+    }
+    const uint32_t n_long = (uint32_t)which.size();
+    const int blocks = n_long < 4 ? (int)n_long : 4;
+    struct Dev {
+        std::vector<void *> ptrs;
+        cudaError_t get(void **p, size_t bytes) {
+            cudaError_t e = cudaMalloc(p, bytes ? bytes : 4);
+            if (e == cudaSuccess) ptrs.push_back(*p);
+            return e;
+        }
+        ~Dev() { for (void *p : ptrs) cudaFree(p); }
+    } dev;
+    sg::LongParams lp{};
+    uint64_t *d_keys = nullptr;
+    uint32_t *d_off = nullptr;
+    SG_CUDA(dev.get((void **)&d_keys, all_keys.size() * 8));
+    SG_CUDA(dev.get((void **)&d_off, key_off.size() * 4));
+    SG_CUDA(dev.get((void **)&lp.terms, all_keys.size() * 4));
+    SG_CUDA(dev.get((void **)&lp.counters, (size_t)blocks * ix->dev.n_ids * 4));
+    SG_CUDA(dev.get((void **)&lp.out_ids, (size_t)n_long * k * 4));
+    SG_CUDA(dev.get((void **)&lp.out_scores, (size_t)n_long * k * 8));
+    SG_CUDA(dev.get((void **)&lp.out_counts, (size_t)n_long * 4));
+    if (!all_keys.empty()) SG_CUDA(cudaMemcpy(d_keys, all_keys.data(), all_keys.size() * 8, cudaMemcpyHostToDevice));
+    SG_CUDA(cudaMemcpy(d_off, key_off.data(), key_off.size() * 4, cudaMemcpyHostToDevice));
+    lp.keys = d_keys;
+    lp.key_off = d_off;
+    lp.n_long = n_long;
+    lp.metric = metric;
+    lp.mode = mode;
+    lp.alpha = alpha;
+    lp.k = k;
+    SG_CUDA(sg::launch_long_queries(ix->dev, lp, blocks, nullptr));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    std::vector<uint32_t> ids((size_t)n_long * k), counts(n_long);
+    std::vector<double> scores((size_t)n_long * k);
+    SG_CUDA(cudaMemcpy(ids.data(), lp.out_ids, ids.size() * 4, cudaMemcpyDeviceToHost));
+    SG_CUDA(cudaMemcpy(scores.data(), lp.out_scores, scores.size() * 8, cudaMemcpyDeviceToHost));
+    SG_CUDA(cudaMemcpy(counts.data(), lp.out_counts, counts.size() * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n_long; i++) {
+        const uint32_t q = which[i];
+        out_counts[q] = counts[i];
+        std::memcpy(out_ids + (size_t)q * k, ids.data() + (size_t)i * k, (size_t)counts[i] * 4);
+        std::memcpy(out_scores + (size_t)q * k, scores.data() + (size_t)i * k, (size_t)counts[i] * 8);
+    }
+    return SG_OK;
+}
+
+// sg_search_batch with page-locked result rows, 16,384 queries or more: ONE set of kernels for the whole batch, started at
+// once; the queries travel to the device in chunks on the copy stream while the kernels run, a counter copied behind every
+// chunk tells the tokenizing kernel how far they are (wait_for_query, sg_common.cuh).  Only the first chunk's copy (~12 us)
+// is exposed, and every kernel's start-up and tail is paid once per call instead of once per slice.
+// A chunk that holds non-ASCII bytes is lower-cased on the host (strings.ToLower) into an area of its own behind the raw
+// bytes, with offsets of its own; that is why every chunk carries its n + 1 offsets (kArriveOffPad apart).
+static int search_batch_chunked(sg_index *ix, CallCtx *c, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                                uint32_t k, uint32_t *m_ids, double *m_scores, uint32_t *out_counts, int mode, uint32_t n_chunks) {
+    const uint32_t total = q_off[n_q];
+    uint32_t chunk_q = (n_q + n_chunks - 1) / n_chunks;
+    chunk_q = (chunk_q + 31u) & ~31u;  // whole 128-byte lines of offsets per chunk
+    n_chunks = (n_q + chunk_q - 1) / chunk_q;
+    const size_t raw_area = ((size_t)total + 127) & ~(size_t)127;
+    SG_CUDA(c->q_bytes.reserve(raw_area + (size_t)total * 3 + 128 * (size_t)n_chunks + 128));  // raw bytes | lowered chunks (worst case 3x)
+    SG_CUDA(c->q_off.reserve((size_t)n_chunks * (chunk_q + sg::kArriveOffPad) + 1));
+    SG_CUDA(c->counts.reserve(n_q));
+    SG_CUDA(c->work.reserve((size_t)kMaxSlices * sg::kWorkWords));
+    SG_CUDA(c->plans.reserve((size_t)n_q * ix->plan_stride));
+    SG_CUDA(c->wtab.reserve(ix->wtab_bytes * kMaxSlices));
+    if (!c->arrived.p) {
+        SG_CUDA(c->arrived.reserve(1));
+        SG_CUDA(cudaMemset(c->arrived.p, 0, sizeof(uint32_t)));
+        c->arrive_epoch = 0;
+    }
+    if (c->arrive_epoch > 0x7FFF0000u) {  // (the kernels compare with a signed difference; start over long before it wraps)
+        SG_CUDA(cudaMemset(c->arrived.p, 0, sizeof(uint32_t)));
+        c->arrive_epoch = 0;
+    }
+    static const int trace = env_int("SG_TRACE", 0);
+    const auto t_begin = std::chrono::steady_clock::now();
+    cudaStream_t st = c->stream, cs = c->copy_stream;
+    uint32_t *d_too_long = nullptr;
+    c->too_long[0] = c->too_long[1] = 0u;  // [1]: a kernel gave up waiting for a chunk
+    SG_CUDA(cudaHostGetDevicePointer((void **)&d_too_long, c->too_long, 0));
+    uint32_t *arrive_vals = c->too_long + 8;
+    const ArriveArgs arrive{c->arrived.p, c->arrive_epoch, chunk_q};
+    std::vector<std::string> low_bytes(n_chunks);
+    std::vector<std::vector<uint32_t>> low_off(n_chunks);
+    size_t low_cursor = raw_area;
+    int rc = SG_OK;
+    auto copy_chunk = [&](uint32_t ch) -> int {
+        const uint32_t lo = ch * chunk_q, hi = lo + chunk_q < n_q ? lo + chunk_q : n_q;
+        const uint32_t b0 = q_off[lo], b1 = q_off[hi];
+        uint32_t *d_off = c->q_off.p + (size_t)ch * (chunk_q + sg::kArriveOffPad);
+        // the raw bytes go first: nearly every chunk is plain ASCII and is used as it is (the device lowers A-Z itself)
+        if (b1 > b0) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p + b0, q_bytes + b0, b1 - b0, cudaMemcpyHostToDevice, cs));
+        unsigned char high = 0;  // no early exit: the loop vectorises
+        for (uint32_t i = b0; i < b1; i++) high |= (unsigned char)q_bytes[i];
+        if (high & 0x80) {
+            std::string &lb = low_bytes[ch];
+            std::vector<uint32_t> &lof = low_off[ch];
+            lof.resize((size_t)(hi - lo) + 1);
+            lb.reserve((size_t)(b1 - b0) * 3 / 2 + 16);
+            for (uint32_t q = lo; q < hi; q++) {
+                lof[q - lo] = (uint32_t)(low_cursor + lb.size());
+                sg::to_lower((const uint8_t *)q_bytes + q_off[q], q_off[q + 1] - q_off[q], &lb);
+            }
+            lof[hi - lo] = (uint32_t)(low_cursor + lb.size());
+            if (!lb.empty()) SG_CUDA(cudaMemcpyAsync(c->q_bytes.p + low_cursor, lb.data(), lb.size(), cudaMemcpyHostToDevice, cs));
+            SG_CUDA(cudaMemcpyAsync(d_off, lof.data(), lof.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+            low_cursor += (lb.size() + 127) & ~(size_t)127;
+        } else {
+            SG_CUDA(cudaMemcpyAsync(d_off, q_off + lo, ((size_t)(hi - lo) + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+        }
+        arrive_vals[ch] = arrive.base + ch + 1u;
+        SG_CUDA(cudaMemcpyAsync(c->arrived.p, arrive_vals + ch, sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+        return SG_OK;
+    };
+    auto enqueue_all = [&]() -> int {
+        int r = copy_chunk(0);
+        if (r != SG_OK) return r;
+        r = enqueue_search(ix, c->q_bytes.p, c->q_off.p, n_q, metric, alpha, k, m_ids, m_scores, c->counts.p, nullptr, c->work.p, c->plans.p,
+                           c->wtab.p, st, mode, nullptr, nullptr, 1, d_too_long, nullptr, &arrive);
+        if (r != SG_OK) return r;
+        SG_CUDA(cudaMemcpyAsync(out_counts, c->counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        for (uint32_t ch = 1; ch < n_chunks; ch++)
+            if ((r = copy_chunk(ch)) != SG_OK) return r;
+        return SG_OK;
+    };
+    rc = enqueue_all();
+    const auto t_enqueued = std::chrono::steady_clock::now();
+    if (rc != SG_OK) {
+        // a kernel may be waiting for chunks that will never come: make every query it has not seen yet empty (all offsets
+        // zero), release it, then drain
+        cudaMemsetAsync(c->q_off.p, 0, ((size_t)n_chunks * (chunk_q + sg::kArriveOffPad) + 1) * sizeof(uint32_t), cs);
+        arrive_vals[kMaxChunks] = arrive.base + n_chunks;
+        cudaMemcpyAsync(c->arrived.p, arrive_vals + kMaxChunks, sizeof(uint32_t), cudaMemcpyHostToDevice, cs);
+    }
+    c->arrive_epoch += n_chunks;
+    {
+        const cudaError_t e1 = cudaStreamSynchronize(cs), e2 = cudaStreamSynchronize(st);
+        const cudaError_t e = e1 != cudaSuccess ? e1 : e2;
+        if (rc == SG_OK && e != cudaSuccess) { cudaGetLastError(); rc = fail(SG_ERR_CUDA, std::string("sg_search_batch: ") + cudaGetErrorString(e)); }
+    }
+    if (rc != SG_OK) return rc;
+    if (((volatile uint32_t *)c->too_long)[1] != 0u) return fail(SG_ERR_CUDA, "sg_search_batch: a chunk of queries did not reach the device in time");
+    if (trace)
+        std::fprintf(stderr, "sg_search_batch: %u queries in %u chunks under one launch (rows stored into page-locked host memory): enqueue %.1f us, wait %.1f us\n",
+                     n_q, n_chunks, std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count(),
+                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_enqueued).count());
+    if (*(volatile uint32_t *)c->too_long == 0u) return SG_OK;
+    return -100;  // some query was refused: the caller answers it (answer_long_queries)
+}
+
 static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
                              uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int mode) {
     int rc = validate_search(ix, n_q, metric, alpha, k);
@@ -784,6 +989,13 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         m_counts = (uint32_t *)mapped_host_range(out_counts, (size_t)n_q * sizeof(uint32_t));
     }
     const bool direct = m_ids && m_scores && m_counts;
+    static const int want_chunks = env_int("SG_DIRECT_CHUNKS", 8);
+    if (direct && want_chunks > 0 && n_q >= 16384) {
+        const uint32_t n_chunks = (uint32_t)want_chunks > kMaxChunks ? kMaxChunks : (uint32_t)want_chunks;
+        rc = search_batch_chunked(ix, c, q_bytes, q_off, n_q, metric, alpha, k, m_ids, m_scores, out_counts, mode, n_chunks);
+        if (rc != -100) return rc;
+        return answer_long_queries(ix, q_bytes, q_off, n_q, metric, alpha, k, out_ids, out_scores, out_counts, mode);
+    }
     std::vector<uint32_t> bounds{0u};  // slice sl = queries [bounds[sl], bounds[sl + 1])
     if (direct && ix->direct_slice_queries == 0) {
         if (n_q >= 16384)
@@ -928,10 +1140,7 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         for (auto &e : tev) cudaEventDestroy(e);
     }
     if (direct && *(volatile uint32_t *)c->too_long == 0u) return SG_OK;  // the kernel saw no such query: nothing to look for
-    for (uint32_t q = 0; q < n_q; q++)
-        if (out_counts[q] == SG_COUNT_UNSUPPORTED)
-            return fail(SG_ERR_QUERY_TOO_LONG, "query " + std::to_string(q) + " has more than 128 n-grams");
-    return SG_OK;
+    return answer_long_queries(ix, q_bytes, q_off, n_q, metric, alpha, k, out_ids, out_scores, out_counts, mode);
 }
 
 int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
@@ -1090,7 +1299,7 @@ int sg_merge_topk_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k,
                          const double *d_part_scores, const uint32_t *d_part_counts, uint32_t *d_out_ids,
                          double *d_out_scores, uint32_t *d_out_counts, void *stream) {
     if (n_parts < 1 || n_parts > 32) return fail(SG_ERR_INVALID, "n_parts must be in 1..32");
-    if (k < 1 || k > SG_MAX_TOPK) return fail(SG_ERR_INVALID, "topK is invalid");
+    if (k < 1 || k > SG_MAX_TOPK_SHARED) return fail(SG_ERR_INVALID, "topK is invalid");
     if (n_q == 0) return SG_OK;
     if (!d_part_ids || !d_part_scores || !d_part_counts || !d_out_ids || !d_out_scores || !d_out_counts)
         return fail(SG_ERR_INVALID, "null buffer");
@@ -1120,7 +1329,7 @@ int sg_search_batch_packed_device(sg_index *ix, const char *d_q_bytes, const uin
 int sg_merge_topk_packed_device(int device, uint32_t n_parts, uint32_t n_q, uint32_t k, const void *d_parts, uint32_t *d_out_ids,
                                 double *d_out_scores, uint32_t *d_out_counts, void *stream) {
     if (n_parts < 1 || n_parts > 32) return fail(SG_ERR_INVALID, "n_parts must be in 1..32");
-    if (k < 1 || k > SG_MAX_TOPK) return fail(SG_ERR_INVALID, "topK is invalid");
+    if (k < 1 || k > SG_MAX_TOPK_SHARED) return fail(SG_ERR_INVALID, "topK is invalid");
     if (n_q == 0) return SG_OK;
     if (!d_parts || !d_out_ids || !d_out_scores || !d_out_counts) return fail(SG_ERR_INVALID, "null buffer");
     DeviceGuard guard;
@@ -1340,6 +1549,7 @@ int sg_sharded_search_batch(sg_sharded *sx, const char *q_bytes, const uint32_t 
     if (!sx) return fail(SG_ERR_INVALID, "null handle");
     int rc = validate_search(sx->shards[0].ix, n_q, metric, alpha, k);
     if (rc != SG_OK) return rc;
+    if (k > SG_MAX_TOPK_SHARED) return fail(SG_ERR_INVALID, "topK above 1024 is not served by the shard merge");
     if (n_q == 0) return SG_OK;
     if (!q_off || !out_ids || !out_scores || !out_counts) return fail(SG_ERR_INVALID, "null buffer");
     const uint32_t total_bytes = q_off[n_q];
@@ -1653,6 +1863,7 @@ int sg_predict_batch(sg_index *ix, sg_lm *lm, const char *w_bytes, const uint32_
                      const uint32_t *ctx_off, uint32_t n_q, double similarity, uint32_t k, uint32_t *out_ids, uint32_t *out_counts) {
     int rc = validate_search(ix, n_q, SG_COSINE, similarity, k);
     if (rc != SG_OK) return rc;
+    if (k > SG_MAX_TOPK_SHARED) return fail(SG_ERR_INVALID, "topK above 1024 is not served by sg_predict_batch");
     if (!lm || !w_off || !ctx_off || !out_ids || !out_counts) return fail(SG_ERR_INVALID, "null argument");
     if (n_q == 0) return SG_OK;
     if (!ix->bitmap_engine) return fail(SG_ERR_UNSUPPORTED, "sg_predict_batch needs the bitmap engine");

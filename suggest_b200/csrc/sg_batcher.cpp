@@ -162,7 +162,7 @@ int sg_batcher_create(sg_index *ix, uint32_t max_batch, uint32_t max_wait_us, ui
     if (!out) return sg_internal_fail(SG_ERR_INVALID, "null out");
     *out = nullptr;
     if (!ix) return sg_internal_fail(SG_ERR_INVALID, "null index");
-    if (max_batch < 1 || max_batch > (1u << 20) || max_k < 1 || max_k > SG_MAX_TOPK) return sg_internal_fail(SG_ERR_INVALID, "max_batch / max_k out of range");
+    if (max_batch < 1 || max_batch > (1u << 20) || max_k < 1 || max_k > SG_MAX_TOPK_SHARED) return sg_internal_fail(SG_ERR_INVALID, "max_batch / max_k out of range");
     sg_batcher *b = new (std::nothrow) sg_batcher();
     if (!b) return sg_internal_fail(SG_ERR_NOMEM, "out of host memory");
     b->ix = ix;

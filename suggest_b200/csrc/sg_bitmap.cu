@@ -21,6 +21,7 @@
 //   sg_window_kernel         per len(tokens) = 0..128: segment window, T(segment), T(bitmap word)   (tiny)
 //   sg_tokens_kernel         tokenise every query -> len(tokens), term ids
 //   sg_bitmap_search_kernel  count, compare, resolve, score, top-k
+#include <cstddef>
 #include <map>
 #include <mutex>
 #include <utility>
@@ -44,7 +45,9 @@ constexpr int kResolveSlots = 1 << kMaxBucketShift;
 constexpr uint32_t kRowSlots = kMaxQueryTokens + 8;  // padded to a multiple of 8 with the all-zero row
 constexpr uint32_t kTileWords = 32;        // bitmap words per tile: lane l owns word l
 constexpr int kSegCache = 256;             // segment starts kept in shared memory per CTA
-constexpr int kResolveThreads = 128;       // sg_resolve_kernel: one thread per flagged bitmap word
+constexpr int kResolveThreads = 256;       // sg_resolve_kernel
+constexpr int kResolveGroup = 8;           // lanes that resolve one flagged bitmap word together (four words per warp)
+constexpr int kResolveLists = 4;           // lists a lane takes per round: 32 lists of a query are one round of loads
 
 // Per-warp shared memory of sg_bitmap_search_kernel.  The count loop itself only reads `row`; everything
 // else belongs to the cold path (a bucket reached its threshold), which keeps its state here so that the hot loop's
@@ -55,7 +58,9 @@ struct WarpSmem {
     uint32_t lm_valid, lm_from, lm_to; // spellchecker completions: rank by the language model (LmContext of the query)
     const uint64_t *lm_vals;
     uint32_t q;                        // number of the query inside the launch (collect mode)
-    uint32_t pad[7];
+    uint32_t pad[3];
+    double *tk_score;                  // the warp's sorted top-k: behind this struct in shared memory, or - k > kSmemTopK - a slice
+    uint32_t *tk_id;                   // of SearchParams::tk_global in HBM
     uint32_t flag[32];                 // per lane: buckets of its word that reached the threshold
     uint32_t bias[32];                 // per lane: 2^M - T(word), what the planes started from
     alignas(16) uint32_t row[kRowSlots];   // word offset of the bitmap row of every list
@@ -65,6 +70,7 @@ struct WarpSmem {
 };
 constexpr uint32_t kBitmapWarpFixedSmem = (uint32_t)sizeof(WarpSmem);
 static_assert(sizeof(WarpSmem) % 16 == 0, "top-k scores follow and need 8-byte alignment");
+static_assert(offsetof(WarpSmem, tk_score) % 8 == 0, "pointer alignment");
 
 // What the cold path needs of the kernel arguments, copied once per CTA (a noinline callee cannot take the address of
 // a kernel parameter without a local copy per thread).
@@ -94,8 +100,8 @@ __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32
     l = u ^ c;
 }
 
-__device__ __forceinline__ double *warp_tk_score(WarpSmem *ws) { return (double *)(ws + 1); }
-__device__ __forceinline__ uint32_t *warp_tk_id(WarpSmem *ws, uint32_t k) { return (uint32_t *)(warp_tk_score(ws) + k); }
+__device__ __forceinline__ double *warp_tk_score(WarpSmem *ws) { return ws->tk_score; }
+__device__ __forceinline__ uint32_t *warp_tk_id(WarpSmem *ws, uint32_t) { return ws->tk_id; }
 
 // Score of a completion (Autocomplete collectors): FirstKCollectorManager.Collect scores a position with -position
 // (pkg/suggest/collector.go:104-106); the spellchecker's lmCollector (pkg/spellchecker/collector.go:61-78) with
@@ -498,7 +504,9 @@ __global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_
     if (blockIdx.x == 0 && threadIdx.x < kWorkWords) p.work_counter[threadIdx.x] = 0u;  // counters of the kernels behind this one
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < p.n_q; q += n_warps) {
         int size_a = 0, n_lists = 0;
-        const bool unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
+        const bool arrived = wait_for_query(p, q, lane);
+        bool unsupported = false;
+        if (arrived) unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
         if (p.mode == 1 && n_lists < size_a) n_lists = 0;  // a query token that is in no list: nothing can hold them all
         if (unsupported) { size_a = 0; n_lists = 0; }
         uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
@@ -576,6 +584,13 @@ __device__ __forceinline__ void bitmap_search_body(const DevIndex &ix, const Sea
     for (uint32_t i = threadIdx.x; i <= min(ix.n_segments, (uint32_t)kSegCache); i += blockDim.x) s_bc.seg_cache[i] = ix.seg_start[i];
     __syncthreads();
     WarpSmem *ws = (WarpSmem *)(smem + (size_t)warp * p.warp_smem);
+    if (lane == 0) {
+        double *sc = (double *)(ws + 1);
+        if (p.tk_global != nullptr) sc = (double *)(p.tk_global + (size_t)(blockIdx.x * kBitmapWarps + warp) * (((size_t)p.k * 12u + 15u) & ~(size_t)15u));
+        ws->tk_score = sc;
+        ws->tk_id = (uint32_t *)(sc + p.k);
+    }
+    __syncwarp();
     const double *tk_score = warp_tk_score(ws);
     const uint32_t *tk_id = warp_tk_id(ws, p.k);
     const uint32_t zero_row = ix.n_terms * ix.row_words;
@@ -810,31 +825,62 @@ __device__ __forceinline__ uint32_t count_and_flag(const DevIndex &ix, const Sea
     return n_entries;
 }
 
-__global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_count_kernel(const DevIndex ix, const SearchParams p) {
+// kFused: the kernel tokenizes the query itself (tokenize_query, the same code sg_tokens_kernel runs) and writes the plan for
+// sg_resolve_kernel, instead of reading a plan sg_tokens_kernel wrote: one launch and one pass over the plans less, and the
+// tokenizer's chains of dependent loads (offsets -> bytes -> hash probe) hide under the row reads of the other warps.
+template <bool kFused>
+__device__ __forceinline__ void count_body(const DevIndex &ix, const SearchParams &p) {
     __shared__ __align__(16) uint32_t s_rows[kBitmapWarps][kRowSlots];
+    __shared__ __align__(16) uint32_t s_tok[kFused ? kBitmapWarps : 1][kFused ? kMaxRunes + 2 * kMaxQueryTokens : 1];
+    __shared__ uint8_t s_ascii[128];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    if (kFused) {
+        if (threadIdx.x < 128) s_ascii[threadIdx.x] = ix.ascii_code[threadIdx.x];
+        __syncthreads();
+    }
     uint32_t *row = s_rows[warp];
+    uint32_t *s_runes = s_tok[kFused ? warp : 0];
+    uint32_t *s_lterm = s_runes + kMaxRunes;
+    uint32_t *s_hash = s_lterm + kMaxQueryTokens;
     const uint32_t zero_row = ix.n_terms * ix.row_words;
     uint32_t q = 0;
     if (lane == 0) q = take_query(p.work_counter + kWorkQuery);
     q = __shfl_sync(kFull, q, 0);
     while (q < p.n_q) {
         uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
-        const uint4 h0 = __ldg((const uint4 *)plan_base), h1 = __ldg((const uint4 *)plan_base + 1);  // TokenPlan
-        const uint32_t t0 = __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + lane);
         uint32_t q_next = 0;
-        if (lane == 0) q_next = take_query(p.work_counter + kWorkQuery);
-        const bool unsupported = (h0.x & 1u) != 0u;
-        const int size_a = (int)h0.y, n_lists = (int)h0.z;
-        const WordRange win{h1.x, h1.y};
+        bool unsupported;
+        int size_a, n_lists;
+        WordRange win;
+        uint32_t t0 = 0;
+        if (kFused) {
+            if (lane == 0) q_next = take_query(p.work_counter + kWorkQuery);
+            unsupported = false;
+            size_a = n_lists = 0;
+            if (wait_for_query(p, q, lane)) unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
+            if (unsupported) { size_a = 0; n_lists = 0; }
+            win = p.wt.win[size_a];
+            for (int j = lane; j < n_lists; j += 32) ((uint32_t *)(plan_base + kTokTermsOffset))[j] = s_lterm[j];  // for sg_resolve_kernel
+        } else {
+            const uint4 h0 = __ldg((const uint4 *)plan_base), h1 = __ldg((const uint4 *)plan_base + 1);  // TokenPlan
+            t0 = __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + lane);
+            if (lane == 0) q_next = take_query(p.work_counter + kWorkQuery);
+            unsupported = (h0.x & 1u) != 0u;
+            size_a = (int)h0.y;
+            n_lists = (int)h0.z;
+            win = WordRange{h1.x, h1.y};
+        }
         uint32_t n_entries = 0;
         bool dirty = false;
         if (n_lists > 0 && win.y > win.x) {
             const int n_pad = (n_lists + 7) & ~7;
             for (int j = lane; j < n_pad; j += 32) {
                 uint32_t r = zero_row;
-                if (j < n_lists) r = (j < 32 ? t0 : __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + j)) * ix.row_words;
+                if (j < n_lists) {
+                    if (kFused) r = s_lterm[j] * ix.row_words;
+                    else r = (j < 32 ? t0 : __ldg((const uint32_t *)(plan_base + kTokTermsOffset) + j)) * ix.row_words;
+                }
                 row[j] = r;
             }
             __syncwarp();
@@ -846,11 +892,14 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_cou
         if (lane == 0) {
             p.lean_head[q] = kNilNode;
             p.lean_pending[q] = n_entries;
-            ((uint32_t *)plan_base)[6] = n_entries;  // TokenPlan::n_flagged
-            if (dirty) {
-                atomicOr((uint32_t *)plan_base, kPlanDirty);
-                p.work_counter[kWorkDirtyAny] = 1u;
+            if (kFused) {
+                ((uint4 *)plan_base)[0] = make_uint4((unsupported ? 1u : 0u) | (dirty ? kPlanDirty : 0u), (uint32_t)size_a, (uint32_t)n_lists, 0u);
+                ((uint4 *)plan_base)[1] = make_uint4(win.x, win.y, n_entries, 0u);
+            } else {
+                ((uint32_t *)plan_base)[6] = n_entries;  // TokenPlan::n_flagged
+                if (dirty) atomicOr((uint32_t *)plan_base, kPlanDirty);
             }
+            if (dirty) p.work_counter[kWorkDirtyAny] = 1u;
         }
         if (n_entries == 0u && !dirty) {  // nothing reached its threshold: the answer is the empty row
             if (!p.sparse_rows) {
@@ -867,18 +916,27 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_cou
     }
 }
 
-// ---- sg_resolve_kernel: one THREAD per flagged bitmap word ----
-// A flagged bucket is counted exactly by bit-sliced addition again, now over the documents of the bucket: the bits of a
-// (term, bucket) pair (DevIndex::fine, found through rank4 + popcounts: one 16-byte and one 4-byte load, then the pair's
-// bits) are added into 8 bit planes that start at 2^8 - T, so a document with overlap >= T is the carry out of the top
-// plane and its overlap is the planes' value + T.  128 documents at a time (four words per plane).  All of it is private to
-// the thread: no shared memory, no inter-lane traffic, ~70 warp instructions per flagged word instead of ~600 with a warp
-// per word, and the independent loads of 32 flagged words are in flight per warp.
+__global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_count_kernel(const DevIndex ix, const SearchParams p) {
+    count_body<false>(ix, p);
+}
+
+__global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_tokens_count_kernel(const DevIndex ix, const SearchParams p) {
+    count_body<true>(ix, p);
+}
+
+// ---- sg_resolve_kernel: eight lanes per flagged bitmap word, four words per warp ----
+// A flagged bucket is counted per document from the bits of its (term, bucket) pairs (DevIndex::fine, found through rank4 +
+// popcounts: one 16-byte and one 4-byte load, then the pair's bits): lane g of the group takes lists g, g + 8, ..., two at a
+// time so that their loads are in flight together, and adds one to a byte counter in shared memory for every document a
+// list has; then every lane compares 16 counters with the threshold (SIMD-in-a-word).  128 documents per pass.
+// The chain of dependent loads of a word is short (flag entry -> plan -> {row word group, rank} -> pair bits) and
+// thousands of words are in flight per SM; a warp per word (round 2's first version) left the GPU waiting on ~10
+// dependent round trips per word at 5 words per warp, a thread per word spent ~3,500 instructions on bit-sliced adds.
 // Survivors: a query whose only flagged word (TokenPlan::n_flagged == 1, the usual case) holds one survivor is written
-// straight to its row.  Otherwise survivors are linked to the query ({slot, overlap | segment << 16, next, taken}), every
-// flagged word of the query "arrives" (atomicSub on lean_pending), and the thread that arrives last selects: pass 0
-// scores every survivor, then the best remaining one is taken k times ((score desc, id asc), Candidate.Less,
-// pkg/suggest/collector.go:20-26).  The list lives in L2 (.cg accesses): other SMs wrote it.
+// straight to its row.  Otherwise survivors are scored where they are found and linked to the query ({id, next, score}),
+// every flagged word of the query "arrives" (atomicSub on lean_pending), and the thread that arrives last selects the k
+// best ((score desc, id asc), Candidate.Less, pkg/suggest/collector.go:20-26).  The list lives in L2 (.cg accesses): other
+// SMs wrote it.
 __device__ __forceinline__ bool plan_is_dirty(const uint8_t *plan_base) { return (*(const volatile uint32_t *)plan_base & kPlanDirty) != 0u; }
 
 __device__ __forceinline__ void mark_dirty(const SearchParams &p, uint32_t q) {
@@ -886,11 +944,16 @@ __device__ __forceinline__ void mark_dirty(const SearchParams &p, uint32_t q) {
     p.work_counter[kWorkDirtyAny] = 1u;
 }
 
-__device__ __forceinline__ void link_survivor(const SearchParams &p, uint32_t q, uint32_t slot, int count, int size_b) {
+// A survivor is scored by the lane that found it (original id from perm, 1 - Distance in float64) and linked in front of
+// its query's list: node = {id, next | taken << 31, score}.
+__device__ __forceinline__ void link_survivor(const DevIndex &ix, const SearchParams &p, uint32_t q, int size_a, uint32_t slot, int count,
+                                              int size_b) {
     const uint32_t idx = atomicAdd(p.work_counter + kWorkNodeCursor, 1u);
     if (idx < p.n_q * kNodesPerQuery) {
+        const uint32_t id = __ldg(ix.perm + slot);
+        const double score = metric_score(p.metric, count, size_a, size_b);
         const uint32_t prev = atomicExch(p.lean_head + q, idx);
-        __stcg(p.lean_nodes + idx, make_uint4(slot, (uint32_t)count | (uint32_t)size_b << 16, prev, 0u));
+        __stcg(p.lean_nodes + idx, make_uint4(id, prev & 0x7FFFFFFFu, (uint32_t)__double2loint(score), (uint32_t)__double2hiint(score)));  // bit 31: taken
     } else {
         mark_dirty(p, q);  // out of nodes: the fallback kernel answers this query
     }
@@ -904,68 +967,101 @@ __device__ __forceinline__ void write_row_end(const DevIndex &ix, const SearchPa
     p.out_counts[q] = n_out;  // (a query with too many n-grams has no lists and never gets here)
 }
 
-// every flagged word of query q is resolved and this thread arrived last: select the k best survivors
-__device__ __noinline__ void select_survivors(const DevIndex &ix, const SearchParams &p, uint32_t q, int size_a) {
-    double *node_score = (double *)(p.lean_nodes + (size_t)p.n_q * kNodesPerQuery);
-    for (uint32_t n = __ldcg(p.lean_head + q); n != kNilNode;) {  // pass 0: original id and score of every survivor
-        uint4 node = __ldcg(p.lean_nodes + n);
-        const uint32_t id = __ldg(ix.perm + node.x);
-        __stcg(node_score + n, metric_score(p.metric, (int)(node.y & 0xFFFFu), size_a, (int)(node.y >> 16)));
-        node.x = id;
-        node.w = 0u;
-        __stcg(p.lean_nodes + n, node);
-        n = node.z;
-    }
+// Every flagged word of query q is resolved and this thread arrived last: the k best survivors, (score desc, id asc).
+// k <= kSelectLocal: one walk of the list, insertion into a sorted array in local memory; larger k: the best node that is
+// not taken yet, k times (nodes carry a taken bit).  One dependent load per node either way: scores travel with the nodes.
+constexpr uint32_t kSelectLocal = 32;
+struct SelectArgs {  // by value: a reference to the kernel parameters would make every thread copy them to local memory
+    uint32_t k, id_base;
+    int32_t sparse_rows;
+    const uint32_t *lean_head;
+    uint4 *lean_nodes;
+    uint32_t *out_ids, *out_counts;
+    double *out_scores;
+};
+__device__ __noinline__ void select_survivors(const SelectArgs p, uint32_t q) {
     const size_t row = (size_t)q * p.k;
     uint32_t n_out = 0;
-    for (; n_out < p.k; n_out++) {
-        uint32_t best = kNilNode, best_id = 0;
-        double best_score = 0.0;
+    if (p.k <= kSelectLocal) {
+        double bs[kSelectLocal];
+        uint32_t bi[kSelectLocal];
         for (uint32_t n = __ldcg(p.lean_head + q); n != kNilNode;) {
             const uint4 node = __ldcg(p.lean_nodes + n);
-            if (node.w == 0u) {
-                const double sc = __ldcg(node_score + n);
-                if (best == kNilNode || sc > best_score || (sc == best_score && node.x < best_id)) { best = n; best_score = sc; best_id = node.x; }
-            }
-            n = node.z;
+            const double sc = __hiloint2double((int)node.w, (int)node.z);
+            n = node.y & 0x7FFFFFFFu;
+            if (n == 0x7FFFFFFFu) n = kNilNode;
+            uint32_t at = n_out;  // position of the new entry: behind everything that is better
+            while (at > 0 && (bs[at - 1] < sc || (bs[at - 1] == sc && bi[at - 1] > node.x))) at--;
+            if (at >= p.k) continue;
+            const uint32_t last = n_out < p.k ? n_out : p.k - 1;
+            for (uint32_t j = last; j > at; j--) { bs[j] = bs[j - 1]; bi[j] = bi[j - 1]; }
+            bs[at] = sc;
+            bi[at] = node.x;
+            if (n_out < p.k) n_out++;
         }
-        if (best == kNilNode) break;
-        __stcg(&p.lean_nodes[best].w, 1u);
-        p.out_ids[row + n_out] = ix.id_base + best_id;
-        p.out_scores[row + n_out] = best_score;
+        for (uint32_t j = 0; j < n_out; j++) { p.out_ids[row + j] = p.id_base + bi[j]; p.out_scores[row + j] = bs[j]; }
+    } else {
+        for (; n_out < p.k; n_out++) {
+            uint32_t best = kNilNode, best_id = 0;
+            double best_score = 0.0;
+            for (uint32_t n = __ldcg(p.lean_head + q); n != kNilNode;) {
+                const uint4 node = __ldcg(p.lean_nodes + n);
+                if (!(node.y >> 31)) {
+                    const double sc = __hiloint2double((int)node.w, (int)node.z);
+                    if (best == kNilNode || sc > best_score || (sc == best_score && node.x < best_id)) { best = n; best_score = sc; best_id = node.x; }
+                }
+                n = node.y & 0x7FFFFFFFu;
+                if (n == 0x7FFFFFFFu) n = kNilNode;
+            }
+            if (best == kNilNode) break;
+            atomicOr(&p.lean_nodes[best].y, 0x80000000u);
+            p.out_ids[row + n_out] = p.id_base + best_id;
+            p.out_scores[row + n_out] = best_score;
+        }
     }
-    write_row_end(ix, p, q, n_out);
+    if (!p.sparse_rows)
+        for (uint32_t j = n_out; j < p.k; j++) { p.out_ids[row + j] = 0u; p.out_scores[row + j] = 0.0; }
+    p.out_counts[q] = n_out;
 }
 
 __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIndex ix, const SearchParams p) {
     __shared__ uint32_t s_seg[kSegCache + 1];
+    __shared__ __align__(16) uint32_t s_cnt[kResolveThreads / kResolveGroup][32];  // per group: 128 byte counters, one per document
     for (uint32_t i = threadIdx.x; i <= min(ix.n_segments, (uint32_t)kSegCache); i += blockDim.x) s_seg[i] = ix.seg_start[i];
     __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (kResolveGroup - 1);                       // lane inside the group
+    const unsigned gmask = ((1u << kResolveGroup) - 1u) << (lane & ~(kResolveGroup - 1));
+    uint32_t *cnt = s_cnt[threadIdx.x / kResolveGroup];
     const uint32_t bshift = ix.bshift, W = 1u << bshift;
     const uint32_t n_entries = min(((const volatile uint32_t *)p.work_counter)[kWorkFlagCursor], p.n_q * kFlagsPerQuery);
-    const uint32_t n_threads = gridDim.x * blockDim.x;
+    const uint32_t n_groups = gridDim.x * (kResolveThreads / kResolveGroup);
     const int S = (int)ix.n_segments, cached = min(S, kSegCache);
-    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n_entries; e += n_threads) {
+    for (uint32_t e = blockIdx.x * (kResolveThreads / kResolveGroup) + threadIdx.x / kResolveGroup; e < n_entries; e += n_groups) {
         const uint4 f = __ldg(p.lean_flags + e);
         const uint32_t q = f.x, w = f.y;
         uint32_t mask = f.z;
         const uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
         const uint4 h0 = __ldg((const uint4 *)plan_base);  // len(tokens), list count: never change (the flags word may)
         const uint32_t n_flagged = __ldcg((const uint32_t *)plan_base + 6);  // written by sg_count_kernel
+        const uint32_t *terms = (const uint32_t *)(plan_base + kTokTermsOffset);
+        // the first round's term ids travel with the header, not behind it: the plan's term area is 128 entries whatever the
+        // list count (entries past it are stale and ignored below)
+        uint32_t term0[kResolveLists];
+#pragma unroll
+        for (int u = 0; u < kResolveLists; u++) term0[u] = __ldg(terms + gl + u * kResolveGroup);
         const int size_a = (int)h0.y, n_lists = (int)h0.z;
         if (plan_is_dirty(plan_base)) continue;  // answered by the fallback kernel; nobody waits for this word
-        const uint32_t *terms = (const uint32_t *)(plan_base + kTokTermsOffset);
         const uint8_t *seg_thr = p.wt.seg_thr + (size_t)size_a * ix.n_segments;
         const bool sole = n_flagged == 1u;
-        // the first survivor stays in registers: usually it is the only one
+        if (p.debug & 4u) continue;
+        // this lane's first survivor stays in registers: usually it is the only one of the query
         uint32_t n_surv = 0, s_slot = 0;
         int s_count = 0, s_b = 0;
         auto survivor = [&](uint32_t slot, int count, int B) {
+            if (p.debug & 2u) return;
             if (n_surv == 0) { s_slot = slot; s_count = count; s_b = B; }
-            else {
-                if (n_surv == 1) link_survivor(p, q, s_slot, s_count, s_b);
-                link_survivor(p, q, slot, count, B);
-            }
+            else link_survivor(ix, p, q, size_a, slot, count, B);
             n_surv++;
         };
         while (mask) {
@@ -989,107 +1085,117 @@ __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIn
             if (T == 0) continue;  // the word's threshold came from a neighbouring segment
             if (bshift == 0u) {   // one bit per document: the overlap is the number of lists with the bit
                 int count = 0;
-                for (int j = 0; j < n_lists; j++) count += (int)((__ldg(ix.bitmaps + (size_t)__ldg(terms + j) * ix.row_words + w) >> bit) & 1u);
-                if (count >= T) survivor(bucket, count, B);
+                for (int j = gl; j < n_lists; j += kResolveGroup)
+                    count += (int)((__ldg(ix.bitmaps + (size_t)__ldg(terms + j) * ix.row_words + w) >> bit) & 1u);
+#pragma unroll
+                for (int o = kResolveGroup / 2; o; o >>= 1) count += __shfl_xor_sync(gmask, count, o);
+                if (count >= T && gl == 0) survivor(bucket, count, B);
                 continue;
             }
-            const uint32_t chunk_bits = W < 128u ? W : 128u;      // documents counted per pass
-            const uint32_t chunk_words = chunk_bits < 32u ? 1u : chunk_bits >> 5;
+            const uint32_t chunk_bits = W < 128u ? W : 128u;  // documents counted per pass
             for (uint32_t c0 = 0; c0 < W; c0 += 128u) {
-                uint32_t pl[8][4], ov[4];
-                const uint32_t bias = 256u - (uint32_t)T;
+                *(uint4 *)(cnt + 4 * gl) = make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp(gmask);
+                // lists gl, gl + 8, gl + 16, gl + 24 of a round together: every load of a level is issued before anything waits
+                // (absent lists and lists without the bucket read a harmless address instead of branching around the load)
+                for (int j0 = gl; j0 < n_lists; j0 += kResolveLists * kResolveGroup) {
+                    uint32_t term[kResolveLists];
 #pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    ov[x] = 0u;
+                    for (int u = 0; u < kResolveLists; u++) {
+                        const int j = j0 + u * kResolveGroup;
+                        term[u] = j0 == gl ? term0[u] : __ldg(terms + (j < n_lists ? j : j0));
+                        if (j >= n_lists) term[u] = ix.n_terms;  // absent list: the all-zero row (1 KB, stays in L1), no bucket, no pair
+                    }
+                    uint4 grp[kResolveLists];
+                    uint32_t rk[kResolveLists];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) pl[j][x] = 0u - ((bias >> j) & 1u);
-                }
-                for (int j0 = 0; j0 < n_lists; j0 += 4) {
-                    uint4 grp[4];
-                    uint32_t rk[4], in[4];
+                    for (int u = 0; u < kResolveLists; u++) {
+                        const size_t at = (size_t)term[u] * ix.row_words + w;
+                        grp[u] = __ldg((const uint4 *)(ix.bitmaps + (at & ~(size_t)3)));
+                        rk[u] = __ldg(ix.rank4 + (at >> 2));
+                    }
+                    uint4 m[kResolveLists];
+                    bool has[kResolveLists];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        grp[u] = make_uint4(0u, 0u, 0u, 0u);
-                        rk[u] = 0u;
-                        in[u] = 0u;
-                        if (j0 + u < n_lists) {
-                            const size_t at = (size_t)__ldg(terms + j0 + u) * ix.row_words + w;
-                            grp[u] = __ldg((const uint4 *)(ix.bitmaps + (at & ~(size_t)3)));
-                            rk[u] = __ldg(ix.rank4 + (at >> 2));
-                            in[u] = (uint32_t)(at & 3);
-                        }
+                    for (int u = 0; u < kResolveLists; u++) {
+                        const uint32_t in = (uint32_t)(((size_t)term[u] * ix.row_words + w) & 3);
+                        const uint32_t rw = in == 0 ? grp[u].x : in == 1 ? grp[u].y : in == 2 ? grp[u].z : grp[u].w;
+                        has[u] = j0 + u * kResolveGroup < n_lists && ((rw >> bit) & 1u);
+                        uint32_t pair = rk[u] + (uint32_t)__popc(rw & ((1u << bit) - 1u));
+                        if (in > 0) pair += (uint32_t)__popc(grp[u].x);
+                        if (in > 1) pair += (uint32_t)__popc(grp[u].y);
+                        if (in > 2) pair += (uint32_t)__popc(grp[u].z);
+                        const uint64_t bitpos = has[u] && !(p.debug & 1u) ? ((uint64_t)pair << bshift) + c0 : 0ull;
+                        m[u] = make_uint4(0u, 0u, 0u, 0u);
+                        if (chunk_bits == 128u) m[u] = __ldg((const uint4 *)(ix.fine + (bitpos >> 5)));
+                        else if (chunk_bits == 64u) { const uint2 v = __ldg((const uint2 *)(ix.fine + (bitpos >> 5))); m[u].x = v.x; m[u].y = v.y; }
+                        else if (chunk_bits == 32u) m[u].x = __ldg(ix.fine + (bitpos >> 5));
+                        else m[u].x = (__ldg(ix.fine + (bitpos >> 5)) >> (uint32_t)(bitpos & 31u)) & ((1u << chunk_bits) - 1u);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t rw = in[u] == 0 ? grp[u].x : in[u] == 1 ? grp[u].y : in[u] == 2 ? grp[u].z : grp[u].w;
-                        if (!((rw >> bit) & 1u)) continue;
-                        uint32_t pair = rk[u] + (uint32_t)__popc(rw & ((1u << bit) - 1u));
-                        if (in[u] > 0) pair += (uint32_t)__popc(grp[u].x);
-                        if (in[u] > 1) pair += (uint32_t)__popc(grp[u].y);
-                        if (in[u] > 2) pair += (uint32_t)__popc(grp[u].z);
-                        const uint64_t bitpos = ((uint64_t)pair << bshift) + c0;
-                        uint32_t m[4] = {0u, 0u, 0u, 0u};
-                        if (chunk_bits == 128u) {
-                            const uint4 v = __ldg((const uint4 *)(ix.fine + (bitpos >> 5)));
-                            m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
-                        } else if (chunk_bits == 64u) {
-                            const uint2 v = __ldg((const uint2 *)(ix.fine + (bitpos >> 5)));
-                            m[0] = v.x; m[1] = v.y;
-                        } else if (chunk_bits == 32u) {
-                            m[0] = __ldg(ix.fine + (bitpos >> 5));
-                        } else {
-                            m[0] = (__ldg(ix.fine + (bitpos >> 5)) >> (uint32_t)(bitpos & 31u)) & ((1u << chunk_bits) - 1u);
-                        }
+                    for (int u = 0; u < kResolveLists; u++) {
+                        if (!has[u]) continue;
+                        const uint32_t mw[4] = {m[u].x, m[u].y, m[u].z, m[u].w};
 #pragma unroll
                         for (int x = 0; x < 4; x++) {
-                            if ((uint32_t)x >= chunk_words) break;
-                            uint32_t carry = m[x];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const uint32_t t = pl[j][x] & carry;
-                                pl[j][x] ^= carry;
-                                carry = t;
+                            uint32_t o = mw[x];
+                            while (o) {  // one byte counter per document: a list adds one to every document it has
+                                const uint32_t b = 32u * (uint32_t)x + (uint32_t)__ffs(o) - 1u;
+                                o &= o - 1u;
+                                atomicAdd(cnt + (b >> 2), 1u << (8u * (b & 3u)));
                             }
-                            ov[x] |= carry;
                         }
                     }
                 }
+                __syncwarp(gmask);
+                // documents whose counter reached the threshold: lane gl scans counters 16 gl .. 16 gl + 15
+                const uint4 mine = *(const uint4 *)(cnt + 4 * gl);
+                const uint32_t cw[4] = {mine.x, mine.y, mine.z, mine.w};
+                const uint32_t t4 = (uint32_t)T * 0x01010101u;
 #pragma unroll
                 for (int x = 0; x < 4; x++) {
-                    uint32_t o = ov[x];
-                    while (o) {
-                        const uint32_t b = (uint32_t)__ffs(o) - 1u;
-                        o &= o - 1u;
-                        int count = T;  // the planes hold bias + overlap - 256 = overlap - T
-#pragma unroll
-                        for (int j = 0; j < 8; j++) count += (int)((pl[j][x] >> b) & 1u) << j;
-                        survivor(id_lo + c0 + 32u * (uint32_t)x + b, count, B);
+                    uint32_t ge = __vcmpgeu4(cw[x], t4);  // 0xFF in every byte that is >= T
+                    while (ge) {
+                        const uint32_t byte = ((uint32_t)__ffs(ge) - 1u) >> 3;
+                        ge &= ~(0xFFu << (8u * byte));
+                        survivor(id_lo + c0 + 16u * (uint32_t)gl + 4u * (uint32_t)x + byte, (int)((cw[x] >> (8u * byte)) & 0xFFu), B);
                     }
                 }
+                __syncwarp(gmask);
             }
         }
-        if (sole && n_surv <= 1u) {  // the whole answer of the query is known here: no list, no atomics
+        // what the group found
+        uint32_t total = n_surv;
+#pragma unroll
+        for (int o = kResolveGroup / 2; o; o >>= 1) total += __shfl_xor_sync(gmask, total, o);
+        if (sole && total <= 1u) {  // the whole answer of the query is known here: no list, no atomics
             if (n_surv == 1u) {
                 const size_t row = (size_t)q * p.k;
                 p.out_ids[row] = ix.id_base + __ldg(ix.perm + s_slot);
                 p.out_scores[row] = metric_score(p.metric, s_count, size_a, s_b);
             }
-            write_row_end(ix, p, q, n_surv);
+            if (gl == 0) write_row_end(ix, p, q, total);
             continue;
         }
-        if (n_surv == 1u) link_survivor(p, q, s_slot, s_count, s_b);
-        bool last = sole;
-        if (!sole) {
-            __threadfence();  // this thread's nodes are visible before its arrival is
-            last = atomicSub(p.lean_pending + q, 1u) == 1u;
-            if (last) __threadfence();
+        if (n_surv >= 1u) link_survivor(ix, p, q, size_a, s_slot, s_count, s_b);
+        __threadfence();  // the nodes are visible before the arrival is
+        __syncwarp(gmask);
+        if (gl == 0) {
+            bool last = sole;
+            if (!sole) {
+                last = atomicSub(p.lean_pending + q, 1u) == 1u;
+                if (last) __threadfence();
+            }
+            if (last && !plan_is_dirty(plan_base))
+                select_survivors(SelectArgs{p.k, ix.id_base, p.sparse_rows, p.lean_head, p.lean_nodes, p.out_ids, p.out_counts, p.out_scores}, q);
         }
-        if (last && !plan_is_dirty(plan_base)) select_survivors(ix, p, q, size_a);
+        __syncwarp(gmask);
     }
 }
 
 // ---------------- launcher (host) ----------------
-size_t bitmap_warp_smem(uint32_t k) { return ((size_t)kBitmapWarpFixedSmem + (size_t)k * 12u + 15u) & ~(size_t)15u; }
+// k > kSmemTopK: the top-k lives in HBM (SearchParams::tk_global), the warp keeps only its fixed state in shared memory
+size_t bitmap_warp_smem(uint32_t k) { return ((size_t)kBitmapWarpFixedSmem + (k <= kSmemTopK ? (size_t)k * 12u : 0u) + 15u) & ~(size_t)15u; }
 
 // The dynamic shared-memory opt-in is a per-device attribute of a kernel, shared by every index and host thread of
 // the process: only ever raise it.  CTAs per SM are cached per (kernel, device, k).
@@ -1122,9 +1228,9 @@ cudaError_t bitmap_search_occupancy(int device, uint32_t k, int *blocks_per_sm) 
 
 cudaError_t lean_occupancy(int device, uint32_t k, int *count_per_sm, int *resolve_per_sm) {
     (void)k;
-    cudaError_t e = kernel_occupancy((const void *)sg_count_kernel, 1, device, 0, 0, count_per_sm);
+    cudaError_t e = kernel_occupancy((const void *)sg_tokens_count_kernel, 1, device, 0, 0, count_per_sm);  // (the unfused kernel needs no more)
     if (e != cudaSuccess) return e;
-    *resolve_per_sm = 8;  // CTAs of kResolveThreads per SM the grid is sized for (the kernel strides over the flagged words)
+    *resolve_per_sm = 2048 / kResolveThreads;  // CTAs of kResolveThreads per SM the grid is sized for (the kernel strides over the flagged words)
     return cudaSuccess;
 }
 
@@ -1160,7 +1266,7 @@ cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int 
 // sg_window_kernel (optional) + sg_tokens_kernel + sg_count_kernel + sg_resolve_kernel + sg_bitmap_search_kernel (only_dirty);
 // stage_events: 6 events around the five kernels
 cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm_count, int count_per_sm, int resolve_per_sm,
-                               int search_per_sm, bool run_window, cudaStream_t stream, cudaEvent_t *stage_events) {
+                               int search_per_sm, bool run_window, bool fused, cudaStream_t stream, cudaEvent_t *stage_events) {
     const size_t smem = (size_t)kBitmapWarps * p.warp_smem;
     cudaError_t e;
     if (stage_events) cudaEventRecord(stage_events[0], stream);
@@ -1169,15 +1275,21 @@ cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm
         if (e != cudaSuccess) return e;
     }
     if (stage_events) cudaEventRecord(stage_events[1], stream);
-    const int tok_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
-    sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    if (stage_events) cudaEventRecord(stage_events[2], stream);
     const int need = (int)((p.n_q + kBitmapWarps - 1) / kBitmapWarps);
     int blocks = sm_count * count_per_sm;
     if (blocks > need) blocks = need;
-    sg_count_kernel<<<blocks, kBitmapWarps * 32, 0, stream>>>(ix, p);
+    if (fused) {
+        // (the counters of the launch are zeroed by the caller: no kernel runs before this one)
+        if (stage_events) cudaEventRecord(stage_events[2], stream);
+        sg_tokens_count_kernel<<<blocks, kBitmapWarps * 32, 0, stream>>>(ix, p);
+    } else {
+        const int tok_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
+        sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (stage_events) cudaEventRecord(stage_events[2], stream);
+        sg_count_kernel<<<blocks, kBitmapWarps * 32, 0, stream>>>(ix, p);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (stage_events) cudaEventRecord(stage_events[3], stream);
@@ -1186,9 +1298,11 @@ cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (stage_events) cudaEventRecord(stage_events[4], stream);
+    // normally no query is dirty and this kernel only looks at the flag: one CTA per SM keeps that look cheap
     SearchParams pf = p;
     pf.only_dirty = 1;
-    blocks = sm_count * search_per_sm;
+    (void)search_per_sm;
+    blocks = sm_count;
     if (blocks > need) blocks = need;
     sg_bitmap_search_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, pf);
     if (stage_events) cudaEventRecord(stage_events[5], stream);

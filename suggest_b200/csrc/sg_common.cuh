@@ -51,7 +51,7 @@ __device__ int metric_max_y(int m, double a, int size) {
 __device__ __noinline__ int metric_threshold(int m, double a, int sa, int sb) {
     switch (m) {
     case kJaccard: return f2i(ceil(__ddiv_rn(__dmul_rn(a, (double)(sa + sb)), __dadd_rn(1.0, a))));
-    case kCosine: return f2i(ceil(__dmul_rn(a, __dsqrt_rn((double)(sa * sb)))));
+    case kCosine: return f2i(ceil(__dmul_rn(a, __dsqrt_rn((double)((long long)sa * sb)))));  // Go's int is 64-bit: no overflow for long queries
     case kDice: return f2i(ceil(__dmul_rn(__dmul_rn(0.5, a), (double)(sa + sb))));
     case kOverlap: return f2i(ceil(__dmul_rn(a, (double)min(sa, sb))));
     default: return sa;
@@ -63,7 +63,7 @@ __device__ __noinline__ double metric_score(int m, int c, int sa, int sb) {
     double d;
     switch (m) {
     case kJaccard: d = __dsub_rn(1.0, __ddiv_rn((double)c, (double)(sa + sb - c))); break;
-    case kCosine: d = __dsub_rn(1.0, __ddiv_rn((double)c, __dsqrt_rn((double)(sa * sb)))); break;
+    case kCosine: d = __dsub_rn(1.0, __ddiv_rn((double)c, __dsqrt_rn((double)((long long)sa * sb)))); break;
     case kDice: d = __dsub_rn(1.0, __ddiv_rn((double)(2 * c), (double)(sa + sb))); break;
     case kOverlap: d = __dsub_rn(1.0, __ddiv_rn((double)c, (double)min(sa, sb))); break;
     default: d = 0.0; break;
@@ -111,8 +111,12 @@ __device__ __forceinline__ uint32_t lower_bound(const uint32_t *__restrict__ pos
 }
 
 // Go `for range` decoding step (utf8.DecodeRune acceptance), invalid byte -> U+FFFD, width 1
+// Query bytes and offsets are read past L1 (.cg): sg_search_batch lets them arrive by DMA while the kernel is already
+// running (SearchParams::arrived), and a line cached before its neighbour chunk landed would be stale.
+__device__ __forceinline__ uint32_t ldq(const uint8_t *p) { return (uint32_t)__ldcg(p); }
+
 __device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *rune) {
-    uint32_t b0 = s[0];
+    uint32_t b0 = ldq(s);
     if (b0 < 0x80) { *rune = b0; return 1; }
     int need;
     uint32_t r, lo = 0x80, hi = 0xBF;
@@ -122,13 +126,39 @@ __device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *
     else { *rune = 0xFFFD; return 1; }
     if (len < (uint32_t)need + 1) { *rune = 0xFFFD; return 1; }
     for (int i = 1; i <= need; i++) {
-        uint32_t b = s[i];
+        uint32_t b = ldq(s + i);
         uint32_t l = i == 1 ? lo : 0x80, h = i == 1 ? hi : 0xBF;
         if (b < l || b > h) { *rune = 0xFFFD; return 1; }
         r = (r << 6) | (b & 0x3F);
     }
     *rune = r;
     return need + 1;
+}
+
+// sg_search_batch copies the queries to the device in chunks while the kernel that tokenizes them is already running; after
+// every chunk a counter in device memory is bumped (a 4-byte copy on the same copy stream, so it lands behind the chunk).
+// A warp waits here until the chunk of its query has arrived.  Copies do not depend on kernels: no deadlock.
+// Returns false if the chunk did not arrive within ~2 s (a failed copy the host could not report in time): the query is
+// then answered as empty and the host turns the call into an error (too_long_flag[1]) - a kernel must never spin for good.
+__device__ __noinline__ int wait_for_chunk(const uint32_t *arrived, uint32_t need, uint32_t *gave_up_flag) {
+    const long long t0 = clock64();
+    while ((int32_t)(*(const volatile uint32_t *)arrived - need) < 0) {
+        if (clock64() - t0 > 4000000000ll) {
+            if (gave_up_flag != nullptr) gave_up_flag[1] = 1u;
+            return 0;
+        }
+        __nanosleep(200);
+    }
+    return 1;
+}
+
+__device__ __forceinline__ bool wait_for_query(const SearchParams &p, uint32_t q, int lane) {
+    if (p.arrived == nullptr) return true;
+    int ok = 1;
+    if (lane == 0) ok = wait_for_chunk(p.arrived, p.arrive_base + q / p.chunk_queries + 1u, p.too_long_flag);
+    ok = __shfl_sync(kFull, ok, 0);
+    __threadfence();
+    return ok != 0;
 }
 
 // The tokenizer chain of pkg/suggest/tokenizer.go:9-20 for query q of the batch, by one converged warp: wrap ->
@@ -145,7 +175,9 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
                                                const uint8_t *s_ascii = nullptr, uint64_t *s_keys = nullptr) {
     bool unsupported = false;
     int size_a = 0;
-    const uint32_t qb = __ldg(p.q_off + q), qe = __ldg(p.q_off + q + 1);
+    // chunked arrival: every chunk of chunk_queries queries has its own n + 1 offsets, kArriveOffPad entries apart
+    const uint32_t qi = p.chunk_queries ? q + (q / p.chunk_queries) * kArriveOffPad : q;
+    const uint32_t qb = __ldcg(p.q_off + qi), qe = __ldcg(p.q_off + qi + 1);
     const uint32_t qlen = qe - qb;
     const uint8_t *qp = (const uint8_t *)p.q_bytes + qb;
     const int nws = ix.n_wrap_start, nwe = p.mode == 1 ? 0 : ix.n_wrap_end;  // NewAutocompleteTokenizer: no tail wrap
@@ -156,7 +188,7 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
         const int nr = nws + (int)qlen + nwe;
         uint32_t r = ' ';
         if (lane < nws) r = ix.wrap_start[lane];
-        else if (lane < nws + (int)qlen) r = qp[lane - nws];
+        else if (lane < nws + (int)qlen) r = ldq(qp + lane - nws);
         else if (lane < nr) r = ix.wrap_end[lane - nws - (int)qlen];
         if (!__any_sync(kFull, r >= 0x80u)) {
             if (r >= 'A' && r <= 'Z') r += 32;
@@ -200,14 +232,14 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
         }
     }
     bool nonascii = false;
-    for (uint32_t i = lane; i < qlen; i += 32) nonascii |= qp[i] >= 0x80;
+    for (uint32_t i = lane; i < qlen; i += 32) nonascii |= ldq(qp + i) >= 0x80;
     nonascii = __any_sync(kFull, nonascii);
     int nq_runes = 0;
     if (!nonascii) {
         if (nws + qlen + nwe > (uint32_t)kMaxRunes) unsupported = true;
         else {
             for (uint32_t i = lane; i < qlen; i += 32) {
-                uint32_t ch = qp[i];
+                uint32_t ch = ldq(qp + i);
                 s_runes[nws + i] = (ch >= 'A' && ch <= 'Z') ? ch + 32 : ch;
             }
             nq_runes = (int)qlen;

@@ -31,6 +31,7 @@ constexpr uint32_t kWarpFixedSmem = kRingSlots * kSliceBytes + 64 + 128 + 64 + 3
 constexpr int kMaxSearchThreads = 512;       // launch bound of sg_search_kernel (16 warps)
 constexpr uint32_t kCountUnsupported = 0xFFFFFFFFu;     // SG_COUNT_UNSUPPORTED
 constexpr uint32_t kMaxBucketShift = 8;      // at most 256 documents per bitmap bucket
+constexpr uint32_t kSmemTopK = 1024;         // largest k whose per-warp top-k is kept in shared memory (bitmap engine)
 
 // non-ASCII alphabet interval: rune r in [lo, hi] has symbol code base + (r - lo)
 struct RuneRange {
@@ -115,10 +116,11 @@ constexpr uint32_t kPlanDirty = 2u;
 
 // ---- count -> resolve pipeline (sg_count_kernel, sg_resolve_kernel): scratch of one launch, sized per query ----
 // flagged bitmap words {query, word, buckets that reached their threshold, 0}: sg_count_kernel -> sg_resolve_kernel
-// survivors {slot, overlap | segment << 16, next node of the query, taken}, a linked list per query, + a score per node
+// survivors {original id, next node of the query | taken << 31, score (two words)}, a linked list per query
 constexpr uint32_t kFlagsPerQuery = 32, kNodesPerQuery = 8;
-constexpr uint32_t kLeanScratchPerQuery = kFlagsPerQuery * 16 + kNodesPerQuery * (16 + 8) + 8;  // + pending[q], head[q]
+constexpr uint32_t kLeanScratchPerQuery = kFlagsPerQuery * 16 + kNodesPerQuery * 16 + 8;  // + pending[q], head[q]
 constexpr uint32_t kNilNode = 0xFFFFFFFFu;
+constexpr uint32_t kArriveOffPad = 32;       // offsets of chunk c start at c * (chunk_queries + kArriveOffPad): no 128-byte line is shared by two chunks
 // counters of one launch, zeroed by sg_tokens_kernel: SearchParams::work_counter points at kWorkWords of them
 enum { kWorkQuery = 0, kWorkFallbackQuery = 1, kWorkFlagCursor = 2, kWorkNodeCursor = 3, kWorkDirtyAny = 4, kWorkWords = 8 };
 
@@ -181,12 +183,34 @@ struct SearchParams {
     uint32_t *lean_pending;   // [n_q] flagged words of the query not yet resolved
     uint32_t *lean_head;      // [n_q] first survivor node of the query, kNilNode: none
     int32_t only_dirty;       // sg_bitmap_search_kernel: answer only the queries marked kPlanDirty (and exit at once if none is)
+    // ---- queries that arrive while the kernel runs (sg_search_batch, page-locked rows) ----
+    const uint32_t *arrived;  // nullptr: everything is there.  Else: chunks copied so far = *arrived - arrive_base
+    uint32_t arrive_base;
+    uint32_t chunk_queries;   // queries per chunk; != 0 also means: q_off holds n + 1 offsets per chunk, kArriveOffPad entries apart
+    uint32_t debug;           // SG_RESOLVE_DEBUG (experiments only; results are wrong with any bit set): 1 skip the pair bits, 2 skip
+                              // survivors, 4 stop behind the plan loads
+    uint8_t *tk_global;       // k > kSmemTopK: 12 * k bytes per warp of the launch for its sorted top-k (scores, then ids); else nullptr
     // ---- sg_candidates_batch (bitmap engine): every candidate of the T-occurrence count instead of a top-k ----
     const uint8_t *custom_thr;        // optional [129][S]: Threshold(alpha, a, B) tabulated by the caller for a metric.Metric that
                                       // is not built in (0 outside [MinY, MaxY]); replaces metric / alpha in sg_window_kernel
     unsigned long long *cand_total;   // non-null: collect mode; candidates found so far (may exceed cand_cap)
     unsigned long long cand_cap;      // entries the four arrays below hold
     uint32_t *cand_query, *cand_ids, *cand_overlap, *cand_segment;  // MergeCandidate (pkg/merger/list_merger.go:33-48) + its query and segment
+};
+
+// queries of more than kMaxQueryTokens n-grams, tokenized on the host (sg_long.cu)
+struct LongParams {
+    const uint64_t *keys;       // packed term keys of every token, query after query (duplicates after normalisation kept)
+    const uint32_t *key_off;    // n_long + 1
+    uint32_t n_long;
+    uint32_t *terms;            // scratch, one per key: term id or kNoTerm
+    uint32_t *counters;         // scratch, n_ids per CTA of the launch
+    int32_t metric, mode;       // mode 1: Autocomplete
+    double alpha;
+    uint32_t k;                 // <= kSmemTopK
+    uint32_t *out_ids;          // [n_long][k]
+    double *out_scores;
+    uint32_t *out_counts;       // [n_long]
 };
 
 SG_HD static inline uint64_t mix64(uint64_t x) {  // splitmix64 finaliser; host and device hash term keys with it

@@ -222,7 +222,7 @@ int sg_exchange_create(int device, uint32_t rank, uint32_t world, uint32_t max_q
     if (!out) return ex_fail(SG_ERR_INVALID, "null out");
     *out = nullptr;
     if (world < 1 || world > sg::kMaxExchangeRanks || rank >= world) return ex_fail(SG_ERR_INVALID, "world must be in 1..16 and rank below it");
-    if (max_queries < 1 || max_k < 1 || max_k > SG_MAX_TOPK) return ex_fail(SG_ERR_INVALID, "max_queries / max_k out of range");
+    if (max_queries < 1 || max_k < 1 || max_k > SG_MAX_TOPK_SHARED) return ex_fail(SG_ERR_INVALID, "max_queries / max_k out of range");
     sg_exchange *ex = new (std::nothrow) sg_exchange();
     if (!ex) return ex_fail(SG_ERR_NOMEM, "out of host memory");
     ex->device = device;

@@ -19,8 +19,12 @@ cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int 
 // count -> resolve pipeline (sg_count_kernel, sg_resolve_kernel, then sg_bitmap_search_kernel for the queries that ran out of
 // scratch); p.lean_* set; stage_events (optional): 6 events around the five kernels
 cudaError_t lean_occupancy(int device, uint32_t k, int *count_per_sm, int *resolve_per_sm);
+// fused: sg_tokens_count_kernel tokenizes and counts in one launch (the caller has zeroed p.work_counter's kWorkWords);
+// else sg_tokens_kernel + sg_count_kernel (needed for p.stats)
 cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm_count, int count_per_sm, int resolve_per_sm,
-                               int search_per_sm, bool run_window, cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
+                               int search_per_sm, bool run_window, bool fused, cudaStream_t stream, cudaEvent_t *stage_events = nullptr);
+// sg_long.cu: one warp per query of more than 128 n-grams (host-tokenized), ScanCount over HBM counters; k <= kSmemTopK
+cudaError_t launch_long_queries(const DevIndex &ix, const LongParams &p, int blocks, cudaStream_t stream);
 cudaError_t launch_merge_topk(uint32_t n_parts, uint32_t n_q, uint32_t k, const uint32_t *part_ids, const double *part_scores,
                               const uint32_t *part_counts, size_t stride_ids, size_t stride_scores, size_t stride_counts,
                               uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int blocks, cudaStream_t stream,

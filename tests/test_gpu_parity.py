@@ -293,10 +293,14 @@ def test_large_k(cars_pair, cars_lines):
     q = cars_lines[:200]
     for k in (1, 32, 33, 250, 1024):
         assert_same(gx, ox, q, O.JACCARD, 0.15, k, f"k={k}")
+    for k in (1025, 3000, 6000):  # above 1024 the per-warp top-k lives in HBM (SearchParams::tk_global)
+        n = assert_same(gx, ox, q[:60], O.JACCARD, 0.01, k, f"k={k}")
+        assert n.max() > 1024
+    assert_same_autocomplete(gx, ox, [b"NISSAN", b"TOYOTA C", b"A"], 2000, "autocomplete limit 2000")
 
 
 def test_invalid_arguments_and_too_long_query(cars_pair):
-    gx, _ = cars_pair
+    gx, ox = cars_pair
     with pytest.raises(S.SuggestError) as e:
         gx.SuggestBatch(["a"], 0.5, S.JaccardMetric(), 0)
     assert e.value.code == _capi.SG_ERR_INVALID
@@ -305,15 +309,27 @@ def test_invalid_arguments_and_too_long_query(cars_pair):
     with pytest.raises(S.SuggestError):
         gx.SuggestBatch(["a"], 1.01, S.JaccardMetric(), 5)
     with pytest.raises(S.SuggestError):
-        gx.SuggestBatch(["a"], 0.5, S.JaccardMetric(), 2000)
-    with pytest.raises(S.SuggestError) as e:
-        gx.SuggestBatch(["ok", "y" * 300], 0.5, S.JaccardMetric(), 5)
-    assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG
-    buf = S.PinnedBuffers(3, 5)  # the direct result path learns of such a query from a flag the kernel sets
-    with pytest.raises(S.SuggestError) as e:
-        gx.SuggestBatch(["ok", "y" * 300, "Nissan March"], 0.5, S.JaccardMetric(), 5, out=buf.out)
-    assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG and buf.counts[1] == _capi.SG_COUNT_UNSUPPORTED and buf.counts[2] > 0
+        gx.SuggestBatch(["a"], 0.5, S.JaccardMetric(), _capi.SG_MAX_TOPK + 1)
+    # a query of more than 128 n-grams is answered (host tokenization + sg_long_query_kernel), not refused
+    long_q = ["ok", "y" * 300, "Nissan March", "nissan " * 30, "NISSAN MARCH " + "z" * 200]
+    assert_same(gx, ox, long_q, O.JACCARD, 0.5, 5, "too long for the batched kernels")
+    assert_same(gx, ox, long_q, O.OVERLAP, 0.6, 5, "too long for the batched kernels, overlap")
+    ids, sc, cnt = gx.SuggestBatch(long_q, 0.5, S.JaccardMetric(), 5)
+    assert cnt[2] > 0
+    buf = S.PinnedBuffers(len(long_q), 5)  # the direct result path learns of such a query from a flag the kernel sets
+    gx.SuggestBatch(long_q, 0.5, S.JaccardMetric(), 5, out=buf.out)
+    assert np.array_equal(buf.counts, cnt) and np.array_equal(buf.ids[2, :cnt[2]], ids[2, :cnt[2]])
     gx.SuggestBatch(["ok", "Nissan March"], 0.5, S.JaccardMetric(), 5, out=(buf.ids[:2], buf.scores[:2], buf.counts[:2]))  # and the flag is per call
+    with pytest.raises(S.SuggestError) as e:  # the device-buffer call still reports it per query
+        import torch
+        data, off = pack_strings(["y" * 300])
+        d_q, d_off = torch.from_numpy(data).cuda(), torch.from_numpy(off.astype(np.int32)).cuda()
+        d_ids, d_sc, d_cnt = torch.zeros(5, dtype=torch.int32).cuda(), torch.zeros(5, dtype=torch.float64).cuda(), torch.zeros(1, dtype=torch.int32).cuda()
+        gx.SuggestBatchDevice(d_q.data_ptr(), d_off.data_ptr(), 1, 0.5, S.JaccardMetric(), 5, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr())
+        torch.cuda.synchronize()
+        if int(d_cnt.cpu().numpy().view(np.uint32)[0]) == _capi.SG_COUNT_UNSUPPORTED:
+            raise S.SuggestError(_capi.SG_ERR_QUERY_TOO_LONG, "reported per query")
+    assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG
     buf.close()
     with pytest.raises(S.SuggestError):
         S.NewRAMBuilder(["a"], IndexDescription(NGramSize=3, Pad="")).Build()
@@ -678,7 +694,46 @@ def test_long_documents_and_queries():
     q2 = queries[:40] + [d[:100] for d in docs2[500:520]]
     assert_same(gx, ox, q2, O.JACCARD, 0.3, 10, "long docs host build")
     assert_same(gx, ox, q2, O.OVERLAP, 0.8, 10, "long docs host build overlap")
-    with pytest.raises(_capi.SuggestError) as e:
-        gx.SuggestBatch([docs2[-1][:200]], 0.5, S.JaccardMetric(), 3)
-    assert e.value.code == _capi.SG_ERR_QUERY_TOO_LONG
+    # queries of 129 .. 399 n-grams: answered like the reference answers them (pkg/merger/list_merger.go:9 saturates at 0xFFFF)
+    q3 = [d[:int(rng.integers(131, len(d) + 1))] for d in docs2[500:]] + [docs2[-1], docs2[-2][5:] + "qq", "short"] + q2[:5]
+    for metric, alpha, k in ((O.JACCARD, 0.3, 10), (O.COSINE, 0.5, 4), (O.DICE, 0.4, 7), (O.OVERLAP, 0.7, 5), (O.EXACT, 1.0, 2)):
+        n = assert_same(gx, ox, q3, metric, alpha, k, f"long queries m={metric}")
+        assert n[:40].sum() > 0
+    assert_same_autocomplete(gx, ox, [d[:int(rng.integers(131, 150))] for d in docs2[500:520]] + ["ab"], 5, "long autocomplete queries")
+    buf = S.PinnedBuffers(len(q3), 10)  # and through the direct result path
+    ids, sc, cnt = gx.SuggestBatch(q3, 0.3, S.JaccardMetric(), 10)
+    gx.SuggestBatch(q3, 0.3, S.JaccardMetric(), 10, out=buf.out)
+    assert np.array_equal(buf.counts, cnt)
+    assert all(np.array_equal(buf.ids[i, :cnt[i]], ids[i, :cnt[i]]) for i in range(len(q3)))
+    gx.close()
+
+
+def test_chunked_arrival_equals_sliced_path():
+    """sg_search_batch with page-locked rows and >= 16,384 queries: one launch, queries arriving in chunks while the
+    kernels run.  Must equal the sliced path (pageable rows) query by query, including chunks that hold non-ASCII bytes
+    (lower-cased on the host into their own area), a query of more than 128 n-grams, empty queries and a ragged last chunk."""
+    docs, (qb, qo), _ = synthetic_workload(50000, 20011)
+    queries = unpack(qb, qo)
+    queries[5] = b""
+    queries[9000] = "ЖИГУЛИ nissan".encode("utf-8")          # chunk 1: non-ASCII
+    queries[9001] = b"\xff\xfe" + queries[9001]
+    queries[17000] = queries[17001] * 9                          # more than 128 n-grams
+    queries[20010] = "Ünïcode tail".encode("utf-8")             # last, ragged chunk
+    gx = build_gpu(TEST_DESCRIPTION, (docs[0], docs[1]))
+    data, off = pack_strings(queries)
+    for metric, alpha, k in ((S.JaccardMetric(), 0.5, 10), (S.CosineMetric(), 0.6, 3)):
+        ids, sc, cnt = gx.SuggestBatch(None, alpha, metric, k, packed=(data, off))
+        buf = S.PinnedBuffers(len(queries), k)
+        for _ in range(3):  # the arrival counter keeps growing across calls
+            gx.SuggestBatch(None, alpha, metric, k, packed=(data, off), out=buf.out)
+            assert np.array_equal(buf.counts, cnt)
+            m = np.arange(k)[None, :] < cnt[:, None]
+            assert np.array_equal(buf.ids[m], ids[m]) and np.array_equal(buf.scores[m], sc[m])
+        assert cnt.sum() > 10000
+        buf.close()
+    ids, sc, cnt = gx.AutocompleteBatch(None, 5, packed=(data, off))
+    buf = S.PinnedBuffers(len(queries), 5)
+    gx.AutocompleteBatch(None, 5, packed=(data, off), out=buf.out)
+    m = np.arange(5)[None, :] < cnt[:, None]
+    assert np.array_equal(buf.counts, cnt) and np.array_equal(buf.ids[m], ids[m])
     gx.close()
