@@ -55,11 +55,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(kernel):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any"""
+def recorded_traffic(kernel, what="dram_bytes_per_launch"):
+    """dram bytes per launch of the dominant kernel (what="source": the profile they come from) as captured with
+    ncu --set full and committed under profiles/ (tools/profile_summary.py); not measured in this run"""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(f"{kernel}_dram_bytes_per_launch")
+            return json.load(f).get(f"{kernel}_{what}")
     except Exception:  # noqa: BLE001
         return None
 
@@ -383,9 +384,12 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
         index.SuggestBatchDevice(B.dq[i].data_ptr(), B.doff[i].data_ptr(), nq, ALPHA, metric, K, B.d_ids[i].data_ptr(),
                                  B.d_sc[i].data_ptr(), B.d_cnt[i].data_ptr(), stats, cs)
 
-    def call_host(b):
+    def call_host(b, slot=0):
+        # the queries of every call come from their own page-locked batch; the result rows go to ONE pooled page-locked
+        # buffer set, the way integration/go/b200.go reuses its pinnedPool rows (eight 8 MB row sets in rotation fall out of
+        # the host's last-level cache, where inbound PCIe writes land, and cost ~15 %)
         i = b % B.n
-        index.SuggestBatch(None, ALPHA, metric, K, packed=B.host_in(i), out=B.host_out(i))
+        index.SuggestBatch(None, ALPHA, metric, K, packed=B.host_in(i), out=B.host_out(slot))
 
     # algorithmic bytes and the engine's own reads, counted by the kernel's stats pass on batch 0 (untimed)
     d_stats = torch.zeros(nq * 4, dtype=torch.int32, device=rig.dev)
@@ -417,8 +421,28 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
                                              B.d_sc[0].data_ptr(), B.d_cnt[0].data_ptr(), cs).items():
                 stage_ms[name] = stage_ms.get(name, 0.0) + ms / n_runs
 
-    e2e_s = rig.time_host(call_host, calls_per_step, steps, warmup)
+    # the same call with the rows as 16-byte {key, score} entries (sg_search_batch_candidates: suggest.Candidate's own layout,
+    # what integration/go/b200.go calls): one PCIe write per candidate instead of two.  This is the e2e figure; the
+    # separate-array call is reported next to it.
+    rows_buf = S.PinnedCandidateRows(nq, K)
+
+    def call_host_rows(b):
+        i = b % B.n
+        index.SuggestBatchCandidates(None, ALPHA, metric, K, packed=B.host_in(i), out=rows_buf.out)
+
+    e2e_arrays_s = rig.time_host(call_host, calls_per_step, steps, warmup)
+    e2e_s = rig.time_host(call_host_rows, calls_per_step, steps, warmup)
     e2e_value = nq * calls_per_step * steps * rig.world / e2e_s
+    e2e_arrays_value = nq * calls_per_step * steps * rig.world / e2e_arrays_s
+    rows_same = True
+    for i in range(B.n):  # untimed: every batch of the ring once more through both calls, for the comparison below
+        call_host(i, slot=i)
+        call_host_rows(i)
+        m_ = np.arange(K)[None, :] < dev_rows[i][2][:, None]
+        rows_same = rows_same and bool(np.array_equal(rows_buf.counts.view(np.int32), dev_rows[i][2]) and
+                                       np.array_equal(rows_buf.rows["key"][m_].view(np.int32), dev_rows[i][0].reshape(nq, K)[m_]) and
+                                       np.array_equal(rows_buf.rows["score"][m_], dev_rows[i][1].reshape(nq, K)[m_]))
+    rows_buf.close()
     same = all(np.array_equal(B.h_cnt[i].numpy(), dev_rows[i][2]) and
                np.array_equal(B.h_ids[i].numpy().reshape(nq, K)[np.arange(K)[None, :] < dev_rows[i][2][:, None]],
                               dev_rows[i][0].reshape(nq, K)[np.arange(K)[None, :] < dev_rows[i][2][:, None]]) for i in range(B.n))
@@ -426,9 +450,10 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
               and all(L.sg_is_pinned(t.data_ptr(), t.numel() * t.element_size()) == 1 for t in (B.h_ids[0], B.h_sc[0], B.h_cnt[0])))
     counts0 = dev_rows[0][2].astype(np.int64)
     h2d = B.h2d_bytes(0) * calls_per_step
-    d2h = int(nq * 4 + 12 * int(counts0.clip(0, K).sum())) if direct else int(nq * K * 12 + nq * 4)
+    d2h = int(nq * 4 + 16 * int(counts0.clip(0, K).sum())) if direct else int(nq * K * 16 + nq * 4)
     out = dict(index=index, batches=B, dev_rows=dev_rows, info=info, layout=layout, build_s=build_s, ms_per_step=ms_per_step,
-               value=value, e2e_value=e2e_value, e2e_s=e2e_s, host_equals_device=bool(same), direct=direct, stage_ms=stage_ms,
+               value=value, e2e_value=e2e_value, e2e_s=e2e_s, e2e_arrays_value=e2e_arrays_value, host_equals_device=bool(same) and rows_same,
+               direct=direct, stage_ms=stage_ms,
                alg_bytes=alg_bytes, engine_bytes=engine_bytes, h2d=h2d, d2h=d2h * calls_per_step, launches=int(launches),
                calls_per_step=calls_per_step, steps=steps, match=float((counts0 > 0).mean()), wall_timed=wall_timed)
     return out
@@ -724,12 +749,15 @@ def main():
                 "l2": "flushed between timed steps (256 MiB write, untimed); inside a step the index stays L2-resident, which "
                       "is the steady state of this workload; the query batches cycle through a ring of 8"},
         "e2e": {"value": r["e2e_value"], "unit": "queries/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                "call": "sg_search_batch_candidates (rows of 16-byte {key, score} entries = suggest.Candidate's layout)",
+                "separate_id_and_score_arrays": {"call": "sg_search_batch", "value": r["e2e_arrays_value"]},
                 "timing": "host wall clock per rank around the timed calls only, max over ranks",
+                "buffers": "queries: a ring of 8 page-locked batches; result rows: one pooled page-locked buffer set (as b200.go's pinnedPool)",
                 "result_path": ("kernel stores into the caller's page-locked rows (valid entries + counts only)" if r["direct"]
                                 else "rows staged in HBM, cudaMemcpyAsync per slice")},
         "gpu_launches": r["launches"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": recorded_traffic(top_kernel), "traffic_source": recorded_traffic("source"),
+                     "traffic": recorded_traffic(top_kernel), "traffic_source": f"ncu --set full capture committed as profiles/{recorded_traffic(top_kernel, 'source')} (not measured in this run)",
                      "peak_kind": peak_kind, "algorithmic_bytes_per_launch": r["alg_bytes"],
                      "algorithmic_bytes_per_query": r["alg_bytes"] / nq, "kernel": top_kernel, "kernel_ms": kernel_ms,
                      "stage_ms": {k_: round(v, 5) for k_, v in stage_ms.items()},

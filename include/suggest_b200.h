@@ -151,6 +151,21 @@ int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, ui
                     uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts);
 
 /*
+ * sg_search_batch with the rows as suggest.Candidate lays them out in memory (pkg/suggest/collector.go:12-17:
+ * {Key index.Position (uint32), Score float64} = 16 bytes with the padding): out_rows[q * k + i] for i < out_counts[q].
+ * A Go caller can view page-locked rows as []Candidate without converting them, and with page-locked rows the kernels
+ * store one 16-byte entry per candidate instead of an id and a score into separate arrays - half the PCIe writes, which is
+ * what bounds the direct result path.  Needs an index with bitmaps (engine 1).
+ */
+typedef struct {
+    uint32_t key;
+    uint32_t reserved;   /* written as 0 */
+    double score;
+} sg_candidate;
+int sg_search_batch_candidates(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                               uint32_t k, sg_candidate *out_rows, uint32_t *out_counts);
+
+/*
  * Batched NGramIndex.Autocomplete with a FirstKCollectorManager(limit)  (pkg/suggest/autocomplete.go:40-77,
  * collector.go:48-115): the query is tokenised without the tail wrap (pkg/suggest/tokenizer.go:23-34), a candidate must
  * hold every query n-gram (threshold = len(tokens), segments len(tokens)..Size()-1) and the `limit` lowest ids win,

@@ -125,12 +125,13 @@ type b200Index struct {
 	batcher *C.sg_batcher
 }
 
-// pinnedRows are page-locked result rows (sg_pinned_alloc): sg_search_batch lets the kernel store straight into them,
-// which a Go-heap slice (pageable) cannot offer.  Pooled, so that a batch call costs no cudaHostAlloc.
+// pinnedRows are page-locked result rows (sg_pinned_alloc) of sg_candidate entries - 16 bytes, {key uint32, pad, score
+// float64}, which is exactly how Candidate{Key index.Position; Score float64} lies in memory (collector.go:12-17) - plus the
+// counts.  sg_search_batch_candidates lets the kernels store straight into them (a Go-heap slice is pageable and would be
+// staged), one PCIe write per candidate.  Pooled, so that a batch call costs no cudaHostAlloc.
 type pinnedRows struct {
 	n, k   int
-	ids    unsafe.Pointer
-	scores unsafe.Pointer
+	rows   unsafe.Pointer
 	counts unsafe.Pointer
 }
 
@@ -145,7 +146,7 @@ func getPinnedRows(n, k int) (*pinnedRows, error) {
 		r.free()
 	}
 	r := &pinnedRows{n: n, k: k}
-	if C.sg_pinned_alloc(C.uint64_t(n*k*4), &r.ids) != 0 || C.sg_pinned_alloc(C.uint64_t(n*k*8), &r.scores) != 0 ||
+	if C.sg_pinned_alloc(C.uint64_t(n*k)*C.uint64_t(unsafe.Sizeof(C.sg_candidate{})), &r.rows) != 0 ||
 		C.sg_pinned_alloc(C.uint64_t(n*4), &r.counts) != 0 {
 		r.free()
 		return nil, lastError()
@@ -155,10 +156,9 @@ func getPinnedRows(n, k int) (*pinnedRows, error) {
 }
 
 func (r *pinnedRows) free() {
-	C.sg_pinned_free(r.ids)
-	C.sg_pinned_free(r.scores)
+	C.sg_pinned_free(r.rows)
 	C.sg_pinned_free(r.counts)
-	r.ids, r.scores, r.counts = nil, nil, nil
+	r.rows, r.counts = nil, nil
 }
 
 func bytesPtr(b []byte) *C.char {
@@ -254,22 +254,29 @@ func (ix *b200Index) SuggestBatch(queries []string, similarity float64, m metric
 	if n == 0 || k <= 0 {
 		return make([][]Candidate, n), nil
 	}
-	// page-locked rows from the pool: the kernel stores the valid entries of every row straight into them
+	// page-locked rows from the pool: the kernels store the valid entries of every row straight into them, laid out as
+	// []Candidate; a row is copied out with one copy(), no per-entry conversion
 	rows, err := getPinnedRows(n, k)
 	if err != nil {
 		return nil, err
 	}
 	defer pinnedPool.Put(rows)
-	ids := (*[1 << 28]C.uint32_t)(rows.ids)[: n*k : n*k]
-	scores := (*[1 << 27]C.double)(rows.scores)[: n*k : n*k]
-	counts := (*[1 << 28]C.uint32_t)(rows.counts)[:n:n]
-	rc := C.sg_search_batch(ix.handle, bytesPtr(bytes), &offsets[0], C.uint32_t(n), code, C.double(similarity), C.uint32_t(k),
-		&ids[0], &scores[0], &counts[0])
+	if unsafe.Sizeof(Candidate{}) != unsafe.Sizeof(C.sg_candidate{}) || unsafe.Offsetof(Candidate{}.Score) != 8 {
+		return nil, errors.New("b200 index: Candidate is not laid out as sg_candidate")
+	}
+	rc := C.sg_search_batch_candidates(ix.handle, bytesPtr(bytes), &offsets[0], C.uint32_t(n), code, C.double(similarity), C.uint32_t(k),
+		(*C.sg_candidate)(rows.rows), (*C.uint32_t)(rows.counts))
 	runtime.KeepAlive(ix)
 	if rc != 0 {
 		return nil, lastError()
 	}
-	return rowsToCandidates(n, k, ids, scores, counts), nil // copies the valid entries out of the pooled rows
+	view := (*[1 << 26]Candidate)(rows.rows)[: n*k : n*k]
+	counts := (*[1 << 28]C.uint32_t)(rows.counts)[:n:n]
+	out := make([][]Candidate, n)
+	for q := 0; q < n; q++ {
+		out[q] = append([]Candidate(nil), view[q*k:q*k+int(counts[q])]...)
+	}
+	return out, nil
 }
 
 // Autocomplete implements Autocomplete (autocomplete.go:40-77).  FirstKCollectorManager(limit) runs on the device

@@ -50,6 +50,8 @@ SIGNATURES = {
     "sg_index_get_layout": (C.c_int, [C.c_void_p, C.POINTER(SgIndexLayout)]),
     "sg_search_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sg_search_batch_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
+                                             C.c_void_p, C.c_void_p]),
     "sg_autocomplete_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "sg_candidates_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_void_p, C.c_uint64,

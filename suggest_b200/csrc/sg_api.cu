@@ -11,6 +11,7 @@
 #include <cstring>
 #include <deque>
 #include <mutex>
+#include <shared_mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -94,6 +95,7 @@ struct CallCtx {
     DevBuf<uint8_t> plans;   // per-query plans, sg_plan_kernel -> sg_search_kernel or sg_tokens_kernel -> sg_bitmap_search_kernel
     DevBuf<uint8_t> wtab;    // window tables of the bitmap engine, one set per slice
     DevBuf<double> scores;
+    DevBuf<uint4> packed;                // staged rows of sg_candidate entries (sg_search_batch_candidates, pageable rows)
     DevBuf<uint32_t> cand;               // sg_candidates_batch: [query | id | overlap | segment] x cap, then the thresholds
     DevBuf<unsigned long long> cand_total;
 };
@@ -135,6 +137,8 @@ struct sg_index {
                                          // Every further slice costs more in launch gaps and kernel tails than it hides
                                          // (measured: "25" 186 M q/s, "10,40" 184, "6,20,50" 187 / Cosine 140, 137, 132)
     bool direct_out = true;              // SG_DIRECT_OUT=0: always stage the rows in HBM and copy them back
+    int direct_chunks = 4;               // SG_DIRECT_CHUNKS: chunks the queries of a call with page-locked rows arrive in under one launch
+                                         // (search_batch_chunked); 0: such calls are cut into slices like the others
     size_t l2_persist_bytes = 0;         // persisting-L2 carve-out used for the posting array (0: none)
     size_t l2_window_bytes = 0;
     float l2_hit_ratio = 1.0f;
@@ -263,6 +267,14 @@ int finish_setup(sg_index *ix) {
         if (eng && std::strcmp(eng, "bitmap") == 0 && !ix->bitmap_engine) return fail(SG_ERR_NOMEM, "the bucket bitmaps do not fit their memory budget");
         ix->plan_stride = ix->bitmap_engine ? sg::kTokStride : sg::kPlanStride;
         if (ix->bitmap_engine) {
+            SG_CUDA(sg::preload_bitmap_kernels());
+            {   // ... and the driver's own memset path, which the pipeline uses on its launching stream
+                void *scratch = nullptr;
+                SG_CUDA(cudaMalloc(&scratch, 64));
+                cudaMemsetAsync(scratch, 0, 64, nullptr);
+                cudaStreamSynchronize(nullptr);
+                cudaFree(scratch);
+            }
             // the exact level under the bitmaps (sg_fine.cu) and with it the count -> resolve pipeline; SG_PIPELINE=classic keeps
             // every search on sg_bitmap_search_kernel
             const char *pl = std::getenv("SG_PIPELINE");
@@ -331,6 +343,7 @@ int finish_setup(sg_index *ix) {
         }
     }
     ix->direct_out = env_int("SG_DIRECT_OUT", 1) != 0;
+    ix->direct_chunks = env_int("SG_DIRECT_CHUNKS", 4);
     ix->max_warps = env_int("SG_WARPS", kMaxWarps);
     if (ix->max_warps < 1) ix->max_warps = 1;
     if (ix->max_warps > kMaxWarps) ix->max_warps = kMaxWarps;
@@ -342,7 +355,7 @@ void destroy(sg_index *ix) {
     DeviceGuard guard;
     guard.set(ix->device);
     for (CallCtx *c : ix->pool) {
-        c->arrived.release(); c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->plans.release(); c->wtab.release(); c->cand.release(); c->cand_total.release();
+        c->arrived.release(); c->q_bytes.release(); c->q_off.release(); c->ids.release(); c->counts.release(); c->work.release(); c->scores.release(); c->packed.release(); c->plans.release(); c->wtab.release(); c->cand.release(); c->cand_total.release();
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -434,7 +447,7 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
                    uint32_t k, uint32_t *d_ids, double *d_scores, uint32_t *d_counts, uint32_t *d_stats, uint32_t *d_work,
                    uint8_t *d_plans, uint8_t *d_wtab, cudaStream_t stream, int mode = 0, cudaEvent_t *stage_events = nullptr,
                    const sg::LmContext *d_lm_ctx = nullptr, int sparse_rows = 0, uint32_t *too_long_flag = nullptr,
-                   const CollectArgs *collect = nullptr, const ArriveArgs *arrive = nullptr) {
+                   const CollectArgs *collect = nullptr, const ArriveArgs *arrive = nullptr, uint4 *d_packed = nullptr) {
     Geometry g{};
     int rc = SG_OK;
     if (!ix->bitmap_engine && (rc = geometry(ix, n_q, k, &g)) != SG_OK) return rc;
@@ -448,6 +461,7 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
     p.out_ids = d_ids;
     p.out_scores = d_scores;
     p.out_counts = d_counts;
+    p.out_packed = d_packed;  // rows of sg_candidate entries instead of d_ids / d_scores (bitmap engine)
     p.stats = d_stats;
     p.work_counter = d_work;
     p.plans = d_plans;
@@ -792,11 +806,19 @@ void sg_pinned_free(void *p) {
 
 int sg_is_pinned(const void *p, uint64_t bytes) { return mapped_host_range(p, (size_t)bytes) != nullptr ? 1 : 0; }
 
+// where the rows of a host-buffer call go: separate id / score arrays (sg_search_batch) or rows of 16-byte sg_candidate
+// entries, suggest.Candidate's own layout (sg_search_batch_candidates)
+struct OutRows {
+    uint32_t *ids;
+    double *scores;
+    sg_candidate *rows;
+};
+
 // Queries the batched kernels refused (more than 128 n-grams: count SG_COUNT_UNSUPPORTED) are answered here, after the
 // batch: host tokenization (the index build's chain, sg_text.cpp), one warp per query on the device (sg_long.cu).  The
 // reference has no such limit (pkg/merger/list_merger.go:9 saturates overlaps at 0xFFFF).  Synchronous, rare.
 static int answer_long_queries(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha, uint32_t k,
-                               uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int mode) {
+                               const OutRows &out, uint32_t *out_counts, int mode) {
     std::vector<uint32_t> which;
     for (uint32_t q = 0; q < n_q; q++)
         if (out_counts[q] == SG_COUNT_UNSUPPORTED) which.push_back(q);
@@ -853,8 +875,12 @@ static int answer_long_queries(sg_index *ix, const char *q_bytes, const uint32_t
     for (uint32_t i = 0; i < n_long; i++) {
         const uint32_t q = which[i];
         out_counts[q] = counts[i];
-        std::memcpy(out_ids + (size_t)q * k, ids.data() + (size_t)i * k, (size_t)counts[i] * 4);
-        std::memcpy(out_scores + (size_t)q * k, scores.data() + (size_t)i * k, (size_t)counts[i] * 8);
+        if (out.rows) {
+            for (uint32_t j = 0; j < counts[i]; j++) out.rows[(size_t)q * k + j] = sg_candidate{ids[(size_t)i * k + j], 0u, scores[(size_t)i * k + j]};
+            continue;
+        }
+        std::memcpy(out.ids + (size_t)q * k, ids.data() + (size_t)i * k, (size_t)counts[i] * 4);
+        std::memcpy(out.scores + (size_t)q * k, scores.data() + (size_t)i * k, (size_t)counts[i] * 8);
     }
     return SG_OK;
 }
@@ -866,7 +892,7 @@ static int answer_long_queries(sg_index *ix, const char *q_bytes, const uint32_t
 // A chunk that holds non-ASCII bytes is lower-cased on the host (strings.ToLower) into an area of its own behind the raw
 // bytes, with offsets of its own; that is why every chunk carries its n + 1 offsets (kArriveOffPad apart).
 static int search_batch_chunked(sg_index *ix, CallCtx *c, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
-                                uint32_t k, uint32_t *m_ids, double *m_scores, uint32_t *out_counts, int mode, uint32_t n_chunks) {
+                                uint32_t k, uint32_t *m_ids, double *m_scores, uint4 *m_rows, uint32_t *out_counts, int mode, uint32_t n_chunks) {
     const uint32_t total = q_off[n_q];
     uint32_t chunk_q = (n_q + n_chunks - 1) / n_chunks;
     chunk_q = (chunk_q + 31u) & ~31u;  // whole 128-byte lines of offsets per chunk
@@ -931,11 +957,13 @@ static int search_batch_chunked(sg_index *ix, CallCtx *c, const char *q_bytes, c
         int r = copy_chunk(0);
         if (r != SG_OK) return r;
         r = enqueue_search(ix, c->q_bytes.p, c->q_off.p, n_q, metric, alpha, k, m_ids, m_scores, c->counts.p, nullptr, c->work.p, c->plans.p,
-                           c->wtab.p, st, mode, nullptr, nullptr, 1, d_too_long, nullptr, &arrive);
+                           c->wtab.p, st, mode, nullptr, nullptr, 1, d_too_long, nullptr, &arrive, m_rows);
         if (r != SG_OK) return r;
-        SG_CUDA(cudaMemcpyAsync(out_counts, c->counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         for (uint32_t ch = 1; ch < n_chunks; ch++)
             if ((r = copy_chunk(ch)) != SG_OK) return r;
+        // The copy of the counts is enqueued LAST.  It waits for the kernels, the kernels wait for the chunks: a copy engine
+        // serves its queue in order, and were this copy queued ahead of the chunks on the same engine, nothing would ever move.
+        SG_CUDA(cudaMemcpyAsync(out_counts, c->counts.p, (size_t)n_q * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         return SG_OK;
     };
     rc = enqueue_all();
@@ -954,7 +982,7 @@ static int search_batch_chunked(sg_index *ix, CallCtx *c, const char *q_bytes, c
         if (rc == SG_OK && e != cudaSuccess) { cudaGetLastError(); rc = fail(SG_ERR_CUDA, std::string("sg_search_batch: ") + cudaGetErrorString(e)); }
     }
     if (rc != SG_OK) return rc;
-    if (((volatile uint32_t *)c->too_long)[1] != 0u) return fail(SG_ERR_CUDA, "sg_search_batch: a chunk of queries did not reach the device in time");
+    if (((volatile uint32_t *)c->too_long)[1] != 0u) return -101;  // a chunk did not reach the device in time: the caller runs the sliced path
     if (trace)
         std::fprintf(stderr, "sg_search_batch: %u queries in %u chunks under one launch (rows stored into page-locked host memory): enqueue %.1f us, wait %.1f us\n",
                      n_q, n_chunks, std::chrono::duration<double, std::micro>(t_enqueued - t_begin).count(),
@@ -964,11 +992,15 @@ static int search_batch_chunked(sg_index *ix, CallCtx *c, const char *q_bytes, c
 }
 
 static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
-                             uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts, int mode) {
+                             uint32_t k, const OutRows &out, uint32_t *out_counts, int mode) {
     int rc = validate_search(ix, n_q, metric, alpha, k);
     if (rc != SG_OK) return rc;
     if (n_q == 0) return SG_OK;
-    if (!q_off || !out_ids || !out_scores || !out_counts) return fail(SG_ERR_INVALID, "null buffer");
+    uint32_t *const out_ids = out.ids;
+    double *const out_scores = out.scores;
+    sg_candidate *const out_rows = out.rows;
+    if (!q_off || !out_counts || (out_rows ? false : (!out_ids || !out_scores))) return fail(SG_ERR_INVALID, "null buffer");
+    if (out_rows && !ix->bitmap_engine) return fail(SG_ERR_UNSUPPORTED, "sg_search_batch_candidates needs an index with bitmaps (engine 1)");
     const uint32_t total = q_off[n_q];
     if (total && !q_bytes) return fail(SG_ERR_INVALID, "null query bytes");
 
@@ -983,19 +1015,37 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     // need to cut the batch into small slices to overlap that copy.  Entries at and behind out_counts[q] are not written.
     uint32_t *m_ids = nullptr, *m_counts = nullptr;
     double *m_scores = nullptr;
+    uint4 *m_rows = nullptr;
+    static_assert(sizeof(sg_candidate) == sizeof(uint4), "sg_candidate is 16 bytes");
     if (ix->direct_out && ix->bitmap_engine) {
-        m_ids = (uint32_t *)mapped_host_range(out_ids, (size_t)n_q * k * sizeof(uint32_t));
-        m_scores = (double *)mapped_host_range(out_scores, (size_t)n_q * k * sizeof(double));
+        if (out_rows) {
+            m_rows = (uint4 *)mapped_host_range(out_rows, (size_t)n_q * k * sizeof(sg_candidate));
+        } else {
+            m_ids = (uint32_t *)mapped_host_range(out_ids, (size_t)n_q * k * sizeof(uint32_t));
+            m_scores = (double *)mapped_host_range(out_scores, (size_t)n_q * k * sizeof(double));
+        }
         m_counts = (uint32_t *)mapped_host_range(out_counts, (size_t)n_q * sizeof(uint32_t));
     }
-    const bool direct = m_ids && m_scores && m_counts;
-    static const int want_chunks = env_int("SG_DIRECT_CHUNKS", 8);
+    const bool direct = (out_rows ? m_rows != nullptr : (m_ids && m_scores)) && m_counts;
+    // A chunked call has kernels on the device that wait for copies the host has yet to enqueue.  Nothing else of this
+    // library is enqueued on the device meanwhile (exclusive; the sliced path holds the lock shared): a copy of another
+    // call that waits for ITS kernel could sit in front of our chunks in a copy engine's queue while that kernel waits for
+    // the SMs ours holds.  Should the chunks still not arrive (work of the host application in the way), the kernels give
+    // up after ~2 s and the batch is answered again by the sliced path, which never waits on the device.
+    static std::shared_mutex device_gate[64];
+    std::shared_mutex &gate = device_gate[ix->device & 63];
+    const int want_chunks = ix->direct_chunks;
     if (direct && want_chunks > 0 && n_q >= 16384) {
         const uint32_t n_chunks = (uint32_t)want_chunks > kMaxChunks ? kMaxChunks : (uint32_t)want_chunks;
-        rc = search_batch_chunked(ix, c, q_bytes, q_off, n_q, metric, alpha, k, m_ids, m_scores, out_counts, mode, n_chunks);
-        if (rc != -100) return rc;
-        return answer_long_queries(ix, q_bytes, q_off, n_q, metric, alpha, k, out_ids, out_scores, out_counts, mode);
+        {
+            std::unique_lock<std::shared_mutex> exclusive(gate);
+            rc = search_batch_chunked(ix, c, q_bytes, q_off, n_q, metric, alpha, k, m_ids, m_scores, m_rows, out_counts, mode, n_chunks);
+        }
+        if (rc == -100) return answer_long_queries(ix, q_bytes, q_off, n_q, metric, alpha, k, out, out_counts, mode);
+        if (rc != -101) return rc;
+        // -101: the chunks did not arrive in time; fall through to the sliced path
     }
+    std::shared_lock<std::shared_mutex> shared(gate);
     std::vector<uint32_t> bounds{0u};  // slice sl = queries [bounds[sl], bounds[sl + 1])
     if (direct && ix->direct_slice_queries == 0) {
         if (n_q >= 16384)
@@ -1013,8 +1063,12 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
     SG_CUDA(c->q_bytes.reserve((size_t)total * 3 + 64 * (size_t)n_slices + 64));
     SG_CUDA(c->q_off.reserve((size_t)n_q + n_slices + 1));
     if (!direct) {
-        SG_CUDA(c->ids.reserve((size_t)n_q * k));
-        SG_CUDA(c->scores.reserve((size_t)n_q * k));
+        if (out_rows) {
+            SG_CUDA(c->packed.reserve((size_t)n_q * k));
+        } else {
+            SG_CUDA(c->ids.reserve((size_t)n_q * k));
+            SG_CUDA(c->scores.reserve((size_t)n_q * k));
+        }
     }
     SG_CUDA(c->counts.reserve(n_q));  // direct rows too: counts are staged (one copy per slice instead of a PCIe write per query)
     SG_CUDA(c->work.reserve((size_t)kMaxSlices * sg::kWorkWords));
@@ -1088,10 +1142,11 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 1], cs);
         SG_CUDA(cudaEventRecord(c->h2d_done[sl], cs));
         SG_CUDA(cudaStreamWaitEvent(st, c->h2d_done[sl], 0));
-        rc = enqueue_search(ix, d_q_bytes, d_off, hi - lo, metric, alpha, k, (direct ? m_ids : c->ids.p) + (size_t)lo * k,
-                            (direct ? m_scores : c->scores.p) + (size_t)lo * k, c->counts.p + lo, nullptr,
+        uint4 *d_rows = out_rows ? (direct ? m_rows : c->packed.p) + (size_t)lo * k : nullptr;
+        rc = enqueue_search(ix, d_q_bytes, d_off, hi - lo, metric, alpha, k, out_rows ? nullptr : (direct ? m_ids : c->ids.p) + (size_t)lo * k,
+                            out_rows ? nullptr : (direct ? m_scores : c->scores.p) + (size_t)lo * k, c->counts.p + lo, nullptr,
                             c->work.p + (size_t)sl * sg::kWorkWords, c->plans.p + (size_t)lo * ix->plan_stride, c->wtab.p + (size_t)sl * ix->wtab_bytes, st,
-                            mode, nullptr, nullptr, direct ? 1 : 0, direct ? d_too_long : nullptr);
+                            mode, nullptr, nullptr, direct ? 1 : 0, direct ? d_too_long : nullptr, nullptr, nullptr, d_rows);
         if (rc != SG_OK) return rc;
         if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 2], st);
         if (direct) {
@@ -1102,10 +1157,15 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
             if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 3], st);
             continue;
         }
-        SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, c->ids.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t),
-                                cudaMemcpyDeviceToHost, st));
-        SG_CUDA(cudaMemcpyAsync(out_scores + (size_t)lo * k, c->scores.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(double),
-                                cudaMemcpyDeviceToHost, st));
+        if (out_rows) {
+            SG_CUDA(cudaMemcpyAsync(out_rows + (size_t)lo * k, c->packed.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(sg_candidate),
+                                    cudaMemcpyDeviceToHost, st));
+        } else {
+            SG_CUDA(cudaMemcpyAsync(out_ids + (size_t)lo * k, c->ids.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaMemcpyAsync(out_scores + (size_t)lo * k, c->scores.p + (size_t)lo * k, (size_t)(hi - lo) * k * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+        }
         SG_CUDA(cudaMemcpyAsync(out_counts + lo, c->counts.p + lo, (size_t)(hi - lo) * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (trace >= 2) cudaEventRecord(tev[(size_t)sl * 4 + 3], st);
     }
@@ -1140,17 +1200,23 @@ static int search_batch_impl(sg_index *ix, const char *q_bytes, const uint32_t *
         for (auto &e : tev) cudaEventDestroy(e);
     }
     if (direct && *(volatile uint32_t *)c->too_long == 0u) return SG_OK;  // the kernel saw no such query: nothing to look for
-    return answer_long_queries(ix, q_bytes, q_off, n_q, metric, alpha, k, out_ids, out_scores, out_counts, mode);
+    return answer_long_queries(ix, q_bytes, q_off, n_q, metric, alpha, k, out, out_counts, mode);
 }
 
 int sg_search_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
                     uint32_t k, uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
-    return search_batch_impl(ix, q_bytes, q_off, n_q, metric, alpha, k, out_ids, out_scores, out_counts, 0);
+    return search_batch_impl(ix, q_bytes, q_off, n_q, metric, alpha, k, OutRows{out_ids, out_scores, nullptr}, out_counts, 0);
+}
+
+int sg_search_batch_candidates(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
+                               uint32_t k, sg_candidate *out_rows, uint32_t *out_counts) {
+    if (!out_rows && n_q) return fail(SG_ERR_INVALID, "null buffer");
+    return search_batch_impl(ix, q_bytes, q_off, n_q, metric, alpha, k, OutRows{nullptr, nullptr, out_rows}, out_counts, 0);
 }
 
 int sg_autocomplete_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, uint32_t limit,
                           uint32_t *out_ids, double *out_scores, uint32_t *out_counts) {
-    return search_batch_impl(ix, q_bytes, q_off, n_q, SG_EXACT, 1.0, limit, out_ids, out_scores, out_counts, 1);
+    return search_batch_impl(ix, q_bytes, q_off, n_q, SG_EXACT, 1.0, limit, OutRows{out_ids, out_scores, nullptr}, out_counts, 1);
 }
 
 int sg_candidates_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric, double alpha,
@@ -1287,7 +1353,9 @@ int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d
     if (se != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(se));
     if (names_out && names_cap) {
         const char *names = !ix->bitmap_engine ? "sg_plan_kernel,sg_search_kernel"
-                            : ix->lean_pipeline ? "sg_window_kernel,sg_tokens_kernel,sg_count_kernel,sg_resolve_kernel,sg_bitmap_search_kernel"
+                            : ix->lean_pipeline ? (env_int("SG_FUSED_TOKENS", 1) != 0
+                                                       ? "sg_window_kernel,(tokenizer fused into the next kernel),sg_tokens_count_kernel,sg_resolve_kernel,sg_bitmap_search_kernel"
+                                                       : "sg_window_kernel,sg_tokens_kernel,sg_count_kernel,sg_resolve_kernel,sg_bitmap_search_kernel")
                                                 : "sg_window_kernel,sg_tokens_kernel,sg_bitmap_search_kernel";
         std::strncpy(names_out, names, names_cap - 1);
         names_out[names_cap - 1] = 0;

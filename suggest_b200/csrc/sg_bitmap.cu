@@ -100,6 +100,12 @@ __device__ __forceinline__ void csa(uint32_t &h, uint32_t &l, uint32_t a, uint32
     l = u ^ c;
 }
 
+// one entry of a result row: separate id / score arrays, or 16-byte {id, 0, score} entries (SearchParams::out_packed)
+__device__ __forceinline__ void store_entry(uint32_t *out_ids, double *out_scores, uint4 *out_packed, size_t at, uint32_t id, double score) {
+    if (out_packed != nullptr) out_packed[at] = make_uint4(id, 0u, (uint32_t)__double2loint(score), (uint32_t)__double2hiint(score));
+    else { out_ids[at] = id; out_scores[at] = score; }
+}
+
 __device__ __forceinline__ double *warp_tk_score(WarpSmem *ws) { return ws->tk_score; }
 __device__ __forceinline__ uint32_t *warp_tk_id(WarpSmem *ws, uint32_t) { return ws->tk_id; }
 
@@ -489,9 +495,12 @@ __global__ void __launch_bounds__(kWindowThreads) sg_window_kernel(const DevInde
 // admissible postings / lists of SURVEY.md section 8(d) (the algorithmic bytes of the roofline) and the bitmap words the
 // engine reads for the count: 16 bytes per query {postings, lists, bitmap words, 0}.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_kernel(const DevIndex ix, const SearchParams p) {
+template <bool kArrive>
+__device__ __forceinline__ void tokens_body(const DevIndex &ix, const SearchParams &p) {
     __shared__ __align__(16) uint32_t s_scratch[kPlanThreads / 32][kMaxRunes + 2 * kMaxQueryTokens];
     __shared__ uint8_t s_ascii[128];
+    __shared__ uint32_t s_seen;
+    if (kArrive && threadIdx.x == 0) s_seen = p.arrive_base;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x < 128) s_ascii[threadIdx.x] = ix.ascii_code[threadIdx.x];
@@ -504,9 +513,9 @@ __global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_
     if (blockIdx.x == 0 && threadIdx.x < kWorkWords) p.work_counter[threadIdx.x] = 0u;  // counters of the kernels behind this one
     for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < p.n_q; q += n_warps) {
         int size_a = 0, n_lists = 0;
-        const bool arrived = wait_for_query(p, q, lane);
         bool unsupported = false;
-        if (arrived) unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
+        if (!kArrive || wait_for_query(p, q, lane, &s_seen))
+            unsupported = tokenize_query<false, kArrive>(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
         if (p.mode == 1 && n_lists < size_a) n_lists = 0;  // a query token that is in no list: nothing can hold them all
         if (unsupported) { size_a = 0; n_lists = 0; }
         uint8_t *plan_base = p.plans + (size_t)q * kTokStride;
@@ -547,6 +556,15 @@ __global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_
         }
         __syncwarp();
     }
+}
+
+__global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_kernel(const DevIndex ix, const SearchParams p) {
+    tokens_body<false>(ix, p);
+}
+
+// the same with queries that arrive in chunks while the kernel runs (SearchParams::arrived, sg_search_batch)
+__global__ void __launch_bounds__(kPlanThreads, SG_TOKENS_MIN_BLOCKS) sg_tokens_arrive_kernel(const DevIndex ix, const SearchParams p) {
+    tokens_body<true>(ix, p);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -656,8 +674,7 @@ __device__ __forceinline__ void bitmap_search_body(const DevIndex &ix, const Sea
         const uint32_t n_out = p.sparse_rows ? (uint32_t)tk_len : p.k;
         for (uint32_t j = lane; j < n_out; j += 32) {
             const bool has = (int)j < tk_len;
-            p.out_ids[row + j] = has ? ix.id_base + tk_id[j] : 0u;
-            p.out_scores[row + j] = has ? tk_score[j] : 0.0;
+            store_entry(p.out_ids, p.out_scores, p.out_packed, row + j, has ? ix.id_base + tk_id[j] : 0u, has ? tk_score[j] : 0.0);
         }
         if (lane == 0) {
             // collect mode reports len(tokens): the caller's Distance(inter, sizeA, sizeB) needs it
@@ -828,14 +845,16 @@ __device__ __forceinline__ uint32_t count_and_flag(const DevIndex &ix, const Sea
 // kFused: the kernel tokenizes the query itself (tokenize_query, the same code sg_tokens_kernel runs) and writes the plan for
 // sg_resolve_kernel, instead of reading a plan sg_tokens_kernel wrote: one launch and one pass over the plans less, and the
 // tokenizer's chains of dependent loads (offsets -> bytes -> hash probe) hide under the row reads of the other warps.
-template <bool kFused>
+template <bool kFused, bool kArrive>
 __device__ __forceinline__ void count_body(const DevIndex &ix, const SearchParams &p) {
     __shared__ __align__(16) uint32_t s_rows[kBitmapWarps][kRowSlots];
     __shared__ __align__(16) uint32_t s_tok[kFused ? kBitmapWarps : 1][kFused ? kMaxRunes + 2 * kMaxQueryTokens : 1];
     __shared__ uint8_t s_ascii[128];
+    __shared__ uint32_t s_seen;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     if (kFused) {
+        if (kArrive && threadIdx.x == 0) s_seen = p.arrive_base;
         if (threadIdx.x < 128) s_ascii[threadIdx.x] = ix.ascii_code[threadIdx.x];
         __syncthreads();
     }
@@ -858,7 +877,8 @@ __device__ __forceinline__ void count_body(const DevIndex &ix, const SearchParam
             if (lane == 0) q_next = take_query(p.work_counter + kWorkQuery);
             unsupported = false;
             size_a = n_lists = 0;
-            if (wait_for_query(p, q, lane)) unsupported = tokenize_query(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
+            if (!kArrive || wait_for_query(p, q, lane, &s_seen))
+                unsupported = tokenize_query<false, kArrive>(ix, p, q, s_runes, s_lterm, s_hash, lane, &size_a, &n_lists, s_ascii);
             if (unsupported) { size_a = 0; n_lists = 0; }
             win = p.wt.win[size_a];
             for (int j = lane; j < n_lists; j += 32) ((uint32_t *)(plan_base + kTokTermsOffset))[j] = s_lterm[j];  // for sg_resolve_kernel
@@ -904,7 +924,7 @@ __device__ __forceinline__ void count_body(const DevIndex &ix, const SearchParam
         if (n_entries == 0u && !dirty) {  // nothing reached its threshold: the answer is the empty row
             if (!p.sparse_rows) {
                 const size_t r0 = (size_t)q * p.k;
-                for (uint32_t j = lane; j < p.k; j += 32) { p.out_ids[r0 + j] = 0u; p.out_scores[r0 + j] = 0.0; }
+                for (uint32_t j = lane; j < p.k; j += 32) store_entry(p.out_ids, p.out_scores, p.out_packed, r0 + j, 0u, 0.0);
             }
             if (lane == 0) {
                 p.out_counts[q] = unsupported ? kCountUnsupported : 0u;
@@ -917,11 +937,16 @@ __device__ __forceinline__ void count_body(const DevIndex &ix, const SearchParam
 }
 
 __global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_count_kernel(const DevIndex ix, const SearchParams p) {
-    count_body<false>(ix, p);
+    count_body<false, false>(ix, p);
 }
 
 __global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_tokens_count_kernel(const DevIndex ix, const SearchParams p) {
-    count_body<true>(ix, p);
+    count_body<true, false>(ix, p);
+}
+
+// the same with queries that arrive in chunks while the kernel runs (SearchParams::arrived, sg_search_batch)
+__global__ void __launch_bounds__(kBitmapWarps * 32, SG_COUNT_MIN_BLOCKS) sg_tokens_count_arrive_kernel(const DevIndex ix, const SearchParams p) {
+    count_body<true, true>(ix, p);
 }
 
 // ---- sg_resolve_kernel: eight lanes per flagged bitmap word, four words per warp ----
@@ -962,7 +987,7 @@ __device__ __forceinline__ void link_survivor(const DevIndex &ix, const SearchPa
 __device__ __forceinline__ void write_row_end(const DevIndex &ix, const SearchParams &p, uint32_t q, uint32_t n_out) {
     if (!p.sparse_rows) {
         const size_t row = (size_t)q * p.k;
-        for (uint32_t j = n_out; j < p.k; j++) { p.out_ids[row + j] = 0u; p.out_scores[row + j] = 0.0; }
+        for (uint32_t j = n_out; j < p.k; j++) store_entry(p.out_ids, p.out_scores, p.out_packed, row + j, 0u, 0.0);
     }
     p.out_counts[q] = n_out;  // (a query with too many n-grams has no lists and never gets here)
 }
@@ -978,6 +1003,7 @@ struct SelectArgs {  // by value: a reference to the kernel parameters would mak
     uint4 *lean_nodes;
     uint32_t *out_ids, *out_counts;
     double *out_scores;
+    uint4 *out_packed;
 };
 __device__ __noinline__ void select_survivors(const SelectArgs p, uint32_t q) {
     const size_t row = (size_t)q * p.k;
@@ -999,7 +1025,7 @@ __device__ __noinline__ void select_survivors(const SelectArgs p, uint32_t q) {
             bi[at] = node.x;
             if (n_out < p.k) n_out++;
         }
-        for (uint32_t j = 0; j < n_out; j++) { p.out_ids[row + j] = p.id_base + bi[j]; p.out_scores[row + j] = bs[j]; }
+        for (uint32_t j = 0; j < n_out; j++) store_entry(p.out_ids, p.out_scores, p.out_packed, row + j, p.id_base + bi[j], bs[j]);
     } else {
         for (; n_out < p.k; n_out++) {
             uint32_t best = kNilNode, best_id = 0;
@@ -1015,12 +1041,11 @@ __device__ __noinline__ void select_survivors(const SelectArgs p, uint32_t q) {
             }
             if (best == kNilNode) break;
             atomicOr(&p.lean_nodes[best].y, 0x80000000u);
-            p.out_ids[row + n_out] = p.id_base + best_id;
-            p.out_scores[row + n_out] = best_score;
+            store_entry(p.out_ids, p.out_scores, p.out_packed, row + n_out, p.id_base + best_id, best_score);
         }
     }
     if (!p.sparse_rows)
-        for (uint32_t j = n_out; j < p.k; j++) { p.out_ids[row + j] = 0u; p.out_scores[row + j] = 0.0; }
+        for (uint32_t j = n_out; j < p.k; j++) store_entry(p.out_ids, p.out_scores, p.out_packed, row + j, 0u, 0.0);
     p.out_counts[q] = n_out;
 }
 
@@ -1171,8 +1196,7 @@ __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIn
         if (sole && total <= 1u) {  // the whole answer of the query is known here: no list, no atomics
             if (n_surv == 1u) {
                 const size_t row = (size_t)q * p.k;
-                p.out_ids[row] = ix.id_base + __ldg(ix.perm + s_slot);
-                p.out_scores[row] = metric_score(p.metric, s_count, size_a, s_b);
+                store_entry(p.out_ids, p.out_scores, p.out_packed, row, ix.id_base + __ldg(ix.perm + s_slot), metric_score(p.metric, s_count, size_a, s_b));
             }
             if (gl == 0) write_row_end(ix, p, q, total);
             continue;
@@ -1187,7 +1211,7 @@ __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIn
                 if (last) __threadfence();
             }
             if (last && !plan_is_dirty(plan_base))
-                select_survivors(SelectArgs{p.k, ix.id_base, p.sparse_rows, p.lean_head, p.lean_nodes, p.out_ids, p.out_counts, p.out_scores}, q);
+                select_survivors(SelectArgs{p.k, ix.id_base, p.sparse_rows, p.lean_head, p.lean_nodes, p.out_ids, p.out_counts, p.out_scores, p.out_packed}, q);
         }
         __syncwarp(gmask);
     }
@@ -1234,6 +1258,21 @@ cudaError_t lean_occupancy(int device, uint32_t k, int *count_per_sm, int *resol
     return cudaSuccess;
 }
 
+// CUDA loads a kernel's code at its first launch (lazy module loading), and that load can wait for the device to go idle.
+// sg_search_batch launches kernels that wait on the device for copies the host has yet to enqueue: a first launch behind
+// such a kernel would never return.  Every kernel of this file is therefore loaded when an index is created.
+cudaError_t preload_bitmap_kernels() {
+    const void *kernels[] = {(const void *)sg_window_kernel, (const void *)sg_tokens_kernel, (const void *)sg_tokens_arrive_kernel,
+                             (const void *)sg_count_kernel, (const void *)sg_tokens_count_kernel, (const void *)sg_tokens_count_arrive_kernel,
+                             (const void *)sg_resolve_kernel, (const void *)sg_bitmap_search_kernel, (const void *)sg_bitmap_collect_kernel};
+    for (const void *k : kernels) {
+        cudaFuncAttributes attr;
+        cudaError_t e = cudaFuncGetAttributes(&attr, k);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 cudaError_t launch_window(const DevIndex &ix, const SearchParams &p, cudaStream_t stream) {
     sg_window_kernel<<<kWindowRows, kWindowThreads, 0, stream>>>(ix, p);
     return cudaGetLastError();
@@ -1250,7 +1289,8 @@ cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int 
     }
     if (stage_events) cudaEventRecord(stage_events[1], stream);
     const int tok_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
-    sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
+    if (p.arrived != nullptr) sg_tokens_arrive_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
+    else sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (stage_events) cudaEventRecord(stage_events[2], stream);
@@ -1281,10 +1321,12 @@ cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm
     if (fused) {
         // (the counters of the launch are zeroed by the caller: no kernel runs before this one)
         if (stage_events) cudaEventRecord(stage_events[2], stream);
-        sg_tokens_count_kernel<<<blocks, kBitmapWarps * 32, 0, stream>>>(ix, p);
+        if (p.arrived != nullptr) sg_tokens_count_arrive_kernel<<<blocks, kBitmapWarps * 32, 0, stream>>>(ix, p);
+        else sg_tokens_count_kernel<<<blocks, kBitmapWarps * 32, 0, stream>>>(ix, p);
     } else {
         const int tok_blocks = (int)((p.n_q + kPlanThreads / 32 - 1) / (kPlanThreads / 32));
-        sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
+        if (p.arrived != nullptr) sg_tokens_arrive_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
+        else sg_tokens_kernel<<<tok_blocks < sm_count * 8 ? tok_blocks : sm_count * 8, kPlanThreads, 0, stream>>>(ix, p);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         if (stage_events) cudaEventRecord(stage_events[2], stream);

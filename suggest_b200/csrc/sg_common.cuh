@@ -113,10 +113,11 @@ __device__ __forceinline__ uint32_t lower_bound(const uint32_t *__restrict__ pos
 // Go `for range` decoding step (utf8.DecodeRune acceptance), invalid byte -> U+FFFD, width 1
 // Query bytes and offsets are read past L1 (.cg): sg_search_batch lets them arrive by DMA while the kernel is already
 // running (SearchParams::arrived), and a line cached before its neighbour chunk landed would be stale.
-__device__ __forceinline__ uint32_t ldq(const uint8_t *p) { return (uint32_t)__ldcg(p); }
+template <bool kArrive>
+__device__ __forceinline__ uint32_t ldq(const uint8_t *p) { return kArrive ? (uint32_t)__ldcg(p) : (uint32_t)*p; }
 
 __device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *rune) {
-    uint32_t b0 = ldq(s);
+    uint32_t b0 = s[0];  // (plain loads: non-ASCII chunks of an arriving batch live in a 128-byte aligned area of their own)
     if (b0 < 0x80) { *rune = b0; return 1; }
     int need;
     uint32_t r, lo = 0x80, hi = 0xBF;
@@ -126,7 +127,7 @@ __device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *
     else { *rune = 0xFFFD; return 1; }
     if (len < (uint32_t)need + 1) { *rune = 0xFFFD; return 1; }
     for (int i = 1; i <= need; i++) {
-        uint32_t b = ldq(s + i);
+        uint32_t b = s[i];
         uint32_t l = i == 1 ? lo : 0x80, h = i == 1 ? hi : 0xBF;
         if (b < l || b > h) { *rune = 0xFFFD; return 1; }
         r = (r << 6) | (b & 0x3F);
@@ -140,22 +141,26 @@ __device__ __noinline__ int utf8_step(const uint8_t *s, uint32_t len, uint32_t *
 // A warp waits here until the chunk of its query has arrived.  Copies do not depend on kernels: no deadlock.
 // Returns false if the chunk did not arrive within ~2 s (a failed copy the host could not report in time): the query is
 // then answered as empty and the host turns the call into an error (too_long_flag[1]) - a kernel must never spin for good.
-__device__ __noinline__ int wait_for_chunk(const uint32_t *arrived, uint32_t need, uint32_t *gave_up_flag) {
+// s_seen: per-CTA copy of the counter in shared memory, so that a warp whose chunk is known to be there does not touch
+// the counter's L2 line at all (thousands of warps polling one line every few hundred nanoseconds is a hot spot of its own).
+__device__ __noinline__ int wait_for_chunk(const uint32_t *arrived, uint32_t need, uint32_t *gave_up_flag, volatile uint32_t *s_seen) {
+    if ((int32_t)(*s_seen - need) >= 0) return 1;
     const long long t0 = clock64();
-    while ((int32_t)(*(const volatile uint32_t *)arrived - need) < 0) {
+    for (;;) {
+        const uint32_t now = *(const volatile uint32_t *)arrived;
+        if ((int32_t)(now - *s_seen) > 0) *s_seen = now;
+        if ((int32_t)(now - need) >= 0) return 1;
         if (clock64() - t0 > 4000000000ll) {
             if (gave_up_flag != nullptr) gave_up_flag[1] = 1u;
             return 0;
         }
-        __nanosleep(200);
+        __nanosleep(1000);
     }
-    return 1;
 }
 
-__device__ __forceinline__ bool wait_for_query(const SearchParams &p, uint32_t q, int lane) {
-    if (p.arrived == nullptr) return true;
+__device__ __forceinline__ bool wait_for_query(const SearchParams &p, uint32_t q, int lane, volatile uint32_t *s_seen) {
     int ok = 1;
-    if (lane == 0) ok = wait_for_chunk(p.arrived, p.arrive_base + q / p.chunk_queries + 1u, p.too_long_flag);
+    if (lane == 0) ok = wait_for_chunk(p.arrived, p.arrive_base + q / p.chunk_queries + 1u, p.too_long_flag, s_seen);
     ok = __shfl_sync(kFull, ok, 0);
     __threadfence();
     return ok != 0;
@@ -169,15 +174,22 @@ __device__ __forceinline__ bool wait_for_query(const SearchParams &p, uint32_t q
 // s_ascii (optional): a shared-memory copy of ix.ascii_code, which enables the fast path below.
 // kKeys = true (documents, sg_gpubuild.cu): no term lookup; the packed key of every token goes to s_keys[kMaxQueryTokens]
 // in token order and *n_lists_out = len(tokens).
-template <bool kKeys = false>
+template <bool kKeys = false, bool kArrive = false>
 __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchParams &p, uint32_t q, uint32_t *s_runes,
                                                uint32_t *s_lterm, uint32_t *s_hash, int lane, int *size_a_out, int *n_lists_out,
                                                const uint8_t *s_ascii = nullptr, uint64_t *s_keys = nullptr) {
     bool unsupported = false;
     int size_a = 0;
     // chunked arrival: every chunk of chunk_queries queries has its own n + 1 offsets, kArriveOffPad entries apart
-    const uint32_t qi = p.chunk_queries ? q + (q / p.chunk_queries) * kArriveOffPad : q;
-    const uint32_t qb = __ldcg(p.q_off + qi), qe = __ldcg(p.q_off + qi + 1);
+    uint32_t qb, qe;
+    if (kArrive) {
+        const uint32_t qi = q + (q / p.chunk_queries) * kArriveOffPad;
+        qb = __ldcg(p.q_off + qi);
+        qe = __ldcg(p.q_off + qi + 1);
+    } else {
+        qb = __ldg(p.q_off + q);
+        qe = __ldg(p.q_off + q + 1);
+    }
     const uint32_t qlen = qe - qb;
     const uint8_t *qp = (const uint8_t *)p.q_bytes + qb;
     const int nws = ix.n_wrap_start, nwe = p.mode == 1 ? 0 : ix.n_wrap_end;  // NewAutocompleteTokenizer: no tail wrap
@@ -188,7 +200,7 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
         const int nr = nws + (int)qlen + nwe;
         uint32_t r = ' ';
         if (lane < nws) r = ix.wrap_start[lane];
-        else if (lane < nws + (int)qlen) r = ldq(qp + lane - nws);
+        else if (lane < nws + (int)qlen) r = ldq<kArrive>(qp + lane - nws);
         else if (lane < nr) r = ix.wrap_end[lane - nws - (int)qlen];
         if (!__any_sync(kFull, r >= 0x80u)) {
             if (r >= 'A' && r <= 'Z') r += 32;
@@ -232,14 +244,14 @@ __device__ __forceinline__ bool tokenize_query(const DevIndex &ix, const SearchP
         }
     }
     bool nonascii = false;
-    for (uint32_t i = lane; i < qlen; i += 32) nonascii |= ldq(qp + i) >= 0x80;
+    for (uint32_t i = lane; i < qlen; i += 32) nonascii |= ldq<kArrive>(qp + i) >= 0x80;
     nonascii = __any_sync(kFull, nonascii);
     int nq_runes = 0;
     if (!nonascii) {
         if (nws + qlen + nwe > (uint32_t)kMaxRunes) unsupported = true;
         else {
             for (uint32_t i = lane; i < qlen; i += 32) {
-                uint32_t ch = ldq(qp + i);
+                uint32_t ch = ldq<kArrive>(qp + i);
                 s_runes[nws + i] = (ch >= 'A' && ch <= 'Z') ? ch + 32 : ch;
             }
             nq_runes = (int)qlen;

@@ -166,6 +166,8 @@ struct SearchParams {
     uint32_t *out_ids;
     double *out_scores;
     uint32_t *out_counts;
+    uint4 *out_packed;        // non-null: rows of 16-byte {id, 0, score} entries (sg_candidate = suggest.Candidate's layout) instead of
+                              // out_ids / out_scores: one store - one PCIe write when the rows are page-locked host memory - per entry
     uint32_t *stats;          // optional, 16-byte aligned: {admissible postings, admissible lists, 32-bit words the engine reads for the count, 0} per query
     uint32_t *work_counter;   // kWorkWords counters of the launch (bitmap engine: zeroed by sg_tokens_kernel; scan-count engine: word 0, zeroed before launch)
     uint8_t *plans;           // n_q * kPlanStride bytes of scratch

@@ -13,6 +13,7 @@ cudaError_t launch_search(const DevIndex &ix, const SearchParams &p, int blocks,
 size_t bitmap_warp_smem(uint32_t k);
 // opt in to the shared memory the kernel needs at this k (raised, never lowered) and how many CTAs fit an SM (cached)
 cudaError_t bitmap_search_occupancy(int device, uint32_t k, int *blocks_per_sm);
+cudaError_t preload_bitmap_kernels();  // forces the lazy load of every kernel of sg_bitmap.cu (see there)
 cudaError_t launch_window(const DevIndex &ix, const SearchParams &p, cudaStream_t stream);  // sg_window_kernel alone (fills p.wt)
 cudaError_t launch_bitmap_search(const DevIndex &ix, const SearchParams &p, int sm_count, int blocks_per_sm, bool run_window,
                                  cudaStream_t stream, cudaEvent_t *stage_events = nullptr);

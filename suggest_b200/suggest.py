@@ -42,6 +42,39 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
+CANDIDATE_DTYPE = np.dtype([("key", "<u4"), ("reserved", "<u4"), ("score", "<f8")])  # sg_candidate = suggest.Candidate in memory
+
+
+class PinnedCandidateRows:
+    """Page-locked rows of sg_candidate entries + counts for NGramIndex.SuggestBatchCandidates (pass `.out`)."""
+
+    def __init__(self, n_q, k):
+        self._ptrs = []
+        self.rows = self._alloc((n_q, k), CANDIDATE_DTYPE)
+        self.counts = self._alloc((n_q,), np.uint32)
+        self.out = (self.rows, self.counts)
+
+    def _alloc(self, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _capi.check(_capi.lib().sg_pinned_alloc(max(n, 1), C.byref(p)))
+        self._ptrs.append(p.value)
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        ptrs, self._ptrs = self._ptrs, []
+        self.rows = self.counts = self.out = None
+        for p in ptrs:
+            _capi.lib().sg_pinned_free(p)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PinnedBuffers:
     """Result buffers for SuggestBatch / AutocompleteBatch in page-locked memory (sg_pinned_alloc): the search kernel
     stores the candidates straight into them, entries at and behind counts[q] are left as they were.  Pass `.out` as
@@ -283,6 +316,22 @@ class NGramIndex:
                                          max(k, 0), _ptr(ids), _ptr(scores), _ptr(counts))
         _capi.check(rc)
         return ids, scores, counts
+
+    def SuggestBatchCandidates(self, queries, similarity, metric, topK, packed=None, out=None):
+        """sg_search_batch_candidates: the rows as suggest.Candidate lays them out (CANDIDATE_DTYPE: key, reserved, score;
+        16 bytes).  Returns (rows[n_q, k], counts[n_q]); `out` = PinnedCandidateRows(n_q, k).out for the direct path."""
+        data, off = packed if packed is not None else pack_strings(queries)
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        n_q, k = len(off) - 1, max(int(topK), 0)
+        if out is None:
+            rows = np.zeros((n_q, k), dtype=CANDIDATE_DTYPE)
+            counts = np.zeros(n_q, dtype=np.uint32)
+        else:
+            rows, counts = out
+        _capi.check(_capi.lib().sg_search_batch_candidates(self.handle, _ptr(data), _ptr(off), n_q, metric.code, float(similarity), k,
+                                                           _ptr(rows), _ptr(counts)))
+        return rows, counts
 
     # -- Autocomplete ---------------------------------------------------------------------------
     def Autocomplete(self, query, limit) -> List[Candidate]:

@@ -737,3 +737,32 @@ def test_chunked_arrival_equals_sliced_path():
     m = np.arange(5)[None, :] < cnt[:, None]
     assert np.array_equal(buf.counts, cnt) and np.array_equal(buf.ids[m], ids[m])
     gx.close()
+
+
+def test_candidate_rows_equal_separate_arrays(cars_pair, cars_lines):
+    """sg_search_batch_candidates (rows of 16-byte {key, 0, score} entries, suggest.Candidate's layout) returns what
+    sg_search_batch returns: pageable rows (staged), page-locked rows (stored by the kernels), a batch large enough for the
+    chunked-arrival path, a query of more than 128 n-grams, k above 1024."""
+    gx, ox = cars_pair
+    queries = list(cars_lines[:700]) + [b"", b"nissan " * 30, "ЖИГУЛИ".encode("utf-8")]
+    for metric, alpha, k in ((S.JaccardMetric(), 0.5, 10), (S.CosineMetric(), 0.3, 50), (S.JaccardMetric(), 0.05, 1500)):
+        ids, sc, cnt = gx.SuggestBatch(queries, alpha, metric, k)
+        m = np.arange(k)[None, :] < cnt[:, None]
+        rows, n = gx.SuggestBatchCandidates(queries, alpha, metric, k)
+        assert np.array_equal(n, cnt) and np.array_equal(rows["key"][m], ids[m]) and np.array_equal(rows["score"][m], sc[m])
+        assert not rows["reserved"][m].any()
+        buf = S.PinnedCandidateRows(len(queries), k)
+        buf.rows["key"][...] = 0xDEADBEEF
+        rows, n = gx.SuggestBatchCandidates(queries, alpha, metric, k, out=buf.out)
+        assert np.array_equal(n, cnt) and np.array_equal(rows["key"][m], ids[m]) and np.array_equal(rows["score"][m], sc[m])
+        assert np.all(rows["key"][~m] == 0xDEADBEEF)  # the direct path writes the valid entries only
+        buf.close()
+    docs, (qb, qo), _ = synthetic_workload(40000, 18000)
+    big = build_gpu(TEST_DESCRIPTION, (docs[0], docs[1]))
+    ids, sc, cnt = big.SuggestBatch(None, 0.5, S.JaccardMetric(), 10, packed=(qb, qo))
+    buf = S.PinnedCandidateRows(18000, 10)
+    rows, n = big.SuggestBatchCandidates(None, 0.5, S.JaccardMetric(), 10, packed=(qb, qo), out=buf.out)
+    m = np.arange(10)[None, :] < cnt[:, None]
+    assert np.array_equal(n, cnt) and np.array_equal(rows["key"][m], ids[m]) and np.array_equal(rows["score"][m], sc[m]) and cnt.sum() > 9000
+    buf.close()
+    big.close()

@@ -28,9 +28,10 @@ buf = S.PinnedBuffers(NQ, K)
 ref = None
 for metric in (S.JaccardMetric(), S.CosineMetric()):
     ref = None
-    for env in (dict(SG_DIRECT_OUT=0), dict(SG_DIRECT_SLICE_QUERIES=65536), dict(SG_DIRECT_SLICE_QUERIES=32768),
+    for env in (dict(SG_DIRECT_CHUNKS=4), dict(SG_DIRECT_CHUNKS=8), dict(SG_DIRECT_OUT=0), dict(SG_DIRECT_SLICE_QUERIES=65536), dict(SG_DIRECT_SLICE_QUERIES=32768),
                 dict(SG_DIRECT_SLICE_QUERIES=16384), dict(), dict(SG_DIRECT_SPLIT="12,38"), dict(SG_DIRECT_SPLIT="8,30"),
-                dict(SG_DIRECT_SPLIT="25"), dict(SG_DIRECT_SPLIT="12"), dict(SG_DIRECT_SPLIT="6,20,50"), dict(SG_DIRECT_SPLIT="15,50")):
+                dict(SG_DIRECT_SPLIT="25"), dict(SG_DIRECT_SPLIT="12"), dict(SG_DIRECT_SPLIT="6,20,50"), dict(SG_DIRECT_SPLIT="15,50"),
+                dict(SG_DIRECT_SPLIT="50"), dict(SG_DIRECT_SPLIT="33,66"), dict(SG_DIRECT_SPLIT="25,50,75"), dict(SG_DIRECT_SPLIT="40")):
         for k_, v in env.items():
             os.environ[k_] = str(v)
         index = S.NewRAMBuilder((d_bytes, d_off), desc).Build()
