@@ -344,9 +344,9 @@ class Batches:
         return int(self.raw[i][0].nbytes + 4 * (N_QUERIES + 1))
 
 
-def make_batches(d_bytes, d_off, rng, n):
+def make_batches(d_bytes, d_off, rng, n, subs=2):
     from suggest_b200.workload import synthetic_queries
-    return [synthetic_queries(d_bytes, d_off, N_QUERIES, rng)[:2] for _ in range(n)]
+    return [synthetic_queries(d_bytes, d_off, N_QUERIES, rng, subs)[:2] for _ in range(n)]
 
 
 def l2_peak():
@@ -360,7 +360,7 @@ def l2_peak():
 
 
 def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard", ngram=3, letters="uniform", steps=None,
-                       warmup=None, calls_per_step=BATCHES_PER_STEP, ring=RING, with_stages=True):
+                       warmup=None, calls_per_step=BATCHES_PER_STEP, ring=RING, with_stages=True, desc=None, subs=2):
     """the headline measurement (and every config #3 point): one index on this rank, RING batches, value + e2e"""
     from suggest_b200 import _capi
     from suggest_b200.suggest import IndexDescription
@@ -369,13 +369,13 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
     steps = steps or args.steps
     warmup = args.warmup if warmup is None else warmup
     metric = {"Jaccard": S.JaccardMetric(), "Cosine": S.CosineMetric(), "Dice": S.DiceMetric()}[metric_name]
-    description = IndexDescription(Name="bench", NGramSize=ngram, Alphabet=DESCRIPTION["alphabet"], Pad=DESCRIPTION["pad"],
-                                   Wrap=DESCRIPTION["wrap"], Device=rig.local)
+    desc = desc or DESCRIPTION
+    description = IndexDescription(Name="bench", NGramSize=ngram, Alphabet=desc["alphabet"], Pad=desc["pad"], Wrap=desc["wrap"], Device=rig.local)
     t0 = time.perf_counter()
     index = S.NewRAMBuilder((d_bytes, d_off), description).Build()
     build_s = time.perf_counter() - t0
     info, layout = index.info(), index.layout()
-    B = Batches(rig, make_batches(d_bytes, d_off, rng, ring), K)
+    B = Batches(rig, make_batches(d_bytes, d_off, rng, ring, subs), K)
     nq = N_QUERIES
     cs = rig.stream.cuda_stream
 
@@ -467,18 +467,32 @@ def measure_config3(rig, args, S, d_bytes, d_off):
     z_bytes, z_off, z_rng = synthetic_dictionary(N_DOCS, skew="zipf")
     plan = [(m, n, "uniform") for n in (2, 3, 4) for m in ("Jaccard", "Cosine", "Dice") if not (m == "Jaccard" and n == 3)]
     plan += [(m, 3, "zipf") for m in ("Jaccard", "Cosine", "Dice")]
+    # the reference's own real-language dictionary (pkg/suggest/testdata/words.dict, 235,886 English words, committed as a
+    # fixture), its index description from testdata/config.json, queries = entries with one substituted letter
+    words = None
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "words.dict"), "rb") as f:
+            lines = f.read().split(b"\n")[:-1]
+        w_off = np.zeros(len(lines) + 1, dtype=np.uint64)
+        w_off[1:] = np.cumsum([len(x) for x in lines])
+        words = (np.frombuffer(b"".join(lines), dtype=np.uint8).copy(), w_off)
+        plan += [(m, 3, "words.dict") for m in ("Jaccard", "Cosine", "Dice")]
+    except OSError:
+        pass
+    words_desc = dict(ngram_size=3, wrap=("^", "$"), pad="$", alphabet=("english", "numbers", "$^"))
     for metric_name, ngram, letters in plan:
-        data, off = (z_bytes, z_off) if letters == "zipf" else (d_bytes, d_off)
+        data, off = (z_bytes, z_off) if letters == "zipf" else words if letters == "words.dict" else (d_bytes, d_off)
         rng = np.random.default_rng(777 + ngram)
         r = measure_replicated(rig, args, S, data, off, rng, metric_name, ngram, letters, steps=3, warmup=1, calls_per_step=4, ring=2,
-                               with_stages=False)
+                               with_stages=False, desc=words_desc if letters == "words.dict" else None, subs=1 if letters == "words.dict" else 2)
         points.append({"metric": metric_name, "ngram": ngram, "letters": letters, "bucket_shift": int(r["layout"]["bucket_shift"]),
                        "value": r["value"], "e2e": r["e2e_value"], "ms_per_batch": r["ms_per_step"] / r["calls_per_step"],
                        "host_equals_device": r["host_equals_device"], "queries_with_a_match": r["match"]})
         r["index"].close()
     worst = min(points, key=lambda p: p["e2e"])
     return {"points": points, "min_qps_e2e": worst["e2e"], "min_point": {k_: worst[k_] for k_ in ("metric", "ngram", "letters")},
-            "note": "3 steps x 4 batches of 65,536 queries per point, same dictionary (n-gram size and metric vary), plus Zipf letters"}
+            "note": "3 steps x 4 batches of 65,536 queries per point: the 1M dictionary (n-gram size and metric vary), its Zipf-lettered "
+                    "variant, and the reference's words.dict (235,886 English words, queries with one substituted letter)"}
 
 
 def measure_single_query(d_bytes, d_off, q_bytes, q_off):

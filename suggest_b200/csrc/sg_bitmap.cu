@@ -829,14 +829,14 @@ __device__ __forceinline__ uint32_t count_and_flag(const DevIndex &ix, const Sea
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(p.work_counter + kWorkFlagCursor, n);
         base = __shfl_sync(kFull, base, 0);
-        if (base + n <= cap) {
-            const unsigned below = (1u << lane) - 1u;
-            if (ts.ov[0] != 0u) p.lean_flags[base + (uint32_t)__popc(m0 & below)] = make_uint4(q, wf + 2u * (uint32_t)lane, ts.ov[0], 0u);
-            if (ts.ov[1] != 0u) p.lean_flags[base + n0 + (uint32_t)__popc(m1 & below)] = make_uint4(q, wf + 2u * (uint32_t)lane + 1u, ts.ov[1], 0u);
-            n_entries += n;
-        } else {
-            dirty = true;
-        }
+        // Every slot below cap that was reserved is written, also when the reservation runs over the end of the list:
+        // sg_resolve_kernel reads min(cursor, cap) entries (and skips those of a dirty query).
+        const unsigned below = (1u << lane) - 1u;
+        const uint32_t i0 = base + (uint32_t)__popc(m0 & below), i1 = base + n0 + (uint32_t)__popc(m1 & below);
+        if (ts.ov[0] != 0u && i0 < cap) p.lean_flags[i0] = make_uint4(q, wf + 2u * (uint32_t)lane, ts.ov[0], 0u);
+        if (ts.ov[1] != 0u && i1 < cap) p.lean_flags[i1] = make_uint4(q, wf + 2u * (uint32_t)lane + 1u, ts.ov[1], 0u);
+        if (base + n <= cap) n_entries += n;
+        else dirty = true;
         w = wf + kTileWords2;
     }
     return n_entries;
@@ -1202,9 +1202,10 @@ __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIn
             continue;
         }
         if (n_surv >= 1u) link_survivor(ix, p, q, size_a, s_slot, s_count, s_b);
-        __threadfence();  // the nodes are visible before the arrival is
+        __threadfence();  // every lane's nodes are on their way to L2 ...
         __syncwarp(gmask);
         if (gl == 0) {
+            __threadfence();  // ... and the lane that announces the arrival orders them (all lanes', through the barrier) before it
             bool last = sole;
             if (!sole) {
                 last = atomicSub(p.lean_pending + q, 1u) == 1u;

@@ -117,7 +117,13 @@ constexpr uint32_t kPlanDirty = 2u;
 // ---- count -> resolve pipeline (sg_count_kernel, sg_resolve_kernel): scratch of one launch, sized per query ----
 // flagged bitmap words {query, word, buckets that reached their threshold, 0}: sg_count_kernel -> sg_resolve_kernel
 // survivors {original id, next node of the query | taken << 31, score (two words)}, a linked list per query
-constexpr uint32_t kFlagsPerQuery = 32, kNodesPerQuery = 8;
+#ifndef SG_FLAGS_PER_QUERY
+#define SG_FLAGS_PER_QUERY 32
+#endif
+#ifndef SG_NODES_PER_QUERY
+#define SG_NODES_PER_QUERY 8
+#endif
+constexpr uint32_t kFlagsPerQuery = SG_FLAGS_PER_QUERY, kNodesPerQuery = SG_NODES_PER_QUERY;
 constexpr uint32_t kLeanScratchPerQuery = kFlagsPerQuery * 16 + kNodesPerQuery * 16 + 8;  // + pending[q], head[q]
 constexpr uint32_t kNilNode = 0xFFFFFFFFu;
 constexpr uint32_t kArriveOffPad = 32;       // offsets of chunk c start at c * (chunk_queries + kArriveOffPad): no 128-byte line is shared by two chunks

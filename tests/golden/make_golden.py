@@ -6,6 +6,8 @@ that the GPU box (which has no /root/reference) can run configuration #1 of BASE
 on-disk index checks:
   cars.dict        pkg/suggest/testdata/cars.dict          (5,066 lines, one entry per line)
   cars.hd, cars.dl pkg/suggest/testdata/db/cars.{hd,dl}    (index v5.1 written by the Go indexer)
+  words.dict       pkg/suggest/testdata/words.dict         (235,886 English words, one per line: the real-language dictionary of
+                   bench.py's config3 sweep and of the DESIGN.md measurements)
   roaring_samples.npz  twelve roaring-bitmap posting lists (> 256 ids) cut out of db/words.dl together with
                    the ids a rebuild of words.dict gives for the same (segment, term)
   lm/1-gm, 2-gm, 3-gm, test.lm   pkg/lm/testdata/fixtures (Google n-gram text of the "i am sam" corpus and the binary
@@ -25,6 +27,7 @@ def main():
     if not os.path.isdir(REF):
         sys.exit("reference checkout not present; fixtures are already committed")
     shutil.copyfile(os.path.join(REF, "cars.dict"), os.path.join(HERE, "cars.dict"))
+    shutil.copyfile(os.path.join(REF, "words.dict"), os.path.join(HERE, "words.dict"))
     for name in ("cars.hd", "cars.dl"):
         shutil.copyfile(os.path.join(REF, "db", name), os.path.join(HERE, name))
     os.makedirs(os.path.join(HERE, "lm"), exist_ok=True)

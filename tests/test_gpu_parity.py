@@ -744,8 +744,9 @@ def test_candidate_rows_equal_separate_arrays(cars_pair, cars_lines):
     sg_search_batch returns: pageable rows (staged), page-locked rows (stored by the kernels), a batch large enough for the
     chunked-arrival path, a query of more than 128 n-grams, k above 1024."""
     gx, ox = cars_pair
-    queries = list(cars_lines[:700]) + [b"", b"nissan " * 30, "ЖИГУЛИ".encode("utf-8")]
+    base = list(cars_lines[:700]) + [b"", "ЖИГУЛИ".encode("utf-8")]
     for metric, alpha, k in ((S.JaccardMetric(), 0.5, 10), (S.CosineMetric(), 0.3, 50), (S.JaccardMetric(), 0.05, 1500)):
+        queries = base + ([b"nissan " * 30] if k <= 1024 else [])  # (a query of more than 128 n-grams is served up to topK 1024)
         ids, sc, cnt = gx.SuggestBatch(queries, alpha, metric, k)
         m = np.arange(k)[None, :] < cnt[:, None]
         rows, n = gx.SuggestBatchCandidates(queries, alpha, metric, k)
@@ -766,3 +767,41 @@ def test_candidate_rows_equal_separate_arrays(cars_pair, cars_lines):
     assert np.array_equal(n, cnt) and np.array_equal(rows["key"][m], ids[m]) and np.array_equal(rows["score"][m], sc[m]) and cnt.sum() > 9000
     buf.close()
     big.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's real-language dictionary (pkg/suggest/testdata/words.dict), both pipelines
+# ---------------------------------------------------------------------------------------------------
+WORDS_DESCRIPTION = dict(ngram_size=3, wrap=("^", "$"), pad="$", alphabet=("english", "numbers", "$^"))
+
+
+@pytest.mark.parametrize("pipeline", ["classic", "lean"])
+def test_words_dict_against_oracle(pipeline):
+    """235,886 English words, one bit per document: frequent n-grams, low thresholds, hundreds of candidates per query -
+    the launch-wide scratch of the count -> resolve pipeline overflows and the fallback kernel answers what is left"""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "words.dict")
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")[:-1]
+    rng = np.random.default_rng(31)
+    queries = []
+    for i in rng.integers(0, len(lines), size=6000):
+        w = bytearray(lines[int(i)])
+        if w:
+            w[int(rng.integers(0, len(w)))] = int(rng.integers(97, 123))
+        queries.append(bytes(w))
+    gx = build_gpu(WORDS_DESCRIPTION, lines, dict(SG_PIPELINE=pipeline))
+    assert gx.layout()["pipeline"] == (1 if pipeline == "lean" else 0) and gx.layout()["bucket_shift"] == 0
+    ox = O.OracleIndex(**WORDS_DESCRIPTION).add_docs(lines)
+    for metric, alpha, k in ((O.JACCARD, 0.5, 10), (O.COSINE, 0.5, 10), (O.DICE, 0.5, 5)):
+        n = assert_same(gx, ox, queries, metric, alpha, k, f"words.dict {pipeline} m={metric}")
+        assert n.sum() > 3000
+    # the same through page-locked rows, and once more: the scratch is per call
+    data, off = pack_strings(queries)
+    ids, sc, cnt = gx.SuggestBatch(None, 0.5, S.CosineMetric(), 10, packed=(data, off))
+    buf = S.PinnedBuffers(len(queries), 10)
+    for _ in range(2):
+        gx.SuggestBatch(None, 0.5, S.CosineMetric(), 10, packed=(data, off), out=buf.out)
+        m = np.arange(10)[None, :] < cnt[:, None]
+        assert np.array_equal(buf.counts, cnt) and np.array_equal(buf.ids[m], ids[m]) and np.array_equal(buf.scores[m], sc[m])
+    buf.close()
+    gx.close()
