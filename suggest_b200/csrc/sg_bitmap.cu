@@ -1076,7 +1076,11 @@ __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIn
 #pragma unroll
         for (int u = 0; u < kResolveLists; u++) term0[u] = __ldg(terms + gl + u * kResolveGroup);
         const int size_a = (int)h0.y, n_lists = (int)h0.z;
-        if (plan_is_dirty(plan_base)) continue;  // answered by the fallback kernel; nobody waits for this word
+        // answered by the fallback kernel; nobody waits for this word.  ONE lane looks: the flag can change between the looks
+        // of two lanes, and a group that disagreed about it would split around the shuffles and barriers below.
+        uint32_t is_dirty = gl == 0 ? (uint32_t)plan_is_dirty(plan_base) : 0u;
+        is_dirty = __shfl_sync(gmask, is_dirty, lane & ~(kResolveGroup - 1));
+        if (is_dirty) continue;
         const uint8_t *seg_thr = p.wt.seg_thr + (size_t)size_a * ix.n_segments;
         const bool sole = n_flagged == 1u;
         if (p.debug & 4u) continue;
@@ -1202,10 +1206,9 @@ __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIn
             continue;
         }
         if (n_surv >= 1u) link_survivor(ix, p, q, size_a, s_slot, s_count, s_b);
-        __threadfence();  // every lane's nodes are on their way to L2 ...
         __syncwarp(gmask);
         if (gl == 0) {
-            __threadfence();  // ... and the lane that announces the arrival orders them (all lanes', through the barrier) before it
+            __threadfence();  // the nodes of every lane of the group (ordered before this by the barrier) are visible before the arrival is
             bool last = sole;
             if (!sole) {
                 last = atomicSub(p.lean_pending + q, 1u) == 1u;
@@ -1341,11 +1344,10 @@ cudaError_t launch_lean_search(const DevIndex &ix, const SearchParams &p, int sm
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (stage_events) cudaEventRecord(stage_events[4], stream);
-    // normally no query is dirty and this kernel only looks at the flag: one CTA per SM keeps that look cheap
+    // normally no query is dirty and every CTA of this kernel only looks at the flag
     SearchParams pf = p;
     pf.only_dirty = 1;
-    (void)search_per_sm;
-    blocks = sm_count;
+    blocks = sm_count * search_per_sm;
     if (blocks > need) blocks = need;
     sg_bitmap_search_kernel<<<blocks, kBitmapWarps * 32, smem, stream>>>(ix, pf);
     if (stage_events) cudaEventRecord(stage_events[5], stream);

@@ -36,7 +36,8 @@ for rep in range(2):
     ix.SuggestBatchDevice(dq.data_ptr(), doff.data_ptr(), nq, 0.5, m, k, ids.data_ptr(), sc.data_ptr(), cnt.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     res[f"device{rep}"] = (ids.cpu().numpy().view(np.uint32).reshape(nq, k), sc.cpu().numpy().reshape(nq, k), cnt.cpu().numpy().view(np.uint32))
-print(ix.StageTimes(dq.data_ptr(), doff.data_ptr(), nq, 0.5, m, k, ids.data_ptr(), sc.data_ptr(), cnt.data_ptr(), torch.cuda.current_stream().cuda_stream), flush=True)
+for _ in range(6):
+    print(ix.StageTimes(dq.data_ptr(), doff.data_ptr(), nq, 0.5, m, k, ids.data_ptr(), sc.data_ptr(), cnt.data_ptr(), torch.cuda.current_stream().cuda_stream), flush=True)
 res["pageable"] = ix.SuggestBatch(None, 0.5, m, k, packed=(q, qo))
 buf = S.PinnedBuffers(nq, k)
 hq, hoff = torch.from_numpy(q).pin_memory(), torch.from_numpy(qo.astype(np.int32)).pin_memory()
