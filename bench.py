@@ -28,6 +28,11 @@ batch, which also checks the GPU results.
 import argparse
 import json
 import os
+
+# Concurrent calls of one process use three CUDA streams each; with the default 8 hardware queues two calls in flight can
+# share a queue and wait for each other's kernels (measured: 2 callers 131M q/s at 8 queues, 240M at 32).  A deployment
+# knob of the CUDA driver, read when the context is created - set before torch is imported.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import subprocess
 import sys
 import time
@@ -305,12 +310,77 @@ class Rig:
             for b in range(calls_per_step):
                 call(b)
         self.barrier()
+        cpu = host_cpu_probe()
         t0 = time.perf_counter()
         for _ in range(steps):
             for b in range(calls_per_step):
                 call(b)
         dt = time.perf_counter() - t0
+        cpu_busy = host_cpu_probe(cpu)
+        self.last_host = {"per_rank_s": self.all_ranks(dt), "host_cpus": os.cpu_count(), "host_cpus_busy_rank0_view": cpu_busy}
         return self.max_over_ranks(dt)
+
+    def time_host_callers(self, make_call, n_callers, calls_per_step, steps, warmup):
+        """the same with n_callers host threads, each making its share of every step's calls with its own result rows (the
+        reference's callers are one goroutine per request; ctypes releases the GIL for the duration of a call)"""
+        import threading
+        calls = [make_call(t) for t in range(n_callers)]
+        warm, gate = threading.Barrier(n_callers + 1), threading.Barrier(n_callers + 1)
+        errors = []
+
+        def run(t):
+            try:
+                # warm-up with all callers at once: the library creates a call context (streams, staging in HBM) per call in flight
+                for b in range(t, calls_per_step * warmup, n_callers):
+                    calls[t](b)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+            warm.wait()
+            gate.wait()
+            try:
+                for b in range(t, calls_per_step * steps, n_callers):
+                    calls[t](b)
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        threads = [threading.Thread(target=run, args=(t,)) for t in range(n_callers)]
+        for th in threads:
+            th.start()
+        warm.wait()
+        self.barrier()
+        cpu = host_cpu_probe()
+        t0 = time.perf_counter()
+        gate.wait()
+        for th in threads:
+            th.join()
+        dt = time.perf_counter() - t0
+        cpu_busy = host_cpu_probe(cpu)
+        if errors:
+            raise errors[0]
+        self.last_host = {"per_rank_s": self.all_ranks(dt), "host_cpus": os.cpu_count(), "host_cpus_busy_rank0_view": cpu_busy,
+                          "callers": n_callers}
+        return self.max_over_ranks(dt)
+
+    def all_ranks(self, x):
+        if self.world == 1:
+            return [float(x)]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(t, self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev))
+        return [round(float(v), 6) for v in t.tolist()]
+
+
+def host_cpu_probe(before=None):
+    """busy host CPUs (all processes of the box) over an interval, from /proc/stat: probe() before, probe(before) after"""
+    try:
+        f = open("/proc/stat").readline().split()[1:]
+        v = [int(x) for x in f]
+        now = (sum(v), v[3] + (v[4] if len(v) > 4 else 0))
+    except (OSError, ValueError, IndexError):
+        return None
+    if before is None:
+        return now
+    total, idle = now[0] - before[0], now[1] - before[1]
+    return round((total - idle) / total * (os.cpu_count() or 1), 2) if total > 0 else None
 
 
 class Batches:
@@ -360,7 +430,7 @@ def l2_peak():
 
 
 def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard", ngram=3, letters="uniform", steps=None,
-                       warmup=None, calls_per_step=BATCHES_PER_STEP, ring=RING, with_stages=True, desc=None, subs=2):
+                       warmup=None, calls_per_step=BATCHES_PER_STEP, ring=RING, with_stages=True, desc=None, subs=2, with_callers=None):
     """the headline measurement (and every config #3 point): one index on this rank, RING batches, value + e2e"""
     from suggest_b200 import _capi
     from suggest_b200.suggest import IndexDescription
@@ -431,8 +501,30 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
         index.SuggestBatchCandidates(None, ALPHA, metric, K, packed=B.host_in(i), out=rows_buf.out)
 
     e2e_arrays_s = rig.time_host(call_host, calls_per_step, steps, warmup)
-    e2e_s = rig.time_host(call_host_rows, calls_per_step, steps, warmup)
+    e2e_one_s = rig.time_host(call_host_rows, calls_per_step, steps, warmup)
+    e2e_one_host = rig.last_host
+    # the headline e2e: the same call from a few host threads at once, so that one call's copies and host-side work run under
+    # another call's kernels (a single caller leaves the GPU idle ~1/3 of every call: first copy in, last copy out, wake-up)
+    with_callers = with_stages if with_callers is None else with_callers
+    n_callers = max(1, min(3, host_threads() // max(rig.world, 1) - 1)) if with_callers else 1
+    caller_rows = [rows_buf] + [S.PinnedCandidateRows(nq, K) for _ in range(n_callers - 1)]
+
+    def make_caller(t):
+        out = caller_rows[t].out
+
+        def call(b):
+            index.SuggestBatchCandidates(None, ALPHA, metric, K, packed=B.host_in(b % B.n), out=out)
+        return call
+
+    if n_callers > 1:
+        e2e_s = rig.time_host_callers(make_caller, n_callers, calls_per_step, steps, warmup)
+        e2e_host = rig.last_host
+    else:
+        e2e_s, e2e_host = e2e_one_s, e2e_one_host
+    for r_ in caller_rows[1:]:
+        r_.close()
     e2e_value = nq * calls_per_step * steps * rig.world / e2e_s
+    e2e_one_value = nq * calls_per_step * steps * rig.world / e2e_one_s
     e2e_arrays_value = nq * calls_per_step * steps * rig.world / e2e_arrays_s
     rows_same = True
     for i in range(B.n):  # untimed: every batch of the ring once more through both calls, for the comparison below
@@ -452,7 +544,7 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
     h2d = B.h2d_bytes(0) * calls_per_step
     d2h = int(nq * 4 + 16 * int(counts0.clip(0, K).sum())) if direct else int(nq * K * 16 + nq * 4)
     out = dict(index=index, batches=B, dev_rows=dev_rows, info=info, layout=layout, build_s=build_s, ms_per_step=ms_per_step,
-               value=value, e2e_value=e2e_value, e2e_s=e2e_s, e2e_arrays_value=e2e_arrays_value, host_equals_device=bool(same) and rows_same,
+               value=value, e2e_value=e2e_value, e2e_s=e2e_s, e2e_host=e2e_host, e2e_one_value=e2e_one_value, e2e_one_host=e2e_one_host, e2e_arrays_value=e2e_arrays_value, host_equals_device=bool(same) and rows_same,
                direct=direct, stage_ms=stage_ms,
                alg_bytes=alg_bytes, engine_bytes=engine_bytes, h2d=h2d, d2h=d2h * calls_per_step, launches=int(launches),
                calls_per_step=calls_per_step, steps=steps, match=float((counts0 > 0).mean()), wall_timed=wall_timed)
@@ -592,11 +684,14 @@ def measure_config4(rig, args, S, n_docs, steps, warmup, exchanges=("fused", "nc
             B.dq[i].copy_(B.hq[i], non_blocking=True)
             B.doff[i].copy_(B.hoff[i], non_blocking=True)
             sx.SuggestBatchDevice(B.dq[i], B.doff[i], nq, ALPHA, S.JaccardMetric(), K, B.d_ids[i], B.d_sc[i], B.d_cnt[i])
-            B.h_ids[i].copy_(B.d_ids[i], non_blocking=True)
-            B.h_sc[i].copy_(B.d_sc[i], non_blocking=True)
-            B.h_cnt[i].copy_(B.d_cnt[i], non_blocking=True)
+            # every rank holds every merged row; rank r hands the host the rows it merged (queries [lo, hi), sg_exchange.cu):
+            # together the ranks deliver each row exactly once
+            B.h_ids[i][lo * K:hi * K].copy_(B.d_ids[i][lo * K:hi * K], non_blocking=True)
+            B.h_sc[i][lo * K:hi * K].copy_(B.d_sc[i][lo * K:hi * K], non_blocking=True)
+            B.h_cnt[i][lo:hi].copy_(B.d_cnt[i][lo:hi], non_blocking=True)
             torch.cuda.synchronize()
 
+        lo, hi = nq * rig.rank // rig.world, nq * (rig.rank + 1) // rig.world
         ms = rig.time_device(call_device, calls_per_step, steps, warmup)
         sx.check_exchange()
         rows = (B.d_ids[0].cpu().numpy().copy(), B.d_sc[0].cpu().numpy().copy(), B.d_cnt[0].cpu().numpy().copy())
@@ -615,7 +710,8 @@ def measure_config4(rig, args, S, n_docs, steps, warmup, exchanges=("fused", "nc
             torch.cuda.synchronize()
             search_ms = rig.max_over_ranks(ev0.elapsed_time(ev1)) / calls_per_step
         res = {"value": nq * calls_per_step / (ms * 1e-3), "ms_per_batch": ms / calls_per_step,
-               "e2e": nq * calls_per_step * steps / e2e_s,
+               "e2e": nq * calls_per_step * steps / e2e_s, "e2e_host": rig.last_host,
+               "e2e_how": "per batch: H2D of all queries on every rank, search + exchange, D2H of the rows this rank merged (1/N), synchronize",
                "stage_ms": {"search": search_ms if search_ms is not None else ms / calls_per_step,
                             "exchange_and_merge": (ms / calls_per_step - search_ms) if search_ms is not None else 0.0}}
         if check:
@@ -764,8 +860,10 @@ def main():
                       "is the steady state of this workload; the query batches cycle through a ring of 8"},
         "e2e": {"value": r["e2e_value"], "unit": "queries/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                 "call": "sg_search_batch_candidates (rows of 16-byte {key, score} entries = suggest.Candidate's layout)",
-                "separate_id_and_score_arrays": {"call": "sg_search_batch", "value": r["e2e_arrays_value"]},
-                "timing": "host wall clock per rank around the timed calls only, max over ranks",
+                "callers": r["e2e_host"].get("callers", 1),
+                "one_caller": {"value": r["e2e_one_value"], "host": r["e2e_one_host"]},
+                "separate_id_and_score_arrays": {"call": "sg_search_batch", "callers": 1, "value": r["e2e_arrays_value"]},
+                "timing": "host wall clock per rank around the timed calls only, max over ranks", "host": r["e2e_host"],
                 "buffers": "queries: a ring of 8 page-locked batches; result rows: one pooled page-locked buffer set (as b200.go's pinnedPool)",
                 "result_path": ("kernel stores into the caller's page-locked rows (valid entries + counts only)" if r["direct"]
                                 else "rows staged in HBM, cudaMemcpyAsync per slice")},

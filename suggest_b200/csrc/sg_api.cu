@@ -137,7 +137,9 @@ struct sg_index {
                                          // Every further slice costs more in launch gaps and kernel tails than it hides
                                          // (measured: "25" 186 M q/s, "10,40" 184, "6,20,50" 187 / Cosine 140, 137, 132)
     bool direct_out = true;              // SG_DIRECT_OUT=0: always stage the rows in HBM and copy them back
-    int direct_chunks = 4;               // SG_DIRECT_CHUNKS: chunks the queries of a call with page-locked rows arrive in under one launch
+    int direct_chunks = 0;               // SG_DIRECT_CHUNKS: chunks the queries of a call with page-locked rows arrive in under one launch
+                                         // (0, the default: slices on two streams - calls of several host threads then overlap; a chunked
+                                         // call has the device to itself)
                                          // (search_batch_chunked); 0: such calls are cut into slices like the others
     size_t l2_persist_bytes = 0;         // persisting-L2 carve-out used for the posting array (0: none)
     size_t l2_window_bytes = 0;
@@ -347,7 +349,7 @@ int finish_setup(sg_index *ix) {
         }
     }
     ix->direct_out = env_int("SG_DIRECT_OUT", 1) != 0;
-    ix->direct_chunks = env_int("SG_DIRECT_CHUNKS", 4);
+    ix->direct_chunks = env_int("SG_DIRECT_CHUNKS", 0);
     ix->max_warps = env_int("SG_WARPS", kMaxWarps);
     if (ix->max_warps < 1) ix->max_warps = 1;
     if (ix->max_warps > kMaxWarps) ix->max_warps = kMaxWarps;

@@ -550,8 +550,9 @@ __device__ __forceinline__ void tokens_body(const DevIndex &ix, const SearchPara
             if (lane == 0) {
                 // what the bitmap engine itself reads for the count: every (padded) list's words of the window, whole tiles
                 const WordRange win = p.wt.win[size_a];
-                const uint32_t tiles = n_lists > 0 && win.y > win.x ? (win.y - (win.x & ~(kTileWords - 1)) + kTileWords - 1) / kTileWords : 0u;
-                ((uint4 *)p.stats)[q] = make_uint4(st_postings, st_lists, tiles * kTileWords * (uint32_t)((n_lists + 7) & ~7), 0u);
+                const uint32_t tw = p.lean_flags != nullptr ? 64u : kTileWords;  // (sg_count_kernel reads 64-word tiles: kTileWords2)
+                const uint32_t tiles = n_lists > 0 && win.y > win.x ? (win.y - (win.x & ~(tw - 1)) + tw - 1) / tw : 0u;
+                ((uint4 *)p.stats)[q] = make_uint4(st_postings, st_lists, tiles * tw * (uint32_t)((n_lists + 7) & ~7), 0u);
             }
         }
         __syncwarp();
@@ -719,7 +720,7 @@ __global__ void __launch_bounds__(kBitmapWarps * 32, SG_BITMAP_MIN_BLOCKS) sg_bi
 // bytes per warp-load).  A B200 SM issues 4-byte warp-loads at a rate that caps L2 -> SM traffic near 9.5 TB/s chip-wide;
 // with 8-byte loads the same cache delivers ~17 TB/s (tools/l2bench.cu, profiles/l2_peak.json), and the count of
 // config #2 is bound by exactly that.  Used by sg_count_kernel.
-constexpr uint32_t kTileWords2 = 64;
+constexpr uint32_t kTileWords2 = 64;  // (sg_tokens_kernel's stats pass repeats the 64)
 template <int M>
 struct TileState2 {
     uint32_t c[M][2];   // planes of this lane's two words

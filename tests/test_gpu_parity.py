@@ -448,6 +448,42 @@ def test_concurrent_searches_on_one_handle(cars_pair, cars_lines):
     assert not errors, errors[:2]
 
 
+def test_concurrent_callers_with_page_locked_rows():
+    """three host threads, each with its own page-locked query batch and candidate rows, calling
+    sg_search_batch_candidates on one index at the same time (large batches: the kernels store the rows straight into the
+    callers' buffers).  Every call must equal the oracle."""
+    docs, _, _ = synthetic_workload(60000, 16)
+    gx = build_gpu(TEST_DESCRIPTION, (docs[0], docs[1]))
+    ox = O.OracleIndex(**TEST_DESCRIPTION).add_packed(docs[0], docs[1])
+    nq, k, errors = 20000, 10, []
+    from suggest_b200.workload import synthetic_queries
+
+    def worker(seed):
+        try:
+            q, qo, _ = synthetic_queries(docs[0], docs[1], nq, np.random.default_rng(seed))
+            want = ox.suggest_batch(None, O.JACCARD, 0.5, k, O.CANONICAL, threads=2, packed=(q, qo.astype(np.uint64)))
+            rows = S.PinnedCandidateRows(nq, k)
+            for _ in range(6):
+                rows.counts[:] = 0xFFFFFFFF
+                gx.SuggestBatchCandidates(None, 0.5, S.JaccardMetric(), k, packed=(q, qo.astype(np.uint32)), out=rows.out)
+                m = np.arange(k)[None, :] < want[2][:, None]
+                if not (np.array_equal(rows.counts, want[2]) and np.array_equal(rows.rows["key"][m], want[0][m])
+                        and np.array_equal(rows.rows["score"][m], want[1][m])):
+                    errors.append(f"caller {seed}: rows differ from the oracle")
+            rows.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    ts = [threading.Thread(target=worker, args=(s_,)) for s_ in (1, 2, 3)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    gx.close()
+    ox.close()
+    assert not errors, errors[:2]
+
+
 # ---------------------------------------------------------------------------------------------------
 # BASELINE.json config #2 at full size: properties + a sample against the oracle
 # ---------------------------------------------------------------------------------------------------
@@ -708,10 +744,13 @@ def test_long_documents_and_queries():
     gx.close()
 
 
-def test_chunked_arrival_equals_sliced_path():
-    """sg_search_batch with page-locked rows and >= 16,384 queries: one launch, queries arriving in chunks while the
-    kernels run.  Must equal the sliced path (pageable rows) query by query, including chunks that hold non-ASCII bytes
-    (lower-cased on the host into their own area), a query of more than 128 n-grams, empty queries and a ragged last chunk."""
+@pytest.mark.parametrize("chunks", ["4", "0"])
+def test_chunked_arrival_equals_sliced_path(chunks, monkeypatch):
+    """sg_search_batch with page-locked rows and >= 16,384 queries.  SG_DIRECT_CHUNKS=4: one launch, queries arriving in
+    chunks while the kernels run; 0 (the default): slices on two streams, rows stored into the caller's buffers.  Both must
+    equal the staged path (pageable rows) query by query, including chunks that hold non-ASCII bytes (lower-cased on the host
+    into their own area), a query of more than 128 n-grams, empty queries and a ragged last chunk."""
+    monkeypatch.setenv("SG_DIRECT_CHUNKS", chunks)  # read when the index is created
     docs, (qb, qo), _ = synthetic_workload(50000, 20011)
     queries = unpack(qb, qo)
     queries[5] = b""
