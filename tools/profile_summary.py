@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """ncu report -> the text summary committed under profiles/ (run here, no GPU needed).
 
-usage: profile_summary.py <prof.ncu-rep> <out.md> [title] [kernel name]
+usage: profile_summary.py <prof.ncu-rep> <out.md> [title] [kernel name] [workload of the launch]
 """
 import csv
 import io
@@ -40,11 +40,12 @@ def main():
     rep, out = sys.argv[1], sys.argv[2]
     title = sys.argv[3] if len(sys.argv) > 3 else os.path.basename(rep)
     kernel = sys.argv[4] if len(sys.argv) > 4 else "sg_bitmap_search_kernel"
+    workload = sys.argv[5] if len(sys.argv) > 5 else "65,536 queries of BASELINE.json config #2"
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     lines = [f"# {title}", "", f"source: `{rep}` (ncu --set full --clock-control none --import-source on; one launch of "
-             f"{kernel} = 65,536 queries of BASELINE.json config #2)", "", "| metric | unit | value |", "|---|---|---|"]
+             f"{kernel} = {workload})", "", "| metric | unit | value |", "|---|---|---|"]
     vals = {}
     for k in KEYS:
         if k in hdr:
