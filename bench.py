@@ -269,6 +269,7 @@ class Rig:
             dist.init_process_group("nccl", device_id=self.dev)
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
         self.stream = torch.cuda.current_stream()
+        self.stream2 = torch.cuda.Stream(device=self.dev)  # second launching stream of the device-resident leg (see time_device)
 
     def barrier(self):
         self.torch.cuda.synchronize()
@@ -283,9 +284,10 @@ class Rig:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    def time_device(self, call, calls_per_step, steps, warmup, before_timed=None):
-        """CUDA events around every step (calls_per_step calls back to back on the launching stream), L2 flushed between
-        steps (untimed), barrier + synchronize on both sides, max over ranks.  -> ms per step"""
+    def time_device(self, call, calls_per_step, steps, warmup, before_timed=None, two_streams=False):
+        """CUDA events around every step (calls_per_step calls back to back on the launching stream - or, two_streams,
+        alternating between two streams with the events fencing both), L2 flushed between steps (untimed), barrier +
+        synchronize on both sides, max over ranks.  -> ms per step"""
         torch = self.torch
         for _ in range(warmup):
             for b in range(calls_per_step):
@@ -297,8 +299,14 @@ class Rig:
         for s in range(steps):
             self.flush.fill_(s & 0xFF)
             ev[s][0].record()
+            if two_streams:  # the step's calls alternate between two streams; both start behind ev[0], ev[1] waits for both
+                self.stream2.wait_event(ev[s][0])
             for b in range(calls_per_step):
                 call(b)
+            if two_streams:
+                tail = torch.cuda.Event()
+                tail.record(self.stream2)
+                self.stream.wait_event(tail)
             ev[s][1].record()
         self.barrier()
         return self.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
@@ -430,7 +438,7 @@ def l2_peak():
 
 
 def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard", ngram=3, letters="uniform", steps=None,
-                       warmup=None, calls_per_step=BATCHES_PER_STEP, ring=RING, with_stages=True, desc=None, subs=2, with_callers=None):
+                       warmup=None, calls_per_step=BATCHES_PER_STEP, ring=RING, with_stages=True, desc=None, subs=2, with_callers=None, two_streams=True):
     """the headline measurement (and every config #3 point): one index on this rank, RING batches, value + e2e"""
     from suggest_b200 import _capi
     from suggest_b200.suggest import IndexDescription
@@ -449,10 +457,15 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
     nq = N_QUERIES
     cs = rig.stream.cuda_stream
 
+    cs2 = rig.stream2.cuda_stream
+
     def call_device(b, stats=0):
+        # Device-resident calls alternate between two streams (a server with two batches in flight): sg_resolve_kernel of one
+        # call is bound by chains of dependent loads and leaves issue slots to sg_tokens_count_kernel of the next.  Batch i
+        # of the ring (B.n is even) always runs on the same stream, so its result rows are never written from both.
         i = b % B.n
         index.SuggestBatchDevice(B.dq[i].data_ptr(), B.doff[i].data_ptr(), nq, ALPHA, metric, K, B.d_ids[i].data_ptr(),
-                                 B.d_sc[i].data_ptr(), B.d_cnt[i].data_ptr(), stats, cs)
+                                 B.d_sc[i].data_ptr(), B.d_cnt[i].data_ptr(), stats, cs2 if (two_streams and (b & 1)) else cs)
 
     def call_host(b, slot=0):
         # the queries of every call come from their own page-locked batch; the result rows go to ONE pooled page-locked
@@ -475,9 +488,16 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
     def timed_region_starts():
         mark["launches"], mark["t"] = L.sg_kernel_launches(), time.perf_counter()
 
-    ms_per_step = rig.time_device(call_device, calls_per_step, steps, warmup, timed_region_starts)
+    ms_per_step = rig.time_device(call_device, calls_per_step, steps, warmup, timed_region_starts, two_streams=two_streams)
     launches = L.sg_kernel_launches() - mark["launches"]   # kernels of this library launched inside the timed region
-    wall_timed = time.perf_counter() - mark["t"]
+    wall_timed_ = time.perf_counter() - mark["t"]
+    one_stream_value = None
+    if two_streams and with_stages:  # the same calls back to back on ONE stream, for comparison (short)
+        two_streams = False
+        ms_one = rig.time_device(call_device, calls_per_step, max(3, steps // 4), 1)
+        two_streams = True
+        one_stream_value = nq * calls_per_step * rig.world / (ms_one * 1e-3)
+    wall_timed = wall_timed_
     value = nq * calls_per_step * rig.world / (ms_per_step * 1e-3)
     dev_rows = [(B.d_ids[i].cpu().numpy().copy(), B.d_sc[i].cpu().numpy().copy(), B.d_cnt[i].cpu().numpy().copy()) for i in range(B.n)]
 
@@ -544,7 +564,7 @@ def measure_replicated(rig, args, S, d_bytes, d_off, rng, metric_name="Jaccard",
     h2d = B.h2d_bytes(0) * calls_per_step
     d2h = int(nq * 4 + 16 * int(counts0.clip(0, K).sum())) if direct else int(nq * K * 16 + nq * 4)
     out = dict(index=index, batches=B, dev_rows=dev_rows, info=info, layout=layout, build_s=build_s, ms_per_step=ms_per_step,
-               value=value, e2e_value=e2e_value, e2e_s=e2e_s, e2e_host=e2e_host, e2e_one_value=e2e_one_value, e2e_one_host=e2e_one_host, e2e_arrays_value=e2e_arrays_value, host_equals_device=bool(same) and rows_same,
+               value=value, one_stream_value=one_stream_value, e2e_value=e2e_value, e2e_s=e2e_s, e2e_host=e2e_host, e2e_one_value=e2e_one_value, e2e_one_host=e2e_one_host, e2e_arrays_value=e2e_arrays_value, host_equals_device=bool(same) and rows_same,
                direct=direct, stage_ms=stage_ms,
                alg_bytes=alg_bytes, engine_bytes=engine_bytes, h2d=h2d, d2h=d2h * calls_per_step, launches=int(launches),
                calls_per_step=calls_per_step, steps=steps, match=float((counts0 > 0).mean()), wall_timed=wall_timed)
@@ -852,7 +872,9 @@ def main():
         "dtype": "u32 bitmap words / f64 scores" if layout["engine"] == 1 else "u32 postings / u8 counters / f64 scores",
         "data": "synthetic", "config": cfg,
         "run": {"batches_per_step": r["calls_per_step"], "queries_per_step_per_gpu": nq * r["calls_per_step"], "ring_of_batches": RING,
-                "parallelism": "replicated index, queries split", "postings": int(info["n_postings"]),
+                "parallelism": "replicated index, queries split",
+                "device_resident_leg": "calls alternate between two CUDA streams (two batches in flight)",
+                "value_with_one_stream": r["one_stream_value"], "postings": int(info["n_postings"]),
                 "index_bytes": int(info["device_bytes"]), "index_build_s": round(r["build_s"], 2),
                 "engine": "bitmap" if layout["engine"] == 1 else "scancount", "bucket_shift": int(layout["bucket_shift"]),
                 "bitmap_bytes": int(layout["bitmap_bytes"]),
