@@ -495,6 +495,20 @@ __global__ void __launch_bounds__(kWindowThreads) sg_window_kernel(const DevInde
 // admissible postings / lists of SURVEY.md section 8(d) (the algorithmic bytes of the roofline) and the bitmap words the
 // engine reads for the count: 16 bytes per query {postings, lists, bitmap words, 0}.
 // ---------------------------------------------------------------------------------------------------------------
+// sg_count_kernel's tiles (defined with it below; the stats pass of sg_tokens_kernel repeats its arithmetic)
+#ifndef SG_TILE_ALIGN
+#define SG_TILE_ALIGN 64
+#endif
+constexpr uint32_t kTileAlign2 = SG_TILE_ALIGN;   // words the first tile of a window is aligned to
+__device__ __forceinline__ uint32_t first_tile_word(uint32_t win_lo, uint32_t win_hi, uint32_t row_words) {
+    // SG_TILE_ALIGN=32: tiles start at a 128-byte boundary at or below the window instead of a 256-byte one (a quarter of a
+    // tile less per query on average; measured 155 vs 156 us on config #2 - the kernel is bound by the chain of dependent
+    // loads in front of a query's count, not by the count's units - so 64 stays).  A row is whole 64-word tiles
+    // (choose_layout): a window that ends in the row's last words must not run a tile over the end of the row.
+    const uint32_t w = win_lo & ~(kTileAlign2 - 1);
+    return w + (win_hi - w + 63u) / 64u * 64u > row_words ? (win_lo & ~63u) : w;
+}
+
 template <bool kArrive>
 __device__ __forceinline__ void tokens_body(const DevIndex &ix, const SearchParams &p) {
     __shared__ __align__(16) uint32_t s_scratch[kPlanThreads / 32][kMaxRunes + 2 * kMaxQueryTokens];
@@ -551,7 +565,8 @@ __device__ __forceinline__ void tokens_body(const DevIndex &ix, const SearchPara
                 // what the bitmap engine itself reads for the count: every (padded) list's words of the window, whole tiles
                 const WordRange win = p.wt.win[size_a];
                 const uint32_t tw = p.lean_flags != nullptr ? 64u : kTileWords;  // (sg_count_kernel reads 64-word tiles: kTileWords2)
-                const uint32_t tiles = n_lists > 0 && win.y > win.x ? (win.y - (win.x & ~(tw - 1)) + tw - 1) / tw : 0u;
+                const uint32_t w_first = p.lean_flags != nullptr ? first_tile_word(win.x, win.y, ix.row_words) : (win.x & ~(tw - 1));
+                const uint32_t tiles = n_lists > 0 && win.y > win.x ? (win.y - w_first + tw - 1) / tw : 0u;
                 ((uint4 *)p.stats)[q] = make_uint4(st_postings, st_lists, tiles * tw * (uint32_t)((n_lists + 7) & ~7), 0u);
             }
         }
@@ -727,6 +742,9 @@ struct TileState2 {
     uint32_t ov[2], bias[2];
 };
 
+// two adjacent row words
+__device__ __forceinline__ uint2 ld_row2(const uint32_t *p) { return __ldg((const uint2 *)p); }
+
 template <int M>
 __device__ __forceinline__ uint32_t count_until_flag2(const uint32_t *__restrict__ bitmaps, const uint32_t *s_row,
                                                       const uint8_t *__restrict__ word_thr, uint32_t w_begin, uint32_t win_hi,
@@ -739,14 +757,14 @@ __device__ __forceinline__ uint32_t count_until_flag2(const uint32_t *__restrict
 #define SG_LOAD_BLOCK2(R)                                                                                     \
     do {                                                                                                      \
         const uint4 r0_ = *(const uint4 *)(s_row + ld_block * 8u), r1_ = *(const uint4 *)(s_row + ld_block * 8u + 4u); \
-        R##0 = __ldg((const uint2 *)(ld_ptr + r0_.x));                                                        \
-        R##1 = __ldg((const uint2 *)(ld_ptr + r0_.y));                                                        \
-        R##2 = __ldg((const uint2 *)(ld_ptr + r0_.z));                                                        \
-        R##3 = __ldg((const uint2 *)(ld_ptr + r0_.w));                                                        \
-        R##4 = __ldg((const uint2 *)(ld_ptr + r1_.x));                                                        \
-        R##5 = __ldg((const uint2 *)(ld_ptr + r1_.y));                                                        \
-        R##6 = __ldg((const uint2 *)(ld_ptr + r1_.z));                                                        \
-        R##7 = __ldg((const uint2 *)(ld_ptr + r1_.w));                                                        \
+        R##0 = ld_row2(ld_ptr + r0_.x);                                                                       \
+        R##1 = ld_row2(ld_ptr + r0_.y);                                                                       \
+        R##2 = ld_row2(ld_ptr + r0_.z);                                                                       \
+        R##3 = ld_row2(ld_ptr + r0_.w);                                                                       \
+        R##4 = ld_row2(ld_ptr + r1_.x);                                                                       \
+        R##5 = ld_row2(ld_ptr + r1_.y);                                                                       \
+        R##6 = ld_row2(ld_ptr + r1_.z);                                                                       \
+        R##7 = ld_row2(ld_ptr + r1_.w);                                                                       \
         if (++ld_block == n_blocks) {                                                                         \
             ld_block = 0;                                                                                     \
             ld_ptr += kTileWords2;                                                                            \
@@ -821,7 +839,7 @@ __device__ __forceinline__ uint32_t count_and_flag(const DevIndex &ix, const Sea
                                                    uint32_t q, int lane, bool &dirty) {
     const uint32_t cap = p.n_q * kFlagsPerQuery;
     uint32_t n_entries = 0;
-    for (uint32_t w = win_lo & ~(kTileWords2 - 1); w < win_hi;) {
+    for (uint32_t w = first_tile_word(win_lo, win_hi, ix.row_words); w < win_hi;) {
         TileState2<M> ts;
         const uint32_t wf = count_until_flag2<M>(ix.bitmaps, s_row, word_thr, w, win_hi, n_lists, lane, ts);
         if (wf == kInf) break;
