@@ -899,10 +899,12 @@ def main():
                               "engine answers the same queries from per-term bucket bitmaps that stay in L2, so this is NOT a "
                               "fraction of a hardware limit and can exceed 1; roofline_engine is the hardware-side view"
                               if layout["engine"] == 1 else "posting lists are read once per query by sg_search_kernel")},
-        "roofline_engine": {"bound": "l2 / issue slots (bitmaps are L2-resident; see profiles/ ncu summary)",
+        "roofline_engine": {"bound": "latency of L2 reads at 32 warps per SM (issue slots 60 % busy, L2 38 %, L1 53 % of peak: no unit is saturated; bitmaps are L2-resident)",
                             "engine_bytes_per_launch": r["engine_bytes"], "engine_bytes_per_query": r["engine_bytes"] / nq,
                             "achieved": engine_gbs, "unit": "GB/s", "peak": l2_gbs, "peak_kind": l2_how,
                             "frac": (engine_gbs / l2_gbs) if l2_gbs else None,
+                            "counters": recorded_traffic(top_kernel, "counters"),
+                            "counters_note": "ncu --set full capture of the same kernel on the same workload, committed under profiles/ (not measured in this run)",
                             "note": "bitmap words the count reads (whole 32-word tiles x lists padded to 8) x 4 B over the dominant "
                                     "kernel's duration, against the measured L2 -> SM read bandwidth"},
         "clocks": clocks, "wall_s_timed_region": wall,
