@@ -137,6 +137,8 @@ struct sg_index {
                                          // Every further slice costs more in launch gaps and kernel tails than it hides
                                          // (measured: "25" 186 M q/s, "10,40" 184, "6,20,50" 187 / Cosine 140, 137, 132)
     bool direct_out = true;              // SG_DIRECT_OUT=0: always stage the rows in HBM and copy them back
+    uint32_t lean_flags_per_query = sg::kFlagsPerQuery, lean_nodes_per_query = sg::kNodesPerQuery;  // SG_LEAN_FLAGS_PER_QUERY / SG_LEAN_NODES_PER_QUERY: scratch a launch
+                                         // may use per query (pooled; at most what is allocated) - the tests shrink it to force the fallback
     int direct_chunks = 0;               // SG_DIRECT_CHUNKS: chunks the queries of a call with page-locked rows arrive in under one launch
                                          // (0, the default: slices on two streams - calls of several host threads then overlap; a chunked
                                          // call has the device to itself)
@@ -350,6 +352,8 @@ int finish_setup(sg_index *ix) {
     }
     ix->direct_out = env_int("SG_DIRECT_OUT", 1) != 0;
     ix->direct_chunks = env_int("SG_DIRECT_CHUNKS", 0);
+    ix->lean_flags_per_query = (uint32_t)std::min<long long>(std::max<long long>(env_int("SG_LEAN_FLAGS_PER_QUERY", (int)sg::kFlagsPerQuery), 0), sg::kFlagsPerQuery);
+    ix->lean_nodes_per_query = (uint32_t)std::min<long long>(std::max<long long>(env_int("SG_LEAN_NODES_PER_QUERY", (int)sg::kNodesPerQuery), 0), sg::kNodesPerQuery);
     ix->max_warps = env_int("SG_WARPS", kMaxWarps);
     if (ix->max_warps < 1) ix->max_warps = 1;
     if (ix->max_warps > kMaxWarps) ix->max_warps = kMaxWarps;
@@ -566,6 +570,8 @@ int enqueue_search(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off,
             p.lean_nodes = (uint4 *)at;
             at += (size_t)n_q * sg::kNodesPerQuery * sizeof(uint4);
             p.lean_pending = (uint32_t *)at;
+            p.flag_cap = n_q * ix->lean_flags_per_query;
+            p.node_cap = n_q * ix->lean_nodes_per_query;
             p.lean_head = p.lean_pending + n_q;
             int count_per_sm = 0, resolve_per_sm = 0;
             SG_CUDA(sg::lean_occupancy(ix->device, k, &count_per_sm, &resolve_per_sm));

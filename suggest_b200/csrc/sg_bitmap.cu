@@ -837,7 +837,7 @@ template <int M>
 __device__ __forceinline__ uint32_t count_and_flag(const DevIndex &ix, const SearchParams &p, const uint32_t *s_row,
                                                    const uint8_t *__restrict__ word_thr, uint32_t win_lo, uint32_t win_hi, int n_lists,
                                                    uint32_t q, int lane, bool &dirty) {
-    const uint32_t cap = p.n_q * kFlagsPerQuery;
+    const uint32_t cap = p.flag_cap;
     uint32_t n_entries = 0;
     for (uint32_t w = first_tile_word(win_lo, win_hi, ix.row_words); w < win_hi;) {
         TileState2<M> ts;
@@ -993,7 +993,7 @@ __device__ __forceinline__ void mark_dirty(const SearchParams &p, uint32_t q) {
 __device__ __forceinline__ void link_survivor(const DevIndex &ix, const SearchParams &p, uint32_t q, int size_a, uint32_t slot, int count,
                                               int size_b) {
     const uint32_t idx = atomicAdd(p.work_counter + kWorkNodeCursor, 1u);
-    if (idx < p.n_q * kNodesPerQuery) {
+    if (idx < p.node_cap) {
         const uint32_t id = __ldg(ix.perm + slot);
         const double score = metric_score(p.metric, count, size_a, size_b);
         const uint32_t prev = atomicExch(p.lean_head + q, idx);
@@ -1078,7 +1078,7 @@ __global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIn
     const unsigned gmask = ((1u << kResolveGroup) - 1u) << (lane & ~(kResolveGroup - 1));
     uint32_t *cnt = s_cnt[threadIdx.x / kResolveGroup];
     const uint32_t bshift = ix.bshift, W = 1u << bshift;
-    const uint32_t n_entries = min(((const volatile uint32_t *)p.work_counter)[kWorkFlagCursor], p.n_q * kFlagsPerQuery);
+    const uint32_t n_entries = min(((const volatile uint32_t *)p.work_counter)[kWorkFlagCursor], p.flag_cap);
     const uint32_t n_groups = gridDim.x * (kResolveThreads / kResolveGroup);
     const int S = (int)ix.n_segments, cached = min(S, kSegCache);
     for (uint32_t e = blockIdx.x * (kResolveThreads / kResolveGroup) + threadIdx.x / kResolveGroup; e < n_entries; e += n_groups) {

@@ -118,7 +118,7 @@ constexpr uint32_t kPlanDirty = 2u;
 // flagged bitmap words {query, word, buckets that reached their threshold, 0}: sg_count_kernel -> sg_resolve_kernel
 // survivors {original id, next node of the query | taken << 31, score (two words)}, a linked list per query
 #ifndef SG_FLAGS_PER_QUERY
-#define SG_FLAGS_PER_QUERY 32
+#define SG_FLAGS_PER_QUERY 64           // (Zipf-lettered Cosine 0.5 flags 19 words per query)
 #endif
 #ifndef SG_NODES_PER_QUERY
 #define SG_NODES_PER_QUERY 8
@@ -188,6 +188,7 @@ struct SearchParams {
     // ---- count -> resolve pipeline (bitmap engine, Suggest top-k) ----
     uint4 *lean_flags;        // n_q * kFlagsPerQuery entries; nullptr: the launch runs sg_bitmap_search_kernel only
     uint4 *lean_nodes;        // n_q * kNodesPerQuery entries
+    uint32_t flag_cap, node_cap;  // entries of the two lists this launch may use (<= what is allocated; the tests shrink them)
     uint32_t *lean_pending;   // [n_q] flagged words of the query not yet resolved
     uint32_t *lean_head;      // [n_q] first survivor node of the query, kNilNode: none
     int32_t only_dirty;       // sg_bitmap_search_kernel: answer only the queries marked kPlanDirty (and exit at once if none is)

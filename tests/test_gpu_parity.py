@@ -844,3 +844,21 @@ def test_words_dict_against_oracle(pipeline):
         assert np.array_equal(buf.counts, cnt) and np.array_equal(buf.ids[m], ids[m]) and np.array_equal(buf.scores[m], sc[m])
     buf.close()
     gx.close()
+
+
+@pytest.mark.parametrize("flags,nodes", [(1, 8), (64, 0), (2, 1), (0, 8)])
+def test_pipeline_scratch_overflow_against_oracle(flags, nodes):
+    """The count -> resolve pipeline with its launch-wide scratch shrunk (SG_LEAN_FLAGS_PER_QUERY / SG_LEAN_NODES_PER_QUERY
+    entries per query, pooled): the list of flagged words overflows, the survivor nodes overflow, both, or nothing fits at
+    all - the queries concerned are marked dirty at different points of the pipeline and answered by the fallback kernel.
+    Every query must equal the oracle, whichever kernel answered it."""
+    docs, (qb, qo), _ = synthetic_workload(40000, 3000, seed=77)
+    queries = unpack(qb, qo)
+    gx = build_gpu(TEST_DESCRIPTION, (docs[0], docs[1]), dict(SG_LEAN_FLAGS_PER_QUERY=flags, SG_LEAN_NODES_PER_QUERY=nodes, SG_BUCKET_SHIFT=4))
+    assert gx.layout()["pipeline"] == 1
+    ox = O.OracleIndex(**TEST_DESCRIPTION).add_packed(docs[0], docs[1])
+    for metric, alpha, k in ((O.JACCARD, 0.3, 10), (O.COSINE, 0.4, 40), (O.DICE, 0.5, 5)):
+        n = assert_same(gx, ox, queries, metric, alpha, k, f"scratch {flags}/{nodes} m={metric}")
+        assert n.sum() > 2000
+    gx.close()
+    ox.close()
