@@ -293,12 +293,12 @@ void sg_exchange_free(sg_exchange *ex);
  * Replaces nothing of the reference and serves its calling pattern: Service.Suggest is called with ONE query per goroutine
  * (internal/suggest/api/suggest_handler.go:42-76, cmd/suggest/cmd/eval.go:60, pkg/spellchecker/spellchecker.go:67).
  * sg_suggest_one blocks the calling thread until its row is there; any number of host threads may call it at once.
- * Their queries are coalesced by one worker thread into sg_search_batch calls over page-locked buffers the batcher owns:
- * a batch closes when it holds max_batch queries, when its oldest query has waited max_wait_us, or - under load - as soon
- * as the previous batch has returned.  Queries of one batch share (metric, similarity); k is per query (<= max_k).
+ * Their queries are coalesced by worker threads (two: two batches in flight; SG_BATCHER_WORKERS) into sg_search_batch
+ * calls over page-locked buffers the batcher owns: a batch closes when it holds max_batch queries, when its oldest query
+ * has waited max_wait_us, or - under load - as soon as a worker's previous batch has returned.  Queries of one batch share (metric, similarity); k is per query (<= max_k).
  * out_ids / out_scores: room for k entries; *out_count receives the number of candidates ((score desc, id asc) order).
  * Errors are per query (SG_ERR_QUERY_TOO_LONG for one query does not fail its batch mates).
- * sg_batcher_free serves what is queued, then stops the worker; the index must outlive the batcher.
+ * sg_batcher_free serves what is queued, then stops the workers; the index must outlive the batcher.
  */
 typedef struct sg_batcher sg_batcher;
 typedef struct {

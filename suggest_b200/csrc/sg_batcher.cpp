@@ -3,15 +3,17 @@
 // The reference's callers issue one query per goroutine (internal/suggest/api/suggest_handler.go:42-76 per HTTP request,
 // cmd/suggest/cmd/eval.go:60, pkg/spellchecker/spellchecker.go:67); a GPU call per query would spend ~60 us of launch and
 // copy latency on ~4 ns of work.  A batcher owns one worker thread: callers (any number of host threads - cgo calls block
-// an OS thread each) append their query to the open batch and sleep; the worker closes a batch when it is full, when its
-// oldest query has waited max_wait_us, or - the usual case under load - as soon as the previous batch has returned, so
-// the batch size follows the arrival rate by itself.  The batch runs through sg_search_batch with page-locked buffers
+// an OS thread each) append their query to the open batch and sleep; a worker closes a batch when it is full, when its
+// oldest query has waited max_wait_us, or - the usual case under load - as soon as its previous batch has returned, so
+// the batch size follows the arrival rate by itself.  Two workers (SG_BATCHER_WORKERS) keep two batches in flight: one
+// batch's copies and host-side work run under the other's kernels.  The batch runs through sg_search_batch with page-locked buffers
 // owned by the batcher (the kernel stores the result rows straight into them; a caller's Go-heap slices never force the
 // staged path), the rows are handed out, the callers wake.  Queries of one batch share (metric, similarity); k is the
 // largest asked for (a top-k list is a prefix of every longer one).
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -42,6 +44,14 @@ struct Request {
 
 }  // namespace
 
+struct Worker {  // one batch in flight: a thread and the page-locked staging it owns
+    std::thread thread;
+    char *q_bytes = nullptr;
+    size_t q_cap = 0;
+    uint32_t *q_off = nullptr, *ids = nullptr, *counts = nullptr;
+    double *scores = nullptr;
+};
+
 struct sg_batcher {
     sg_index *ix = nullptr;
     uint32_t max_batch = 0, max_wait_us = 0, max_k = 0;
@@ -49,19 +59,14 @@ struct sg_batcher {
     std::condition_variable cv_work, cv_done;
     std::deque<Request *> queue;
     bool stop = false;
-    std::thread worker;
-    // page-locked staging, owned by the worker
-    char *q_bytes = nullptr;
-    size_t q_cap = 0;
-    uint32_t *q_off = nullptr, *ids = nullptr, *counts = nullptr;
-    double *scores = nullptr;
+    std::vector<Worker> workers;
     // statistics
     std::atomic<uint64_t> n_batches{0}, n_queries{0}, max_seen{0};
 };
 
 namespace {
 
-void run_batch(sg_batcher *b, std::vector<Request *> &batch) {
+void run_batch(sg_batcher *bt, Worker *b, std::vector<Request *> &batch) {
     const uint32_t n = (uint32_t)batch.size();
     uint32_t k = 1;
     size_t total = 0;
@@ -88,7 +93,7 @@ void run_batch(sg_batcher *b, std::vector<Request *> &batch) {
             at += batch[i]->len;
         }
         b->q_off[n] = (uint32_t)at;
-        rc = sg_search_batch(b->ix, b->q_bytes, b->q_off, n, batch[0]->metric, batch[0]->alpha, k, b->ids, b->scores, b->counts);
+        rc = sg_search_batch(bt->ix, b->q_bytes, b->q_off, n, batch[0]->metric, batch[0]->alpha, k, b->ids, b->scores, b->counts);
         if (rc != SG_OK) err = sg_last_error();
     }
     if (rc == SG_ERR_QUERY_TOO_LONG) {
@@ -106,13 +111,13 @@ void run_batch(sg_batcher *b, std::vector<Request *> &batch) {
         std::memcpy(r->out_scores, b->scores + (size_t)i * k, (size_t)c * sizeof(double));
         *r->out_count = c;
     }
-    b->n_batches.fetch_add(1, std::memory_order_relaxed);
-    b->n_queries.fetch_add(n, std::memory_order_relaxed);
-    uint64_t seen = b->max_seen.load(std::memory_order_relaxed);
-    while (n > seen && !b->max_seen.compare_exchange_weak(seen, n, std::memory_order_relaxed)) {}
+    bt->n_batches.fetch_add(1, std::memory_order_relaxed);
+    bt->n_queries.fetch_add(n, std::memory_order_relaxed);
+    uint64_t seen = bt->max_seen.load(std::memory_order_relaxed);
+    while (n > seen && !bt->max_seen.compare_exchange_weak(seen, n, std::memory_order_relaxed)) {}
 }
 
-void worker_loop(sg_batcher *b) {
+void worker_loop(sg_batcher *b, Worker *w) {
     std::vector<Request *> batch;
     for (;;) {
         batch.clear();
@@ -125,6 +130,7 @@ void worker_loop(sg_batcher *b) {
             const auto deadline = b->queue.front()->arrived + std::chrono::microseconds(b->max_wait_us);
             while (!b->stop && b->queue.size() < b->max_batch && std::chrono::steady_clock::now() < deadline)
                 b->cv_work.wait_until(lk, deadline);
+            if (b->queue.empty()) continue;  // another worker took the batch this one was waiting to fill
             const int metric = b->queue.front()->metric;
             const double alpha = b->queue.front()->alpha;
             for (auto it = b->queue.begin(); it != b->queue.end() && batch.size() < b->max_batch;) {
@@ -136,7 +142,7 @@ void worker_loop(sg_batcher *b) {
                 }
             }
         }
-        run_batch(b, batch);
+        run_batch(b, w, batch);
         {
             std::lock_guard<std::mutex> lk(b->mu);
             for (Request *r : batch) r->done = true;
@@ -146,11 +152,13 @@ void worker_loop(sg_batcher *b) {
 }
 
 void release(sg_batcher *b) {
-    sg_pinned_free(b->q_bytes);
-    sg_pinned_free(b->q_off);
-    sg_pinned_free(b->ids);
-    sg_pinned_free(b->counts);
-    sg_pinned_free(b->scores);
+    for (Worker &w : b->workers) {
+        sg_pinned_free(w.q_bytes);
+        sg_pinned_free(w.q_off);
+        sg_pinned_free(w.ids);
+        sg_pinned_free(w.counts);
+        sg_pinned_free(w.scores);
+    }
     delete b;
 }
 
@@ -169,20 +177,28 @@ int sg_batcher_create(sg_index *ix, uint32_t max_batch, uint32_t max_wait_us, ui
     b->max_batch = max_batch;
     b->max_wait_us = max_wait_us;
     b->max_k = max_k;
-    b->q_cap = (size_t)max_batch * 64 + 4096;
-    void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    int rc = sg_pinned_alloc(b->q_cap, &p[0]);
-    if (rc == SG_OK) rc = sg_pinned_alloc(((size_t)max_batch + 1) * sizeof(uint32_t), &p[1]);
-    if (rc == SG_OK) rc = sg_pinned_alloc((size_t)max_batch * max_k * sizeof(uint32_t), &p[2]);
-    if (rc == SG_OK) rc = sg_pinned_alloc((size_t)max_batch * sizeof(uint32_t), &p[3]);
-    if (rc == SG_OK) rc = sg_pinned_alloc((size_t)max_batch * max_k * sizeof(double), &p[4]);
-    b->q_bytes = (char *)p[0];
-    b->q_off = (uint32_t *)p[1];
-    b->ids = (uint32_t *)p[2];
-    b->counts = (uint32_t *)p[3];
-    b->scores = (double *)p[4];
+    int n_workers = 2;  // batches in flight
+    if (const char *v = std::getenv("SG_BATCHER_WORKERS")) n_workers = std::atoi(v);
+    if (n_workers < 1) n_workers = 1;
+    if (n_workers > 8) n_workers = 8;
+    b->workers.resize((size_t)n_workers);  // (never resized again: the threads hold pointers into it)
+    int rc = SG_OK;
+    for (Worker &w : b->workers) {
+        w.q_cap = (size_t)max_batch * 64 + 4096;
+        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (rc == SG_OK) rc = sg_pinned_alloc(w.q_cap, &p[0]);
+        if (rc == SG_OK) rc = sg_pinned_alloc(((size_t)max_batch + 1) * sizeof(uint32_t), &p[1]);
+        if (rc == SG_OK) rc = sg_pinned_alloc((size_t)max_batch * max_k * sizeof(uint32_t), &p[2]);
+        if (rc == SG_OK) rc = sg_pinned_alloc((size_t)max_batch * sizeof(uint32_t), &p[3]);
+        if (rc == SG_OK) rc = sg_pinned_alloc((size_t)max_batch * max_k * sizeof(double), &p[4]);
+        w.q_bytes = (char *)p[0];
+        w.q_off = (uint32_t *)p[1];
+        w.ids = (uint32_t *)p[2];
+        w.counts = (uint32_t *)p[3];
+        w.scores = (double *)p[4];
+    }
     if (rc != SG_OK) { release(b); return rc; }
-    b->worker = std::thread(worker_loop, b);
+    for (Worker &w : b->workers) w.thread = std::thread(worker_loop, b, &w);
     *out = b;
     return SG_OK;
 }
@@ -233,7 +249,8 @@ void sg_batcher_free(sg_batcher *b) {
         b->stop = true;
     }
     b->cv_work.notify_all();
-    if (b->worker.joinable()) b->worker.join();  // serves what is still queued, then returns
+    for (Worker &w : b->workers)
+        if (w.thread.joinable()) w.thread.join();  // serve what is still queued, then return
     release(b);
 }
 
