@@ -166,6 +166,20 @@ int sg_search_batch_candidates(sg_index *ix, const char *q_bytes, const uint32_t
                                uint32_t k, sg_candidate *out_rows, uint32_t *out_counts);
 
 /*
+ * The same call without waiting for it: several batches in flight from ONE host thread.  The reference overlaps its
+ * requests with goroutines (internal/suggest/api/suggest_handler.go:42-76); a host that drives the library from a single
+ * thread gets the same overlap here - one call's copies and host-side work run under another call's kernels.
+ * submit returns at once with a ticket; a few worker threads of the library (SG_SUBMIT_WORKERS, default 3) run
+ * sg_search_batch_candidates itself; sg_ticket_wait blocks until the call has returned, hands back its status (and its
+ * message through sg_last_error) and frees the ticket.  Every buffer of the call belongs to the library from submit to
+ * wait.  Every ticket must be waited for exactly once; sg_index_free serves what was submitted before it frees the index.
+ */
+typedef struct sg_ticket sg_ticket;
+int sg_search_batch_candidates_submit(sg_index *ix, const char *q_bytes, const uint32_t *q_off, uint32_t n_q, int metric,
+                                      double alpha, uint32_t k, sg_candidate *out_rows, uint32_t *out_counts, sg_ticket **ticket);
+int sg_ticket_wait(sg_ticket *ticket);
+
+/*
  * Batched NGramIndex.Autocomplete with a FirstKCollectorManager(limit)  (pkg/suggest/autocomplete.go:40-77,
  * collector.go:48-115): the query is tokenised without the tail wrap (pkg/suggest/tokenizer.go:23-34), a candidate must
  * hold every query n-gram (threshold = len(tokens), segments len(tokens)..Size()-1) and the `limit` lowest ids win,

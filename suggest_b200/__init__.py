@@ -6,9 +6,9 @@ libsuggest_b200.so (include/suggest_b200.h).  Names follow the reference: pkg/su
 """
 from . import collector, metric
 from .metric import CosineMetric, DiceMetric, ExactMetric, JaccardMetric, OverlapMetric
-from .suggest import (CANDIDATE_DTYPE, Batcher, Candidate, PinnedCandidateRows, IndexDescription, NewBatcher, PinnedBuffers, NGramIndex, NewRAMBuilder, NewFSBuilder, NewSearchConfig, NewService,
+from .suggest import (CANDIDATE_DTYPE, Batcher, Candidate, PinnedCandidateRows, Ticket, IndexDescription, NewBatcher, PinnedBuffers, NGramIndex, NewRAMBuilder, NewFSBuilder, NewSearchConfig, NewService,
                       ResultItem, SearchConfig, Service, SuggestError, pack_strings)
 
-__all__ = ["collector", "metric", "CosineMetric", "DiceMetric", "ExactMetric", "JaccardMetric", "OverlapMetric", "CANDIDATE_DTYPE", "PinnedCandidateRows", "Batcher", "NewBatcher", "Candidate", "PinnedBuffers",
+__all__ = ["collector", "metric", "CosineMetric", "DiceMetric", "ExactMetric", "JaccardMetric", "OverlapMetric", "CANDIDATE_DTYPE", "PinnedCandidateRows", "Ticket", "Batcher", "NewBatcher", "Candidate", "PinnedBuffers",
            "IndexDescription", "NGramIndex", "NewRAMBuilder", "NewFSBuilder", "NewSearchConfig", "NewService",
            "ResultItem", "SearchConfig", "Service", "SuggestError", "pack_strings"]

@@ -52,6 +52,9 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "sg_search_batch_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
                                              C.c_void_p, C.c_void_p]),
+    "sg_search_batch_candidates_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_uint32,
+                                                    C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "sg_ticket_wait": (C.c_int, [C.c_void_p]),
     "sg_autocomplete_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_void_p]),
     "sg_candidates_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_double, C.c_void_p, C.c_uint64,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsuggest_b200.so")
-SOURCES = ["sg_api.cu", "sg_kernels.cu", "sg_bitmap.cu", "sg_exchange.cu", "sg_fine.cu", "sg_long.cu", "sg_lm.cu", "sg_gpubuild.cu", "sg_text.cpp", "sg_index.cpp", "sg_disk.cpp", "sg_hostapi.cpp", "sg_batcher.cpp"]
+SOURCES = ["sg_api.cu", "sg_kernels.cu", "sg_bitmap.cu", "sg_exchange.cu", "sg_fine.cu", "sg_long.cu", "sg_lm.cu", "sg_gpubuild.cu", "sg_text.cpp", "sg_index.cpp", "sg_disk.cpp", "sg_hostapi.cpp", "sg_batcher.cpp", "sg_submit.cpp"]
 DEPS = SOURCES + ["sg_common.cuh", "sg_device.h", "sg_host.h", "sg_kernels.h", "sg_exchange.h", "unicode_lower.inc", "../../include/suggest_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--fmad=false",

@@ -755,8 +755,11 @@ int sg_index_open_disk(const sg_config *cfg, const char *hd_path, const char *dl
     return SG_OK;
 }
 
+void sg_internal_drop_submit_pool(sg_index *ix);  // sg_submit.cpp
+
 void sg_index_free(sg_index *ix) {
     if (!ix) return;
+    sg_internal_drop_submit_pool(ix);  // calls submitted and not yet waited for are served first
     {
         std::unique_lock<std::mutex> lk(ix->mu);
         ix->closing = true;

@@ -45,6 +45,28 @@ def _ptr(a):
 CANDIDATE_DTYPE = np.dtype([("key", "<u4"), ("reserved", "<u4"), ("score", "<f8")])  # sg_candidate = suggest.Candidate in memory
 
 
+class Ticket:
+    """a submitted call (NGramIndex.SubmitBatchCandidates); keeps the call's buffers alive until it is waited for"""
+
+    def __init__(self, handle, buffers):
+        self._handle, self._buffers = handle, buffers
+
+    def wait(self):
+        handle, self._handle = self._handle, None
+        if handle is None:
+            raise RuntimeError("the ticket was already waited for")
+        _capi.check(_capi.lib().sg_ticket_wait(handle))
+        _, _, rows, counts = self._buffers
+        return rows, counts
+
+    def __del__(self):
+        try:
+            if self._handle is not None:  # never waited for: the library still owns the buffers; wait before they go
+                self.wait()
+        except Exception:
+            pass
+
+
 class PinnedCandidateRows:
     """Page-locked rows of sg_candidate entries + counts for NGramIndex.SuggestBatchCandidates (pass `.out`)."""
 
@@ -332,6 +354,19 @@ class NGramIndex:
         _capi.check(_capi.lib().sg_search_batch_candidates(self.handle, _ptr(data), _ptr(off), n_q, metric.code, float(similarity), k,
                                                            _ptr(rows), _ptr(counts)))
         return rows, counts
+
+    def SubmitBatchCandidates(self, similarity, metric, topK, packed, out):
+        """sg_search_batch_candidates_submit: SuggestBatchCandidates without waiting for it.  -> Ticket; `.wait()` returns
+        (rows, counts).  `packed` = (bytes uint8, offsets uint32) and `out` = PinnedCandidateRows(...).out must stay
+        untouched until then (they are passed as they are: no copies are made here)."""
+        data, off = packed
+        if data.dtype != np.uint8 or off.dtype != np.uint32 or not data.flags.c_contiguous or not off.flags.c_contiguous:
+            raise ValueError("SubmitBatchCandidates takes contiguous uint8 bytes and uint32 offsets")
+        rows, counts = out
+        ticket = C.c_void_p()
+        _capi.check(_capi.lib().sg_search_batch_candidates_submit(self.handle, _ptr(data), _ptr(off), len(off) - 1, metric.code, float(similarity),
+                                                                  max(int(topK), 0), _ptr(rows), _ptr(counts), C.byref(ticket)))
+        return Ticket(ticket, (data, off, rows, counts))
 
     # -- Autocomplete ---------------------------------------------------------------------------
     def Autocomplete(self, query, limit) -> List[Candidate]:

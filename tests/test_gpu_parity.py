@@ -862,3 +862,47 @@ def test_pipeline_scratch_overflow_against_oracle(flags, nodes):
         assert n.sum() > 2000
     gx.close()
     ox.close()
+
+
+def test_submit_and_wait_equal_the_synchronous_call():
+    """sg_search_batch_candidates_submit / sg_ticket_wait: five batches in flight from this one thread (three worker threads
+    of the library), page-locked and pageable rows, an invalid call (its status and message arrive at wait), and tickets
+    still open when the index is freed."""
+    docs, _, _ = synthetic_workload(60000, 16)
+    gx = build_gpu(TEST_DESCRIPTION, (docs[0], docs[1]))
+    from suggest_b200.workload import synthetic_queries
+    nq, k = 20000, 10
+    batches, want, tickets, bufs = [], [], [], []
+    for seed in range(5):
+        q, qo, _ = synthetic_queries(docs[0], docs[1], nq, np.random.default_rng(100 + seed))
+        batches.append((q, qo.astype(np.uint32)))
+        rows, counts = gx.SuggestBatchCandidates(None, 0.5, S.JaccardMetric(), k, packed=batches[-1])
+        want.append((rows.copy(), counts.copy()))
+    for i, b in enumerate(batches):
+        if i % 2 == 0:
+            buf = S.PinnedCandidateRows(nq, k)
+            out = buf.out
+        else:  # pageable rows: staged in HBM and copied
+            buf = None
+            out = (np.zeros((nq, k), dtype=S.CANDIDATE_DTYPE), np.zeros(nq, dtype=np.uint32))
+        bufs.append(buf)
+        tickets.append(gx.SubmitBatchCandidates(0.5, S.JaccardMetric(), k, b, out))
+    for t, (w_rows, w_counts) in zip(tickets, want):
+        rows, counts = t.wait()
+        m = np.arange(k)[None, :] < w_counts[:, None]
+        assert np.array_equal(counts, w_counts)
+        assert np.array_equal(rows["key"][m], w_rows["key"][m]) and np.array_equal(rows["score"][m], w_rows["score"][m])
+    with pytest.raises(RuntimeError):
+        tickets[0].wait()  # a ticket is waited for once
+    bad = gx.SubmitBatchCandidates(1.5, S.JaccardMetric(), k, batches[0], bufs[0].out)  # similarity out of range
+    with pytest.raises(_capi.SuggestError, match="similarity"):
+        bad.wait()
+    # tickets still open when the index goes: sg_index_free serves them first
+    open_tickets = [gx.SubmitBatchCandidates(0.5, S.JaccardMetric(), k, batches[i], bufs[i].out) for i in (0, 2, 4)]
+    gx.close()
+    for t, i in zip(open_tickets, (0, 2, 4)):
+        rows, counts = t.wait()
+        assert np.array_equal(counts, want[i][1])
+    for b in bufs:
+        if b is not None:
+            b.close()
