@@ -1068,7 +1068,10 @@ __device__ __noinline__ void select_survivors(const SelectArgs p, uint32_t q) {
     p.out_counts[q] = n_out;
 }
 
-__global__ void __launch_bounds__(kResolveThreads) sg_resolve_kernel(const DevIndex ix, const SearchParams p) {
+#ifndef SG_RESOLVE_MIN_BLOCKS
+#define SG_RESOLVE_MIN_BLOCKS 4           // 64 registers; 5 (48 registers) measures the same, 6 and 8 spill and are slower, 1 (more registers, fewer warps) is 35 % slower
+#endif
+__global__ void __launch_bounds__(kResolveThreads, SG_RESOLVE_MIN_BLOCKS) sg_resolve_kernel(const DevIndex ix, const SearchParams p) {
     __shared__ uint32_t s_seg[kSegCache + 1];
     __shared__ __align__(16) uint32_t s_cnt[kResolveThreads / kResolveGroup][32];  // per group: 128 byte counters, one per document
     for (uint32_t i = threadIdx.x; i <= min(ix.n_segments, (uint32_t)kSegCache); i += blockDim.x) s_seg[i] = ix.seg_start[i];
