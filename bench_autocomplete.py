@@ -41,6 +41,52 @@ def main():
             "config": {"workload": "prefixes of 3-8 letters of dictionary entries, 64K-query batch, host buffers (queries pageable, result rows page-locked; H2D + kernels + rows to the host timed)",
                        "n_docs": N, "k": K},
             "gpu_launches": int(L.sg_kernel_launches() - l0), "results": {"mean_completions": float(counts.mean())}}
+    # device-resident leg + roofline of the dominant kernel (the same objects as bench.py's main line)
+    import torch
+    import bench as B
+    dev = torch.device("cuda", 0)
+    dq, doff = torch.from_numpy(np.ascontiguousarray(data)).to(dev), torch.from_numpy(off.astype(np.int32)).to(dev)
+    d_ids = torch.zeros(NQ * K, dtype=torch.int32, device=dev)
+    d_sc = torch.zeros(NQ * K, dtype=torch.float64, device=dev)
+    d_cnt = torch.zeros(NQ, dtype=torch.int32, device=dev)
+    d_stats = torch.zeros(NQ * 4, dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    index.AutocompleteBatchDevice(dq.data_ptr(), doff.data_ptr(), NQ, K, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), d_stats.data_ptr(), st)
+    torch.cuda.synchronize()
+    stats = d_stats.cpu().numpy().view(np.uint32).reshape(NQ, 4).astype(np.int64)
+    # 4 B per admissible posting + 8 B per admissible non-empty list + query bytes + 12 B per returned entry
+    alg_bytes = int(4 * stats[:, 0].sum() + 8 * stats[:, 1].sum() + int(off[-1]) + 12 * K * NQ)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        index.AutocompleteBatchDevice(dq.data_ptr(), doff.data_ptr(), NQ, K, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), 0, st)
+    dev_ms = 0.0
+    for s_ in range(STEPS):
+        flush.fill_(s_ & 0xFF)  # > L2, untimed
+        e0.record()
+        index.AutocompleteBatchDevice(dq.data_ptr(), doff.data_ptr(), NQ, K, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), 0, st)
+        e1.record()
+        torch.cuda.synchronize()
+        dev_ms += e0.elapsed_time(e1) / STEPS
+    stage = {}
+    for s_ in range(10):
+        flush.fill_(s_ & 0xFF)
+        for name, ms in index.AutocompleteStageTimes(dq.data_ptr(), doff.data_ptr(), NQ, K, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), st).items():
+            stage[name] = stage.get(name, 0.0) + ms / 10
+    top = max(stage, key=stage.get)
+    peak, peak_kind = B.measured_peak()
+    achieved = alg_bytes / (stage[top] * 1e-3) / 1e9
+    same_dev = bool(np.array_equal(d_cnt.cpu().numpy().view(np.uint32), counts))
+    line["e2e"] = {"value": line["value"], "unit": "queries/s", "h2d_bytes_per_step": int(data.nbytes + off.nbytes),
+                   "d2h_bytes_per_step": int(4 * NQ + 12 * int(counts.sum()))}
+    line["value"] = NQ / (dev_ms * 1e-3)   # inputs resident in HBM; the host-buffer figure is e2e
+    line["ms_per_step"] = dev_ms
+    line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "peak_kind": peak_kind, "kernel": top, "kernel_ms": stage[top], "stage_ms": {k_: round(v, 5) for k_, v in stage.items()},
+                        "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_query": alg_bytes / NQ,
+                        "note": "algorithmic bytes = posting lists of every segment from len(tokens) up (SURVEY.md 8(d) formula); the "
+                                "engine answers from the bucket bitmaps and, for one- and two-n-gram prefixes, from the shorter posting run"}
+    line["results"]["device_rows_equal_host_rows"] = same_dev
     ox = O.OracleIndex(3, ("$", "$"), "$", ("english", "russian", "numbers", "$")).add_packed(d_bytes, d_off)
     n = 2000
     t0 = time.perf_counter()

@@ -232,6 +232,17 @@ int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d
                           float *ms_out, char *names_out, uint32_t names_cap);
 
 /*
+ * sg_autocomplete_batch with every buffer resident on the index's device (as sg_search_batch_device is to
+ * sg_search_batch; d_stats as there, for the admissible lists of NGramIndex.Autocomplete: every segment from len(tokens)
+ * up), and the measurement aid for it.
+ */
+int sg_autocomplete_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, uint32_t limit,
+                                 uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, uint32_t *d_stats, void *stream);
+int sg_autocomplete_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, uint32_t limit,
+                                uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream, float *ms_out,
+                                char *names_out, uint32_t names_cap);
+
+/*
  * Cross-shard reduce for record-id-range shards: for every query pick the k best of n_parts
  * per-shard results (layout [part][query][k] as an all-gather of sg_search_batch_device outputs
  * delivers them) under the same (score desc, id asc) order.  Device buffers.

@@ -1311,9 +1311,19 @@ int sg_candidates_batch(sg_index *ix, const char *q_bytes, const uint32_t *q_off
     return SG_OK;
 }
 
+static int search_batch_device_impl(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
+                                    uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, uint32_t *d_stats,
+                                    void *stream, int mode);
+
 int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric,
                            double alpha, uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts,
                            uint32_t *d_stats, void *stream) {
+    return search_batch_device_impl(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, d_stats, stream, 0);
+}
+
+static int search_batch_device_impl(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
+                                    uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, uint32_t *d_stats,
+                                    void *stream, int mode) {
     int rc = validate_search(ix, n_q, metric, alpha, k);
     if (rc != SG_OK) return rc;
     if (n_q == 0) return SG_OK;
@@ -1328,15 +1338,36 @@ int sg_search_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *
     const size_t plan_bytes = ((size_t)n_q * ix->plan_stride + 255) & ~(size_t)255;
     SG_CUDA(cudaMallocAsync(&plans, plan_bytes + ix->wtab_bytes, (cudaStream_t)stream));
     rc = enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, d_stats,
-                        ix->work_ring + (size_t)slot * sg::kWorkWords, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, (cudaStream_t)stream);
+                        ix->work_ring + (size_t)slot * sg::kWorkWords, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, (cudaStream_t)stream, mode);
     cudaError_t fe = cudaFreeAsync(plans, (cudaStream_t)stream);
     if (rc == SG_OK && fe != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(fe));
     return rc;
 }
 
+int sg_autocomplete_batch_device(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, uint32_t limit,
+                                 uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, uint32_t *d_stats, void *stream) {
+    return search_batch_device_impl(ix, d_q_bytes, d_q_off, n_q, SG_EXACT, 1.0, limit, d_out_ids, d_out_scores, d_out_counts, d_stats, stream, 1);
+}
+
+static int stage_times_impl(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
+                            uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream,
+                            float *ms_out, char *names_out, uint32_t names_cap, int mode);
+
 int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
                           uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream,
                           float *ms_out, char *names_out, uint32_t names_cap) {
+    return stage_times_impl(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, stream, ms_out, names_out, names_cap, 0);
+}
+
+int sg_autocomplete_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, uint32_t limit,
+                                uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream, float *ms_out,
+                                char *names_out, uint32_t names_cap) {
+    return stage_times_impl(ix, d_q_bytes, d_q_off, n_q, SG_EXACT, 1.0, limit, d_out_ids, d_out_scores, d_out_counts, stream, ms_out, names_out, names_cap, 1);
+}
+
+static int stage_times_impl(sg_index *ix, const char *d_q_bytes, const uint32_t *d_q_off, uint32_t n_q, int metric, double alpha,
+                            uint32_t k, uint32_t *d_out_ids, double *d_out_scores, uint32_t *d_out_counts, void *stream,
+                            float *ms_out, char *names_out, uint32_t names_cap, int mode) {
     int rc = validate_search(ix, n_q, metric, alpha, k);
     if (rc != SG_OK) return rc;
     if (n_q == 0 || !ms_out) return fail(SG_ERR_INVALID, "empty batch or null output");
@@ -1351,7 +1382,7 @@ int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d
     const size_t plan_bytes = ((size_t)n_q * ix->plan_stride + 255) & ~(size_t)255;
     SG_CUDA(cudaMalloc(&plans, plan_bytes + ix->wtab_bytes));
     rc = enqueue_search(ix, d_q_bytes, d_q_off, n_q, metric, alpha, k, d_out_ids, d_out_scores, d_out_counts, nullptr,
-                        ix->work_ring + (size_t)slot * sg::kWorkWords, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, st, 0, ev);
+                        ix->work_ring + (size_t)slot * sg::kWorkWords, (uint8_t *)plans, (uint8_t *)plans + plan_bytes, st, mode, ev);
     cudaError_t se = cudaStreamSynchronize(st);
     if (env_int("SG_TRACE", 0) >= 1 && ix->bitmap_engine && se == cudaSuccess) {  // counters of the launch (sg_device.h: kWork*)
         uint32_t w[sg::kWorkWords] = {0};
@@ -1359,7 +1390,8 @@ int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d
         std::fprintf(stderr, "sg_search_stage_times: %u queries: flagged bitmap words %u, survivor nodes %u, dirty %u, fallback queries taken %u\n", n_q,
                      w[sg::kWorkFlagCursor], w[sg::kWorkNodeCursor], w[sg::kWorkDirtyAny], w[sg::kWorkFallbackQuery]);
     }
-    const int n_stages = !ix->bitmap_engine ? 2 : ix->lean_pipeline ? 5 : 3;
+    const bool lean = ix->lean_pipeline && mode == 0 && k <= sg::kSmemTopK;  // (what enqueue_search runs the pipeline for)
+    const int n_stages = !ix->bitmap_engine ? 2 : lean ? 5 : 3;
     if (rc == SG_OK && se == cudaSuccess)
         for (int i = 0; i < n_stages; i++) cudaEventElapsedTime(ms_out + i, ev[i], ev[i + 1]);
     for (auto &e : ev) cudaEventDestroy(e);
@@ -1368,7 +1400,7 @@ int sg_search_stage_times(sg_index *ix, const char *d_q_bytes, const uint32_t *d
     if (se != cudaSuccess) return fail(SG_ERR_CUDA, cudaGetErrorString(se));
     if (names_out && names_cap) {
         const char *names = !ix->bitmap_engine ? "sg_plan_kernel,sg_search_kernel"
-                            : ix->lean_pipeline ? (env_int("SG_FUSED_TOKENS", 1) != 0
+                            : lean ? (env_int("SG_FUSED_TOKENS", 1) != 0
                                                        ? "sg_window_kernel,(tokenizer fused into the next kernel),sg_tokens_count_kernel,sg_resolve_kernel,sg_bitmap_search_kernel"
                                                        : "sg_window_kernel,sg_tokens_kernel,sg_count_kernel,sg_resolve_kernel,sg_bitmap_search_kernel")
                                                 : "sg_window_kernel,sg_tokens_kernel,sg_bitmap_search_kernel";

@@ -407,6 +407,20 @@ class NGramIndex:
         return dict(zip(names.value.decode().split(","), [float(ms[i]) for i in range(n)]))
 
 
+    def AutocompleteBatchDevice(self, d_q_bytes, d_q_off, n_q, limit, d_ids, d_scores, d_counts, d_stats=0, stream=0):
+        """sg_autocomplete_batch_device: every argument is a device pointer (int); asynchronous on `stream`."""
+        _capi.check(_capi.lib().sg_autocomplete_batch_device(self.handle, d_q_bytes, d_q_off, n_q, int(limit), d_ids, d_scores, d_counts,
+                                                             d_stats or None, stream or None))
+
+    def AutocompleteStageTimes(self, d_q_bytes, d_q_off, n_q, limit, d_ids, d_scores, d_counts, stream=0):
+        """sg_autocomplete_stage_times: {kernel name: ms} of one device-resident Autocomplete launch."""
+        ms = (C.c_float * 8)()
+        names = C.create_string_buffer(256)
+        n = _capi.check(_capi.lib().sg_autocomplete_stage_times(self.handle, d_q_bytes, d_q_off, n_q, int(limit), d_ids, d_scores, d_counts,
+                                                                stream or None, ms, names, 256))
+        return dict(zip(names.value.decode().split(","), [float(ms[i]) for i in range(n)]))
+
+
 class Batcher:
     """sg_batcher_*: the micro-batcher in front of sg_search_batch for callers that issue ONE query per thread, as the
     reference's do (internal/suggest/api/suggest_handler.go:42-76: one goroutine per HTTP request).  Suggest blocks the

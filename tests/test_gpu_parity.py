@@ -906,3 +906,35 @@ def test_submit_and_wait_equal_the_synchronous_call():
     for b in bufs:
         if b is not None:
             b.close()
+
+
+def test_autocomplete_device_entry_equals_host_entry(cars_pair, cars_lines):
+    """sg_autocomplete_batch_device (buffers resident on the device) against sg_autocomplete_batch (itself checked against
+    the oracle above), the stage-time aid, and the sanity of the stats pass in autocomplete mode"""
+    import torch
+    gx, ox = cars_pair
+    prefixes = [bytes(line[:n]).lower() for line in cars_lines[:400] for n in (3, 5, 8) if len(line) >= n]
+    limit = 7
+    ids, sc, cnt = gx.AutocompleteBatch(prefixes, limit)
+    data, off = pack_strings(prefixes)
+    dev = torch.device("cuda", 0)
+    dq, doff = torch.from_numpy(np.ascontiguousarray(data)).to(dev), torch.from_numpy(off.astype(np.int32)).to(dev)
+    n = len(prefixes)
+    d_ids = torch.zeros(n * limit, dtype=torch.int32, device=dev)
+    d_sc = torch.zeros(n * limit, dtype=torch.float64, device=dev)
+    d_cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+    d_stats = torch.zeros(n * 4, dtype=torch.int32, device=dev)
+    gx.AutocompleteBatchDevice(dq.data_ptr(), doff.data_ptr(), n, limit, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(), d_stats.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    g_cnt = d_cnt.cpu().numpy().view(np.uint32)
+    m = np.arange(limit)[None, :] < cnt[:, None]
+    assert np.array_equal(g_cnt, cnt)
+    assert np.array_equal(d_ids.cpu().numpy().view(np.uint32).reshape(n, limit)[m], ids[m])
+    assert np.array_equal(d_sc.cpu().numpy().reshape(n, limit)[m], sc[m])
+    times = gx.AutocompleteStageTimes(dq.data_ptr(), doff.data_ptr(), n, limit, d_ids.data_ptr(), d_sc.data_ptr(), d_cnt.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream)
+    assert "sg_bitmap_search_kernel" in times and all(v >= 0 for v in times.values())
+    # the stats pass (SURVEY.md 8(d) figures for Autocomplete): a prefix with completions has admissible lists, every list a posting
+    stats = d_stats.cpu().numpy().view(np.uint32).reshape(n, 4)
+    assert np.all(stats[cnt > 0, 1] > 0) and np.all(stats[:, 0] >= stats[:, 1]) and np.all(stats[cnt > 0, 0] >= cnt[cnt > 0])
