@@ -17,10 +17,19 @@
 // (pkg/metric/*.go, pkg/suggest/scorer.go:29-31, collector.go:20-26).  No atomics and no shared-memory table on the
 // counting path: every lane owns its words.
 //
-// Three launches per batch:
-//   sg_window_kernel         per len(tokens) = 0..128: segment window, T(segment), T(bitmap word)   (tiny)
-//   sg_tokens_kernel         tokenise every query -> len(tokens), term ids
-//   sg_bitmap_search_kernel  count, compare, resolve, score, top-k
+// Launches per batch.  Suggest top-k on an index with the exact level (sg_fine.cu) runs the count -> resolve pipeline
+// (second half of this file):
+//   sg_window_kernel         per len(tokens) = 0..128: segment window, T(segment), T(bitmap word)   (tiny; cached per
+//                            (metric, similarity))
+//   sg_tokens_count_kernel   tokenise every query, count (two words per lane, 8-byte loads), append the bitmap words in
+//                            which a bucket reached its threshold to a launch-wide list
+//   sg_resolve_kernel        eight lanes per flagged word: exact per-document counts from the bit-per-document level,
+//                            survivors scored and linked to their query, k best selected by whoever resolves a query's
+//                            last word
+//   sg_bitmap_search_kernel  (only_dirty) the queries the pipeline ran out of scratch for; normally looks at one flag
+// Autocomplete, the spellchecker's collector, collect mode, k > 1024 and indexes without the exact level:
+//   sg_window_kernel, sg_tokens_kernel (tokenise -> len(tokens), term ids), sg_bitmap_search_kernel (count, compare,
+//   resolve from the posting lists, score, top-k - all in the warp that owns the query)
 #include <cstddef>
 #include <map>
 #include <mutex>
